@@ -1,0 +1,643 @@
+// abi.cu -- the C ABI of ndsmf.so (include/ndsm_b200.h).  Section 1 re-exports the reference's
+// BIND(C) surface (fortran/ndsm_python_wrapper.f90:56-234) with identical semantics.
+#include <chrono>
+#include <cstring>
+#include <thread>
+#include <vector>
+
+#include "../../include/ndsm_b200.h"
+#include "vecpot.hpp"
+
+using namespace ndsm;
+
+namespace ndsm {
+extern bool g_debug;
+void debug_msg(const char* sub, const char* msg);
+}  // namespace ndsm
+
+static void error_msg(const char* msg, const char* sub, const char* eid) {  // ndsm_root.f90:476-488
+  fprintf(stderr, "ERROR(%s):%s:%s\n", sub, msg, eid);
+}
+
+static double now_s() {
+  return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
+static cudaStream_t g_stream = nullptr;
+static int g_device = -1;
+
+// Select the device (env NDSM_DEVICE, else the current one) and create the library stream.
+static int ensure_device(const char* sub) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0) {
+    cudaGetLastError();
+    error_msg("no CUDA device available (this library has no CPU fallback)", sub, "NDSM_B200_ERR_CUDA");
+    return NDSM_B200_ERR_CUDA;
+  }
+  int want = -1;
+  if (const char* e = getenv("NDSM_DEVICE")) want = atoi(e);
+  if (want < 0) {
+    if (cudaGetDevice(&want) != cudaSuccess) want = 0;
+  }
+  if (want >= n) want = 0;
+  if (g_device != want) {
+    if (cudaSetDevice(want) != cudaSuccess) {
+      error_msg("cudaSetDevice failed", sub, "NDSM_B200_ERR_CUDA");
+      return NDSM_B200_ERR_CUDA;
+    }
+    if (g_stream) { cudaStreamDestroy(g_stream); g_stream = nullptr; }
+    g_device = want;
+  } else {
+    cudaSetDevice(want);
+  }
+  if (!g_stream && cudaStreamCreateWithFlags(&g_stream, cudaStreamNonBlocking) != cudaSuccess) {
+    error_msg("cudaStreamCreate failed", sub, "NDSM_B200_ERR_CUDA");
+    return NDSM_B200_ERR_CUDA;
+  }
+  return 0;
+}
+
+static int fail(const NdsmError& e, const char* sub) {
+  int code = (e.code == 2) ? NDSM_B200_ERR_SHAPE : (e.code == 4) ? NDSM_B200_ERR_STENCIL : NDSM_B200_ERR_CUDA;
+  if (e.code == 2) error_msg("mesh too small for a multigrid hierarchy (min(nshape) < 4)", sub, "NDSM_B200_ERR_SHAPE");
+  else if (e.code == 4) error_msg("restriction stencil exceeds compiled capacity", sub, "NDSM_B200_ERR_STENCIL");
+  else error_msg("CUDA failure", sub, "NDSM_B200_ERR_CUDA");
+  cudaGetLastError();
+  return code;
+}
+
+static const int imap_cp[6] = {0, 0, 1, 1, 2, 2};
+static const int imap_nc[6][2] = {{1, 2}, {1, 2}, {0, 2}, {0, 2}, {0, 1}, {0, 1}};
+
+// extract_bn, dir=+1 (ndsm_vector_potential.f90:699-743) on the caller's host array
+static void gather_face_host(const double* B, int nx, int ny, int nz, int f, double* face) {
+  const int c = imap_cp[f];
+  const size_t N = (size_t)nx * ny * nz;
+  const double* Bc = B + c * N;
+  const int layer = (f % 2 == 0) ? 0 : (c == 0 ? nx : c == 1 ? ny : nz) - 1;
+  if (c == 0) {
+    for (int k = 0; k < nz; ++k)
+      for (int j = 0; j < ny; ++j) face[j + (size_t)ny * k] = Bc[layer + (size_t)nx * (j + (size_t)ny * k)];
+  } else if (c == 1) {
+    for (int k = 0; k < nz; ++k)
+      memcpy(face + (size_t)nx * k, Bc + (size_t)nx * (layer + (size_t)ny * k), sizeof(double) * nx);
+  } else {
+    memcpy(face, Bc + (size_t)nx * ny * layer, sizeof(double) * nx * ny);
+  }
+}
+
+static bool all_zero_host(const double* a, size_t n) {
+  unsigned nt = std::thread::hardware_concurrency();
+  if (nt == 0) nt = 1;
+  if (nt > 16) nt = 16;
+  if (n < (1u << 22)) nt = 1;
+  std::vector<int> nz(nt, 0);
+  std::vector<std::thread> th;
+  auto work = [&](unsigned t) {
+    size_t b = n * t / nt, e = n * (t + 1) / nt;
+    const unsigned long long* p = reinterpret_cast<const unsigned long long*>(a);
+    unsigned long long acc = 0;
+    for (size_t i = b; i < e; ++i) acc |= (p[i] << 1);  // ignore the sign bit: -0.0 counts as zero
+    nz[t] = acc != 0;
+  };
+  for (unsigned t = 1; t < nt; ++t) th.emplace_back(work, t);
+  work(0);
+  for (auto& x : th) x.join();
+  for (int v : nz)
+    if (v) return false;
+  return true;
+}
+
+struct DBuf {
+  double* p = nullptr;
+  explicit DBuf(size_t n) {
+    if (cudaMalloc(&p, (n ? n : 1) * sizeof(double)) != cudaSuccess) { p = nullptr; throw NdsmError(3); }
+  }
+  ~DBuf() { if (p) cudaFree(p); }
+  DBuf(const DBuf&) = delete;
+  DBuf& operator=(const DBuf&) = delete;
+};
+
+extern "C" {
+
+// ------------------------------------------------------------------------------------------
+// 1. Reference surface
+// ------------------------------------------------------------------------------------------
+int ndsm_vector_solve(size_t nsize, const int* nshape4, int* ioptc, double* ropt, const double* x, const double* y,
+                      const double* z, double* A, double* B) {
+  static const char* SUB = "ndsm_vector_solve";
+  const double t0 = now_s();
+  if (!nshape4 || !ioptc || !ropt || !x || !y || !z || !A || !B) {
+    error_msg("NULL argument", SUB, "NDSM_B200_ERR_ARG");
+    return NDSM_B200_ERR_ARG;
+  }
+  long long iopt[IOPT_LEN];
+  for (int i = 0; i < IOPT_LEN; ++i) iopt[i] = ioptc[i];
+  g_debug = (iopt[IOPT_DEBUG] == IOPT_TRUE);  // ndsm_python_wrapper.f90:98
+  const int nx = nshape4[0], ny = nshape4[1], nz = nshape4[2];
+  auto finish = [&](int ierr) {
+    iopt[IOPT_IERR] = ierr;
+    ropt[ROPT_TIM] = now_s() - t0;  // :145-148
+    for (int i = 0; i < IOPT_LEN; ++i) ioptc[i] = (int)iopt[i];
+    g_report.ms_total = ropt[ROPT_TIM] * 1e3;
+    if (g_debug) debug_msg(SUB, "Exiting Fortran lib...");
+    return ierr;
+  };
+  if (nx < 2 || ny < 2 || nz < 2) return finish(NDSM_B200_ERR_NOT_CONVERGED);  // ndsm_vector_potential.f90:213-216
+  if (nshape4[3] != 3 || nsize != (size_t)3 * nx * ny * nz) {
+    error_msg("nsize/nshape4 inconsistent", SUB, "NDSM_B200_ERR_ARG");
+    return finish(NDSM_B200_ERR_ARG);
+  }
+  if (int e = ensure_device(SUB)) return finish(e);
+  g_report = Report();
+  const size_t N = (size_t)nx * ny * nz;
+  try {
+    cudaStream_t st = g_stream;
+    // --- stage the six boundary faces (the interior of B is never read) and upload them
+    double t1 = now_s();
+    size_t fsz[6], ftot = 0;
+    for (int f = 0; f < 6; ++f) { fsz[f] = (size_t)nshape4[imap_nc[f][0]] * nshape4[imap_nc[f][1]]; ftot += fsz[f]; }
+    double* hfaces = nullptr;
+    CUDA_CHECK(cudaMallocHost(&hfaces, ftot * sizeof(double)));
+    DBuf dfaces(ftot);
+    double* bn[6];
+    {
+      size_t o = 0;
+      for (int f = 0; f < 6; ++f) {
+        gather_face_host(B, nx, ny, nz, f, hfaces + o);
+        bn[f] = dfaces.p + o;
+        o += fsz[f];
+      }
+    }
+    CUDA_CHECK(cudaMemcpyAsync(dfaces.p, hfaces, ftot * sizeof(double), cudaMemcpyHostToDevice, st));
+    // --- A is the initial guess as received (reference never zeroes it); ndsm.py passes zeros
+    DBuf dA(3 * N), dB(3 * N);
+    const bool zero_guess = all_zero_host(A, 3 * N);
+    if (!zero_guess) CUDA_CHECK(cudaMemcpyAsync(dA.p, A, 3 * N * sizeof(double), cudaMemcpyHostToDevice, st));
+    CUDA_CHECK(cudaStreamSynchronize(st));
+    cudaFreeHost(hfaces);
+    g_report.ms_in = (now_s() - t1) * 1e3;
+    if (g_debug) debug_msg(SUB, "Calling compute_vector_potential...");
+    int ierr = vector_solve_core(nshape4, iopt, ropt, x, y, z, bn, zero_guess ? nullptr : dA.p, dA.p, dB.p, st,
+                                 g_report, nullptr, false);
+    t1 = now_s();
+    CUDA_CHECK(cudaMemcpyAsync(A, dA.p, 3 * N * sizeof(double), cudaMemcpyDeviceToHost, st));
+    CUDA_CHECK(cudaMemcpyAsync(B, dB.p, 3 * N * sizeof(double), cudaMemcpyDeviceToHost, st));
+    CUDA_CHECK(cudaStreamSynchronize(st));
+    g_report.ms_out = (now_s() - t1) * 1e3;
+    return finish(ierr);
+  } catch (const NdsmError& e) {
+    return finish(fail(e, SUB));
+  }
+}
+
+int get_iopt_len(void) { return IOPT_LEN; }
+int get_iopt_ierr(void) { return IOPT_LEN; }  // sic, ndsm_python_wrapper.f90:170-174
+int get_iopt_ms(void) { return IOPT_MS; }
+int get_iopt_ncycles(void) { return IOPT_NCYCLES; }
+int get_iopt_debug(void) { return IOPT_DEBUG; }
+int get_iopt_dumax(void) { return IOPT_DUMAX; }
+int get_iopt_iopt_nmaxex(void) { return IOPT_NMAXEX; }
+int get_iopt_true(void) { return IOPT_TRUE; }
+int get_iopt_false(void) { return IOPT_FALSE; }
+int get_ropt_tim(void) { return ROPT_TIM; }
+int get_ropt_vtol(void) { return ROPT_VTOL; }
+int get_ropt_ctol(void) { return ROPT_CTOL; }
+
+// ------------------------------------------------------------------------------------------
+// 2. Device-resident entry and scalar Poisson backend
+// ------------------------------------------------------------------------------------------
+int ndsm_b200_vector_solve_device(const int* nshape4, int* ioptc, double* ropt, const double* x, const double* y,
+                                  const double* z, double* dA, double* dB) {
+  static const char* SUB = "ndsm_b200_vector_solve_device";
+  const double t0 = now_s();
+  if (!nshape4 || !ioptc || !ropt || !x || !y || !z || !dA || !dB) return NDSM_B200_ERR_ARG;
+  long long iopt[IOPT_LEN];
+  for (int i = 0; i < IOPT_LEN; ++i) iopt[i] = ioptc[i];
+  g_debug = (iopt[IOPT_DEBUG] == IOPT_TRUE);
+  const int nx = nshape4[0], ny = nshape4[1], nz = nshape4[2];
+  auto finish = [&](int ierr) {
+    iopt[IOPT_IERR] = ierr;
+    ropt[ROPT_TIM] = now_s() - t0;
+    for (int i = 0; i < IOPT_LEN; ++i) ioptc[i] = (int)iopt[i];
+    g_report.ms_total = ropt[ROPT_TIM] * 1e3;
+    return ierr;
+  };
+  if (nx < 2 || ny < 2 || nz < 2) return finish(NDSM_B200_ERR_NOT_CONVERGED);
+  if (int e = ensure_device(SUB)) return finish(e);
+  g_report = Report();
+  const size_t N = (size_t)nx * ny * nz;
+  try {
+    cudaStream_t st = g_stream;
+    size_t fsz[6], ftot = 0;
+    for (int f = 0; f < 6; ++f) { fsz[f] = (size_t)nshape4[imap_nc[f][0]] * nshape4[imap_nc[f][1]]; ftot += fsz[f]; }
+    DBuf dfaces(ftot);
+    double* bn[6];
+    size_t o = 0;
+    for (int f = 0; f < 6; ++f) {
+      bn[f] = dfaces.p + o;
+      o += fsz[f];
+      const int c = imap_cp[f];
+      const int layer = (f % 2 == 0) ? 0 : nshape4[c] - 1;
+      extract_face(dB + c * N, nx, ny, nz, c, layer, bn[f], st);  // ndsm_vector_potential.f90:283-293
+    }
+    int ierr = vector_solve_core(nshape4, iopt, ropt, x, y, z, bn, dA, dA, dB, st, g_report, nullptr, false);
+    CUDA_CHECK(cudaStreamSynchronize(st));
+    return finish(ierr);
+  } catch (const NdsmError& e) {
+    return finish(fail(e, SUB));
+  }
+}
+
+}  // extern "C"
+
+// ------------------------------------------------------------------------------------------
+// host-only planning
+// ------------------------------------------------------------------------------------------
+struct ndsm_b200_plan {
+  int ndim;
+  std::vector<HostLevel> lv;
+};
+
+extern "C" {
+ndsm_b200_plan* ndsm_b200_plan_create(int ndim, const int* nshape, int ngrids, const double* x, const double* y,
+                                      const double* z) {
+  if (!nshape || !x || !y || (ndim == 3 && !z)) return nullptr;
+  try {
+    const double* mesh[3] = {x, y, z};
+    int sh[3] = {nshape[0], nshape[1], ndim == 3 ? nshape[2] : 1};
+    ndsm_b200_plan* p = new ndsm_b200_plan();
+    p->ndim = ndim;
+    p->lv = build_hierarchy(ndim, sh, ngrids, mesh);
+    return p;
+  } catch (const NdsmError&) {
+    return nullptr;
+  }
+}
+void ndsm_b200_plan_destroy(ndsm_b200_plan* p) { delete p; }
+int ndsm_b200_plan_ngrids(const ndsm_b200_plan* p) { return p ? (int)p->lv.size() : -1; }
+int ndsm_b200_plan_level(const ndsm_b200_plan* p, int level, int* shape3, long long* layout4, double* weights5) {
+  if (!p || level < 0 || level >= (int)p->lv.size()) return NDSM_B200_ERR_ARG;
+  const HostLevel& L = p->lv[level];
+  if (shape3) for (int d = 0; d < 3; ++d) shape3[d] = L.n[d];
+  if (layout4) { layout4[0] = L.g.hp; layout4[1] = L.g.mcnt; layout4[2] = L.g.ps; layout4[3] = L.g.cs; }
+  if (weights5) { weights5[0] = L.w.wx; weights5[1] = L.w.wy; weights5[2] = L.w.wz; weights5[3] = L.w.w1; weights5[4] = L.w.wc; }
+  return 0;
+}
+int ndsm_b200_plan_mesh(const ndsm_b200_plan* p, int level, int dim, double* out) {
+  if (!p || !out || level < 0 || level >= (int)p->lv.size() || dim < 0 || dim >= p->ndim) return NDSM_B200_ERR_ARG;
+  const auto& m = p->lv[level].mesh[dim];
+  memcpy(out, m.data(), m.size() * sizeof(double));
+  return 0;
+}
+int ndsm_b200_plan_interp(const ndsm_b200_plan* p, int level, int dim, int* lo, double* wl, double* wh) {
+  if (!p || level < 0 || level + 1 >= (int)p->lv.size() || dim < 0 || dim >= 3) return NDSM_B200_ERR_ARG;
+  const HostLevel& L = p->lv[level];
+  memcpy(lo, L.lo[dim].data(), L.lo[dim].size() * sizeof(int));
+  memcpy(wl, L.wl[dim].data(), L.wl[dim].size() * sizeof(double));
+  memcpy(wh, L.wh[dim].data(), L.wh[dim].size() * sizeof(double));
+  return 0;
+}
+int ndsm_b200_plan_restrict(const ndsm_b200_plan* p, int level, int dim, int* first, int* count, double* c2,
+                            double* w2) {
+  if (!p || level < 0 || level + 1 >= (int)p->lv.size() || dim < 0 || dim >= 3) return NDSM_B200_ERR_ARG;
+  const HostLevel& L = p->lv[level];
+  memcpy(first, L.first[dim].data(), L.first[dim].size() * sizeof(int));
+  memcpy(count, L.count[dim].data(), L.count[dim].size() * sizeof(int));
+  memcpy(c2, L.c2[dim].data(), L.c2[dim].size() * sizeof(double));
+  *w2 = L.w2[dim];
+  return 0;
+}
+int ndsm_b200_ngrids_for(int nmin) { return ngrids_for(nmin); }
+}  // extern "C"
+
+// ------------------------------------------------------------------------------------------
+// 3. MG_HANDLE seam
+// ------------------------------------------------------------------------------------------
+struct ndsm_b200_mg {
+  MG* mg = nullptr;
+  double* rhs0 = nullptr;  // level-0 rhs owned by the handle (colour-split)
+  SolveTrace tr;
+};
+
+static void upload_split(MG& mg, const double* dense, double* split, const Grid& g) {
+  const size_t n = (size_t)g.nx * g.ny * g.nz;
+  DBuf d(n);
+  CUDA_CHECK(cudaMemcpyAsync(d.p, dense, n * sizeof(double), cudaMemcpyHostToDevice, mg.stream()));
+  CUDA_CHECK(cudaMemsetAsync(split, 0, (size_t)2 * g.cs * sizeof(double), mg.stream()));
+  split_from_dense(d.p, split, g, 0.0, mg.stream());
+  CUDA_CHECK(cudaStreamSynchronize(mg.stream()));
+}
+static void download_split(MG& mg, const double* split, double* dense, const Grid& g) {
+  const size_t n = (size_t)g.nx * g.ny * g.nz;
+  DBuf d(n);
+  dense_from_split(split, d.p, g, mg.stream());
+  CUDA_CHECK(cudaMemcpyAsync(dense, d.p, n * sizeof(double), cudaMemcpyDeviceToHost, mg.stream()));
+  CUDA_CHECK(cudaStreamSynchronize(mg.stream()));
+}
+static double* handle_array(ndsm_b200_mg* h, int which, int level) {
+  MG& mg = *h->mg;
+  if (level < 0 || level >= mg.ngrids()) return nullptr;
+  if (which == 0) return mg.level(level).u;
+  if (which == 2) return mg.r_scratch();
+  if (which == 1) {
+    if (level > 0) return mg.level(level).rhs;
+    if (!h->rhs0) {
+      const size_t n = mg.level_doubles(0);
+      CUDA_CHECK(cudaMalloc(&h->rhs0, n * sizeof(double)));
+      CUDA_CHECK(cudaMemsetAsync(h->rhs0, 0, n * sizeof(double), mg.stream()));
+      mg.set_level0_rhs(h->rhs0);
+    }
+    return h->rhs0;
+  }
+  return nullptr;
+}
+
+#define HANDLE_GUARD(sub)                               \
+  if (!h || !h->mg) return NDSM_B200_ERR_ARG;           \
+  if (int e__ = ensure_device(sub)) return e__;         \
+  try {
+#define HANDLE_END(sub)         \
+  }                             \
+  catch (const NdsmError& e) {  \
+    return fail(e, sub);        \
+  }                             \
+  return 0;
+
+extern "C" {
+
+ndsm_b200_mg* ndsm_b200_new_mg_handle(int ndim, const int* nshape, int ngrids, const double* x, const double* y,
+                                      const double* z, int du_max, int nmax_exact) {
+  static const char* SUB = "ndsm_b200_new_mg_handle";
+  if ((ndim != 2 && ndim != 3) || !nshape || !x || !y || (ndim == 3 && !z)) return nullptr;
+  if (ensure_device(SUB)) return nullptr;
+  try {
+    const double* mesh[3] = {x, y, z};
+    int sh[3] = {nshape[0], nshape[1], ndim == 3 ? nshape[2] : 1};
+    ndsm_b200_mg* h = new ndsm_b200_mg();
+    h->mg = new MG(ndim, sh, ngrids, mesh, g_stream);
+    h->mg->set_options(5, 1e-13, "NNNNNN", du_max != 0, nmax_exact);
+    // the handle always owns a (zero) level-0 rhs so every operator can be called standalone
+    handle_array(h, 1, 0);
+    CUDA_CHECK(cudaStreamSynchronize(g_stream));
+    return h;
+  } catch (const NdsmError& e) {
+    fail(e, SUB);
+    return nullptr;
+  }
+}
+void ndsm_b200_delete_mg_handle(ndsm_b200_mg* h) {
+  if (!h) return;
+  delete h->mg;
+  if (h->rhs0) cudaFree(h->rhs0);
+  delete h;
+}
+int ndsm_b200_mg_set_options(ndsm_b200_mg* h, int ms, double ex_tol, const char* copt) {
+  if (!h || !h->mg || !copt) return NDSM_B200_ERR_ARG;
+  if ((int)strlen(copt) < 2 * h->mg->ndim()) return NDSM_B200_ERR_ARG;
+  // du_max / nmax_exact were fixed at construction like new_mg_handle's arguments
+  h->mg->set_options(ms, ex_tol, copt, h->mg->du_max(), h->mg->nmax_exact());
+  return 0;
+}
+int ndsm_b200_mg_ngrids(const ndsm_b200_mg* h) { return (h && h->mg) ? h->mg->ngrids() : -1; }
+int ndsm_b200_mg_level_shape(const ndsm_b200_mg* h, int level, int* shape3) {
+  if (!h || !h->mg || level < 0 || level >= h->mg->ngrids()) return NDSM_B200_ERR_ARG;
+  const Grid& g = h->mg->level(level).g;
+  shape3[0] = g.nx; shape3[1] = g.ny; shape3[2] = g.nz;
+  return 0;
+}
+int ndsm_b200_mg_level_mesh(const ndsm_b200_mg* h, int level, int dim, double* out) {
+  if (!h || !h->mg || level < 0 || level >= h->mg->ngrids() || dim < 0 || dim >= h->mg->ndim()) return NDSM_B200_ERR_ARG;
+  const auto& m = h->mg->level(level).mesh[dim];
+  memcpy(out, m.data(), m.size() * sizeof(double));
+  return 0;
+}
+int ndsm_b200_mg_put(ndsm_b200_mg* h, int which, int level, const double* dense) {
+  HANDLE_GUARD("ndsm_b200_mg_put")
+  double* a = handle_array(h, which, level);
+  if (!a || !dense) return NDSM_B200_ERR_ARG;
+  upload_split(*h->mg, dense, a, h->mg->level(level).g);
+  HANDLE_END("ndsm_b200_mg_put")
+}
+int ndsm_b200_mg_get(ndsm_b200_mg* h, int which, int level, double* dense) {
+  HANDLE_GUARD("ndsm_b200_mg_get")
+  double* a = handle_array(h, which, level);
+  if (!a || !dense) return NDSM_B200_ERR_ARG;
+  download_split(*h->mg, a, dense, h->mg->level(level).g);
+  HANDLE_END("ndsm_b200_mg_get")
+}
+int ndsm_b200_mg_relax(ndsm_b200_mg* h, int level, int nsweeps) {
+  HANDLE_GUARD("ndsm_b200_mg_relax")
+  if (level < 0 || level >= h->mg->ngrids()) return NDSM_B200_ERR_ARG;
+  for (int s = 0; s < nsweeps; ++s) h->mg->relax(level);
+  CUDA_CHECK(cudaStreamSynchronize(h->mg->stream()));
+  HANDLE_END("ndsm_b200_mg_relax")
+}
+int ndsm_b200_mg_residual(ndsm_b200_mg* h, int level) {
+  HANDLE_GUARD("ndsm_b200_mg_residual")
+  if (level < 0 || level >= h->mg->ngrids()) return NDSM_B200_ERR_ARG;
+  h->mg->residual(level);
+  CUDA_CHECK(cudaStreamSynchronize(h->mg->stream()));
+  HANDLE_END("ndsm_b200_mg_residual")
+}
+int ndsm_b200_mg_restrict(ndsm_b200_mg* h, int level) {
+  HANDLE_GUARD("ndsm_b200_mg_restrict")
+  if (level < 0 || level + 1 >= h->mg->ngrids()) return NDSM_B200_ERR_ARG;
+  h->mg->restrict_to(level);
+  CUDA_CHECK(cudaStreamSynchronize(h->mg->stream()));
+  HANDLE_END("ndsm_b200_mg_restrict")
+}
+int ndsm_b200_mg_interp_add(ndsm_b200_mg* h, int level) {
+  HANDLE_GUARD("ndsm_b200_mg_interp_add")
+  if (level < 1 || level >= h->mg->ngrids()) return NDSM_B200_ERR_ARG;
+  h->mg->interp_add_from(level);
+  CUDA_CHECK(cudaStreamSynchronize(h->mg->stream()));
+  HANDLE_END("ndsm_b200_mg_interp_add")
+}
+int ndsm_b200_mg_solve_exact(ndsm_b200_mg* h, int level, int* iters) {
+  HANDLE_GUARD("ndsm_b200_mg_solve_exact")
+  if (level < 0 || level >= h->mg->ngrids()) return NDSM_B200_ERR_ARG;
+  h->mg->solve_exact(level);
+  const int n = h->mg->last_nexact();
+  if (iters) *iters = n;
+  HANDLE_END("ndsm_b200_mg_solve_exact")
+}
+int ndsm_b200_mg_v_cycle(ndsm_b200_mg* h) {
+  HANDLE_GUARD("ndsm_b200_mg_v_cycle")
+  h->mg->v_cycle();
+  CUDA_CHECK(cudaStreamSynchronize(h->mg->stream()));
+  HANDLE_END("ndsm_b200_mg_v_cycle")
+}
+int ndsm_b200_mg_solve(ndsm_b200_mg* h, double vc_tol, int nmax, double* u_dense, const double* rhs_dense,
+                       double* du_last, int* ncycles) {
+  static const char* SUB = "ndsm_b200_mg_solve";
+  if (!h || !h->mg || !u_dense) return NDSM_B200_ERR_ARG;
+  if (int e = ensure_device(SUB)) return e;
+  try {
+    MG& mg = *h->mg;
+    const Grid& g = mg.level(0).g;
+    DBuf us(mg.level_doubles(0));
+    upload_split(mg, u_dense, us.p, g);
+    double* rhs = handle_array(h, 1, 0);
+    if (rhs_dense) upload_split(mg, rhs_dense, rhs, g);
+    else CUDA_CHECK(cudaMemsetAsync(rhs, 0, mg.level_doubles(0) * sizeof(double), mg.stream()));
+    h->tr = SolveTrace();
+    g_report = Report();
+    int ierr = mg.solve(us.p, rhs, vc_tol, nmax, du_last, &h->tr);
+    mg.set_level0_rhs(h->rhs0);
+    g_report.solves[0] = h->tr;
+    if (ncycles) *ncycles = (int)h->tr.du.size();
+    download_split(mg, us.p, u_dense, g);
+    return ierr;
+  } catch (const NdsmError& e) {
+    return fail(e, SUB);
+  }
+}
+int ndsm_b200_mg_update_u(ndsm_b200_mg* h, const double* u_old_dense, double* u_new_dense, double* du_max,
+                          double* du_mean) {
+  HANDLE_GUARD("ndsm_b200_mg_update_u")
+  MG& mg = *h->mg;
+  const Grid& g = mg.level(0).g;
+  DBuf a(mg.level_doubles(0)), b(mg.level_doubles(0)), scr(reduce_scratch_doubles() + 8);
+  upload_split(mg, u_new_dense, a.p, g);
+  upload_split(mg, u_old_dense, b.p, g);
+  diff_reduce(a.p, b.p, g, true, scr.p, scr.p + reduce_scratch_doubles(), mg.stream());
+  double out[2];
+  CUDA_CHECK(cudaMemcpyAsync(out, scr.p + reduce_scratch_doubles(), sizeof out, cudaMemcpyDeviceToHost, mg.stream()));
+  CUDA_CHECK(cudaStreamSynchronize(mg.stream()));
+  if (du_max) *du_max = out[0];
+  if (du_mean) *du_mean = out[1] / (double)((i64)g.nx * g.ny * g.nz);
+  download_split(mg, a.p, u_new_dense, g);
+  HANDLE_END("ndsm_b200_mg_update_u")
+}
+
+int ndsm_b200_poisson_solve(int ndim, const int* nshape, const char* copt, int ms, int ncycles_max, int nmaxex,
+                            int du_max, double vc_tol, double ex_tol, const double* x, const double* y,
+                            const double* z, double* u, const double* rhs, double* du_last, int* ncycles) {
+  ndsm_b200_mg* h = ndsm_b200_new_mg_handle(ndim, nshape, -1, x, y, z, du_max, nmaxex);
+  if (!h) return NDSM_B200_ERR_CUDA;
+  int rc = ndsm_b200_mg_set_options(h, ms, ex_tol, copt);
+  if (rc == 0) rc = ndsm_b200_mg_solve(h, vc_tol, ncycles_max, u, rhs, du_last, ncycles);
+  ndsm_b200_delete_mg_handle(h);
+  return rc;
+}
+
+// ------------------------------------------------------------------------------------------
+// driver stage hooks
+// ------------------------------------------------------------------------------------------
+int ndsm_b200_bc_setup(const int* nshape4, const int* ioptc, const double* ropt, const double* x, const double* y,
+                       const double* z, const double* B, double* phi6, double** chi6, double** At1_6,
+                       double** At2_6) {
+  static const char* SUB = "ndsm_b200_bc_setup";
+  if (int e = ensure_device(SUB)) return e;
+  long long iopt[IOPT_LEN];
+  for (int i = 0; i < IOPT_LEN; ++i) iopt[i] = ioptc[i];
+  g_debug = (iopt[IOPT_DEBUG] == IOPT_TRUE);
+  const int nx = nshape4[0], ny = nshape4[1], nz = nshape4[2];
+  try {
+    cudaStream_t st = g_stream;
+    size_t fsz[6], ftot = 0;
+    for (int f = 0; f < 6; ++f) { fsz[f] = (size_t)nshape4[imap_nc[f][0]] * nshape4[imap_nc[f][1]]; ftot += fsz[f]; }
+    std::vector<double> hf(ftot);
+    DBuf dfaces(ftot);
+    double* bn[6];
+    size_t o = 0;
+    for (int f = 0; f < 6; ++f) {
+      gather_face_host(B, nx, ny, nz, f, hf.data() + o);
+      bn[f] = dfaces.p + o;
+      o += fsz[f];
+    }
+    CUDA_CHECK(cudaMemcpyAsync(dfaces.p, hf.data(), ftot * sizeof(double), cudaMemcpyHostToDevice, st));
+    CUDA_CHECK(cudaStreamSynchronize(st));
+    BcCapture cap;
+    for (int f = 0; f < 6; ++f) {
+      cap.chi[f] = chi6 ? chi6[f] : nullptr;
+      cap.At1[f] = At1_6 ? At1_6[f] : nullptr;
+      cap.At2[f] = At2_6 ? At2_6[f] : nullptr;
+    }
+    g_report = Report();
+    int ierr = vector_solve_core(nshape4, iopt, ropt, x, y, z, bn, nullptr, nullptr, nullptr, st, g_report, &cap, true);
+    if (phi6) for (int f = 0; f < 6; ++f) phi6[f] = g_report.phi[f];
+    return ierr;
+  } catch (const NdsmError& e) {
+    return fail(e, SUB);
+  }
+}
+
+int ndsm_b200_flux_curl(const int* nshape4, int flxcrl, const double* x, const double* y, const double* z,
+                        const double* phi6, double* A, double* B) {
+  static const char* SUB = "ndsm_b200_flux_curl";
+  if (int e = ensure_device(SUB)) return e;
+  const int nx = nshape4[0], ny = nshape4[1], nz = nshape4[2];
+  const size_t N = (size_t)nx * ny * nz;
+  try {
+    cudaStream_t st = g_stream;
+    const double* mesh[3] = {x, y, z};
+    double Lq[3], dq[3];
+    for (int d = 0; d < 3; ++d) {
+      double lo = mesh[d][0], hi = mesh[d][0];
+      for (int i = 1; i < nshape4[d]; ++i) { lo = mesh[d][i] < lo ? mesh[d][i] : lo; hi = mesh[d][i] > hi ? mesh[d][i] : hi; }
+      Lq[d] = hi - lo;
+      dq[d] = mesh[d][1] - mesh[d][0];
+    }
+    const int sh[3] = {nx, ny, nz};
+    MG mg(3, sh, 1, mesh, st);  // only the level-0 layout is needed
+    const Grid g = mg.level(0).g;
+    DBuf dA(3 * N), dB(3 * N), dAs(2 * (size_t)g.cs), dm((size_t)nx + ny + nz);
+    CUDA_CHECK(cudaMemcpyAsync(dA.p, A, 3 * N * sizeof(double), cudaMemcpyHostToDevice, st));
+    CUDA_CHECK(cudaMemcpyAsync(dB.p, B, 3 * N * sizeof(double), cudaMemcpyHostToDevice, st));
+    CUDA_CHECK(cudaMemcpyAsync(dm.p, x, nx * sizeof(double), cudaMemcpyHostToDevice, st));
+    CUDA_CHECK(cudaMemcpyAsync(dm.p + nx, y, ny * sizeof(double), cudaMemcpyHostToDevice, st));
+    CUDA_CHECK(cudaMemcpyAsync(dm.p + nx + ny, z, nz * sizeof(double), cudaMemcpyHostToDevice, st));
+    const bool flux_first = (flxcrl != 1);
+    for (int c = 0; c < 3; ++c) {
+      CUDA_CHECK(cudaMemsetAsync(dAs.p, 0, 2 * (size_t)g.cs * sizeof(double), st));
+      split_from_dense(dA.p + c * N, dAs.p, g, 0.0, st);
+      unsplit_A(dAs.p, g, c, dm.p, dm.p + nx, dm.p + nx + ny, phi6, Lq, flux_first, dA.p + c * N, st);
+    }
+    curl_dense(dA.p, nx, ny, nz, dq[0], dq[1], dq[2], dB.p, st);
+    if (!flux_first) add_flux_dense(dA.p, dB.p, nx, ny, nz, dm.p, dm.p + nx, dm.p + nx + ny, phi6, Lq, st);
+    CUDA_CHECK(cudaMemcpyAsync(A, dA.p, 3 * N * sizeof(double), cudaMemcpyDeviceToHost, st));
+    CUDA_CHECK(cudaMemcpyAsync(B, dB.p, 3 * N * sizeof(double), cudaMemcpyDeviceToHost, st));
+    CUDA_CHECK(cudaStreamSynchronize(st));
+    return 0;
+  } catch (const NdsmError& e) {
+    return fail(e, SUB);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// 4. Introspection
+// ------------------------------------------------------------------------------------------
+int ndsm_b200_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+  return n;
+}
+unsigned long long ndsm_b200_launch_count(void) { return g_launches; }
+int ndsm_b200_trace_nsolves(void) { return 9; }
+int ndsm_b200_trace_ncycles(int s) { return (s >= 0 && s < 9) ? (int)g_report.solves[s].du.size() : -1; }
+double ndsm_b200_trace_du(int s, int c) {
+  if (s < 0 || s >= 9 || c < 0 || c >= (int)g_report.solves[s].du.size()) return -1.0;
+  return g_report.solves[s].du[c];
+}
+int ndsm_b200_trace_nexact(int s, int c) {
+  if (s < 0 || s >= 9 || c < 0 || c >= (int)g_report.solves[s].nexact.size()) return -1;
+  return g_report.solves[s].nexact[c];
+}
+int ndsm_b200_last_timing(double* out8) {
+  if (!out8) return NDSM_B200_ERR_ARG;
+  out8[0] = g_report.ms_total; out8[1] = g_report.ms_in; out8[2] = g_report.ms_bc; out8[3] = g_report.ms_solve3d;
+  out8[4] = g_report.ms_post; out8[5] = g_report.ms_out; out8[6] = g_report.ms_device;
+  out8[7] = (double)g_report.launches;
+  return 0;
+}
+void ndsm_b200_profile_enable(int on) { prof_enable(on != 0); if (on) prof_reset(); }
+int ndsm_b200_profile_get(int cls, unsigned long long* count, double* total_ms) {
+  if (cls < 0 || cls >= PROF_NCLASS || !count || !total_ms) return NDSM_B200_ERR_ARG;
+  prof_get(cls, count, total_ms);
+  return 0;
+}
+const char* ndsm_b200_version(void) { return "ndsm-b200 0.1 (sm_100a, fp64, -fmad=false)"; }
+
+}  // extern "C"

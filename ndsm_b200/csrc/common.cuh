@@ -1,0 +1,55 @@
+// common.cuh -- shared types for the B200 (sm_100a) NDSM hot path.
+//
+// Data layout in HBM ("colour-split" / checkerboard-compressed):
+//   A level of global shape (nx,ny,nz) stores its red and black points in two separate
+//   sub-arrays so that one colour pass of the red/black Gauss-Seidel smoother
+//   (reference: ndsm_optimized.f90:103-167) streams each array exactly once:
+//     colour c = (i+j+k)&1                     (0-based global indices)
+//     offset   = c*cs + (k-k0)*ps + j*hp + (i>>1)
+//   hp = half-row pitch (multiple of 8 doubles = 64 B), ps = plane stride (multiple of 32
+//   doubles), cs = colour stride.  Neighbours of a point always have the other colour, and
+//   within the other colour's row they sit at compressed index m-1+s / m+s (x) or m (y,z),
+//   where m = i>>1 and s = i&1.  Padding entries are never written and stay zero.
+//   2D faces are levels with nz == 1.
+//   [k0,k0+nzl) are the z-planes owned by this rank (z-slab decomposition); pointers handed
+//   to kernels point at local plane 0, halo planes live at plane -1 and nzl.
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+
+typedef long long i64;
+
+struct Grid {
+  int nx, ny, nz;  // global level shape (nz == 1 for a 2D face)
+  int k0, nzl;     // owned z-planes [k0, k0+nzl)
+  int hp;          // half-row pitch (doubles)
+  int mcnt;        // compressed row length = (nx+1)/2
+  i64 ps, cs;      // plane stride, colour stride (doubles)
+};
+
+struct Bounds {    // inclusive 0-based index range of non-Dirichlet points (ndsm_optimized.f90:68-76)
+  int lb[3], ub[3];
+};
+
+// Restriction stencil capacity per dimension (see tables in mg.cu; ratio <= 8/3 -> <= 7 points)
+#define NDSM_RMAX 8
+
+#define CUDA_CHECK(call)                                                                      \
+  do {                                                                                        \
+    cudaError_t e__ = (call);                                                                 \
+    if (e__ != cudaSuccess) {                                                                 \
+      fprintf(stderr, "ERROR(%s):%s:%s:%d\n", __func__, cudaGetErrorString(e__), __FILE__, __LINE__); \
+      throw NdsmError(e__);                                                                   \
+    }                                                                                         \
+  } while (0)
+
+struct NdsmError {
+  int code;
+  explicit NdsmError(int c) : code(c) {}
+};
+
+__host__ __device__ inline i64 gidx(const Grid& g, int i, int j, int k) {
+  return (i64)((i + j + k) & 1) * g.cs + (i64)(k - g.k0) * g.ps + (i64)j * g.hp + (i >> 1);
+}

@@ -1,0 +1,896 @@
+// kernels.cu -- hand-written FP64 CUDA kernels (sm_100a) for the NDSM multigrid V-cycle path.
+//
+// All kernels are HBM-bound stream/stencil operations (7-point FP64 stencil ~0.45 flop/B),
+// so there is no tensor-core work here.  The file is compiled with -fmad=false: the
+// reference is built for baseline x86-64 (no FMA), and every expression below keeps the
+// reference's evaluation order so that results are bit-identical to a serial run of the
+// reference arithmetic wherever the operation is order-deterministic.
+#include "kernels.cuh"
+
+#include <algorithm>
+#include <vector>
+
+namespace ndsm {
+
+unsigned long long g_launches = 0;
+#define LAUNCHED() (++g_launches)
+
+static inline int cdiv(i64 a, i64 b) { return (int)((a + b - 1) / b); }
+
+// ---------------------------------------------------------------------------------------
+// event-based per-class kernel timing (off by default)
+// ---------------------------------------------------------------------------------------
+static bool g_prof_on = false;
+struct ProfPair { cudaEvent_t a, b; int cls; };
+static std::vector<ProfPair> g_prof_pending;
+static std::vector<cudaEvent_t> g_prof_pool;
+static unsigned long long g_prof_count[PROF_NCLASS] = {0};
+static double g_prof_ms[PROF_NCLASS] = {0};
+static cudaEvent_t g_prof_open[PROF_NCLASS];
+
+static cudaEvent_t prof_event() {
+  if (!g_prof_pool.empty()) { cudaEvent_t e = g_prof_pool.back(); g_prof_pool.pop_back(); return e; }
+  cudaEvent_t e;
+  cudaEventCreate(&e);
+  return e;
+}
+void prof_enable(bool on) { g_prof_on = on; }
+bool prof_enabled() { return g_prof_on; }
+void prof_begin(int cls, cudaStream_t st) {
+  if (!g_prof_on) return;
+  g_prof_open[cls] = prof_event();
+  cudaEventRecord(g_prof_open[cls], st);
+}
+void prof_end(int cls, cudaStream_t st) {
+  if (!g_prof_on) return;
+  cudaEvent_t b = prof_event();
+  cudaEventRecord(b, st);
+  g_prof_pending.push_back(ProfPair{g_prof_open[cls], b, cls});
+}
+void prof_collect() {
+  for (auto& p : g_prof_pending) {
+    float ms = 0;
+    if (cudaEventElapsedTime(&ms, p.a, p.b) == cudaSuccess) { g_prof_ms[p.cls] += ms; g_prof_count[p.cls]++; }
+    g_prof_pool.push_back(p.a);
+    g_prof_pool.push_back(p.b);
+  }
+  g_prof_pending.clear();
+}
+void prof_get(int cls, unsigned long long* count, double* total_ms) {
+  *count = g_prof_count[cls];
+  *total_ms = g_prof_ms[cls];
+}
+void prof_reset() {
+  for (int c = 0; c < PROF_NCLASS; ++c) { g_prof_count[c] = 0; g_prof_ms[c] = 0; }
+}
+
+// ---------------------------------------------------------------------------------------
+// block reduction helpers (warp shuffle + shared memory; fixed order => deterministic)
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ double warp_max(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_down_sync(0xffffffffu, v, o));
+  return v;
+}
+// all threads of the block must call; result valid in every thread
+__device__ double block_sum(double v, double* red /*>=33 doubles*/) {
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+  v = warp_sum(v);
+  __syncthreads();
+  if (lane == 0) red[wid] = v;
+  __syncthreads();
+  if (wid == 0) {
+    double t = (lane < nw) ? red[lane] : 0.0;
+    t = warp_sum(t);
+    if (lane == 0) red[32] = t;
+  }
+  __syncthreads();
+  return red[32];
+}
+__device__ double block_max(double v, double* red) {
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+  v = warp_max(v);
+  __syncthreads();
+  if (lane == 0) red[wid] = v;
+  __syncthreads();
+  if (wid == 0) {
+    double t = (lane < nw) ? red[lane] : 0.0;
+    t = warp_max(t);
+    if (lane == 0) red[32] = t;
+  }
+  __syncthreads();
+  return red[32];
+}
+
+// ---------------------------------------------------------------------------------------
+// K1  3D red/black Gauss-Seidel colour pass          (ndsm_optimized.f90:103-167)
+//
+// One thread owns the compressed column (m, j) of the pass colour and marches in z.  The
+// other colour's values of that column at planes k-1, k, k+1 live in a 3-register ring, so
+// each step issues one new z load; the in-plane value Zc is also one of the two x
+// neighbours.  The x/y neighbours are plain coalesced loads served by L1/L2.
+// Algorithmic traffic: read other colour (4 B/pt) + read rhs (4 B/pt) + write own (4 B/pt)
+// per colour pass = 24 B/pt per full sweep (16 B/pt when rhs == 0).
+// ---------------------------------------------------------------------------------------
+#define RELAX_THREADS 256
+template <bool HAS_RHS>
+__global__ void __launch_bounds__(RELAX_THREADS)
+k_relax3d(double* __restrict__ u, const double* __restrict__ rhs, const Grid g, const Bounds b, const int colour,
+          const double wx, const double wy, const double wz, const double w1, const int klo, const int khi,
+          const int zchunk) {
+  const int t = blockIdx.x * RELAX_THREADS + threadIdx.x;
+  const int j = t / g.hp;
+  const int m = t - j * g.hp;
+  if (j < b.lb[1] || j > b.ub[1] || m >= g.mcnt) return;
+  const int kbeg = klo + blockIdx.y * zchunk;
+  const int kend = min(kbeg + zchunk - 1, khi);
+  if (kbeg > kend) return;
+
+  double* __restrict__ own = u + (i64)colour * g.cs;
+  const double* __restrict__ opp = u + (i64)(1 - colour) * g.cs;
+  const double* __restrict__ rh = HAS_RHS ? rhs + (i64)colour * g.cs : nullptr;
+
+  const int jl = (j - 1 < 0) ? 1 : j - 1;                // mirrored Neumann ghost (:116-117)
+  const int jh = (j + 1 > g.ny - 1) ? g.ny - 2 : j + 1;
+  const i64 jo = (i64)j * g.hp + m, jlo = (i64)jl * g.hp + m, jho = (i64)jh * g.hp + m;
+
+  int k = kbeg;
+  const int kl0 = (k - 1 < 0) ? 1 : k - 1;
+  double Zm = opp[(i64)(kl0 - g.k0) * g.ps + jo];
+  double Zc = opp[(i64)(k - g.k0) * g.ps + jo];
+  for (; k <= kend; ++k) {
+    const int kh = (k + 1 > g.nz - 1) ? g.nz - 2 : k + 1;  // (:119-120)
+    const double Zp = opp[(i64)(kh - g.k0) * g.ps + jo];
+    const int s = (j + k + colour) & 1;
+    const int i = 2 * m + s;
+    if (i >= b.lb[0] && i <= b.ub[0]) {
+      const i64 p = (i64)(k - g.k0) * g.ps;
+      double xo;  // the x neighbour that is not Zc; mirrored ghosts coincide with Zc (:113-114)
+      if (s == 0) xo = (m == 0) ? Zc : opp[p + jo - 1];
+      else        xo = (i == g.nx - 1) ? Zc : opp[p + jo + 1];
+      const double yl = opp[p + jlo], yh = opp[p + jho];
+      double unew = ((xo + Zc) * wx + (yh + yl) * wy) + (Zp + Zm) * wz;  // (:123-125)
+      if (HAS_RHS) unew = unew - rh[p + jo];                             // (:126)
+      own[p + jo] = w1 * unew;                                           // (:129)
+    }
+    Zm = Zc;
+    Zc = Zp;
+  }
+}
+
+static int pick_zchunk(int nplanes, int blocks_per_plane) {
+  // enough blocks to fill 148 SMs x 8 resident 256-thread blocks several times over
+  int zc = 16;
+  while (zc > 1 && (i64)blocks_per_plane * cdiv(nplanes, zc) < 148 * 8 * 4) zc >>= 1;
+  return zc;
+}
+
+void relax3d_half(double* u, const double* rhs, const Grid& g, const Bounds& b, int colour, const Weights& w,
+                  cudaStream_t st) {
+  const int klo = max(b.lb[2], g.k0), khi = min(b.ub[2], g.k0 + g.nzl - 1);
+  if (klo > khi) return;
+  const int bpp = cdiv((i64)g.hp * g.ny, RELAX_THREADS);
+  const int zc = pick_zchunk(khi - klo + 1, bpp);
+  dim3 grid(bpp, cdiv(khi - klo + 1, zc));
+  if (rhs)
+    k_relax3d<true><<<grid, RELAX_THREADS, 0, st>>>(u, rhs, g, b, colour, w.wx, w.wy, w.wz, w.w1, klo, khi, zc);
+  else
+    k_relax3d<false><<<grid, RELAX_THREADS, 0, st>>>(u, rhs, g, b, colour, w.wx, w.wy, w.wz, w.w1, klo, khi, zc);
+  LAUNCHED();
+}
+
+// ---------------------------------------------------------------------------------------
+// K2  3D residual                                     (ndsm_optimized.f90:346-447)
+// Same z-march as K1, both colours (blockIdx.z), writes r = 0 on Dirichlet faces.
+// Algorithmic traffic 24 B/pt (read u, read rhs, write r).
+// ---------------------------------------------------------------------------------------
+template <bool HAS_RHS>
+__global__ void __launch_bounds__(RELAX_THREADS)
+k_residual3d(const double* __restrict__ u, const double* __restrict__ rhs, double* __restrict__ r, const Grid g,
+             const Bounds b, const double wx, const double wy, const double wz, const double wc, const int zchunk) {
+  const int t = blockIdx.x * RELAX_THREADS + threadIdx.x;
+  const int j = t / g.hp;
+  const int m = t - j * g.hp;
+  if (j >= g.ny || m >= g.mcnt) return;
+  const int colour = blockIdx.z;
+  const int kbeg = g.k0 + blockIdx.y * zchunk;
+  const int kend = min(kbeg + zchunk - 1, g.k0 + g.nzl - 1);
+  if (kbeg > kend) return;
+
+  const double* __restrict__ own = u + (i64)colour * g.cs;
+  const double* __restrict__ opp = u + (i64)(1 - colour) * g.cs;
+  const double* __restrict__ rh = HAS_RHS ? rhs + (i64)colour * g.cs : nullptr;
+  double* __restrict__ ro = r + (i64)colour * g.cs;
+
+  const int jl = (j - 1 < 0) ? 1 : j - 1;
+  const int jh = (j + 1 > g.ny - 1) ? g.ny - 2 : j + 1;
+  const i64 jo = (i64)j * g.hp + m, jlo = (i64)jl * g.hp + m, jho = (i64)jh * g.hp + m;
+  const bool jin = (j >= b.lb[1] && j <= b.ub[1]);
+
+  int k = kbeg;
+  const int kl0 = (k - 1 < 0) ? 1 : k - 1;
+  double Zm = opp[(i64)(kl0 - g.k0) * g.ps + jo];
+  double Zc = opp[(i64)(k - g.k0) * g.ps + jo];
+  for (; k <= kend; ++k) {
+    const int kh = (k + 1 > g.nz - 1) ? g.nz - 2 : k + 1;
+    const double Zp = opp[(i64)(kh - g.k0) * g.ps + jo];
+    const int s = (j + k + colour) & 1;
+    const int i = 2 * m + s;
+    if (i < g.nx) {
+      const i64 p = (i64)(k - g.k0) * g.ps;
+      double res = 0.0;
+      if (jin && i >= b.lb[0] && i <= b.ub[0] && k >= b.lb[2] && k <= b.ub[2]) {
+        double xo;
+        if (s == 0) xo = (m == 0) ? Zc : opp[p + jo - 1];
+        else        xo = (i == g.nx - 1) ? Zc : opp[p + jo + 1];
+        const double yl = opp[p + jlo], yh = opp[p + jho];
+        double tt = ((xo + Zc) * wx + (yl + yh) * wy) + (Zm + Zp) * wz;  // (:424-426)
+        if (HAS_RHS) tt = tt - rh[p + jo];
+        tt = tt - own[p + jo] * wc;                                       // (:427)
+        res = -tt;                                                        // (:430)
+      }
+      ro[p + jo] = res;
+    }
+    Zm = Zc;
+    Zc = Zp;
+  }
+}
+
+void residual3d(const double* u, const double* rhs, double* r, const Grid& g, const Bounds& b, const Weights& w,
+                cudaStream_t st) {
+  const int bpp = cdiv((i64)g.hp * g.ny, RELAX_THREADS);
+  const int zc = pick_zchunk(g.nzl, bpp * 2);
+  dim3 grid(bpp, cdiv(g.nzl, zc), 2);
+  if (rhs)
+    k_residual3d<true><<<grid, RELAX_THREADS, 0, st>>>(u, rhs, r, g, b, w.wx, w.wy, w.wz, w.wc, zc);
+  else
+    k_residual3d<false><<<grid, RELAX_THREADS, 0, st>>>(u, rhs, r, g, b, w.wx, w.wy, w.wz, w.wc, zc);
+  LAUNCHED();
+}
+
+// ---------------------------------------------------------------------------------------
+// 2D relax / residual (chi solves)  generic N-D path  (ndsm_poisson.f90:280-358,451-618)
+// Colour 0 = (i+j) even is the reference's "red" (all index parities equal, :499-501).
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ bool dirichlet2d(int i, int j, const Grid& g, const Bounds& b) {
+  return i < b.lb[0] || i > b.ub[0] || j < b.lb[1] || j > b.ub[1];
+}
+
+__global__ void __launch_bounds__(256)
+k_relax2d(double* __restrict__ u, const double* __restrict__ rhs, const Grid g, const Bounds b, const int colour,
+          const double wx, const double wy, const double w0) {
+  const int t = blockIdx.x * 256 + threadIdx.x;
+  const int j = t / g.hp;
+  const int m = t - j * g.hp;
+  if (j >= g.ny || m >= g.mcnt) return;
+  const int s = (j + colour) & 1;
+  const int i = 2 * m + s;
+  if (i >= g.nx || dirichlet2d(i, j, g, b)) return;  // (:588-591)
+  double* __restrict__ own = u + (i64)colour * g.cs;
+  const double* __restrict__ opp = u + (i64)(1 - colour) * g.cs;
+  const i64 jo = (i64)j * g.hp + m;
+  // stencil_stride (:626-656): interior (-,+); lower boundary (+,+); upper boundary (-,-)
+  const i64 xm = jo - 1 + s, xp = jo + s;  // compressed positions of i-1 and i+1 in the other colour
+  const i64 x1 = (i == 0) ? xp : xm, x2 = (i == g.nx - 1) ? xm : xp;
+  const i64 ym = jo - g.hp, yp = jo + g.hp;
+  const i64 y1 = (j == 0) ? yp : ym, y2 = (j == g.ny - 1) ? ym : yp;
+  double un = opp[x1] * wx + opp[x2] * wx;  // (:613) 0 + a + b
+  un = (un + opp[y1] * wy) + opp[y2] * wy;
+  own[jo] = (un - rhs[(i64)colour * g.cs + jo]) * w0;  // (:615)
+}
+
+void relax2d_half(double* u, const double* rhs, const Grid& g, const Bounds& b, int colour, const Weights& w,
+                  cudaStream_t st) {
+  k_relax2d<<<cdiv((i64)g.hp * g.ny, 256), 256, 0, st>>>(u, rhs, g, b, colour, w.wx, w.wy, w.w1);
+  LAUNCHED();
+}
+
+__global__ void __launch_bounds__(256)
+k_residual2d(const double* __restrict__ u, const double* __restrict__ rhs, double* __restrict__ r, const Grid g,
+             const Bounds b, const double wx, const double wy) {
+  const int t = blockIdx.x * 256 + threadIdx.x;
+  const int j = t / g.hp;
+  const int m = t - j * g.hp;
+  if (j >= g.ny || m >= g.mcnt) return;
+  const int colour = blockIdx.y;
+  const int s = (j + colour) & 1;
+  const int i = 2 * m + s;
+  if (i >= g.nx) return;
+  const i64 jo = (i64)j * g.hp + m;
+  double res = 0.0;  // (:326-329)
+  if (!dirichlet2d(i, j, g, b)) {
+    const double* __restrict__ own = u + (i64)colour * g.cs;
+    const double* __restrict__ opp = u + (i64)(1 - colour) * g.cs;
+    const i64 xm = jo - 1 + s, xp = jo + s;
+    const i64 x1 = (i == 0) ? xp : xm, x2 = (i == g.nx - 1) ? xm : xp;
+    const i64 ym = jo - g.hp, yp = jo + g.hp;
+    const i64 y1 = (j == 0) ? yp : ym, y2 = (j == g.ny - 1) ? ym : yp;
+    const double uc = own[jo];
+    double lap = ((opp[x1] - 2 * uc) + opp[x2]) * wx;       // (:343)
+    lap = lap + ((opp[y1] - 2 * uc) + opp[y2]) * wy;
+    res = rhs[(i64)colour * g.cs + jo] - lap;               // (:348)
+  }
+  r[(i64)colour * g.cs + jo] = res;
+}
+
+void residual2d(const double* u, const double* rhs, double* r, const Grid& g, const Bounds& b, const Weights& w,
+                cudaStream_t st) {
+  dim3 grid(cdiv((i64)g.hp * g.ny, 256), 2);
+  k_residual2d<<<grid, 256, 0, st>>>(u, rhs, r, g, b, w.wx, w.wy);
+  LAUNCHED();
+}
+
+// ---------------------------------------------------------------------------------------
+// Reductions: K6 (update_u / du_metrics) and the pure-Neumann mean.
+// Two-stage: REDUCE_BLOCKS partial results, then one block combines them in fixed order.
+// ---------------------------------------------------------------------------------------
+#define REDUCE_BLOCKS 592  // 148 SMs x 4
+#define REDUCE_THREADS 256
+size_t reduce_scratch_doubles() { return 2 * REDUCE_BLOCKS + 8; }
+
+template <bool COPY>
+__global__ void __launch_bounds__(REDUCE_THREADS)
+k_diff_partial(double* __restrict__ a, const double* __restrict__ b, const i64 n_per_colour, const i64 cs,
+               double* __restrict__ part) {
+  __shared__ double red[40];
+  double dmax = 0.0, dsum = 0.0;
+  for (int c = 0; c < 2; ++c) {
+    double* __restrict__ ac = a + c * cs;
+    const double* __restrict__ bc = b + c * cs;
+    for (i64 e = (i64)blockIdx.x * REDUCE_THREADS + threadIdx.x; e < n_per_colour;
+         e += (i64)gridDim.x * REDUCE_THREADS) {
+      const double bv = bc[e];
+      const double d = fabs(ac[e] - bv);
+      dmax = fmax(dmax, d);
+      dsum += d;
+      if (COPY) ac[e] = bv;
+    }
+  }
+  dmax = block_max(dmax, red);
+  dsum = block_sum(dsum, red);
+  if (threadIdx.x == 0) {
+    part[2 * blockIdx.x] = dmax;
+    part[2 * blockIdx.x + 1] = dsum;
+  }
+}
+__global__ void __launch_bounds__(REDUCE_THREADS) k_diff_final(const double* __restrict__ part, int nparts,
+                                                               double* __restrict__ out) {
+  __shared__ double red[40];
+  double dmax = 0.0, dsum = 0.0;
+  for (int e = threadIdx.x; e < nparts; e += REDUCE_THREADS) {
+    dmax = fmax(dmax, part[2 * e]);
+    dsum += part[2 * e + 1];
+  }
+  dmax = block_max(dmax, red);
+  dsum = block_sum(dsum, red);
+  if (threadIdx.x == 0) {
+    out[0] = dmax;
+    out[1] = dsum;
+  }
+}
+
+void diff_reduce(double* a, const double* b, const Grid& g, bool copy, double* scratch, double* out,
+                 cudaStream_t st) {
+  const i64 n = (i64)g.nzl * g.ps;
+  const int nb = (int)std::min<i64>(REDUCE_BLOCKS, std::max<i64>(1, cdiv(n, REDUCE_THREADS)));
+  if (copy)
+    k_diff_partial<true><<<nb, REDUCE_THREADS, 0, st>>>(a, b, n, g.cs, scratch);
+  else
+    k_diff_partial<false><<<nb, REDUCE_THREADS, 0, st>>>(a, b, n, g.cs, scratch);
+  LAUNCHED();
+  k_diff_final<<<1, REDUCE_THREADS, 0, st>>>(scratch, nb, out);
+  LAUNCHED();
+}
+
+__global__ void __launch_bounds__(REDUCE_THREADS)
+k_sum_partial(const double* __restrict__ u, const i64 n_per_colour, const i64 cs, double* __restrict__ part) {
+  __shared__ double red[40];
+  double s = 0.0;
+  for (int c = 0; c < 2; ++c)
+    for (i64 e = (i64)blockIdx.x * REDUCE_THREADS + threadIdx.x; e < n_per_colour;
+         e += (i64)gridDim.x * REDUCE_THREADS)
+      s += u[c * cs + e];  // padding entries are zero
+  s = block_sum(s, red);
+  if (threadIdx.x == 0) part[blockIdx.x] = s;
+}
+// every block re-derives the total from the partials (fixed order) and subtracts the mean on valid points
+__global__ void __launch_bounds__(256)
+k_sub_mean(double* __restrict__ u, const Grid g, const double* __restrict__ part, const int nparts,
+           const double inv_count_num /* N as double */) {
+  __shared__ double red[40];
+  double s = 0.0;
+  for (int e = threadIdx.x; e < nparts; e += 256) s += part[e];
+  s = block_sum(s, red);
+  const double mean = s / inv_count_num;
+  const int t = blockIdx.x * 256 + threadIdx.x;
+  const int j = t / g.hp;
+  const int m = t - j * g.hp;
+  if (j >= g.ny || m >= g.mcnt) return;
+  const int kl = blockIdx.y;      // local plane
+  const int colour = blockIdx.z;
+  const int i = 2 * m + ((j + kl + g.k0 + colour) & 1);
+  if (i >= g.nx) return;
+  const i64 o = (i64)colour * g.cs + (i64)kl * g.ps + (i64)j * g.hp + m;
+  u[o] = u[o] - mean;
+}
+
+void subtract_mean(double* u, const Grid& g, double* scratch, cudaStream_t st) {
+  const i64 n = (i64)g.nzl * g.ps;
+  const int nb = (int)std::min<i64>(REDUCE_BLOCKS, std::max<i64>(1, cdiv(n, REDUCE_THREADS)));
+  k_sum_partial<<<nb, REDUCE_THREADS, 0, st>>>(u, n, g.cs, scratch);
+  LAUNCHED();
+  dim3 grid(cdiv((i64)g.hp * g.ny, 256), g.nzl, 2);
+  k_sub_mean<<<grid, 256, 0, st>>>(u, g, scratch, nb, (double)((i64)g.nx * g.ny * g.nz));
+  LAUNCHED();
+}
+
+// ---------------------------------------------------------------------------------------
+// K3  restriction  rhs_c = R r_f      (ndsm_multigrid_core.f90:1043-1063, ndsm_interp.f90:263-290)
+// One thread per coarse point; the stencil is visited x-fastest and the weight is formed as
+// ((((1*c2x)*w2x)*c2y)*w2y)*c2z)*w2z exactly like the reference, so the sum is bit-identical.
+// Algorithmic traffic: 8 B per fine point (read r_f once) + 8 B per coarse point.
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128)
+k_restrict(const double* __restrict__ rf, const Grid gf, double* __restrict__ rc, const Grid gc,
+           const RestrictTab tx, const RestrictTab ty, const RestrictTab tz) {
+  const int t = blockIdx.x * 128 + threadIdx.x;
+  const int jc = t / gc.hp;
+  const int mc = t - jc * gc.hp;
+  if (jc >= gc.ny || mc >= gc.mcnt) return;
+  const int kc = gc.k0 + blockIdx.y;
+  const int colour = blockIdx.z;
+  const int ic = 2 * mc + ((jc + kc + colour) & 1);
+  if (ic >= gc.nx) return;
+  const int ax = tx.first[ic], cx = tx.count[ic];
+  const int ay = ty.first[jc], cy = ty.count[jc];
+  const int az = tz.first[kc], cz = tz.count[kc];
+  const double* __restrict__ wxv = tx.c2 + (i64)ic * NDSM_RMAX;
+  const double* __restrict__ wyv = ty.c2 + (i64)jc * NDSM_RMAX;
+  const double* __restrict__ wzv = tz.c2 + (i64)kc * NDSM_RMAX;
+  double px[NDSM_RMAX];
+#pragma unroll
+  for (int ii = 0; ii < NDSM_RMAX; ++ii) px[ii] = (ii < cx) ? (wxv[ii] * tx.w2) : 0.0;  // (1*c2)*w2
+  double fc = 0.0;
+  for (int kk = 0; kk < cz; ++kk) {
+    const int kf = az + kk;
+    const double wz_ = wzv[kk];
+    for (int jj = 0; jj < cy; ++jj) {
+      const int jf = ay + jj;
+      const double wy_ = wyv[jj];
+      const i64 rowo = (i64)(kf - gf.k0) * gf.ps + (i64)jf * gf.hp;
+      const int par = (jf + kf) & 1;
+#pragma unroll
+      for (int ii = 0; ii < NDSM_RMAX; ++ii) {
+        if (ii < cx) {
+          const int i_f = ax + ii;
+          double w = (px[ii] * wy_) * ty.w2;
+          w = (w * wz_) * tz.w2;
+          fc = fc + w * rf[(i64)((i_f + par) & 1) * gf.cs + rowo + (i_f >> 1)];
+        }
+      }
+    }
+  }
+  rc[(i64)colour * gc.cs + (i64)(kc - gc.k0) * gc.ps + (i64)jc * gc.hp + mc] = fc;
+}
+
+void restrict_level(const double* rf, const Grid& gf, double* rhsc, const Grid& gc, const RestrictTab& tx,
+                    const RestrictTab& ty, const RestrictTab& tz, cudaStream_t st) {
+  dim3 grid(cdiv((i64)gc.hp * gc.ny, 128), gc.nzl, 2);
+  k_restrict<<<grid, 128, 0, st>>>(rf, gf, rhsc, gc, tx, ty, tz);
+  LAUNCHED();
+}
+
+// ---------------------------------------------------------------------------------------
+// K4  prolongation + correction add   u_f += P u_c
+//     (ndsm_multigrid_core.f90:900-919,706-710 ; ndsm_interp.f90:120-156)
+// 8 coarse corners, reduced z -> y -> x as fs(j) = wh*fs(j) + wl*fs(j+NC).
+// Algorithmic traffic: 16 B per fine point + 8 B per coarse point.
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_interp_add(const double* __restrict__ uc, const Grid gc, double* __restrict__ uf, const Grid gf,
+             const InterpTab tx, const InterpTab ty, const InterpTab tz) {
+  const int t = blockIdx.x * 256 + threadIdx.x;
+  const int j = t / gf.hp;
+  const int m = t - j * gf.hp;
+  if (j >= gf.ny || m >= gf.mcnt) return;
+  const int k = gf.k0 + blockIdx.y;
+  const int colour = blockIdx.z;
+  const int i = 2 * m + ((j + k + colour) & 1);
+  if (i >= gf.nx) return;
+  const int x0 = tx.lo[i], y0 = ty.lo[j], z0 = tz.lo[k];
+  const int x1 = min(x0 + 1, gc.nx - 1), y1 = min(y0 + 1, gc.ny - 1), z1 = min(z0 + 1, gc.nz - 1);
+  double f0 = uc[gidx(gc, x0, y0, z0)], f1 = uc[gidx(gc, x1, y0, z0)];
+  double f2 = uc[gidx(gc, x0, y1, z0)], f3 = uc[gidx(gc, x1, y1, z0)];
+  double f4 = uc[gidx(gc, x0, y0, z1)], f5 = uc[gidx(gc, x1, y0, z1)];
+  double f6 = uc[gidx(gc, x0, y1, z1)], f7 = uc[gidx(gc, x1, y1, z1)];
+  const double whz = tz.wh[k], wlz = tz.wl[k];
+  f0 = whz * f0 + wlz * f4;
+  f1 = whz * f1 + wlz * f5;
+  f2 = whz * f2 + wlz * f6;
+  f3 = whz * f3 + wlz * f7;
+  const double why = ty.wh[j], wly = ty.wl[j];
+  f0 = why * f0 + wly * f2;
+  f1 = why * f1 + wly * f3;
+  const double whx = tx.wh[i], wlx = tx.wl[i];
+  f0 = whx * f0 + wlx * f1;
+  const i64 o = (i64)colour * gf.cs + (i64)(k - gf.k0) * gf.ps + (i64)j * gf.hp + m;
+  uf[o] = uf[o] + f0;
+}
+
+void interp_add(const double* uc, const Grid& gc, double* uf, const Grid& gf, const InterpTab& tx,
+                const InterpTab& ty, const InterpTab& tz, cudaStream_t st) {
+  dim3 grid(cdiv((i64)gf.hp * gf.ny, 256), gf.nzl, 2);
+  k_interp_add<<<grid, 256, 0, st>>>(uc, gc, uf, gf, tx, ty, tz);
+  LAUNCHED();
+}
+
+// ---------------------------------------------------------------------------------------
+// K5  coarsest-level solve inside one thread block   (ndsm_multigrid_core.f90:728-800)
+// The level (<= a few thousand points) is held dense in shared memory; each iteration is
+// red pass, black pass, (pure-Neumann mean subtraction), max/mean |u - u_sav| reduction and
+// the u_sav copy, with the reference's loop semantics: test du <= ex_tol BEFORE relaxing,
+// u_sav starts at 0, at most nmax iterations.
+// ---------------------------------------------------------------------------------------
+template <int NDIM>
+__global__ void __launch_bounds__(1024)
+k_solve_exact(double* __restrict__ u, const double* __restrict__ rhs, const Grid g, const Bounds b,
+              const int first_colour, const double wx, const double wy, const double wz, const double w1,
+              const int all_neumann, const int du_max, const double ex_tol, const int nmax,
+              int* __restrict__ info) {
+  extern __shared__ double sm[];
+  __shared__ double red[40];
+  const int N = g.nx * g.ny * g.nz;
+  double* su = sm;
+  double* sr = sm + N;
+  double* ss = sm + 2 * N;
+  const int sxy = g.nx * g.ny;
+  for (int p = threadIdx.x; p < N; p += blockDim.x) {
+    const int k = p / sxy, rem = p - k * sxy, j = rem / g.nx, i = rem - j * g.nx;
+    const i64 o = gidx(g, i, j, k + g.k0);
+    su[p] = u[o];
+    sr[p] = rhs[o];
+    ss[p] = 0.0;
+  }
+  __syncthreads();
+  double du = 1.7976931348623157e308;
+  int iters = 0, converged = 0;
+  for (int it = 0; it < nmax; ++it) {
+    if (du <= ex_tol) { converged = 1; break; }
+    for (int pass = 0; pass < 2; ++pass) {
+      const int colour = first_colour ^ pass;
+      for (int p = threadIdx.x; p < N; p += blockDim.x) {
+        const int k = p / sxy, rem = p - k * sxy, j = rem / g.nx, i = rem - j * g.nx;
+        if (((i + j + k) & 1) != colour) continue;
+        if (i < b.lb[0] || i > b.ub[0] || j < b.lb[1] || j > b.ub[1]) continue;
+        if (NDIM == 3) {
+          if (k < b.lb[2] || k > b.ub[2]) continue;
+          const int xl = (i - 1 < 0) ? 1 : i - 1, xh = (i + 1 > g.nx - 1) ? g.nx - 2 : i + 1;
+          const int yl = (j - 1 < 0) ? 1 : j - 1, yh = (j + 1 > g.ny - 1) ? g.ny - 2 : j + 1;
+          const int zl = (k - 1 < 0) ? 1 : k - 1, zh = (k + 1 > g.nz - 1) ? g.nz - 2 : k + 1;
+          double unew = ((su[xh + j * g.nx + k * sxy] + su[xl + j * g.nx + k * sxy]) * wx +
+                         (su[i + yh * g.nx + k * sxy] + su[i + yl * g.nx + k * sxy]) * wy) +
+                        (su[i + j * g.nx + zh * sxy] + su[i + j * g.nx + zl * sxy]) * wz;
+          unew = unew - sr[p];
+          su[p] = w1 * unew;
+        } else {
+          const int x1 = (i == 0) ? i + 1 : i - 1, x2 = (i == g.nx - 1) ? i - 1 : i + 1;
+          const int y1 = (j == 0) ? j + 1 : j - 1, y2 = (j == g.ny - 1) ? j - 1 : j + 1;
+          double un = su[x1 + j * g.nx] * wx + su[x2 + j * g.nx] * wx;
+          un = (un + su[i + y1 * g.nx] * wy) + su[i + y2 * g.nx] * wy;
+          su[p] = (un - sr[p]) * w1;
+        }
+      }
+      __syncthreads();
+    }
+    if (all_neumann) {
+      double s = 0.0;
+      for (int p = threadIdx.x; p < N; p += blockDim.x) s += su[p];
+      s = block_sum(s, red);
+      const double mean = s / (double)N;
+      for (int p = threadIdx.x; p < N; p += blockDim.x) su[p] = su[p] - mean;
+      __syncthreads();
+    }
+    double dmax = 0.0, dsum = 0.0;
+    for (int p = threadIdx.x; p < N; p += blockDim.x) {
+      const double v = su[p];
+      const double d = fabs(ss[p] - v);
+      dmax = fmax(dmax, d);
+      dsum += d;
+      ss[p] = v;
+    }
+    if (du_max) du = block_max(dmax, red);
+    else du = block_sum(dsum, red) / (double)N;
+    ++iters;
+  }
+  __syncthreads();
+  for (int p = threadIdx.x; p < N; p += blockDim.x) {
+    const int k = p / sxy, rem = p - k * sxy, j = rem / g.nx, i = rem - j * g.nx;
+    u[gidx(g, i, j, k + g.k0)] = su[p];
+  }
+  if (threadIdx.x == 0) {
+    info[0] = iters;
+    info[1] = converged;
+  }
+}
+
+bool solve_exact_smem(int ndim, double* u, const double* rhs, const Grid& g, const Bounds& b, int first_colour,
+                      const Weights& w, bool all_neumann, bool du_max, double ex_tol, int nmax, int* info,
+                      cudaStream_t st) {
+  const i64 N = (i64)g.nx * g.ny * g.nz;
+  const size_t bytes = (size_t)N * 3 * sizeof(double);
+  if (bytes > 200 * 1024 || g.nzl != g.nz) return false;
+  int threads = (int)std::min<i64>(1024, std::max<i64>(64, ((N / 2 + 31) / 32) * 32));
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaFuncSetAttribute(k_solve_exact<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(k_solve_exact<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    attr_set = true;
+  }
+  if (ndim == 3)
+    k_solve_exact<3><<<1, threads, bytes, st>>>(u, rhs, g, b, first_colour, w.wx, w.wy, w.wz, w.w1,
+                                                all_neumann ? 1 : 0, du_max ? 1 : 0, ex_tol, nmax, info);
+  else
+    k_solve_exact<2><<<1, threads, bytes, st>>>(u, rhs, g, b, first_colour, w.wx, w.wy, w.wz, w.w1,
+                                                all_neumann ? 1 : 0, du_max ? 1 : 0, ex_tol, nmax, info);
+  LAUNCHED();
+  return true;
+}
+
+// ---------------------------------------------------------------------------------------
+// layout conversion
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_split_from_dense(const double* __restrict__ dense, double* __restrict__ split, const Grid g, const double shift) {
+  const int i = blockIdx.x * 256 + threadIdx.x;
+  if (i >= g.nx) return;
+  const int j = blockIdx.y, kl = blockIdx.z;
+  split[gidx(g, i, j, kl + g.k0)] = dense[i + (i64)g.nx * (j + (i64)g.ny * kl)] - shift;
+}
+void split_from_dense(const double* dense, double* split, const Grid& g, double shift, cudaStream_t st) {
+  dim3 grid(cdiv(g.nx, 256), g.ny, g.nzl);
+  k_split_from_dense<<<grid, 256, 0, st>>>(dense, split, g, shift);
+  LAUNCHED();
+}
+__global__ void __launch_bounds__(256)
+k_dense_from_split(const double* __restrict__ split, double* __restrict__ dense, const Grid g) {
+  const int i = blockIdx.x * 256 + threadIdx.x;
+  if (i >= g.nx) return;
+  const int j = blockIdx.y, kl = blockIdx.z;
+  dense[i + (i64)g.nx * (j + (i64)g.ny * kl)] = split[gidx(g, i, j, kl + g.k0)];
+}
+void dense_from_split(const double* split, double* dense, const Grid& g, cudaStream_t st) {
+  dim3 grid(cdiv(g.nx, 256), g.ny, g.nzl);
+  k_dense_from_split<<<grid, 256, 0, st>>>(split, dense, g);
+  LAUNCHED();
+}
+
+// ---------------------------------------------------------------------------------------
+// K7 pieces: boundary-condition setup
+// ---------------------------------------------------------------------------------------
+// extract_bn with dir=+1 (ndsm_vector_potential.f90:699-743): face(a,b) of component array Bc
+__global__ void __launch_bounds__(256)
+k_extract_face(const double* __restrict__ Bc, const int nx, const int ny, const int nz, const int dim,
+               const int layer, double* __restrict__ face) {
+  const int n1 = (dim == 0) ? ny : nx;
+  const int n2 = (dim == 2) ? ny : nz;
+  const int a = blockIdx.x * 256 + threadIdx.x;
+  const int bb = blockIdx.y;
+  if (a >= n1 || bb >= n2) return;
+  int i, j, k;
+  if (dim == 0) { i = layer; j = a; k = bb; }
+  else if (dim == 1) { i = a; j = layer; k = bb; }
+  else { i = a; j = bb; k = layer; }
+  face[a + (i64)n1 * bb] = Bc[i + (i64)nx * (j + (i64)ny * k)];
+}
+void extract_face(const double* Bc, int nx, int ny, int nz, int dim, int layer, double* face, cudaStream_t st) {
+  const int n1 = (dim == 0) ? ny : nx;
+  const int n2 = (dim == 2) ? ny : nz;
+  dim3 grid(cdiv(n1, 256), n2);
+  k_extract_face<<<grid, 256, 0, st>>>(Bc, nx, ny, nz, dim, layer, face);
+  LAUNCHED();
+}
+
+// trapz_2D (ndsm_vector_potential.f90:1070-1106): SUM(w*f) with w = 1, 1/2 (edges), 1/4 (corners)
+__global__ void __launch_bounds__(REDUCE_THREADS)
+k_trapz_partial(const double* __restrict__ f, const int n1, const int n2, double* __restrict__ part) {
+  __shared__ double red[40];
+  const i64 n = (i64)n1 * n2;
+  double s = 0.0;
+  for (i64 e = (i64)blockIdx.x * REDUCE_THREADS + threadIdx.x; e < n; e += (i64)gridDim.x * REDUCE_THREADS) {
+    const int j = (int)(e / n1), i = (int)(e - (i64)j * n1);
+    const bool ei = (i == 0 || i == n1 - 1), ej = (j == 0 || j == n2 - 1);
+    const double w = (ei && ej) ? 0.25 : ((ei || ej) ? 0.5 : 1.0);
+    s += w * f[e];
+  }
+  s = block_sum(s, red);
+  if (threadIdx.x == 0) part[blockIdx.x] = s;
+}
+__global__ void __launch_bounds__(REDUCE_THREADS)
+k_trapz_final(const double* __restrict__ part, const int nparts, const double dq1, const double dq2,
+              double* __restrict__ out) {
+  __shared__ double red[40];
+  double s = 0.0;
+  for (int e = threadIdx.x; e < nparts; e += REDUCE_THREADS) s += part[e];
+  s = block_sum(s, red);
+  if (threadIdx.x == 0) out[0] = (s * dq1) * dq2;  // (:1104)
+}
+void trapz_face(const double* face, int n1, int n2, double dq1, double dq2, double* scratch, double* out,
+                cudaStream_t st) {
+  const i64 n = (i64)n1 * n2;
+  const int nb = (int)std::min<i64>(REDUCE_BLOCKS, std::max<i64>(1, cdiv(n, REDUCE_THREADS)));
+  k_trapz_partial<<<nb, REDUCE_THREADS, 0, st>>>(face, n1, n2, scratch);
+  LAUNCHED();
+  k_trapz_final<<<1, REDUCE_THREADS, 0, st>>>(scratch, nb, dq1, dq2, out);
+  LAUNCHED();
+}
+
+// compute_At_bcs (ndsm_vector_potential.f90:977-1031).  With the unit vectors of :88-113,
+// -(grad chi x n) projected on (t1,t2) is (-d2,+d1) on x- and z-faces and (+d2,-d1) on y-faces.
+__global__ void __launch_bounds__(256)
+k_compute_At(const double* __restrict__ chi, const Grid g, const double fac, const int yface,
+             double* __restrict__ At1, double* __restrict__ At2) {
+  const int i = blockIdx.x * 256 + threadIdx.x;
+  const int j = blockIdx.y;
+  if (i >= g.nx || j >= g.ny) return;
+  double d1 = 0.0, d2 = 0.0;
+  if (i != 0 && i != g.nx - 1) d1 = fac * (chi[gidx(g, i + 1, j, 0)] - chi[gidx(g, i - 1, j, 0)]);  // (:1007-1011)
+  if (j != 0 && j != g.ny - 1) d2 = fac * (chi[gidx(g, i, j + 1, 0)] - chi[gidx(g, i, j - 1, 0)]);  // (:1013-1017)
+  const i64 o = i + (i64)g.nx * j;
+  if (yface) { At1[o] = d2; At2[o] = -d1; }
+  else       { At1[o] = -d2; At2[o] = d1; }
+}
+void compute_At(const double* chi_split, const Grid& g2, double fac, int face_id, double* At1, double* At2,
+                cudaStream_t st) {
+  dim3 grid(cdiv(g2.nx, 256), g2.ny);
+  k_compute_At<<<grid, 256, 0, st>>>(chi_split, g2, fac, (face_id == 2 || face_id == 3) ? 1 : 0, At1, At2);
+  LAUNCHED();
+}
+
+// extract_bn with dir=-1 (ndsm_vector_potential.f90:647-682,739): Dirichlet data -> face of A (colour-split)
+__global__ void __launch_bounds__(256)
+k_write_face(double* __restrict__ A, const Grid g, const int dim, const int layer, const double* __restrict__ face) {
+  const int n1 = (dim == 0) ? g.ny : g.nx;
+  const int n2 = (dim == 2) ? g.ny : g.nz;
+  const int a = blockIdx.x * 256 + threadIdx.x;
+  const int bb = blockIdx.y;
+  if (a >= n1 || bb >= n2) return;
+  int i, j, k;
+  if (dim == 0) { i = layer; j = a; k = bb; }
+  else if (dim == 1) { i = a; j = layer; k = bb; }
+  else { i = a; j = bb; k = layer; }
+  if (k < g.k0 || k >= g.k0 + g.nzl) return;
+  A[gidx(g, i, j, k)] = face[a + (i64)n1 * bb];
+}
+void write_face(double* A_split, const Grid& g, int dim, int layer, const double* face, cudaStream_t st) {
+  const int n1 = (dim == 0) ? g.ny : g.nx;
+  const int n2 = (dim == 2) ? g.ny : g.nz;
+  dim3 grid(cdiv(n1, 256), n2);
+  k_write_face<<<grid, 256, 0, st>>>(A_split, g, dim, layer, face);
+  LAUNCHED();
+}
+
+// ---------------------------------------------------------------------------------------
+// K8  flux-balance fields + curl     (ndsm_vector_potential.f90:880-950, 759-872)
+// ---------------------------------------------------------------------------------------
+struct FluxPar { double phi[6]; double Lq[3]; };
+
+__global__ void __launch_bounds__(256)
+k_unsplit_A(const double* __restrict__ As, const Grid g, const int comp, const double* __restrict__ x,
+            const double* __restrict__ y, const double* __restrict__ z, const FluxPar f, const int add_flux,
+            double* __restrict__ Ad) {
+  const int i = blockIdx.x * 256 + threadIdx.x;
+  if (i >= g.nx) return;
+  const int j = blockIdx.y, kl = blockIdx.z, k = kl + g.k0;
+  double a = As[gidx(g, i, j, k)];
+  if (add_flux) {
+    const double X = x[i], Y = y[j], Z = z[k];
+    const double Vq = (f.Lq[0] * f.Lq[1]) * f.Lq[2];
+    const double g1 = (f.phi[1] - f.phi[0]) / Vq, g2 = (f.phi[3] - f.phi[2]) / Vq, g3 = (f.phi[5] - f.phi[4]) / Vq;
+    const double inv3 = 1.0 / 3.0;
+    double A1, A2, A3, Ac;
+    if (comp == 0)      { A1 = -((g3 * Y) * Z); A2 = +((g2 * Z) * Y); A3 = 0.0;             Ac = -((f.phi[4] * f.Lq[2]) * Y) / Vq; }
+    else if (comp == 1) { A1 = 0.0;             A2 = -((g1 * X) * Z); A3 = +((g3 * X) * Z); Ac = -((f.phi[0] * f.Lq[0]) * Z) / Vq; }
+    else                { A1 = +((g1 * X) * Y); A2 = 0.0;             A3 = -((g2 * X) * Y); Ac = -((f.phi[2] * f.Lq[1]) * X) / Vq; }
+    a = (a + Ac) + inv3 * ((A1 + A2) + A3);  // (:932-947)
+  }
+  Ad[i + (i64)g.nx * (j + (i64)g.ny * kl)] = a;
+}
+
+void unsplit_A(const double* As, const Grid& g, int comp, const double* x, const double* y, const double* z,
+               const double* phi, const double* Lq, bool add_flux, double* A_dense, cudaStream_t st) {
+  FluxPar f;
+  for (int q = 0; q < 6; ++q) f.phi[q] = phi[q];
+  for (int q = 0; q < 3; ++q) f.Lq[q] = Lq[q];
+  dim3 grid(cdiv(g.nx, 256), g.ny, g.nzl);
+  k_unsplit_A<<<grid, 256, 0, st>>>(As, g, comp, x, y, z, f, add_flux ? 1 : 0, A_dense);
+  LAUNCHED();
+}
+
+// derivq (ndsm_vector_potential.f90:825-872): weights (c*0.5)/dq, summed left to right from 0
+__device__ __forceinline__ double derivq(const double* __restrict__ u, i64 n, int idx, int nd, i64 stride, double dq) {
+  double d;
+  if (idx == 0) {
+    d = u[n] * ((-3.0 * 0.5) / dq);
+    d = d + u[n + stride] * ((4.0 * 0.5) / dq);
+    d = d + u[n + 2 * stride] * ((-1.0 * 0.5) / dq);
+  } else if (idx == nd - 1) {
+    d = u[n] * ((3.0 * 0.5) / dq);
+    d = d + u[n - stride] * ((-4.0 * 0.5) / dq);
+    d = d + u[n - 2 * stride] * ((1.0 * 0.5) / dq);
+  } else {
+    d = u[n - stride] * ((-1.0 * 0.5) / dq);
+    d = d + u[n + stride] * ((1.0 * 0.5) / dq);
+  }
+  return d;
+}
+__global__ void __launch_bounds__(256)
+k_curl(const double* __restrict__ A, const int nx, const int ny, const int nz, const double dqx, const double dqy,
+       const double dqz, double* __restrict__ B) {
+  const int i = blockIdx.x * 256 + threadIdx.x;
+  if (i >= nx) return;
+  const int j = blockIdx.y, k = blockIdx.z;
+  const i64 N = (i64)nx * ny * nz, sy = nx, sz = (i64)nx * ny;
+  const i64 n = i + sy * j + sz * k;
+  const double* __restrict__ Ax = A;
+  const double* __restrict__ Ay = A + N;
+  const double* __restrict__ Az = A + 2 * N;
+  const double dAx_dy = derivq(Ax, n, j, ny, sy, dqy);
+  const double dAx_dz = derivq(Ax, n, k, nz, sz, dqz);
+  const double dAy_dx = derivq(Ay, n, i, nx, 1, dqx);
+  const double dAy_dz = derivq(Ay, n, k, nz, sz, dqz);
+  const double dAz_dx = derivq(Az, n, i, nx, 1, dqx);
+  const double dAz_dy = derivq(Az, n, j, ny, sy, dqy);
+  B[n] = dAz_dy - dAy_dz;          // (:802-804)
+  B[n + N] = dAx_dz - dAz_dx;
+  B[n + 2 * N] = dAy_dx - dAx_dy;
+}
+void curl_dense(const double* A_dense, int nx, int ny, int nz, double dqx, double dqy, double dqz, double* B_dense,
+                cudaStream_t st) {
+  dim3 grid(cdiv(nx, 256), ny, nz);
+  k_curl<<<grid, 256, 0, st>>>(A_dense, nx, ny, nz, dqx, dqy, dqz, B_dense);
+  LAUNCHED();
+}
+
+// IOPT_FLXCRL = 1 order (:453-466): corrections added to both A and B after the curl
+__global__ void __launch_bounds__(256)
+k_add_flux_dense(double* __restrict__ A, double* __restrict__ B, const int nx, const int ny, const int nz,
+                 const double* __restrict__ x, const double* __restrict__ y, const double* __restrict__ z,
+                 const FluxPar f) {
+  const int i = blockIdx.x * 256 + threadIdx.x;
+  if (i >= nx) return;
+  const int j = blockIdx.y, k = blockIdx.z;
+  const i64 N = (i64)nx * ny * nz;
+  const i64 n = i + (i64)nx * (j + (i64)ny * k);
+  const double X = x[i], Y = y[j], Z = z[k];
+  const double Vq = (f.Lq[0] * f.Lq[1]) * f.Lq[2];
+  const double g1 = (f.phi[1] - f.phi[0]) / Vq, g2 = (f.phi[3] - f.phi[2]) / Vq, g3 = (f.phi[5] - f.phi[4]) / Vq;
+  const double inv3 = 1.0 / 3.0;
+  const double bc[3] = {g1 * X + (f.phi[0] * f.Lq[0]) / Vq, g2 * Y + (f.phi[2] * f.Lq[1]) / Vq,
+                        g3 * Z + (f.phi[4] * f.Lq[2]) / Vq};
+  const double A1[3] = {-((g3 * Y) * Z), 0.0, +((g1 * X) * Y)};
+  const double A2[3] = {+((g2 * Z) * Y), -((g1 * X) * Z), 0.0};
+  const double A3[3] = {0.0, +((g3 * X) * Z), -((g2 * X) * Y)};
+  const double Ac[3] = {-((f.phi[4] * f.Lq[2]) * Y) / Vq, -((f.phi[0] * f.Lq[0]) * Z) / Vq,
+                        -((f.phi[2] * f.Lq[1]) * X) / Vq};
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    B[n + c * N] = B[n + c * N] + bc[c];
+    A[n + c * N] = (A[n + c * N] + Ac[c]) + inv3 * ((A1[c] + A2[c]) + A3[c]);
+  }
+}
+void add_flux_dense(double* A_dense, double* B_dense, int nx, int ny, int nz, const double* x, const double* y,
+                    const double* z, const double* phi, const double* Lq, cudaStream_t st) {
+  FluxPar f;
+  for (int q = 0; q < 6; ++q) f.phi[q] = phi[q];
+  for (int q = 0; q < 3; ++q) f.Lq[q] = Lq[q];
+  dim3 grid(cdiv(nx, 256), ny, nz);
+  k_add_flux_dense<<<grid, 256, 0, st>>>(A_dense, B_dense, nx, ny, nz, x, y, z, f);
+  LAUNCHED();
+}
+
+}  // namespace ndsm

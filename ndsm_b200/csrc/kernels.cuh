@@ -1,0 +1,92 @@
+// kernels.cuh -- launch wrappers for the sm_100a FP64 kernels of the NDSM V-cycle path.
+// Every wrapper enqueues on `st` and returns immediately; all pointers are device pointers
+// that address local plane 0 of a colour-split level (see common.cuh) unless noted "dense".
+#pragma once
+#include "common.cuh"
+
+namespace ndsm {
+
+extern unsigned long long g_launches;  // number of kernels this library has launched
+
+// Optional per-kernel-class timing with CUDA events on the launching stream (bench.py roofline numbers).
+// Classes are recorded only for level-0 launches (tagged by the MG driver through prof_scope()).
+enum ProfClass { PROF_RELAX0 = 0, PROF_RESID0, PROF_RESTRICT0, PROF_INTERP0, PROF_DIFF0, PROF_NCLASS };
+void prof_enable(bool on);
+bool prof_enabled();
+void prof_begin(int cls, cudaStream_t st);  // record start event (no-op when disabled)
+void prof_end(int cls, cudaStream_t st);    // record stop event
+void prof_collect();                        // after a stream sync: fold finished event pairs into the totals
+void prof_get(int cls, unsigned long long* count, double* total_ms);
+void prof_reset();
+
+struct Weights {  // finite-difference weights of one level
+  double wx, wy, wz;  // 1/h^2
+  double w1;          // 3D: 1/(2*(wx+wy+wz))  (ndsm_optimized.f90:92-93); 2D: 1/(2wx+2wy) (ndsm_poisson.f90:483-489)
+  double wc;          // 3D: 2*(wx+wy+wz)      (ndsm_optimized.f90:384)
+};
+
+struct InterpTab {  // prolongation table of one dimension (ndsm_interp.f90:120-146), indexed by fine index
+  const int* lo;
+  const double* wl;
+  const double* wh;
+};
+struct RestrictTab {  // restriction table of one dimension (ndsm_interp.f90:218-252,277-282), by coarse index
+  const int* first;
+  const int* count;
+  const double* c2;  // [n_coarse][NDSM_RMAX] : |dq_c - |q_f - q_c||
+  double w2;         // dq_f / dq_c^2
+};
+
+// K1: one colour pass of the 3D red/black Gauss-Seidel sweep (ndsm_optimized.f90:103-167).
+// rhs may be nullptr (rhs == 0 on the finest level of the vector-potential solves).
+void relax3d_half(double* u, const double* rhs, const Grid& g, const Bounds& b, int colour, const Weights& w,
+                  cudaStream_t st);
+// K2: residual r = rhs - L u on non-Dirichlet points, 0 elsewhere (ndsm_optimized.f90:346-447).
+void residual3d(const double* u, const double* rhs, double* r, const Grid& g, const Bounds& b, const Weights& w,
+                cudaStream_t st);
+// 2D (chi) variants: generic N-D relax / residual specialised to ndim = 2 (ndsm_poisson.f90:280-358,451-618).
+void relax2d_half(double* u, const double* rhs, const Grid& g, const Bounds& b, int colour, const Weights& w,
+                  cudaStream_t st);
+void residual2d(const double* u, const double* rhs, double* r, const Grid& g, const Bounds& b, const Weights& w,
+                cudaStream_t st);
+// u -= sum(u)/N over all points (pure-Neumann gauge; ndsm_poisson.f90:529-547, ndsm_optimized.f90:173-189).
+// scratch: >= reduce_scratch_doubles() doubles.
+void subtract_mean(double* u, const Grid& g, double* scratch, cudaStream_t st);
+// K3: rhs_c = R r_f (ndsm_multigrid_core.f90:1010-1065 + ndsm_interp.f90:186-292), exact reference summation order.
+void restrict_level(const double* rf, const Grid& gf, double* rhsc, const Grid& gc, const RestrictTab& tx,
+                    const RestrictTab& ty, const RestrictTab& tz, cudaStream_t st);
+// K4: u_f += P u_c on every fine point (ndsm_multigrid_core.f90:865-921,692-712 + ndsm_interp.f90:85-158).
+void interp_add(const double* uc, const Grid& gc, double* uf, const Grid& gf, const InterpTab& tx,
+                const InterpTab& ty, const InterpTab& tz, cudaStream_t st);
+// K5: coarsest-level relaxation solve to ex_tol inside ONE thread block (ndsm_multigrid_core.f90:728-800).
+// info[0] = iterations done, info[1] = converged flag.  Returns false if the level does not fit in shared memory.
+bool solve_exact_smem(int ndim, double* u, const double* rhs, const Grid& g, const Bounds& b, int first_colour,
+                      const Weights& w, bool all_neumann, bool du_max, double ex_tol, int nmax, int* info,
+                      cudaStream_t st);
+// K6: out[0] = max|a-b|, out[1] = sum|a-b| over owned planes; then a := b  (update_u: a=caller's u, b=V-cycled u;
+// ndsm_multigrid_core.f90:1077-1122).  With copy=false it is du_metrics (:808-853) and leaves a untouched.
+void diff_reduce(double* a, const double* b, const Grid& g, bool copy, double* scratch, double* out, cudaStream_t st);
+size_t reduce_scratch_doubles();
+
+// layout conversion: dense (nx,ny,nzl) x-fastest <-> colour-split; split = dense - shift
+void split_from_dense(const double* dense, double* split, const Grid& g, double shift, cudaStream_t st);
+void dense_from_split(const double* split, double* dense, const Grid& g, cudaStream_t st);
+
+// K7 pieces: boundary-condition setup (ndsm_vector_potential.f90:283-306,387-399,647-682,977-1031,1070-1106)
+void extract_face(const double* Bc_dense, int nx, int ny, int nz, int dim, int layer, double* face, cudaStream_t st);
+void trapz_face(const double* face, int n1, int n2, double dq1, double dq2, double* scratch, double* out,
+                cudaStream_t st);
+void compute_At(const double* chi_split, const Grid& g2, double fac, int face_id, double* At1, double* At2,
+                cudaStream_t st);
+void write_face(double* A_split, const Grid& g, int dim, int layer, const double* face, cudaStream_t st);
+
+// K8: flux-balance fields + curl (ndsm_vector_potential.f90:759-872,880-950)
+// A_dense[c] = unsplit(A_split[c]) (+ flux-balance potential when add_flux)
+void unsplit_A(const double* As, const Grid& g, int comp, const double* x, const double* y, const double* z,
+               const double* phi /*6*/, const double* Lq /*3*/, bool add_flux, double* A_dense, cudaStream_t st);
+void curl_dense(const double* A_dense /*3 comps*/, int nx, int ny, int nz, double dqx, double dqy, double dqz,
+                double* B_dense, cudaStream_t st);
+void add_flux_dense(double* A_dense, double* B_dense, int nx, int ny, int nz, const double* x, const double* y,
+                    const double* z, const double* phi, const double* Lq, cudaStream_t st);
+
+}  // namespace ndsm

@@ -1,0 +1,179 @@
+// vecpot.cu -- compute_vector_potential on the GPU (ndsm_vector_potential.f90:130-497):
+// face fluxes -> six 2D pure-Neumann chi solves -> At Dirichlet data -> three 3D Laplace
+// solves -> flux-balance fields -> curl.  Everything between the face upload and the final
+// dense A/B arrays stays resident in HBM.
+#include "vecpot.hpp"
+
+#include <chrono>
+#include <cmath>
+#include <memory>
+
+namespace ndsm {
+
+bool g_debug = false;
+Report g_report;
+
+void debug_msg(const char* sub, const char* msg) {  // ndsm_root.f90:493-503
+  fprintf(stderr, "DEBUG(%s):%s\n", sub, msg);
+}
+
+static const int imap_cp[6] = {0, 0, 1, 1, 2, 2};                                 // :82
+static const int imap_nc[6][2] = {{1, 2}, {1, 2}, {0, 2}, {0, 2}, {0, 1}, {0, 1}};  // :83
+
+struct DevBuf {  // RAII device allocation
+  double* p = nullptr;
+  DevBuf() {}
+  explicit DevBuf(size_t n) { alloc(n); }
+  void alloc(size_t n) {
+    if (cudaMalloc(&p, n * sizeof(double)) != cudaSuccess) { p = nullptr; throw NdsmError(3); }
+  }
+  ~DevBuf() { if (p) cudaFree(p); }
+  DevBuf(const DevBuf&) = delete;
+  DevBuf& operator=(const DevBuf&) = delete;
+};
+
+struct EvTimer {
+  cudaEvent_t a, b;
+  cudaStream_t st;
+  explicit EvTimer(cudaStream_t s) : st(s) { cudaEventCreate(&a); cudaEventCreate(&b); }
+  ~EvTimer() { cudaEventDestroy(a); cudaEventDestroy(b); }
+  void start() { cudaEventRecord(a, st); }
+  double stop() {
+    cudaEventRecord(b, st);
+    cudaEventSynchronize(b);
+    float ms = 0;
+    cudaEventElapsedTime(&ms, a, b);
+    return ms;
+  }
+};
+
+int vector_solve_core(const int* nshape, const long long* iopt, const double* ropt, const double* x, const double* y,
+                      const double* z, double* const* bn, const double* A0, double* A_out, double* B_out,
+                      cudaStream_t st, Report& rep, BcCapture* cap, bool stop_after_bc) {
+  const int nx = nshape[0], ny = nshape[1], nz = nshape[2];
+  const i64 N = (i64)nx * ny * nz;
+  const double* mesh[3] = {x, y, z};
+  const bool use_du_max = (iopt[IOPT_DUMAX] == IOPT_TRUE);
+  double Lq[3], dq[3];
+  for (int d = 0; d < 3; ++d) {  // :201-221
+    double lo = mesh[d][0], hi = mesh[d][0];
+    for (int i = 1; i < nshape[d]; ++i) { lo = mesh[d][i] < lo ? mesh[d][i] : lo; hi = mesh[d][i] > hi ? mesh[d][i] : hi; }
+    Lq[d] = hi - lo;
+    dq[d] = mesh[d][1] - mesh[d][0];
+  }
+  const unsigned long long launches0 = g_launches;
+  EvTimer tm(st), tall(st);
+  tall.start();
+
+  // mesh vectors on the device (flux-balance fields)
+  DevBuf dmesh((size_t)nx + ny + nz);
+  double* dx_ = dmesh.p;
+  double* dy_ = dmesh.p + nx;
+  double* dz_ = dmesh.p + nx + ny;
+  CUDA_CHECK(cudaMemcpyAsync(dx_, x, sizeof(double) * nx, cudaMemcpyHostToDevice, st));
+  CUDA_CHECK(cudaMemcpyAsync(dy_, y, sizeof(double) * ny, cudaMemcpyHostToDevice, st));
+  CUDA_CHECK(cudaMemcpyAsync(dz_, z, sizeof(double) * nz, cudaMemcpyHostToDevice, st));
+
+  // ---------------- BC setup (K7) ----------------
+  tm.start();
+  int n1[6], n2[6];
+  for (int f = 0; f < 6; ++f) { n1[f] = nshape[imap_nc[f][0]]; n2[f] = nshape[imap_nc[f][1]]; }
+  DevBuf scr(reduce_scratch_doubles() + 16);
+  double* d_phi = scr.p + reduce_scratch_doubles();
+  for (int f = 0; f < 6; ++f)  // :300-306 -- always dq(1)*dq(2) (reference quirk)
+    trapz_face(bn[f], n1[f], n2[f], dq[0], dq[1], scr.p, d_phi + f, st);
+  double phi[6];
+  CUDA_CHECK(cudaMemcpyAsync(phi, d_phi, sizeof phi, cudaMemcpyDeviceToHost, st));
+  CUDA_CHECK(cudaStreamSynchronize(st));
+  for (int f = 0; f < 6; ++f) rep.phi[f] = phi[f];
+  const double Aq[6] = {Lq[1] * Lq[2], Lq[1] * Lq[2], Lq[0] * Lq[2], Lq[0] * Lq[2], Lq[0] * Lq[1], Lq[0] * Lq[1]};
+
+  DevBuf At[6][2];
+  int ierr_last = 0;
+  if (g_debug) debug_msg("compute_vector_potential", "Solve BVP on each boundary...");
+  for (int pair = 0; pair < 3; ++pair) {  // faces (1,2), (3,4), (5,6) share shape and mesh
+    const int f0 = 2 * pair;
+    const int sh2[3] = {n1[f0], n2[f0], 1};
+    const double* m2[2] = {mesh[imap_nc[f0][0]], mesh[imap_nc[f0][1]]};
+    MG mg(2, sh2, -1, m2, st);
+    mg.set_options((int)iopt[IOPT_MS], ropt[ROPT_CTOL], "NNNN", use_du_max, (int)iopt[IOPT_NMAXEX]);  // :355-357
+    const Grid g2 = mg.level(0).g;
+    DevBuf chi(2 * (size_t)g2.cs), rhs(2 * (size_t)g2.cs);
+    CUDA_CHECK(cudaMemsetAsync(rhs.p, 0, 2 * (size_t)g2.cs * sizeof(double), st));
+    for (int f = f0; f < f0 + 2; ++f) {
+      CUDA_CHECK(cudaMemsetAsync(chi.p, 0, 2 * (size_t)g2.cs * sizeof(double), st));  // :345
+      split_from_dense(bn[f], rhs.p, g2, phi[f] / Aq[f], st);                         // :348
+      double du_last;
+      ierr_last = mg.solve(chi.p, rhs.p, ropt[ROPT_VTOL], (int)iopt[IOPT_NCYCLES], &du_last, &rep.solves[f]);
+      At[f][0].alloc((size_t)n1[f] * n2[f]);
+      At[f][1].alloc((size_t)n1[f] * n2[f]);
+      compute_At(chi.p, g2, 1.0 / (2.0 * dq[imap_cp[f]]), f, At[f][0].p, At[f][1].p, st);  // :394-398 (dq of normal dir)
+      if (cap) {
+        if (cap->chi[f]) {
+          DevBuf dense((size_t)n1[f] * n2[f]);
+          dense_from_split(chi.p, dense.p, g2, st);
+          CUDA_CHECK(cudaMemcpyAsync(cap->chi[f], dense.p, sizeof(double) * n1[f] * n2[f], cudaMemcpyDeviceToHost, st));
+          CUDA_CHECK(cudaStreamSynchronize(st));
+        }
+        if (cap->At1[f]) CUDA_CHECK(cudaMemcpyAsync(cap->At1[f], At[f][0].p, sizeof(double) * n1[f] * n2[f], cudaMemcpyDeviceToHost, st));
+        if (cap->At2[f]) CUDA_CHECK(cudaMemcpyAsync(cap->At2[f], At[f][1].p, sizeof(double) * n1[f] * n2[f], cudaMemcpyDeviceToHost, st));
+        CUDA_CHECK(cudaStreamSynchronize(st));
+      }
+    }
+    CUDA_CHECK(cudaStreamSynchronize(st));
+  }
+  rep.ms_bc = tm.stop();
+  if (stop_after_bc) {
+    rep.launches = g_launches - launches0;
+    return ierr_last;
+  }
+
+  // ---------------- three 3D solves (solve, :598-691) ----------------
+  tm.start();
+  if (g_debug) debug_msg("compute_vector_potential", "Solve BVP 3D...");
+  const int sh3[3] = {nx, ny, nz};
+  std::unique_ptr<MG> mg3(new MG(3, sh3, -1, mesh, st));
+  const Grid g3 = mg3->level(0).g;
+  const size_t lvl = 2 * (size_t)g3.cs;
+  DevBuf As(3 * lvl);
+  if (A0) {
+    for (int c = 0; c < 3; ++c) {
+      CUDA_CHECK(cudaMemsetAsync(As.p + c * lvl, 0, lvl * sizeof(double), st));
+      split_from_dense(A0 + c * N, As.p + c * lvl, g3, 0.0, st);
+    }
+  } else {
+    CUDA_CHECK(cudaMemsetAsync(As.p, 0, 3 * lvl * sizeof(double), st));
+  }
+  static const int wf[3][4] = {{2, 3, 4, 5}, {0, 1, 4, 5}, {0, 1, 2, 3}};  // face write order :647-650,663-666,679-682
+  static const int wa[3][4] = {{0, 0, 0, 0}, {0, 0, 1, 1}, {1, 1, 1, 1}};  // At(1,.) or At(2,.)
+  static const char* cop[3] = {"NDDNDD", "DNDDND", "DDNDDN"};              // :655,671,687
+  for (int c = 0; c < 3; ++c) {
+    double* Ac = As.p + c * lvl;
+    for (int w = 0; w < 4; ++w) {
+      const int f = wf[c][w];
+      const int layer = (f % 2 == 0) ? 0 : nshape[imap_cp[f]] - 1;
+      write_face(Ac, g3, imap_cp[f], layer, At[f][wa[c][w]].p, st);
+    }
+    mg3->set_options(c == 2 ? 5 : (int)iopt[IOPT_MS], ropt[ROPT_CTOL], cop[c], use_du_max, (int)iopt[IOPT_NMAXEX]);  // :685
+    double du_last;
+    mg3->solve(Ac, nullptr, ropt[ROPT_VTOL], (int)iopt[IOPT_NCYCLES], &du_last, &rep.solves[6 + c]);  // rhs = 0 (:640-641)
+  }
+  mg3.reset();  // release the hierarchy before the dense outputs are touched
+  rep.ms_solve3d = tm.stop();
+
+  // ---------------- flux-balance fields + curl (K8) ----------------
+  tm.start();
+  if (g_debug) debug_msg("compute_vector_potential", "Compute B = curl(B) and flux correction...");
+  const bool flux_first = (iopt[IOPT_FLXCRL] != 1);  // :453-477
+  if (!flux_first) printf(" FLAG SET: FLXCRL\n");
+  for (int c = 0; c < 3; ++c)
+    unsplit_A(As.p + c * lvl, g3, c, dx_, dy_, dz_, phi, Lq, flux_first, A_out + c * N, st);
+  curl_dense(A_out, nx, ny, nz, dq[0], dq[1], dq[2], B_out, st);
+  if (!flux_first) add_flux_dense(A_out, B_out, nx, ny, nz, dx_, dy_, dz_, phi, Lq, st);
+  rep.ms_post = tm.stop();
+  rep.ms_device = tall.stop();
+  rep.launches = g_launches - launches0;
+  return ierr_last;  // :480 -- ierr of the LAST chi solve (reference quirk)
+}
+
+}  // namespace ndsm

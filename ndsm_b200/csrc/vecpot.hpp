@@ -1,0 +1,37 @@
+// vecpot.hpp -- device-resident vector-potential driver (compute_vector_potential,
+// ndsm_vector_potential.f90:130-497) on top of the MG class.
+#pragma once
+#include <vector>
+#include "mg.hpp"
+
+namespace ndsm {
+
+enum {  // ndsm_vector_potential.f90:40-57
+  IOPT_LEN = 16, IOPT_MS = 0, IOPT_NCYCLES = 1, IOPT_FACE1 = 2, IOPT_IERR = 3, IOPT_FLXCRL = 4, IOPT_DEBUG = 5,
+  IOPT_DUMAX = 6, IOPT_NMAXEX = 7, IOPT_TRUE = 1, IOPT_FALSE = 0, ROPT_VTOL = 0, ROPT_CTOL = 1, ROPT_TIM = 2
+};
+
+struct Report {
+  SolveTrace solves[9];  // chi faces 1..6, then Ax, Ay, Az
+  double phi[6];
+  // milliseconds
+  double ms_total = 0, ms_in = 0, ms_bc = 0, ms_solve3d = 0, ms_post = 0, ms_out = 0, ms_device = 0;
+  unsigned long long launches = 0;
+};
+extern Report g_report;
+
+// Optional capture of BC-setup intermediates for parity tests (device -> host copies, dense faces)
+struct BcCapture {
+  double* chi[6] = {nullptr};
+  double* At1[6] = {nullptr};
+  double* At2[6] = {nullptr};
+};
+
+// bn[f]: dense device faces (face f has shape (n1,n2) per ndsm_vector_potential.f90:225-246).
+// A0: dense device initial guess (3N) or nullptr for zeros.  A_out/B_out: dense device (3N).
+// stop_after_bc: only run the BC setup (tests).  Returns iopt(IOPT_IERR).
+int vector_solve_core(const int* nshape, const long long* iopt, const double* ropt, const double* x, const double* y,
+                      const double* z, double* const* bn, const double* A0, double* A_out, double* B_out,
+                      cudaStream_t st, Report& rep, BcCapture* cap, bool stop_after_bc);
+
+}  // namespace ndsm

@@ -1,0 +1,1093 @@
+/*
+ * ndsm_oracle.c -- CPU ORACLE (TEST INFRASTRUCTURE, NOT PRODUCT CODE)
+ *
+ * A plain-C restatement of the one hot path of sag2021/ndsm: the multigrid
+ * V-cycle vector-potential solve behind `ndsm_vector_solve`.  Only tests/,
+ * __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs
+ * may load this library, and only as the checker / CPU baseline.  The product
+ * (ndsm_b200/lib/ndsmf.so) never links, loads or calls it.
+ *
+ * Parity pinning: this restatement reproduces the reference's golden tables
+ * tests/integration_test/results_test{1,2}.txt (see tests/test_oracle_golden.py,
+ * fixtures in tests/golden/).  The reference itself (Fortran 2003) cannot be
+ * compiled in this image (no gfortran/flang/f2c), so iteration-path details
+ * that the goldens constrain only weakly (colour order, sweep counts, transfer
+ * weights) are pinned by the file:line citations below, all relative to
+ * /root/reference/fortran/.
+ *
+ * Floating-point: the reference is built with `gfortran -O3` for baseline
+ * x86-64 (Makefile:8) => no FMA contraction, no re-association.  Build this
+ * file with -ffp-contract=off and never -ffast-math.  Expression order below
+ * is the Fortran's, parenthesised explicitly.
+ *
+ * Index convention: 0-based here; "F:" comments give the 1-based Fortran.
+ * Arrays are column-major with x fastest, exactly like the Fortran.
+ */
+#include <math.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+typedef int64_t i64;
+
+/* loops smaller than this run serially: the coarse levels are tiny and an OpenMP
+ * fork/join per sweep there costs far more than the sweep (the reference has no such guard) */
+#define ORC_PAR_MIN 16384
+#define ORC_MAXG 40
+#define ORC_MAXDIM 3
+
+/* ------------------------------------------------------------------ */
+/* Trace (per solve_poisson_bvp call): du history + solve_exact counts */
+/* ------------------------------------------------------------------ */
+#define TR_MAXSOLVE 16
+#define TR_MAXCYC 2048
+static struct {
+  int nsolves;
+  int ncycles[TR_MAXSOLVE];
+  int ierr[TR_MAXSOLVE];
+  double du[TR_MAXSOLVE][TR_MAXCYC];
+  int nexact[TR_MAXSOLVE][TR_MAXCYC];
+  int cur; /* current solve id, -1 if none */
+} g_tr = {0};
+
+void orc_trace_reset(void) { memset(&g_tr, 0, sizeof(g_tr)); g_tr.cur = -1; }
+int orc_trace_nsolves(void) { return g_tr.nsolves; }
+int orc_trace_ncycles(int s) { return (s >= 0 && s < TR_MAXSOLVE) ? g_tr.ncycles[s] : -1; }
+int orc_trace_ierr(int s) { return (s >= 0 && s < TR_MAXSOLVE) ? g_tr.ierr[s] : -1; }
+double orc_trace_du(int s, int c) { return g_tr.du[s][c]; }
+int orc_trace_nexact(int s, int c) { return g_tr.nexact[s][c]; }
+
+/* transfer implementation: 0 = literal per-point (ninterp/nrestrict as written),
+ * 1 = tabulated brackets/weights, same arithmetic and summation order (bit-identical to 0) */
+static int g_transfer_mode = 1;
+void orc_set_transfer_mode(int m) { g_transfer_mode = m; }
+int orc_get_transfer_mode(void) { return g_transfer_mode; }
+
+static int g_debug = 0;
+static void debug_msg(const char* sub, const char* msg) { /* ndsm_root.f90:493-503 */
+  if (g_debug) fprintf(stderr, "DEBUG(%s):%s\n", sub, msg);
+}
+
+static double wtime(void) { /* ndsm_root.f90:521-536 */
+#ifdef _OPENMP
+  return omp_get_wtime();
+#else
+  return (double)clock() / CLOCKS_PER_SEC;
+#endif
+}
+
+int orc_num_threads(void) {
+#ifdef _OPENMP
+  return omp_get_max_threads();
+#else
+  return 1;
+#endif
+}
+
+/* ------------------------------------------------------------------ */
+/* Small parallel helpers: ndsm_multigrid_core.f90:1134-1223            */
+/* ------------------------------------------------------------------ */
+static void zero(double* a, i64 n) {
+#pragma omp parallel for if ((n) > ORC_PAR_MIN)
+  for (i64 i = 0; i < n; ++i) a[i] = 0.0;
+}
+static void copy(double* lhs, const double* rhs, i64 n) {
+#pragma omp parallel for if ((n) > ORC_PAR_MIN)
+  for (i64 i = 0; i < n; ++i) lhs[i] = rhs[i];
+}
+/* mean: plain running sum / N (ndsm_multigrid_core.f90:1199-1223) */
+double orc_mean(i64 n, const double* u) {
+  double s = 0.0;
+#pragma omp parallel for reduction(+ : s) if (n > ORC_PAR_MIN)
+  for (i64 i = 0; i < n; ++i) s = s + u[i];
+  return s / (double)n;
+}
+
+/* du_metrics: ndsm_multigrid_core.f90:808-853 ; out[0]=max, out[1]=mean */
+void orc_du_metrics(i64 n, const double* u1, const double* u2, double* out) {
+  double dmax = 0.0, dsum = 0.0;
+#pragma omp parallel for reduction(max : dmax) reduction(+ : dsum) if (n > ORC_PAR_MIN)
+  for (i64 i = 0; i < n; ++i) {
+    double d = fabs(u1[i] - u2[i]);
+    dmax = d > dmax ? d : dmax;
+    dsum = dsum + d;
+  }
+  out[0] = dmax;
+  out[1] = dsum / (double)n;
+}
+
+/* update_u: ndsm_multigrid_core.f90:1077-1122 ; u_new := u_old, metrics of |u_new-u_old| */
+void orc_update_u(i64 n, const double* u_old, double* u_new, double* du_max, double* du_mean) {
+  double dmax = 0.0, dsum = 0.0;
+#pragma omp parallel for reduction(max : dmax) reduction(+ : dsum) if (n > ORC_PAR_MIN)
+  for (i64 i = 0; i < n; ++i) {
+    double d = fabs(u_new[i] - u_old[i]);
+    dmax = d > dmax ? d : dmax;
+    dsum = dsum + d;
+    u_new[i] = u_old[i];
+  }
+  *du_max = dmax;
+  *du_mean = dsum / (double)n;
+}
+
+/* ------------------------------------------------------------------ */
+/* 3D red/black Gauss-Seidel: ndsm_optimized.f90:40-191                 */
+/* bcs: copt order [x_lo,y_lo,z_lo,x_hi,y_hi,z_hi] (ndsm_poisson.f90:244-245) */
+/* ------------------------------------------------------------------ */
+static int all_neumann(const char* bcs, int n) {
+  for (int i = 0; i < n; ++i)
+    if (bcs[i] != 'N') return 0;
+  return 1;
+}
+
+void orc_relax3d(const char* bcs, i64 nx, i64 ny, i64 nz, const double* x, const double* y,
+                 const double* z, const double* rhs, double* u) {
+  i64 lb[3] = {1, 1, 1}, ub[3] = {nx, ny, nz}; /* 1-based, like the Fortran */
+  for (int d = 0; d < 3; ++d) {
+    if (bcs[d] == 'D') lb[d] += 1;      /* :75 */
+    if (bcs[3 + d] == 'D') ub[d] -= 1;  /* :76 */
+  }
+  const double hx = x[1] - x[0], hy = y[1] - y[0], hz = z[1] - z[0];
+  const double wx = 1.0 / (hx * hx), wy = 1.0 / (hy * hy), wz = 1.0 / (hz * hz); /* :87-89 */
+  double w1 = 2 * ((wx + wy) + wz);                                               /* :92 */
+  w1 = 1.0 / w1;
+  const i64 sy = nx, sz = nx * ny;
+  for (int pass = 0; pass < 2; ++pass) { /* :103-134 then :136-167 */
+#pragma omp parallel for if ((nx * ny * nz) > ORC_PAR_MIN)
+    for (i64 k = lb[2]; k <= ub[2]; ++k) {
+      for (i64 j = lb[1]; j <= ub[1]; ++j) {
+        i64 i0 = lb[0] + ((j + pass + (k % 2)) % 2); /* :106 / :139 */
+        i64 yl = j - 1, yh = j + 1, zl = k - 1, zh = k + 1;
+        if (yl < 1) yl = 2;
+        if (yh > ny) yh = ny - 1;
+        if (zl < 1) zl = 2;
+        if (zh > nz) zh = nz - 1;
+        for (i64 i = i0; i <= ub[0]; i += 2) {
+          i64 xl = i - 1, xh = i + 1;
+          if (xl < 1) xl = 2;
+          if (xh > nx) xh = nx - 1;
+#define U3(a, b, c) u[((a)-1) + ((b)-1) * sy + ((c)-1) * sz]
+          double unew = (((U3(xh, j, k) + U3(xl, j, k)) * wx + (U3(i, yh, k) + U3(i, yl, k)) * wy) +
+                         (U3(i, j, zh) + U3(i, j, zl)) * wz) -
+                        rhs[(i - 1) + (j - 1) * sy + (k - 1) * sz]; /* :123-126 */
+          U3(i, j, k) = w1 * unew;                                  /* :129 */
+        }
+      }
+    }
+  }
+  if (all_neumann(bcs, 6)) { /* :173-189 */
+    double um = orc_mean(nx * ny * nz, u);
+#pragma omp parallel for if ((nx * ny * nz) > ORC_PAR_MIN)
+    for (i64 k = lb[2]; k <= ub[2]; ++k)
+      for (i64 j = lb[1]; j <= ub[1]; ++j)
+        for (i64 i = lb[0]; i <= ub[0]; ++i) U3(i, j, k) = U3(i, j, k) - um;
+  }
+}
+
+/* 3D residual: ndsm_optimized.f90:346-447 */
+void orc_residual3d(const char* bcs, i64 nx, i64 ny, i64 nz, const double* x, const double* y,
+                    const double* z, const double* rhs, const double* u, double* r) {
+  i64 lb[3] = {1, 1, 1}, ub[3] = {nx, ny, nz};
+  for (int d = 0; d < 3; ++d) {
+    if (bcs[d] == 'D') lb[d] += 1;
+    if (bcs[3 + d] == 'D') ub[d] -= 1;
+  }
+  const double hx = x[1] - x[0], hy = y[1] - y[0], hz = z[1] - z[0];
+  const double wx = 1.0 / (hx * hx), wy = 1.0 / (hy * hy), wz = 1.0 / (hz * hz);
+  const double wc = 2 * ((wx + wy) + wz); /* :384 */
+  const i64 sy = nx, sz = nx * ny;
+  zero(r, nx * ny * nz); /* :389-397 */
+#pragma omp parallel for if ((nx * ny * nz) > ORC_PAR_MIN)
+  for (i64 k = lb[2]; k <= ub[2]; ++k) {
+    for (i64 j = lb[1]; j <= ub[1]; ++j) {
+      i64 yl = j - 1, yh = j + 1, zl = k - 1, zh = k + 1;
+      if (yl < 1) yl = 2;
+      if (yh > ny) yh = ny - 1;
+      if (zl < 1) zl = 2;
+      if (zh > nz) zh = nz - 1;
+      for (i64 i = lb[0]; i <= ub[0]; ++i) {
+        i64 xl = i - 1, xh = i + 1;
+        if (xl < 1) xl = 2;
+        if (xh > nx) xh = nx - 1;
+        const i64 n = (i - 1) + (j - 1) * sy + (k - 1) * sz;
+        double t = ((((U3(xl, j, k) + U3(xh, j, k)) * wx + (U3(i, yl, k) + U3(i, yh, k)) * wy) +
+                     (U3(i, j, zl) + U3(i, j, zh)) * wz) -
+                    rhs[n]) -
+                   u[n] * wc; /* :424-427 */
+        r[n] = -t;            /* :430 */
+      }
+    }
+  }
+#undef U3
+  /* :439-445 -- already zero outside lb..ub */
+}
+
+/* ------------------------------------------------------------------ */
+/* Generic N-D relax / residual (used for the 2D chi solves):          */
+/* ndsm_poisson.f90:280-658                                            */
+/* ------------------------------------------------------------------ */
+static inline void lin2nd0(int ndim, const i64* nshape, i64 n, i64* iv) { /* 0-based in/out; ndsm_root.f90:195 */
+  for (int d = 0; d < ndim; ++d) {
+    iv[d] = n % nshape[d];
+    n /= nshape[d];
+  }
+}
+enum { BND_NONE = 0, BND_LOWER = 1, BND_UPPER = 2 };
+static inline void boundary_mask(int ndim, const i64* iv, const i64* nshape, int* bm) { /* :415-438 */
+  for (int d = 0; d < ndim; ++d) bm[d] = (iv[d] == 0) ? BND_LOWER : ((iv[d] == nshape[d] - 1) ? BND_UPPER : BND_NONE);
+}
+static inline int at_dirichlet(int ndim, const int* bm, const char* bcs) { /* :367-399 ; bcs(i,1)=bcs[i], bcs(i,2)=bcs[ndim+i] */
+  for (int d = 0; d < ndim; ++d) {
+    if (bm[d] == BND_LOWER && bcs[d] == 'D') return 1;
+    if (bm[d] == BND_UPPER && bcs[ndim + d] == 'D') return 1;
+  }
+  return 0;
+}
+static inline void stencil_stride(const int* bm, const i64* st, int d, i64* dn) { /* :626-656 */
+  if (bm[d] == BND_NONE) { dn[0] = -st[d]; dn[1] = +st[d]; }
+  else if (bm[d] == BND_LOWER) { dn[0] = +st[d]; dn[1] = +st[d]; }
+  else { dn[0] = -st[d]; dn[1] = -st[d]; }
+}
+
+void orc_relax_nd(int ndim, const i64* nshape, const double* const* q, const char* bcs, double* u,
+                  const double* rhs) {
+  i64 st[ORC_MAXDIM], nsize = 1;
+  for (int d = 0; d < ndim; ++d) { st[d] = nsize; nsize *= nshape[d]; }
+  double wc[ORC_MAXDIM + 1];
+  wc[0] = 0.0; /* :483-489 */
+  for (int d = 0; d < ndim; ++d) {
+    double dq = q[d][1] - q[d][0];
+    wc[d + 1] = 1.0 / (dq * dq);
+    wc[0] = wc[0] + 2.0 * wc[d + 1];
+  }
+  wc[0] = 1.0 / wc[0];
+  for (int pass = 0; pass < 2; ++pass) { /* red :492-507, black :510-525 */
+#pragma omp parallel for if ((nsize) > ORC_PAR_MIN)
+    for (i64 n = 0; n < nsize; ++n) {
+      i64 iv[ORC_MAXDIM];
+      lin2nd0(ndim, nshape, n, iv);
+      /* F: parity = MOD(ivec,2) on 1-based ivec; is_red = all equal.  Same test on 0-based. */
+      int is_red = 1;
+      for (int d = 1; d < ndim; ++d)
+        if (((iv[d] ^ iv[0]) & 1) != 0) is_red = 0;
+      if (is_red != (pass == 0)) continue;
+      int bm[ORC_MAXDIM];
+      boundary_mask(ndim, iv, nshape, bm);
+      if (at_dirichlet(ndim, bm, bcs)) continue; /* :588-591: returns u(n) */
+      double un = 0.0;                           /* :598-613 */
+      for (int d = 0; d < ndim; ++d) {
+        i64 dn[2];
+        stencil_stride(bm, st, d, dn);
+        un = (un + u[n + dn[0]] * wc[d + 1]) + u[n + dn[1]] * wc[d + 1];
+      }
+      u[n] = (un - rhs[n]) * wc[0]; /* :615 */
+    }
+  }
+  if (all_neumann(bcs, 2 * ndim)) { /* :529-547 */
+    double um = orc_mean(nsize, u);
+#pragma omp parallel for if ((nsize) > ORC_PAR_MIN)
+    for (i64 n = 0; n < nsize; ++n) u[n] = u[n] - um;
+  }
+}
+
+void orc_residual_nd(int ndim, const i64* nshape, const double* const* q, const char* bcs,
+                     const double* u, const double* rhs, double* r) {
+  i64 st[ORC_MAXDIM], nsize = 1;
+  for (int d = 0; d < ndim; ++d) { st[d] = nsize; nsize *= nshape[d]; }
+  double wc[ORC_MAXDIM];
+  for (int d = 0; d < ndim; ++d) {
+    double dq = q[d][1] - q[d][0];
+    wc[d] = 1.0 / (dq * dq);
+  }
+#pragma omp parallel for if ((nsize) > ORC_PAR_MIN)
+  for (i64 n = 0; n < nsize; ++n) {
+    i64 iv[ORC_MAXDIM];
+    int bm[ORC_MAXDIM];
+    lin2nd0(ndim, nshape, n, iv);
+    boundary_mask(ndim, iv, nshape, bm);
+    if (at_dirichlet(ndim, bm, bcs)) { r[n] = 0.0; continue; } /* :326-329 */
+    double lap = 0.0;
+    for (int d = 0; d < ndim; ++d) {
+      i64 dn[2];
+      stencil_stride(bm, st, d, dn);
+      lap = lap + ((u[n + dn[0]] - 2 * u[n]) + u[n + dn[1]]) * wc[d]; /* :343 */
+    }
+    r[n] = rhs[n] - lap; /* :348 */
+  }
+}
+
+/* ------------------------------------------------------------------ */
+/* Bracket search: ndsm_interp.f90:373-435 ; returns 0-based lo,hi      */
+/* ------------------------------------------------------------------ */
+void orc_bracket(const double* q, i64 nq, double q0, i64* lo, i64* hi, int* ierr) {
+  if (q0 <= q[0]) { *lo = 0; *hi = 1; *ierr = -1; return; }
+  if (q0 >= q[nq - 1]) { *lo = nq - 2; *hi = nq - 1; *ierr = +1; return; }
+  double dq = q[1] - q[0];
+  i64 l = (i64)floor((q0 - q[0]) / dq) + 1; /* 1-based (:419) */
+  if (l >= nq) { *lo = nq - 2; *hi = nq - 1; }   /* :423-425 */
+  else { *lo = l - 1; *hi = l; }
+  *ierr = 0;
+}
+
+/* ninterp, literal: ndsm_interp.f90:85-158 (ndim <= 3) */
+static double ninterp_lit(int ndim, const i64* nshape, const double* const* q, const double* q0,
+                          const double* f) {
+  i64 b[ORC_MAXDIM][2];
+  int ierr;
+  for (int d = 0; d < ndim; ++d) orc_bracket(q[d], nshape[d], q0[d], &b[d][0], &b[d][1], &ierr);
+  double fs[8];
+  const int nc = 1 << ndim;
+  for (int n = 0; n < nc; ++n) { /* get_interpolation_values :340-363 ; bit d of n selects lo/hi of dim d */
+    i64 lin = 0, st = 1;
+    for (int d = 0; d < ndim; ++d) {
+      lin += b[d][(n >> d) & 1] * st;
+      st *= nshape[d];
+    }
+    fs[n] = f[lin];
+  }
+  for (int d = ndim - 1; d >= 0; --d) { /* :128-154 */
+    double ql = q[d][b[d][0]], qh = q[d][b[d][1]];
+    double dq = qh - ql;
+    double wl = +(q0[d] - ql) / dq;
+    double wh = -(q0[d] - qh) / dq;
+    int NC = 1 << d;
+    for (int j = 0; j < NC; ++j) fs[j] = wh * fs[j] + wl * fs[j + NC];
+  }
+  return fs[0];
+}
+
+/* nrestrict, literal: ndsm_interp.f90:186-292 (ndim <= 3) */
+static double nrestrict_lit(int ndim, const i64* nshape_f, const double* const* qc,
+                            const double* const* qf, const double* q0, const double* f) {
+  i64 b[ORC_MAXDIM][2], ns[ORC_MAXDIM], nsz = 1;
+  double dqc[ORC_MAXDIM], dqf[ORC_MAXDIM], w2[ORC_MAXDIM];
+  for (int d = 0; d < ndim; ++d) {
+    dqc[d] = qc[d][1] - qc[d][0];
+    dqf[d] = qf[d][1] - qf[d][0];
+    w2[d] = dqf[d] / (dqc[d] * dqc[d]); /* :228 */
+    i64 lo, hi;
+    int ierr;
+    orc_bracket(qf[d], nshape_f[d], q0[d] - dqc[d], &lo, &hi, &ierr); /* :234-239 */
+    b[d][0] = (ierr < 0) ? lo : hi;
+    orc_bracket(qf[d], nshape_f[d], q0[d] + dqc[d], &lo, &hi, &ierr); /* :242-247 */
+    b[d][1] = (ierr > 0) ? hi : lo;
+    ns[d] = b[d][1] - b[d][0] + 1;
+    nsz *= ns[d];
+  }
+  double fc = 0.0;
+  for (i64 j = 0; j < nsz; ++j) { /* :263-290 */
+    i64 iv[ORC_MAXDIM], lin = 0, st = 1;
+    lin2nd0(ndim, ns, j, iv);
+    double w = 1.0;
+    for (int d = 0; d < ndim; ++d) {
+      i64 qi = b[d][0] + iv[d];
+      double c1 = fabs(qf[d][qi] - q0[d]);
+      double c2 = fabs(dqc[d] - c1);
+      w = (w * c2) * w2[d]; /* :281 */
+      lin += qi * st;
+      st *= nshape_f[d];
+    }
+    fc = fc + w * f[lin];
+  }
+  return fc;
+}
+
+/* Tabulated 1-D transfer tables (host-side helper; also used by tests to check the
+ * product's tables).  Prolongation: for each fine index, lo (0-based), wl, wh.
+ * Restriction: for each coarse index, first (0-based), count, c2[j] and the scalar w2. */
+void orc_interp_table(i64 nf, const double* qf, i64 nc, const double* qc, i64* lo, double* wl, double* wh) {
+  for (i64 i = 0; i < nf; ++i) {
+    i64 l, h;
+    int ierr;
+    orc_bracket(qc, nc, qf[i], &l, &h, &ierr);
+    double ql = qc[l], qh = qc[h], dq = qh - ql;
+    lo[i] = l;
+    wl[i] = +(qf[i] - ql) / dq;
+    wh[i] = -(qf[i] - qh) / dq;
+  }
+}
+#define ORC_RMAX 8
+/* returns max stencil width, or -1 if it exceeds ORC_RMAX */
+int orc_restrict_table(i64 nf, const double* qf, i64 nc, const double* qc, i64* first, i64* count,
+                       double* c2 /* [nc][ORC_RMAX] */, double* w2out) {
+  double dqc = qc[1] - qc[0], dqf = qf[1] - qf[0];
+  *w2out = dqf / (dqc * dqc);
+  int wmax = 0;
+  for (i64 c = 0; c < nc; ++c) {
+    i64 lo, hi, a, b;
+    int ierr;
+    orc_bracket(qf, nf, qc[c] - dqc, &lo, &hi, &ierr);
+    a = (ierr < 0) ? lo : hi;
+    orc_bracket(qf, nf, qc[c] + dqc, &lo, &hi, &ierr);
+    b = (ierr > 0) ? hi : lo;
+    first[c] = a;
+    count[c] = b - a + 1;
+    if (count[c] > ORC_RMAX) return -1;
+    if (count[c] > wmax) wmax = (int)count[c];
+    for (i64 j = 0; j < ORC_RMAX; ++j) c2[c * ORC_RMAX + j] = 0.0;
+    for (i64 j = a; j <= b; ++j) {
+      double c1 = fabs(qf[j] - qc[c]);
+      c2[c * ORC_RMAX + (j - a)] = fabs(dqc - c1);
+    }
+  }
+  return wmax;
+}
+
+/* mg_interp: ndsm_multigrid_core.f90:865-921 -- u_f = P u_c (overwrites u_f) */
+void orc_mg_interp(int ndim, const i64* nshape_f, const double* const* qf, const i64* nshape_c,
+                   const double* const* qc, const double* u_c, double* u_f) {
+  i64 nsize_f = 1;
+  for (int d = 0; d < ndim; ++d) nsize_f *= nshape_f[d];
+  if (g_transfer_mode == 0) {
+#pragma omp parallel for if ((nsize_f) > ORC_PAR_MIN)
+    for (i64 n = 0; n < nsize_f; ++n) {
+      i64 iv[ORC_MAXDIM];
+      double q0[ORC_MAXDIM];
+      lin2nd0(ndim, nshape_f, n, iv);
+      for (int d = 0; d < ndim; ++d) q0[d] = qf[d][iv[d]];
+      u_f[n] = ninterp_lit(ndim, nshape_c, qc, q0, u_c);
+    }
+    return;
+  }
+  /* tabulated: identical arithmetic, brackets/weights hoisted per dimension */
+  i64* lo[ORC_MAXDIM];
+  double *wl[ORC_MAXDIM], *wh[ORC_MAXDIM];
+  for (int d = 0; d < ndim; ++d) {
+    lo[d] = (i64*)malloc(sizeof(i64) * nshape_f[d]);
+    wl[d] = (double*)malloc(sizeof(double) * nshape_f[d]);
+    wh[d] = (double*)malloc(sizeof(double) * nshape_f[d]);
+    orc_interp_table(nshape_f[d], qf[d], nshape_c[d], qc[d], lo[d], wl[d], wh[d]);
+  }
+  i64 cst[ORC_MAXDIM], s = 1;
+  for (int d = 0; d < ndim; ++d) { cst[d] = s; s *= nshape_c[d]; }
+#pragma omp parallel for if ((nsize_f) > ORC_PAR_MIN)
+  for (i64 n = 0; n < nsize_f; ++n) {
+    i64 iv[ORC_MAXDIM];
+    lin2nd0(ndim, nshape_f, n, iv);
+    double fs[8];
+    const int nc = 1 << ndim;
+    for (int m = 0; m < nc; ++m) {
+      i64 lin = 0;
+      for (int d = 0; d < ndim; ++d) {
+        i64 l = lo[d][iv[d]];
+        lin += (l + ((m >> d) & 1)) * cst[d];
+      }
+      fs[m] = u_c[lin];
+    }
+    for (int d = ndim - 1; d >= 0; --d) {
+      double a = wh[d][iv[d]], b = wl[d][iv[d]];
+      int NC = 1 << d;
+      for (int j = 0; j < NC; ++j) fs[j] = a * fs[j] + b * fs[j + NC];
+    }
+    u_f[n] = fs[0];
+  }
+  for (int d = 0; d < ndim; ++d) { free(lo[d]); free(wl[d]); free(wh[d]); }
+}
+
+/* mg_restrict: ndsm_multigrid_core.f90:1010-1065 -- u_c = R u_f */
+void orc_mg_restrict(int ndim, const i64* nshape_f, const double* const* qf, const i64* nshape_c,
+                     const double* const* qc, const double* u_f, double* u_c) {
+  i64 nsize_c = 1;
+  for (int d = 0; d < ndim; ++d) nsize_c *= nshape_c[d];
+  int mode = g_transfer_mode;
+  i64 *first[ORC_MAXDIM] = {0}, *count[ORC_MAXDIM] = {0};
+  double* c2[ORC_MAXDIM] = {0};
+  double w2[ORC_MAXDIM];
+  if (mode != 0) {
+    for (int d = 0; d < ndim; ++d) {
+      first[d] = (i64*)malloc(sizeof(i64) * nshape_c[d]);
+      count[d] = (i64*)malloc(sizeof(i64) * nshape_c[d]);
+      c2[d] = (double*)malloc(sizeof(double) * nshape_c[d] * ORC_RMAX);
+      if (orc_restrict_table(nshape_f[d], qf[d], nshape_c[d], qc[d], first[d], count[d], c2[d], &w2[d]) < 0) mode = 0;
+    }
+  }
+  if (mode == 0) {
+#pragma omp parallel for if ((nsize_c) > ORC_PAR_MIN)
+    for (i64 n = 0; n < nsize_c; ++n) {
+      i64 iv[ORC_MAXDIM];
+      double q0[ORC_MAXDIM];
+      lin2nd0(ndim, nshape_c, n, iv);
+      for (int d = 0; d < ndim; ++d) q0[d] = qc[d][iv[d]];
+      u_c[n] = nrestrict_lit(ndim, nshape_f, qc, qf, q0, u_f);
+    }
+  } else if (ndim == 3) {
+    const i64 fx = nshape_f[0], fxy = nshape_f[0] * nshape_f[1];
+#pragma omp parallel for if ((nsize_c) > ORC_PAR_MIN)
+    for (i64 n = 0; n < nsize_c; ++n) {
+      i64 iv[3];
+      lin2nd0(3, nshape_c, n, iv);
+      const i64 ax = first[0][iv[0]], ay = first[1][iv[1]], az = first[2][iv[2]];
+      const i64 cx = count[0][iv[0]], cy = count[1][iv[1]], cz = count[2][iv[2]];
+      const double* wxv = c2[0] + iv[0] * ORC_RMAX;
+      const double* wyv = c2[1] + iv[1] * ORC_RMAX;
+      const double* wzv = c2[2] + iv[2] * ORC_RMAX;
+      double fc = 0.0;
+      for (i64 kk = 0; kk < cz; ++kk)
+        for (i64 jj = 0; jj < cy; ++jj) {
+          const double* row = u_f + (az + kk) * fxy + (ay + jj) * fx + ax;
+          for (i64 ii = 0; ii < cx; ++ii) {
+            double w = 1.0;
+            w = (w * wxv[ii]) * w2[0];
+            w = (w * wyv[jj]) * w2[1];
+            w = (w * wzv[kk]) * w2[2];
+            fc = fc + w * row[ii];
+          }
+        }
+      u_c[n] = fc;
+    }
+  } else { /* ndim == 2 (or 1) */
+    const i64 fx = nshape_f[0];
+#pragma omp parallel for if ((nsize_c) > ORC_PAR_MIN)
+    for (i64 n = 0; n < nsize_c; ++n) {
+      i64 iv[ORC_MAXDIM] = {0, 0, 0};
+      lin2nd0(ndim, nshape_c, n, iv);
+      const i64 ax = first[0][iv[0]], cx = count[0][iv[0]];
+      const i64 ay = ndim > 1 ? first[1][iv[1]] : 0, cy = ndim > 1 ? count[1][iv[1]] : 1;
+      double fc = 0.0;
+      for (i64 jj = 0; jj < cy; ++jj)
+        for (i64 ii = 0; ii < cx; ++ii) {
+          double w = 1.0;
+          w = (w * c2[0][iv[0] * ORC_RMAX + ii]) * w2[0];
+          if (ndim > 1) w = (w * c2[1][iv[1] * ORC_RMAX + jj]) * w2[1];
+          fc = fc + w * u_f[(ay + jj) * fx + ax + ii];
+        }
+      u_c[n] = fc;
+    }
+  }
+  for (int d = 0; d < ndim; ++d) { free(first[d]); free(count[d]); free(c2[d]); }
+}
+
+/* ------------------------------------------------------------------ */
+/* MG_HANDLE: ndsm_multigrid_core.f90:86-101, new_mg_handle :165-270    */
+/* ------------------------------------------------------------------ */
+typedef struct {
+  i64 ms;
+  int ngrids;
+  double ex_tol;
+  int ndim;
+  i64 nshape[ORC_MAXG][ORC_MAXDIM];
+  i64 nsize[ORC_MAXG];
+  double* u[ORC_MAXG];
+  double* rhs[ORC_MAXG];
+  double* mesh[ORC_MAXG][ORC_MAXDIM];
+  char copt[2 * ORC_MAXDIM + 2];
+  int du_max;
+  i64 nmax_exact;
+  int last_nexact;
+} orc_mg;
+
+/* ngrids = FLOOR(LOG(nmin/2.0)/LOG(2.0)) : ndsm_vector_potential.f90:341-342,631-632 */
+int orc_ngrids(i64 nmin) { return (int)floor(log((double)nmin / 2.0) / log(2.0)); }
+
+orc_mg* orc_mg_new(int ndim, const i64* nshape, int ngrids, const double* const* mesh, int du_max,
+                   i64 nmax_exact) {
+  if (ngrids < 1 || ngrids > ORC_MAXG || ndim < 1 || ndim > ORC_MAXDIM) return NULL;
+  orc_mg* h = (orc_mg*)calloc(1, sizeof(orc_mg));
+  h->ms = -1; h->ex_tol = -1; h->ndim = ndim; h->ngrids = ngrids;
+  h->du_max = du_max; h->nmax_exact = nmax_exact;
+  for (int d = 0; d < 2 * ORC_MAXDIM; ++d) h->copt[d] = '!';
+  for (int d = 0; d < ndim; ++d) h->nshape[0][d] = nshape[d];
+  for (int g = 1; g < ngrids; ++g)
+    for (int d = 0; d < ndim; ++d) {
+      i64 v = (i64)floor((double)h->nshape[g - 1][d] * 0.5); /* :216 */
+      h->nshape[g][d] = v > 1 ? v : 1;
+    }
+  for (int g = 0; g < ngrids; ++g) {
+    h->nsize[g] = 1;
+    for (int d = 0; d < ndim; ++d) h->nsize[g] *= h->nshape[g][d];
+  }
+  for (int d = 0; d < ndim; ++d) { /* :231-238 */
+    h->mesh[0][d] = (double*)malloc(sizeof(double) * nshape[d]);
+    memcpy(h->mesh[0][d], mesh[d], sizeof(double) * nshape[d]);
+  }
+  for (int g = 1; g < ngrids; ++g)
+    for (int d = 0; d < ndim; ++d) { /* :241-262 */
+      i64 nq = h->nshape[g][d];
+      h->mesh[g][d] = (double*)malloc(sizeof(double) * nq);
+      double qmin = mesh[d][0], qmax = mesh[d][0];
+      for (i64 j = 1; j < nshape[d]; ++j) {
+        if (mesh[d][j] < qmin) qmin = mesh[d][j];
+        if (mesh[d][j] > qmax) qmax = mesh[d][j];
+      }
+      double Lq = qmax - qmin;
+      for (i64 j = 0; j < nq; ++j) h->mesh[g][d][j] = ((double)j * Lq) / (double)(nq - 1) + qmin; /* :258 */
+    }
+  return h;
+}
+
+void orc_mg_delete(orc_mg* h) {
+  if (!h) return;
+  for (int g = 0; g < h->ngrids; ++g) {
+    free(h->u[g]); free(h->rhs[g]);
+    for (int d = 0; d < h->ndim; ++d) free(h->mesh[g][d]);
+  }
+  free(h);
+}
+void orc_mg_set(orc_mg* h, i64 ms, double ex_tol, const char* copt) {
+  h->ms = ms; h->ex_tol = ex_tol;
+  for (int d = 0; d < 2 * h->ndim; ++d) h->copt[d] = copt[d];
+}
+void orc_mg_shape(const orc_mg* h, int g, i64* out) { for (int d = 0; d < h->ndim; ++d) out[d] = h->nshape[g][d]; }
+const double* orc_mg_mesh(const orc_mg* h, int g, int d) { return h->mesh[g][d]; }
+double* orc_mg_u(orc_mg* h, int g) { return h->u[g]; }
+double* orc_mg_rhs(orc_mg* h, int g) { return h->rhs[g]; }
+int orc_mg_last_nexact(const orc_mg* h) { return h->last_nexact; }
+
+/* relax / residual wrappers: ndsm_poisson.f90:163-275 (3D -> optimized, else generic) */
+static void relax(orc_mg* h, int g) {
+  if (h->ndim == 3)
+    orc_relax3d(h->copt, h->nshape[g][0], h->nshape[g][1], h->nshape[g][2], h->mesh[g][0], h->mesh[g][1],
+                h->mesh[g][2], h->rhs[g], h->u[g]);
+  else
+    orc_relax_nd(h->ndim, h->nshape[g], (const double* const*)h->mesh[g], h->copt, h->u[g], h->rhs[g]);
+}
+static void residual(orc_mg* h, int g, double* r) {
+  if (h->ndim == 3)
+    orc_residual3d(h->copt, h->nshape[g][0], h->nshape[g][1], h->nshape[g][2], h->mesh[g][0], h->mesh[g][1],
+                   h->mesh[g][2], h->rhs[g], h->u[g], r);
+  else
+    orc_residual_nd(h->ndim, h->nshape[g], (const double* const*)h->mesh[g], h->copt, h->u[g], h->rhs[g], r);
+}
+void orc_mg_relax(orc_mg* h, int g) { relax(h, g); }
+void orc_mg_residual(orc_mg* h, int g, double* r) { residual(h, g, r); }
+
+/* fine_to_coarse: ndsm_multigrid_core.f90:482-560 (g = fine level, 0-based) */
+static void fine_to_coarse(orc_mg* h, int g) {
+  const int c = g + 1;
+  for (i64 i = 0; i < h->ms; ++i) relax(h, g);
+  double* r = (double*)malloc(sizeof(double) * h->nsize[g]);
+  zero(r, h->nsize[g]);
+  residual(h, g, r);
+  free(h->rhs[c]);
+  h->rhs[c] = (double*)malloc(sizeof(double) * h->nsize[c]);
+  zero(h->rhs[c], h->nsize[c]);
+  orc_mg_restrict(h->ndim, h->nshape[g], (const double* const*)h->mesh[g], h->nshape[c],
+                  (const double* const*)h->mesh[c], r, h->rhs[c]);
+  free(r);
+  free(h->u[c]);
+  h->u[c] = (double*)malloc(sizeof(double) * h->nsize[c]);
+  zero(h->u[c], h->nsize[c]);
+}
+
+/* coarse_to_fine: ndsm_multigrid_core.f90:593-684 (c = coarse level, 0-based) */
+static void coarse_to_fine(orc_mg* h, int c) {
+  const int f = c - 1;
+  for (i64 i = 0; i < h->ms; ++i) relax(h, c);
+  free(h->rhs[c]); h->rhs[c] = NULL;
+  double* cor = (double*)malloc(sizeof(double) * h->nsize[f]);
+  orc_mg_interp(h->ndim, h->nshape[f], (const double* const*)h->mesh[f], h->nshape[c],
+                (const double* const*)h->mesh[c], h->u[c], cor);
+  free(h->u[c]); h->u[c] = NULL;
+  double* uf = h->u[f];
+  const i64 n = h->nsize[f];
+#pragma omp parallel for if ((n) > ORC_PAR_MIN)
+  for (i64 i = 0; i < n; ++i) uf[i] = uf[i] + cor[i]; /* add_correction :692-712 */
+  free(cor);
+  for (i64 i = 0; i < h->ms; ++i) relax(h, f);
+}
+
+/* solve_exact: ndsm_multigrid_core.f90:728-800 */
+static void solve_exact(orc_mg* h, int g) {
+  const i64 n = h->nsize[g];
+  double* usav = (double*)malloc(sizeof(double) * n);
+  zero(usav, n);
+  int converged = 0;
+  double du = HUGE_VAL;
+  int nsteps = 0;
+  for (i64 i = 0; i < h->nmax_exact; ++i) {
+    if (du <= h->ex_tol) { converged = 1; break; } /* :771 */
+    relax(h, g);
+    double m[2];
+    orc_du_metrics(n, usav, h->u[g], m);
+    du = h->du_max ? m[0] : m[1];
+    copy(usav, h->u[g], n);
+    nsteps++;
+  }
+  h->last_nexact = nsteps;
+  if (!converged) printf(" Warning: IOPT_NMAXEX exceeded. Coarse-mesh solution may not have converged\n");
+  free(usav);
+}
+void orc_mg_solve_exact(orc_mg* h, int g) { solve_exact(h, g); }
+
+/* v_cycle: ndsm_multigrid_core.f90:341-377 (from the finest grid) */
+void orc_v_cycle(orc_mg* h) {
+  for (int g = 0; g < h->ngrids - 1; ++g) fine_to_coarse(h, g);
+  solve_exact(h, h->ngrids - 1);
+  for (int g = h->ngrids - 1; g >= 1; --g) coarse_to_fine(h, g);
+}
+
+/* Allocate level-0 slots and load (u, rhs) : ndsm_poisson.f90:92-101 */
+void orc_mg_load(orc_mg* h, const double* u, const double* rhs) {
+  const i64 n = h->nsize[0];
+  if (!h->u[0]) h->u[0] = (double*)malloc(sizeof(double) * n);
+  if (!h->rhs[0]) h->rhs[0] = (double*)malloc(sizeof(double) * n);
+  memcpy(h->u[0], u, sizeof(double) * n);
+  memcpy(h->rhs[0], rhs, sizeof(double) * n);
+}
+
+/* solve_poisson_bvp: ndsm_poisson.f90:63-155 */
+void orc_solve_poisson_bvp(orc_mg* h, double vc_tol, i64 nmax, double* u, const double* rhs,
+                           double* du_last, i64* ierr) {
+  const i64 n = h->nsize[0];
+  orc_mg_load(h, u, rhs);
+  double du = HUGE_VAL;
+  int converged = 0;
+  *ierr = 0;
+  int sid = -1;
+  if (g_tr.nsolves < TR_MAXSOLVE) { sid = g_tr.nsolves++; g_tr.ncycles[sid] = 0; }
+  debug_msg("solve_poisson_bvp", "Performing V cycles...");
+  for (i64 i = 0; i < nmax; ++i) {
+    orc_v_cycle(h);
+    double dmax, dmean;
+    orc_update_u(n, h->u[0], u, &dmax, &dmean); /* :122 */
+    du = h->du_max ? dmax : dmean;
+    if (sid >= 0 && g_tr.ncycles[sid] < TR_MAXCYC) {
+      g_tr.du[sid][g_tr.ncycles[sid]] = du;
+      g_tr.nexact[sid][g_tr.ncycles[sid]] = h->last_nexact;
+      g_tr.ncycles[sid]++;
+    }
+    if (g_debug) {
+      char s[64];
+      snprintf(s, sizeof s, "Solution delta: %12.4E", du);
+      debug_msg("solve_poisson_bvp", s);
+    }
+    if (du < vc_tol) { converged = 1; break; } /* :136 strict < */
+  }
+  *du_last = du;
+  if (!converged) {
+    *ierr = 1;
+    printf(" Warning: IOPT_NCYCLES exceeded. V-cycle iteration may not have converged\n");
+  }
+  if (sid >= 0) g_tr.ierr[sid] = (int)*ierr;
+  memcpy(u, h->u[0], sizeof(double) * n); /* :153 */
+}
+
+/* ------------------------------------------------------------------ */
+/* Vector-potential driver pieces: ndsm_vector_potential.f90            */
+/* ------------------------------------------------------------------ */
+enum { IOPT_LEN = 16, IOPT_MS = 0, IOPT_NCYCLES = 1, IOPT_FACE1 = 2, IOPT_IERR = 3, IOPT_FLXCRL = 4,
+       IOPT_DEBUG = 5, IOPT_DUMAX = 6, IOPT_NMAXEX = 7, IOPT_TRUE = 1, IOPT_FALSE = 0,
+       ROPT_VTOL = 0, ROPT_CTOL = 1, ROPT_TIM = 2 }; /* :40-57 */
+
+/* extract_bn: :699-743 ; cdim 0-based, clay 0-based layer; dir=+1: bc<-b ; dir=-1: b<-bc */
+void orc_extract_bn(const i64* nshape, int cdim, i64 clay, double* b, double* bc, int dir) {
+  i64 lb[3] = {0, 0, 0}, ub[3] = {nshape[0] - 1, nshape[1] - 1, nshape[2] - 1};
+  lb[cdim] = clay; ub[cdim] = clay;
+  i64 n = 0;
+  for (i64 k = lb[2]; k <= ub[2]; ++k)
+    for (i64 j = lb[1]; j <= ub[1]; ++j)
+      for (i64 i = lb[0]; i <= ub[0]; ++i) {
+        i64 m = i + nshape[0] * (j + nshape[1] * k);
+        if (dir == +1) bc[n] = b[m];
+        if (dir == -1) b[m] = bc[n];
+        n++;
+      }
+}
+
+/* trapz_2D: :1070-1106 ; SUM(w*f)*dq1*dq2, column-major sequential sum */
+double orc_trapz2d(i64 n1, i64 n2, double dq1, double dq2, const double* f) {
+  double s = 0.0;
+  for (i64 j = 0; j < n2; ++j)
+    for (i64 i = 0; i < n1; ++i) {
+      double w = 1.0;
+      int ei = (i == 0 || i == n1 - 1), ej = (j == 0 || j == n2 - 1);
+      if (ei || ej) w = 0.5;
+      if (ei && ej) w = 0.25;
+      s = s + w * f[i + n1 * j];
+    }
+  return (s * dq1) * dq2;
+}
+
+/* compute_At_bcs: :977-1031 ; face f (0-based 0..5) selects the unit vectors (:88-113) */
+void orc_compute_At(const i64* nsh, const double* chi, double dq, int face, double* At1, double* At2) {
+  static const double tv1[6][3] = {{0, 1, 0}, {0, 1, 0}, {1, 0, 0}, {1, 0, 0}, {1, 0, 0}, {1, 0, 0}};
+  static const double tv2[6][3] = {{0, 0, 1}, {0, 0, 1}, {0, 0, 1}, {0, 0, 1}, {0, 1, 0}, {0, 1, 0}};
+  static const double nv[6][3] = {{1, 0, 0}, {1, 0, 0}, {0, 1, 0}, {0, 1, 0}, {0, 0, 1}, {0, 0, 1}};
+  const double* t1 = tv1[face]; const double* t2 = tv2[face]; const double* n = nv[face];
+  double c1[3], c2[3];
+  c1[0] = t1[1] * n[2] - t1[2] * n[1]; c1[1] = t1[2] * n[0] - t1[0] * n[2]; c1[2] = t1[0] * n[1] - t1[1] * n[0];
+  c2[0] = t2[1] * n[2] - t2[2] * n[1]; c2[1] = t2[2] * n[0] - t2[0] * n[2]; c2[2] = t2[0] * n[1] - t2[1] * n[0];
+  const double fac = 1.0 / (2.0 * dq); /* :996 */
+  const i64 nq1 = nsh[0], nq2 = nsh[1];
+#pragma omp parallel for if ((nq1 * nq2) > ORC_PAR_MIN)
+  for (i64 j = 0; j < nq2; ++j)
+    for (i64 i = 0; i < nq1; ++i) {
+      double d1 = (i == 0 || i == nq1 - 1) ? 0.0 : fac * (chi[(i + 1) + nq1 * j] - chi[(i - 1) + nq1 * j]);
+      double d2 = (j == 0 || j == nq2 - 1) ? 0.0 : fac * (chi[i + nq1 * (j + 1)] - chi[i + nq1 * (j - 1)]);
+      double g[3];
+      for (int c = 0; c < 3; ++c) g[c] = d1 * c1[c] + d2 * c2[c]; /* :1021 */
+      At1[i + nq1 * j] = -((t1[0] * g[0] + t1[1] * g[1]) + t1[2] * g[2]);
+      At2[i + nq1 * j] = -((t2[0] * g[0] + t2[1] * g[1]) + t2[2] * g[2]);
+    }
+}
+
+/* add_flux_balance_fields: :880-950 ; A,B are (nx,ny,nz,3) */
+void orc_add_flux_balance_fields(const i64* nshape, const double* x, const double* y, const double* z,
+                                 const double* phi, double* B, double* A) {
+  const i64 nx = nshape[0], ny = nshape[1], nz = nshape[2], N = nx * ny * nz;
+  const double* m[3] = {x, y, z};
+  double Lq[3];
+  for (int d = 0; d < 3; ++d) {
+    double lo = m[d][0], hi = m[d][0];
+    for (i64 i = 1; i < nshape[d]; ++i) { if (m[d][i] < lo) lo = m[d][i]; if (m[d][i] > hi) hi = m[d][i]; }
+    Lq[d] = hi - lo;
+  }
+  const double Vq = (Lq[0] * Lq[1]) * Lq[2];
+  const double g1 = (phi[1] - phi[0]) / Vq, g2 = (phi[3] - phi[2]) / Vq, g3 = (phi[5] - phi[4]) / Vq;
+  const double inv3 = 1.0 / 3.0;
+#pragma omp parallel for if ((N) > ORC_PAR_MIN)
+  for (i64 k = 0; k < nz; ++k)
+    for (i64 j = 0; j < ny; ++j)
+      for (i64 i = 0; i < nx; ++i) {
+        const i64 n = i + nx * (j + ny * k);
+        const double X = x[i], Y = y[j], Z = z[k];
+        double bc[3] = {g1 * X + (phi[0] * Lq[0]) / Vq, g2 * Y + (phi[2] * Lq[1]) / Vq, g3 * Z + (phi[4] * Lq[2]) / Vq};
+        double A1[3] = {-((g3 * Y) * Z), 0.0, +((g1 * X) * Y)};
+        double A2[3] = {+((g2 * Z) * Y), -((g1 * X) * Z), 0.0};
+        double A3[3] = {0.0, +((g3 * X) * Z), -((g2 * X) * Y)};
+        double Ac[3] = {-(((phi[4] * Lq[2]) * Y)) / Vq, -(((phi[0] * Lq[0]) * Z)) / Vq, -(((phi[2] * Lq[1]) * X)) / Vq};
+        for (int c = 0; c < 3; ++c) {
+          B[n + c * N] = B[n + c * N] + bc[c];
+          A[n + c * N] = (A[n + c * N] + Ac[c]) + inv3 * ((A1[c] + A2[c]) + A3[c]); /* :947 */
+        }
+      }
+}
+
+/* derivq: :825-872 */
+static inline double derivq(i64 idx, i64 nd, double dq, i64 stride, const double* u, i64 n) {
+  double d = 0.0;
+  if (idx == 0) {
+    d = d + u[n] * ((-3.0 * 0.5) / dq);
+    d = d + u[n + stride] * ((4.0 * 0.5) / dq);
+    d = d + u[n + 2 * stride] * ((-1.0 * 0.5) / dq);
+  } else if (idx == nd - 1) {
+    d = d + u[n] * ((3.0 * 0.5) / dq);
+    d = d + u[n - stride] * ((-4.0 * 0.5) / dq);
+    d = d + u[n - 2 * stride] * ((1.0 * 0.5) / dq);
+  } else {
+    d = d + u[n - stride] * ((-1.0 * 0.5) / dq);
+    d = d + u[n + stride] * ((1.0 * 0.5) / dq);
+  }
+  return d;
+}
+/* curl: :759-813 */
+void orc_curl(const i64* nshape, const double* dq, const double* A, double* B) {
+  const i64 nx = nshape[0], ny = nshape[1], nz = nshape[2], N = nx * ny * nz;
+  const double *Ax = A, *Ay = A + N, *Az = A + 2 * N;
+#pragma omp parallel for if ((N) > ORC_PAR_MIN)
+  for (i64 k = 0; k < nz; ++k)
+    for (i64 j = 0; j < ny; ++j)
+      for (i64 i = 0; i < nx; ++i) {
+        const i64 n = i + nx * (j + ny * k);
+        double dAx_dy = derivq(j, ny, dq[1], nx, Ax, n);
+        double dAx_dz = derivq(k, nz, dq[2], nx * ny, Ax, n);
+        double dAy_dx = derivq(i, nx, dq[0], 1, Ay, n);
+        double dAy_dz = derivq(k, nz, dq[2], nx * ny, Ay, n);
+        double dAz_dx = derivq(i, nx, dq[0], 1, Az, n);
+        double dAz_dy = derivq(j, ny, dq[1], nx, Az, n);
+        B[n] = dAz_dy - dAy_dz;
+        B[n + N] = dAx_dz - dAz_dx;
+        B[n + 2 * N] = dAy_dx - dAx_dy;
+      }
+}
+
+/* BC setup stage (compute_vector_potential :201-399): faces -> phi, chi, At.
+ * bn_out/chi_out/At1_out/At2_out: 6 caller buffers each (may be NULL) sized for the faces. */
+static const int imap_cp[6] = {0, 0, 1, 1, 2, 2};
+static const int imap_nc[6][2] = {{1, 2}, {1, 2}, {0, 2}, {0, 2}, {0, 1}, {0, 1}};
+
+typedef struct {
+  double phi[6];
+  double* chi[6];
+  double* At[6][2];
+  i64 nshape_bn[6][2];
+  i64 nsize_bn[6];
+  i64 ierr_last;
+} orc_bc;
+
+static void bc_free(orc_bc* bc) {
+  for (int f = 0; f < 6; ++f) { free(bc->chi[f]); free(bc->At[f][0]); free(bc->At[f][1]); }
+}
+
+static void bc_setup(const i64* nshape, const i64* iopt, const double* ropt, const double* const* mesh,
+                     const double* dq, const double* Lq, double* B, orc_bc* bc) {
+  const i64 N = nshape[0] * nshape[1] * nshape[2];
+  const int use_du_max = (iopt[IOPT_DUMAX] == IOPT_TRUE);
+  double* bn[6];
+  for (int f = 0; f < 6; ++f) {
+    bc->nshape_bn[f][0] = nshape[imap_nc[f][0]];
+    bc->nshape_bn[f][1] = nshape[imap_nc[f][1]];
+    bc->nsize_bn[f] = bc->nshape_bn[f][0] * bc->nshape_bn[f][1];
+    bn[f] = (double*)malloc(sizeof(double) * bc->nsize_bn[f]);
+    i64 lay = (f % 2 == 0) ? 0 : nshape[imap_cp[f]] - 1;                       /* :280-281 */
+    orc_extract_bn(nshape, imap_cp[f], lay, B + imap_cp[f] * N, bn[f], +1);     /* :284 */
+  }
+  for (int f = 0; f < 6; ++f) /* :300-306 ; always dq(1),dq(2) (quirk Q2) */
+    bc->phi[f] = orc_trapz2d(bc->nshape_bn[f][0], bc->nshape_bn[f][1], dq[0], dq[1], bn[f]);
+  const double Aq[6] = {Lq[1] * Lq[2], Lq[1] * Lq[2], Lq[0] * Lq[2], Lq[0] * Lq[2], Lq[0] * Lq[1], Lq[0] * Lq[1]};
+  debug_msg("compute_vector_potential", "Solve BVP on each boundary...");
+  for (int f = 0; f < 6; ++f) { /* :338-365 */
+    i64 nmin = bc->nshape_bn[f][0] < bc->nshape_bn[f][1] ? bc->nshape_bn[f][0] : bc->nshape_bn[f][1];
+    int ngrids = orc_ngrids(nmin);
+    bc->chi[f] = (double*)calloc(bc->nsize_bn[f], sizeof(double));
+    const double sh = bc->phi[f] / Aq[f];
+    for (i64 n = 0; n < bc->nsize_bn[f]; ++n) bn[f][n] = bn[f][n] - sh; /* :348 */
+    const double* m2[2] = {mesh[imap_nc[f][0]], mesh[imap_nc[f][1]]};
+    orc_mg* h = orc_mg_new(2, bc->nshape_bn[f], ngrids, m2, use_du_max, iopt[IOPT_NMAXEX]);
+    if (!h) { bc->ierr_last = 1; continue; }
+    orc_mg_set(h, iopt[IOPT_MS], ropt[ROPT_CTOL], "NNNNNN");
+    double du_last;
+    orc_solve_poisson_bvp(h, ropt[ROPT_VTOL], iopt[IOPT_NCYCLES], bc->chi[f], bn[f], &du_last, &bc->ierr_last);
+    orc_mg_delete(h);
+  }
+  debug_msg("compute_vector_potential", "Compute vector potential boundary conditions...");
+  for (int f = 0; f < 6; ++f) { /* :387-399 ; dq of the face-normal direction (quirk Q3) */
+    bc->At[f][0] = (double*)calloc(bc->nsize_bn[f], sizeof(double));
+    bc->At[f][1] = (double*)calloc(bc->nsize_bn[f], sizeof(double));
+    orc_compute_At(bc->nshape_bn[f], bc->chi[f], dq[imap_cp[f]], f, bc->At[f][0], bc->At[f][1]);
+  }
+  for (int f = 0; f < 6; ++f) free(bn[f]);
+}
+
+/* solve: :598-691 -- three scalar Laplace solves with mixed BCs */
+static void solve3(const double* ropt, const i64* iopt, const double* const* mesh, const i64* nshape,
+                   orc_bc* bc, double* Ac) {
+  const i64 N = nshape[0] * nshape[1] * nshape[2];
+  const int use_du_max = (iopt[IOPT_DUMAX] == IOPT_TRUE);
+  i64 nmin = nshape[0];
+  for (int d = 1; d < 3; ++d) if (nshape[d] < nmin) nmin = nshape[d];
+  const int ngrids = orc_ngrids(nmin);
+  double* rhs = (double*)calloc(N, sizeof(double));
+  /* per component: the four (face, At index) writes in reference order, BC string, ms */
+  static const int wf[3][4] = {{2, 3, 4, 5}, {0, 1, 4, 5}, {0, 1, 2, 3}};
+  static const int wa[3][4] = {{0, 0, 0, 0}, {0, 0, 1, 1}, {1, 1, 1, 1}};
+  static const char* cop[3] = {"NDDNDD", "DNDDND", "DDNDDN"};
+  for (int c = 0; c < 3; ++c) {
+    double* A = Ac + c * N;
+    for (int w = 0; w < 4; ++w) {
+      int f = wf[c][w];
+      i64 lay = (f % 2 == 0) ? 0 : nshape[imap_cp[f]] - 1;
+      orc_extract_bn(nshape, imap_cp[f], lay, A, bc->At[f][wa[c][w]], -1);
+    }
+    orc_mg* h = orc_mg_new(3, nshape, ngrids, mesh, use_du_max, iopt[IOPT_NMAXEX]);
+    if (!h) continue;
+    orc_mg_set(h, c == 2 ? 5 : iopt[IOPT_MS], ropt[ROPT_CTOL], cop[c]); /* :685 ms=5 for Az */
+    double du_last;
+    i64 ierr;
+    orc_solve_poisson_bvp(h, ropt[ROPT_VTOL], iopt[IOPT_NCYCLES], A, rhs, &du_last, &ierr);
+    orc_mg_delete(h);
+  }
+  free(rhs);
+}
+
+/* compute_vector_potential: :130-497 */
+static void compute_vector_potential(const i64* nshape, i64* iopt, double* ropt, const double* const* mesh,
+                                     double* Apot, double* B) {
+  double Lq[3], dq[3];
+  for (int d = 0; d < 3; ++d) {
+    if (nshape[d] < 2) { iopt[IOPT_IERR] = 1; return; } /* :213-216 */
+    double lo = mesh[d][0], hi = mesh[d][0];
+    for (i64 i = 1; i < nshape[d]; ++i) { if (mesh[d][i] < lo) lo = mesh[d][i]; if (mesh[d][i] > hi) hi = mesh[d][i]; }
+    Lq[d] = hi - lo;
+    dq[d] = mesh[d][1] - mesh[d][0];
+  }
+  orc_bc bc;
+  memset(&bc, 0, sizeof bc);
+  bc_setup(nshape, iopt, ropt, mesh, dq, Lq, B, &bc);
+  debug_msg("compute_vector_potential", "Solve BVP 3D...");
+  solve3(ropt, iopt, mesh, nshape, &bc, Apot);
+  debug_msg("compute_vector_potential", "Compute B = curl(B) and flux correction...");
+  if (iopt[IOPT_FLXCRL] == 1) { /* :453-477 */
+    printf(" FLAG SET: FLXCRL\n");
+    orc_curl(nshape, dq, Apot, B);
+    orc_add_flux_balance_fields(nshape, mesh[0], mesh[1], mesh[2], bc.phi, B, Apot);
+  } else {
+    orc_add_flux_balance_fields(nshape, mesh[0], mesh[1], mesh[2], bc.phi, B, Apot);
+    orc_curl(nshape, dq, Apot, B);
+  }
+  iopt[IOPT_IERR] = bc.ierr_last; /* :480 -- ierr of the LAST 2D chi solve (quirk Q4) */
+  bc_free(&bc);
+}
+
+/* Stage hook for tests: runs only the BC setup and returns phi[6], chi and At faces.
+ * chi/At1/At2: arrays of 6 pointers to caller buffers. */
+int orc_bc_setup(const int* nshape4, const int* ioptc, const double* ropt, const double* x, const double* y,
+                 const double* z, const double* B, double* phi, double** chi, double** At1, double** At2) {
+  i64 nshape[3] = {nshape4[0], nshape4[1], nshape4[2]}, iopt[IOPT_LEN];
+  for (int i = 0; i < IOPT_LEN; ++i) iopt[i] = ioptc[i];
+  const double* mesh[3] = {x, y, z};
+  double Lq[3], dq[3];
+  for (int d = 0; d < 3; ++d) {
+    double lo = mesh[d][0], hi = mesh[d][0];
+    for (i64 i = 1; i < nshape[d]; ++i) { if (mesh[d][i] < lo) lo = mesh[d][i]; if (mesh[d][i] > hi) hi = mesh[d][i]; }
+    Lq[d] = hi - lo; dq[d] = mesh[d][1] - mesh[d][0];
+  }
+  orc_bc bc;
+  memset(&bc, 0, sizeof bc);
+  bc_setup(nshape, iopt, ropt, mesh, dq, Lq, (double*)B, &bc);
+  for (int f = 0; f < 6; ++f) {
+    phi[f] = bc.phi[f];
+    if (chi && chi[f]) memcpy(chi[f], bc.chi[f], sizeof(double) * bc.nsize_bn[f]);
+    if (At1 && At1[f]) memcpy(At1[f], bc.At[f][0], sizeof(double) * bc.nsize_bn[f]);
+    if (At2 && At2[f]) memcpy(At2[f], bc.At[f][1], sizeof(double) * bc.nsize_bn[f]);
+  }
+  bc_free(&bc);
+  return (int)bc.ierr_last;
+}
+
+/* ------------------------------------------------------------------ */
+/* C ABI identical to ndsm_python_wrapper.f90:56-234                    */
+/* ------------------------------------------------------------------ */
+int ndsm_vector_solve(size_t nsize, const int* nshape4, int* ioptc, double* ropt, const double* x,
+                      const double* y, const double* z, double* A, double* B) {
+  (void)nsize;
+  i64 nshape[4] = {nshape4[0], nshape4[1], nshape4[2], nshape4[3]};
+  i64 iopt[IOPT_LEN];
+  for (int i = 0; i < IOPT_LEN; ++i) iopt[i] = ioptc[i];
+  g_debug = (iopt[IOPT_DEBUG] == IOPT_TRUE);
+  double t0 = wtime();
+  const double* mesh[3] = {x, y, z};
+  debug_msg("ndsm_vector_solve", "Calling compute_vector_potential...");
+  compute_vector_potential(nshape, iopt, ropt, mesh, A, B);
+  ropt[ROPT_TIM] = wtime() - t0;
+  for (int i = 0; i < IOPT_LEN; ++i) ioptc[i] = (int)iopt[i];
+  debug_msg("ndsm_vector_solve", "Exiting Fortran lib...");
+  return (int)iopt[IOPT_IERR];
+}
+int get_iopt_len(void) { return IOPT_LEN; }
+int get_iopt_ierr(void) { return IOPT_LEN; } /* sic: ndsm_python_wrapper.f90:171-175 */
+int get_iopt_ms(void) { return IOPT_MS; }
+int get_iopt_ncycles(void) { return IOPT_NCYCLES; }
+int get_iopt_debug(void) { return IOPT_DEBUG; }
+int get_iopt_dumax(void) { return IOPT_DUMAX; }
+int get_iopt_iopt_nmaxex(void) { return IOPT_NMAXEX; }
+int get_iopt_true(void) { return IOPT_TRUE; }
+int get_iopt_false(void) { return IOPT_FALSE; }
+int get_ropt_tim(void) { return ROPT_TIM; }
+int get_ropt_vtol(void) { return ROPT_VTOL; }
+int get_ropt_ctol(void) { return ROPT_CTOL; }
+
+/* ------------------------------------------------------------------ */
+/* Generic scalar Poisson entry: solve_poisson_bvp on a   */
+/* caller-defined 2D/3D problem.  Returns ierr; *ncycles = V-cycles.    */
+/* ------------------------------------------------------------------ */
+int orc_poisson_solve(int ndim, const int* nshape_i, const char* copt, i64 ms, i64 ncycles_max, i64 nmaxex,
+                      int du_max, double vc_tol, double ex_tol, const double* x, const double* y,
+                      const double* z, double* u, const double* rhs, double* du_last, int* ncycles) {
+  i64 nshape[3] = {1, 1, 1}, nmin = 0;
+  for (int d = 0; d < ndim; ++d) { nshape[d] = nshape_i[d]; if (d == 0 || nshape[d] < nmin) nmin = nshape[d]; }
+  const double* mesh[3] = {x, y, z};
+  orc_mg* h = orc_mg_new(ndim, nshape, orc_ngrids(nmin), mesh, du_max, nmaxex);
+  if (!h) return 2;
+  orc_mg_set(h, ms, ex_tol, copt);
+  i64 ierr;
+  int s0 = g_tr.nsolves;
+  orc_solve_poisson_bvp(h, vc_tol, ncycles_max, u, rhs, du_last, &ierr);
+  if (ncycles) *ncycles = (s0 < TR_MAXSOLVE) ? g_tr.ncycles[s0] : -1;
+  orc_mg_delete(h);
+  return (int)ierr;
+}

@@ -1,0 +1,315 @@
+"""Per-kernel parity of the CUDA operators against the CPU oracle, through the C ABI (MG_HANDLE seam).
+
+Tolerance: north_star asks for per-sweep field agreement <= 1e-12 relative.  The smoother, residual,
+restriction and prolongation kernels keep the reference's evaluation order and are compiled with
+-fmad=false, so they are expected to be BIT-IDENTICAL to the oracle; operations whose summation
+order is unspecified in the reference (OpenMP reductions: mean, sum of |du|) are compared at 1e-13.
+"""
+import numpy as np
+import pytest
+
+from conftest import aniso_mesh, rel_err
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-12      # north_star per-sweep tolerance
+TOL_RED = 1e-13  # reductions with unspecified order
+
+SHAPES3 = [(22, 22, 22), (17, 20, 9), (33, 18, 25), (8, 9, 10), (64, 33, 17)]
+COPTS3 = ["NDDNDD", "DNDDND", "DDNDDN", "DDDDDD", "NNDNND", "DNNNDN"]
+SHAPES2 = [(22, 22), (17, 36), (65, 18), (9, 8)]
+COPTS2 = ["NNNN", "DNND", "DDDD", "NDNN"]
+
+
+def rand(shape, seed):
+    return np.random.default_rng(seed).standard_normal(shape[::-1])
+
+
+def mg(gpu_lib, mesh, copt, **kw):
+    from ndsm_b200.mg import MGHandle
+    return MGHandle(mesh, copt, **kw)
+
+
+@pytest.mark.parametrize("shape", SHAPES3)
+@pytest.mark.parametrize("copt", COPTS3)
+def test_relax3d_matches_oracle(gpu_lib, oracle, shape, copt):
+    mesh = aniso_mesh(shape)
+    u0, rhs = rand(shape, 1), rand(shape, 2)
+    h = mg(gpu_lib, mesh, copt)
+    h.put(h.U, 0, u0)
+    h.put(h.RHS, 0, rhs)
+    for nsw in (1, 2):
+        h.relax(0, 1)
+        got = h.get(h.U, 0)
+        want = oracle.relax3d(copt, mesh, rhs, u0, nsweeps=nsw)
+        assert rel_err(got, want) <= TOL
+        assert np.array_equal(got, want), "smoother is expected to be bit-identical to the reference arithmetic"
+    h.close()
+
+
+def test_relax3d_all_neumann_mean_subtraction(gpu_lib, oracle):
+    shape = (20, 14, 12)
+    mesh = aniso_mesh(shape)
+    u0, rhs = rand(shape, 3), rand(shape, 4)
+    h = mg(gpu_lib, mesh, "NNNNNN")
+    h.put(h.U, 0, u0)
+    h.put(h.RHS, 0, rhs)
+    h.relax(0, 2)
+    got = h.get(h.U, 0)
+    want = oracle.relax3d("NNNNNN", mesh, rhs, u0, nsweeps=2)
+    assert rel_err(got, want) <= TOL_RED
+    assert abs(got.mean()) < 1e-13 * np.abs(got).max()
+    h.close()
+
+
+def test_relax3d_on_coarse_levels(gpu_lib, oracle):
+    shape = (44, 36, 40)
+    mesh = aniso_mesh(shape)
+    copt = "NDDNDD"
+    h = mg(gpu_lib, mesh, copt)
+    o = oracle.OracleMG(mesh, copt)
+    assert h.ngrids == o.ngrids
+    for g in range(h.ngrids):
+        assert h.shape(g) == o.shape(g)
+        for a, b in zip(h.level_mesh(g), o.level_mesh(g)):
+            assert np.array_equal(a, b)
+        shp = h.shape(g)
+        u0, rhs = rand(shp, 10 + g), rand(shp, 20 + g)
+        h.put(h.U, g, u0)
+        h.put(h.RHS, g, rhs)
+        h.relax(g, 1)
+        want = oracle.relax3d(copt, h.level_mesh(g), rhs, u0)
+        assert np.array_equal(h.get(h.U, g), want)
+    h.close()
+
+
+@pytest.mark.parametrize("shape", SHAPES3)
+@pytest.mark.parametrize("copt", COPTS3[:4])
+def test_residual3d_matches_oracle(gpu_lib, oracle, shape, copt):
+    mesh = aniso_mesh(shape)
+    u0, rhs = rand(shape, 5), rand(shape, 6)
+    h = mg(gpu_lib, mesh, copt)
+    h.put(h.U, 0, u0)
+    h.put(h.RHS, 0, rhs)
+    got = h.residual(0)
+    want = oracle.residual3d(copt, mesh, rhs, u0)
+    assert rel_err(got, want) <= TOL
+    assert np.array_equal(got, want)
+    h.close()
+
+
+@pytest.mark.parametrize("shape", SHAPES2)
+@pytest.mark.parametrize("copt", COPTS2)
+def test_relax2d_residual2d_match_oracle(gpu_lib, oracle, shape, copt):
+    mesh = aniso_mesh(shape)
+    u0, rhs = rand(shape, 7), rand(shape, 8)
+    h = mg(gpu_lib, mesh, copt)
+    h.put(h.U, 0, u0)
+    h.put(h.RHS, 0, rhs)
+    got_r = h.residual(0)
+    want_r = oracle.residual_nd(copt, mesh, rhs, u0)
+    assert np.array_equal(got_r, want_r)
+    h.relax(0, 2)
+    got = h.get(h.U, 0)
+    want = oracle.relax_nd(copt, mesh, rhs, u0, nsweeps=2)
+    if copt == "NNNN":  # mean subtraction after every sweep: summation order differs
+        assert rel_err(got, want) <= TOL_RED
+    else:
+        assert np.array_equal(got, want)
+    h.close()
+
+
+@pytest.mark.parametrize("shape", SHAPES3 + [(45, 27, 13), (9, 9, 9)])
+def test_restrict_matches_oracle(gpu_lib, oracle, shape):
+    mesh = aniso_mesh(shape)
+    h = mg(gpu_lib, mesh, "NDDNDD")
+    for g in range(h.ngrids - 1):
+        shp = h.shape(g)
+        r = rand(shp, 30 + g)
+        h.put(h.R, g, r)
+        got = h.restrict(g)
+        want_lit = oracle.mg_restrict(h.level_mesh(g), h.level_mesh(g + 1), r, mode=0)
+        want_tab = oracle.mg_restrict(h.level_mesh(g), h.level_mesh(g + 1), r, mode=1)
+        assert np.array_equal(want_lit, want_tab)
+        assert rel_err(got, want_lit) <= TOL
+        assert np.array_equal(got, want_lit)
+        assert not h.get(h.U, g + 1).any()  # u_c zeroed (ndsm_multigrid_core.f90:557-558)
+    h.close()
+
+
+@pytest.mark.parametrize("shape", SHAPES3 + [(45, 27, 13), (9, 9, 9)])
+def test_interp_add_matches_oracle(gpu_lib, oracle, shape):
+    mesh = aniso_mesh(shape)
+    h = mg(gpu_lib, mesh, "DNDDND")
+    for g in range(1, h.ngrids):
+        uc, uf = rand(h.shape(g), 40 + g), rand(h.shape(g - 1), 50 + g)
+        h.put(h.U, g, uc)
+        h.put(h.U, g - 1, uf)
+        got = h.interp_add(g)
+        cor = oracle.mg_interp(h.level_mesh(g - 1), h.level_mesh(g), uc, mode=0)
+        assert np.array_equal(cor, oracle.mg_interp(h.level_mesh(g - 1), h.level_mesh(g), uc, mode=1))
+        want = uf + cor
+        assert rel_err(got, want) <= TOL
+        assert np.array_equal(got, want)
+    h.close()
+
+
+@pytest.mark.parametrize("shape", SHAPES2)
+def test_transfers_2d_match_oracle(gpu_lib, oracle, shape):
+    mesh = aniso_mesh(shape)
+    h = mg(gpu_lib, mesh, "NNNN")
+    for g in range(h.ngrids - 1):
+        r = rand(h.shape(g), 60 + g)
+        h.put(h.R, g, r)
+        assert np.array_equal(h.restrict(g), oracle.mg_restrict(h.level_mesh(g), h.level_mesh(g + 1), r, mode=0))
+        uc, uf = rand(h.shape(g + 1), 70 + g), rand(h.shape(g), 80 + g)
+        h.put(h.U, g + 1, uc)
+        h.put(h.U, g, uf)
+        want = uf + oracle.mg_interp(h.level_mesh(g), h.level_mesh(g + 1), uc, mode=0)
+        assert np.array_equal(h.interp_add(g + 1), want)
+    h.close()
+
+
+def test_prolongation_reproduces_nlinear_function(gpu_lib):
+    """Property of tests/unit_tests/unit_test_interp.f90: N-linear interpolation is exact for an N-linear function."""
+    shape = (30, 22, 26)
+    mesh = aniso_mesh(shape)
+    h = mg(gpu_lib, mesh, "NNDNND")
+    M, B = (0.7, -1.3, 0.4), (0.2, 0.5, -0.9)
+
+    def f(ms):
+        x, y, z = ms
+        Z, Y, X = np.meshgrid(z, y, x, indexing="ij")
+        return (M[0] * X + B[0]) * (M[1] * Y + B[1]) * (M[2] * Z + B[2])
+
+    h.put(h.U, 1, f(h.level_mesh(1)))
+    h.put(h.U, 0, np.zeros(shape[::-1]))
+    got = h.interp_add(1)
+    want = f(mesh)
+    assert np.abs(got - want).max() <= 1e-14 * np.abs(want).max()
+    h.close()
+
+
+def test_galerkin_adjointness(gpu_lib):
+    """Property of tests/unit_tests/unit_test_galerkin.f90: <u_c, R u_f> dV_c == <P u_c, u_f> dV_f."""
+    shape = (32, 28, 36)
+    mesh = aniso_mesh(shape)
+    h = mg(gpu_lib, mesh, "NNNNNN")
+    uc, uf = rand(h.shape(1), 90), rand(h.shape(0), 91)
+    h.put(h.R, 0, uf)
+    Ruf = h.restrict(0)
+    h.put(h.U, 1, uc)
+    h.put(h.U, 0, np.zeros(shape[::-1]))
+    Puc = h.interp_add(1)
+    dV = lambda ms: np.prod([m[1] - m[0] for m in ms])
+    lhs = (uc * Ruf).sum() * dV(h.level_mesh(1))
+    rhs = (Puc * uf).sum() * dV(h.level_mesh(0))
+    assert abs(lhs - rhs) <= 1e-12 * max(abs(lhs), abs(rhs))
+    h.close()
+
+
+@pytest.mark.parametrize("du_max", [True, False])
+@pytest.mark.parametrize("shape,copt", [((4, 4, 4), "NDDNDD"), ((5, 6, 7), "DNDDND"), ((16, 16, 4), "DDNDDN"),
+                                        ((4, 4), "NNNN"), ((16, 4), "NNNN"), ((7, 5), "DNND")])
+def test_solve_exact_matches_oracle(gpu_lib, oracle, shape, copt, du_max):
+    """Coarsest-level relaxation solve inside one thread block: same iteration count and field."""
+    mesh = aniso_mesh(shape)
+    rhs = rand(shape, 100)
+    if copt in ("NNNN",):
+        rhs -= rhs.mean()
+    u0 = np.zeros(shape[::-1])
+    h = mg(gpu_lib, mesh, copt, du_max=du_max, ngrids=1)
+    o = oracle.OracleMG(mesh, copt, du_max=du_max, ngrids=1)
+    h.put(h.U, 0, u0)
+    h.put(h.RHS, 0, rhs)
+    it_gpu = h.solve_exact(0)
+    o.load(u0, rhs)
+    it_cpu = o.solve_exact(0)
+    got, want = h.get(h.U, 0), o.u(0)
+    assert abs(it_gpu - it_cpu) <= (0 if (du_max and copt != "NNNN") else 1)
+    assert rel_err(got, want) <= 1e-11
+    if du_max and copt != "NNNN":
+        assert np.array_equal(got, want)
+    h.close()
+
+
+def test_solve_exact_respects_iteration_limit(gpu_lib):
+    shape = (6, 6, 6)
+    h = mg(gpu_lib, aniso_mesh(shape), "NDDNDD", nmax_exact=7, ngrids=1)
+    h.put(h.RHS, 0, rand(shape, 5))
+    assert h.solve_exact(0) == 7
+    h.close()
+
+
+@pytest.mark.parametrize("du_max", [True, False])
+def test_update_u_matches_oracle(gpu_lib, oracle, du_max):
+    shape = (33, 20, 19)
+    h = mg(gpu_lib, aniso_mesh(shape), "NDDNDD", du_max=du_max)
+    a, b = rand(shape, 1), rand(shape, 2)
+    new, dmax, dmean = h.update_u(b, a)
+    onew, omax, omean = oracle.update_u(b, a)
+    assert np.array_equal(new, b) and np.array_equal(onew, b)
+    assert dmax == omax  # max is order independent
+    assert abs(dmean - omean) <= TOL_RED * omean
+    h.close()
+
+
+@pytest.mark.parametrize("shape,copt", [((22, 22, 22), "NDDNDD"), ((33, 18, 25), "DNDDND"), ((40, 24, 17), "DDNDDN")])
+def test_v_cycle_matches_oracle(gpu_lib, oracle, shape, copt):
+    mesh = aniso_mesh(shape)
+    u0 = rand(shape, 11)
+    rhs = rand(shape, 12)
+    h = mg(gpu_lib, mesh, copt)
+    o = oracle.OracleMG(mesh, copt)
+    h.put(h.U, 0, u0)
+    h.put(h.RHS, 0, rhs)
+    o.load(u0, rhs)
+    for _ in range(2):
+        h.v_cycle()
+        o.v_cycle()
+        got, want = h.get(h.U, 0), o.u(0)
+        assert rel_err(got, want) <= TOL
+        assert np.array_equal(got, want)
+    h.close()
+
+
+@pytest.mark.parametrize("mean", [False, True])
+def test_poisson_solve_3d_matches_oracle(gpu_lib, oracle, mean):
+    """solve_poisson_bvp on config-5 style data: u = cos(pi x) sin(pi y) sin(pi z), copt = NDDNDD."""
+    n = 33
+    x = np.linspace(0, 1, n)
+    mesh = [x, x.copy(), x.copy()]
+    Z, Y, X = np.meshgrid(x, x, x, indexing="ij")
+    uex = np.cos(np.pi * X) * np.sin(np.pi * Y) * np.sin(np.pi * Z)
+    rhs = -3 * np.pi ** 2 * uex
+    u0 = np.zeros_like(uex)
+    h = mg(gpu_lib, mesh, "NDDNDD", du_max=not mean)
+    o = oracle.OracleMG(mesh, "NDDNDD", du_max=not mean)
+    ierr, u, du, nc = h.solve(u0, rhs)
+    oierr, ou, odu, onc = o.solve(u0, rhs)
+    assert ierr == oierr == 0
+    assert abs(nc - onc) <= 1
+    assert rel_err(u, ou) <= 1e-10
+    if not mean:
+        assert nc == onc and np.array_equal(u, ou)
+    assert np.abs(u - uex).max() < 5e-3  # O(h^2) truncation error
+    h.close()
+
+
+def test_poisson_solve_2d_pure_neumann_matches_oracle(gpu_lib, oracle):
+    """2D pure-Neumann problem of tests/unit_tests/unit_test_2D_solve.f90: rhs = a1(2x-Lx) + b1(2y-Ly)."""
+    nx, ny = 27, 36
+    x = np.linspace(0, 1.0, nx)
+    y = np.linspace(0, 1.5, ny)
+    Y, X = np.meshgrid(y, x, indexing="ij")
+    rhs = 1.0 * (2 * X - 1.0) + 0.7 * (2 * Y - 1.5)
+    rhs -= rhs.mean()
+    u0 = np.zeros_like(rhs)
+    h = mg(gpu_lib, [x, y], "NNNN")
+    o = oracle.OracleMG([x, y], "NNNN")
+    ierr, u, du, nc = h.solve(u0, rhs)
+    oierr, ou, odu, onc = o.solve(u0, rhs)
+    assert ierr == oierr == 0
+    assert abs(nc - onc) <= 1
+    assert rel_err(u, ou) <= 1e-10
+    h.close()
