@@ -150,11 +150,19 @@ k_relax3d(double* __restrict__ u, const double* __restrict__ rhs, const Grid g, 
     const int i = 2 * m + s;
     if (i >= b.lb[0] && i <= b.ub[0]) {
       const i64 p = (i64)(k - g.k0) * g.ps;
-      double xo;  // the x neighbour that is not Zc; mirrored ghosts coincide with Zc (:113-114)
-      if (s == 0) xo = (m == 0) ? Zc : opp[p + jo - 1];
-      else        xo = (i == g.nx - 1) ? Zc : opp[p + jo + 1];
+      // x neighbours i-1 / i+1 sit at compressed index m-1+s / m+s of the other colour, one of them
+      // being Zc; mirrored Neumann ghosts (index 2 / n-1 in the reference, :113-114) fold onto the
+      // opposite neighbour
+      double xl, xh;
+      if (s == 0) {
+        xl = (m == 0) ? Zc : opp[p + jo - 1];
+        xh = (i == g.nx - 1) ? xl : Zc;
+      } else {
+        xl = Zc;
+        xh = (i == g.nx - 1) ? Zc : opp[p + jo + 1];
+      }
       const double yl = opp[p + jlo], yh = opp[p + jho];
-      double unew = ((xo + Zc) * wx + (yh + yl) * wy) + (Zp + Zm) * wz;  // (:123-125)
+      double unew = ((xh + xl) * wx + (yh + yl) * wy) + (Zp + Zm) * wz;  // (:123-125)
       if (HAS_RHS) unew = unew - rh[p + jo];                             // (:126)
       own[p + jo] = w1 * unew;                                           // (:129)
     }
@@ -225,11 +233,16 @@ k_residual3d(const double* __restrict__ u, const double* __restrict__ rhs, doubl
       const i64 p = (i64)(k - g.k0) * g.ps;
       double res = 0.0;
       if (jin && i >= b.lb[0] && i <= b.ub[0] && k >= b.lb[2] && k <= b.ub[2]) {
-        double xo;
-        if (s == 0) xo = (m == 0) ? Zc : opp[p + jo - 1];
-        else        xo = (i == g.nx - 1) ? Zc : opp[p + jo + 1];
+        double xl, xh;
+        if (s == 0) {
+          xl = (m == 0) ? Zc : opp[p + jo - 1];
+          xh = (i == g.nx - 1) ? xl : Zc;
+        } else {
+          xl = Zc;
+          xh = (i == g.nx - 1) ? Zc : opp[p + jo + 1];
+        }
         const double yl = opp[p + jlo], yh = opp[p + jho];
-        double tt = ((xo + Zc) * wx + (yl + yh) * wy) + (Zm + Zp) * wz;  // (:424-426)
+        double tt = ((xl + xh) * wx + (yl + yh) * wy) + (Zm + Zp) * wz;  // (:424-426)
         if (HAS_RHS) tt = tt - rh[p + jo];
         tt = tt - own[p + jo] * wc;                                       // (:427)
         res = -tt;                                                        // (:430)
