@@ -146,6 +146,10 @@ int ndsm_b200_last_timing(double* out8);
  * 1 = k_residual3d, 2 = k_restrict, 3 = k_interp_add, 4 = update_u reduction (2 launches). */
 void ndsm_b200_profile_enable(int on);
 int ndsm_b200_profile_get(int cls, unsigned long long* count, double* total_ms);
+/* Device and pinned staging buffers are cached between calls (a 513^3 solve needs ~15 GB and cudaMalloc/cudaFree
+ * of that costs more than the solve).  release_workspace returns the cache to CUDA; workspace_bytes reports it. */
+void ndsm_b200_release_workspace(void);
+unsigned long long ndsm_b200_workspace_bytes(void);
 const char* ndsm_b200_version(void);
 
 #ifdef __cplusplus

@@ -6,6 +6,7 @@
 #include <vector>
 
 #include "../../include/ndsm_b200.h"
+#include "pool.hpp"
 #include "vecpot.hpp"
 
 using namespace ndsm;
@@ -62,6 +63,7 @@ static int fail(const NdsmError& e, const char* sub) {
   if (e.code == 2) error_msg("mesh too small for a multigrid hierarchy (min(nshape) < 4)", sub, "NDSM_B200_ERR_SHAPE");
   else if (e.code == 4) error_msg("restriction stencil exceeds compiled capacity", sub, "NDSM_B200_ERR_STENCIL");
   else error_msg("CUDA failure", sub, "NDSM_B200_ERR_CUDA");
+  cudaDeviceSynchronize();  // buffers released by unwinding may be handed out again by the pool
   cudaGetLastError();
   return code;
 }
@@ -110,10 +112,8 @@ static bool all_zero_host(const double* a, size_t n) {
 
 struct DBuf {
   double* p = nullptr;
-  explicit DBuf(size_t n) {
-    if (cudaMalloc(&p, (n ? n : 1) * sizeof(double)) != cudaSuccess) { p = nullptr; throw NdsmError(3); }
-  }
-  ~DBuf() { if (p) cudaFree(p); }
+  explicit DBuf(size_t n) { p = static_cast<double*>(pool_alloc((n ? n : 1) * sizeof(double))); }
+  ~DBuf() { if (p) pool_free(p); }
   DBuf(const DBuf&) = delete;
   DBuf& operator=(const DBuf&) = delete;
 };
@@ -157,8 +157,7 @@ int ndsm_vector_solve(size_t nsize, const int* nshape4, int* ioptc, double* ropt
     double t1 = now_s();
     size_t fsz[6], ftot = 0;
     for (int f = 0; f < 6; ++f) { fsz[f] = (size_t)nshape4[imap_nc[f][0]] * nshape4[imap_nc[f][1]]; ftot += fsz[f]; }
-    double* hfaces = nullptr;
-    CUDA_CHECK(cudaMallocHost(&hfaces, ftot * sizeof(double)));
+    double* hfaces = static_cast<double*>(pool_alloc_host(ftot * sizeof(double)));
     DBuf dfaces(ftot);
     double* bn[6];
     {
@@ -175,7 +174,7 @@ int ndsm_vector_solve(size_t nsize, const int* nshape4, int* ioptc, double* ropt
     const bool zero_guess = all_zero_host(A, 3 * N);
     if (!zero_guess) CUDA_CHECK(cudaMemcpyAsync(dA.p, A, 3 * N * sizeof(double), cudaMemcpyHostToDevice, st));
     CUDA_CHECK(cudaStreamSynchronize(st));
-    cudaFreeHost(hfaces);
+    pool_free_host(hfaces);
     g_report.ms_in = (now_s() - t1) * 1e3;
     if (g_debug) debug_msg(SUB, "Calling compute_vector_potential...");
     int ierr = vector_solve_core(nshape4, iopt, ropt, x, y, z, bn, zero_guess ? nullptr : dA.p, dA.p, dB.p, st,
@@ -344,7 +343,7 @@ static double* handle_array(ndsm_b200_mg* h, int which, int level) {
     if (level > 0) return mg.level(level).rhs;
     if (!h->rhs0) {
       const size_t n = mg.level_doubles(0);
-      CUDA_CHECK(cudaMalloc(&h->rhs0, n * sizeof(double)));
+      h->rhs0 = static_cast<double*>(pool_alloc(n * sizeof(double)));
       CUDA_CHECK(cudaMemsetAsync(h->rhs0, 0, n * sizeof(double), mg.stream()));
       mg.set_level0_rhs(h->rhs0);
     }
@@ -389,7 +388,7 @@ ndsm_b200_mg* ndsm_b200_new_mg_handle(int ndim, const int* nshape, int ngrids, c
 void ndsm_b200_delete_mg_handle(ndsm_b200_mg* h) {
   if (!h) return;
   delete h->mg;
-  if (h->rhs0) cudaFree(h->rhs0);
+  if (h->rhs0) pool_free(h->rhs0);
   delete h;
 }
 int ndsm_b200_mg_set_options(ndsm_b200_mg* h, int ms, double ex_tol, const char* copt) {
@@ -638,6 +637,11 @@ int ndsm_b200_profile_get(int cls, unsigned long long* count, double* total_ms) 
   prof_get(cls, count, total_ms);
   return 0;
 }
+void ndsm_b200_release_workspace(void) {
+  cudaDeviceSynchronize();
+  pool_release();
+}
+unsigned long long ndsm_b200_workspace_bytes(void) { return (unsigned long long)pool_cached_bytes(); }
 const char* ndsm_b200_version(void) { return "ndsm-b200 0.1 (sm_100a, fp64, -fmad=false)"; }
 
 }  // extern "C"

@@ -118,6 +118,16 @@ __device__ double block_max(double v, double* red) {
 // per colour pass = 24 B/pt per full sweep (16 B/pt when rhs == 0).
 // ---------------------------------------------------------------------------------------
 #define RELAX_THREADS 256
+#define RELAX_UNROLL 4  // z-planes whose loads are issued together (memory-level parallelism)
+
+// offset (in compressed elements, relative to the thread's own column) of the x neighbour that is not
+// the in-column value Zc; 0 means "coincides with Zc" (mirrored Neumann ghost, ndsm_optimized.f90:113-114)
+__device__ __forceinline__ int x_other_offset(int s, int m, int i, int nx) {
+  if (i > nx - 1) return 0;
+  if (s == 0) return (m == 0) ? 0 : -1;
+  return (i == nx - 1) ? 0 : 1;
+}
+
 template <bool HAS_RHS>
 __global__ void __launch_bounds__(RELAX_THREADS)
 k_relax3d(double* __restrict__ u, const double* __restrict__ rhs, const Grid g, const Bounds b, const int colour,
@@ -139,35 +149,46 @@ k_relax3d(double* __restrict__ u, const double* __restrict__ rhs, const Grid g, 
   const int jh = (j + 1 > g.ny - 1) ? g.ny - 2 : j + 1;
   const i64 jo = (i64)j * g.hp + m, jlo = (i64)jl * g.hp + m, jho = (i64)jh * g.hp + m;
 
-  int k = kbeg;
-  const int kl0 = (k - 1 < 0) ? 1 : k - 1;
+  const int kl0 = (kbeg - 1 < 0) ? 1 : kbeg - 1;
   double Zm = opp[(i64)(kl0 - g.k0) * g.ps + jo];
-  double Zc = opp[(i64)(k - g.k0) * g.ps + jo];
-  for (; k <= kend; ++k) {
-    const int kh = (k + 1 > g.nz - 1) ? g.nz - 2 : k + 1;  // (:119-120)
-    const double Zp = opp[(i64)(kh - g.k0) * g.ps + jo];
-    const int s = (j + k + colour) & 1;
-    const int i = 2 * m + s;
-    if (i >= b.lb[0] && i <= b.ub[0]) {
+  double Zc = opp[(i64)(kbeg - g.k0) * g.ps + jo];
+  for (int k0 = kbeg; k0 <= kend; k0 += RELAX_UNROLL) {
+    // phase 1: issue every load of the next RELAX_UNROLL planes (all independent)
+    double Zn[RELAX_UNROLL], XO[RELAX_UNROLL], YL[RELAX_UNROLL], YH[RELAX_UNROLL], RH[RELAX_UNROLL];
+#pragma unroll
+    for (int q = 0; q < RELAX_UNROLL; ++q) {
+      const int k = min(k0 + q, kend);
+      const int kh = (k + 1 > g.nz - 1) ? g.nz - 2 : k + 1;  // (:119-120)
       const i64 p = (i64)(k - g.k0) * g.ps;
-      // x neighbours i-1 / i+1 sit at compressed index m-1+s / m+s of the other colour, one of them
-      // being Zc; mirrored Neumann ghosts (index 2 / n-1 in the reference, :113-114) fold onto the
-      // opposite neighbour
-      double xl, xh;
-      if (s == 0) {
-        xl = (m == 0) ? Zc : opp[p + jo - 1];
-        xh = (i == g.nx - 1) ? xl : Zc;
-      } else {
-        xl = Zc;
-        xh = (i == g.nx - 1) ? Zc : opp[p + jo + 1];
-      }
-      const double yl = opp[p + jlo], yh = opp[p + jho];
-      double unew = ((xh + xl) * wx + (yh + yl) * wy) + (Zp + Zm) * wz;  // (:123-125)
-      if (HAS_RHS) unew = unew - rh[p + jo];                             // (:126)
-      own[p + jo] = w1 * unew;                                           // (:129)
+      const int s = (j + k + colour) & 1;
+      const int i = 2 * m + s;
+      Zn[q] = opp[(i64)(kh - g.k0) * g.ps + jo];
+      XO[q] = opp[p + jo + x_other_offset(s, m, i, g.nx)];
+      YL[q] = opp[p + jlo];
+      YH[q] = opp[p + jho];
+      RH[q] = HAS_RHS ? rh[p + jo] : 0.0;
     }
-    Zm = Zc;
-    Zc = Zp;
+    // phase 2: update
+#pragma unroll
+    for (int q = 0; q < RELAX_UNROLL; ++q) {
+      const int k = k0 + q;
+      if (k <= kend) {
+        const int s = (j + k + colour) & 1;
+        const int i = 2 * m + s;
+        if (i >= b.lb[0] && i <= b.ub[0]) {
+          // x neighbours i-1 / i+1 sit at compressed index m-1+s / m+s of the other colour, one of them
+          // being the in-column value Zc
+          double xl, xh;
+          if (s == 0) { xl = XO[q]; xh = (i == g.nx - 1) ? xl : Zc; }
+          else        { xl = Zc;    xh = XO[q]; }
+          double unew = ((xh + xl) * wx + (YH[q] + YL[q]) * wy) + (Zn[q] + Zm) * wz;  // (:123-125)
+          if (HAS_RHS) unew = unew - RH[q];                                           // (:126)
+          own[(i64)(k - g.k0) * g.ps + jo] = w1 * unew;                               // (:129)
+        }
+        Zm = Zc;
+        Zc = Zn[q];
+      }
+    }
   }
 }
 
@@ -220,37 +241,48 @@ k_residual3d(const double* __restrict__ u, const double* __restrict__ rhs, doubl
   const i64 jo = (i64)j * g.hp + m, jlo = (i64)jl * g.hp + m, jho = (i64)jh * g.hp + m;
   const bool jin = (j >= b.lb[1] && j <= b.ub[1]);
 
-  int k = kbeg;
-  const int kl0 = (k - 1 < 0) ? 1 : k - 1;
+  const int kl0 = (kbeg - 1 < 0) ? 1 : kbeg - 1;
   double Zm = opp[(i64)(kl0 - g.k0) * g.ps + jo];
-  double Zc = opp[(i64)(k - g.k0) * g.ps + jo];
-  for (; k <= kend; ++k) {
-    const int kh = (k + 1 > g.nz - 1) ? g.nz - 2 : k + 1;
-    const double Zp = opp[(i64)(kh - g.k0) * g.ps + jo];
-    const int s = (j + k + colour) & 1;
-    const int i = 2 * m + s;
-    if (i < g.nx) {
+  double Zc = opp[(i64)(kbeg - g.k0) * g.ps + jo];
+  for (int k0 = kbeg; k0 <= kend; k0 += RELAX_UNROLL) {
+    double Zn[RELAX_UNROLL], XO[RELAX_UNROLL], YL[RELAX_UNROLL], YH[RELAX_UNROLL], RH[RELAX_UNROLL], UC[RELAX_UNROLL];
+#pragma unroll
+    for (int q = 0; q < RELAX_UNROLL; ++q) {
+      const int k = min(k0 + q, kend);
+      const int kh = (k + 1 > g.nz - 1) ? g.nz - 2 : k + 1;
       const i64 p = (i64)(k - g.k0) * g.ps;
-      double res = 0.0;
-      if (jin && i >= b.lb[0] && i <= b.ub[0] && k >= b.lb[2] && k <= b.ub[2]) {
-        double xl, xh;
-        if (s == 0) {
-          xl = (m == 0) ? Zc : opp[p + jo - 1];
-          xh = (i == g.nx - 1) ? xl : Zc;
-        } else {
-          xl = Zc;
-          xh = (i == g.nx - 1) ? Zc : opp[p + jo + 1];
-        }
-        const double yl = opp[p + jlo], yh = opp[p + jho];
-        double tt = ((xl + xh) * wx + (yl + yh) * wy) + (Zm + Zp) * wz;  // (:424-426)
-        if (HAS_RHS) tt = tt - rh[p + jo];
-        tt = tt - own[p + jo] * wc;                                       // (:427)
-        res = -tt;                                                        // (:430)
-      }
-      ro[p + jo] = res;
+      const int s = (j + k + colour) & 1;
+      const int i = 2 * m + s;
+      Zn[q] = opp[(i64)(kh - g.k0) * g.ps + jo];
+      XO[q] = opp[p + jo + x_other_offset(s, m, i, g.nx)];
+      YL[q] = opp[p + jlo];
+      YH[q] = opp[p + jho];
+      UC[q] = own[p + jo];
+      RH[q] = HAS_RHS ? rh[p + jo] : 0.0;
     }
-    Zm = Zc;
-    Zc = Zp;
+#pragma unroll
+    for (int q = 0; q < RELAX_UNROLL; ++q) {
+      const int k = k0 + q;
+      if (k <= kend) {
+        const int s = (j + k + colour) & 1;
+        const int i = 2 * m + s;
+        if (i < g.nx) {
+          double res = 0.0;
+          if (jin && i >= b.lb[0] && i <= b.ub[0] && k >= b.lb[2] && k <= b.ub[2]) {
+            double xl, xh;
+            if (s == 0) { xl = XO[q]; xh = (i == g.nx - 1) ? xl : Zc; }
+            else        { xl = Zc;    xh = XO[q]; }
+            double tt = ((xl + xh) * wx + (YL[q] + YH[q]) * wy) + (Zm + Zn[q]) * wz;  // (:424-426)
+            if (HAS_RHS) tt = tt - RH[q];
+            tt = tt - UC[q] * wc;                                                     // (:427)
+            res = -tt;                                                                // (:430)
+          }
+          ro[(i64)(k - g.k0) * g.ps + jo] = res;
+        }
+        Zm = Zc;
+        Zc = Zn[q];
+      }
+    }
   }
 }
 
@@ -342,7 +374,7 @@ void residual2d(const double* u, const double* rhs, double* r, const Grid& g, co
 // Reductions: K6 (update_u / du_metrics) and the pure-Neumann mean.
 // Two-stage: REDUCE_BLOCKS partial results, then one block combines them in fixed order.
 // ---------------------------------------------------------------------------------------
-#define REDUCE_BLOCKS 592  // 148 SMs x 4
+#define REDUCE_BLOCKS 1184  // 148 SMs x 8 resident 256-thread blocks
 #define REDUCE_THREADS 256
 size_t reduce_scratch_doubles() { return 2 * REDUCE_BLOCKS + 8; }
 
@@ -350,17 +382,34 @@ template <bool COPY>
 __global__ void __launch_bounds__(REDUCE_THREADS)
 k_diff_partial(double* __restrict__ a, const double* __restrict__ b, const i64 n_per_colour, const i64 cs,
                double* __restrict__ part) {
+  // 16-byte accesses, four independent load pairs in flight per thread (planes are 256-byte multiples)
   __shared__ double red[40];
   double dmax = 0.0, dsum = 0.0;
+  const i64 n2 = n_per_colour >> 1;
+  const i64 stride = (i64)gridDim.x * REDUCE_THREADS;
   for (int c = 0; c < 2; ++c) {
-    double* __restrict__ ac = a + c * cs;
-    const double* __restrict__ bc = b + c * cs;
-    for (i64 e = (i64)blockIdx.x * REDUCE_THREADS + threadIdx.x; e < n_per_colour;
-         e += (i64)gridDim.x * REDUCE_THREADS) {
-      const double bv = bc[e];
-      const double d = fabs(ac[e] - bv);
-      dmax = fmax(dmax, d);
-      dsum += d;
+    double2* __restrict__ ac = reinterpret_cast<double2*>(a + c * cs);
+    const double2* __restrict__ bc = reinterpret_cast<const double2*>(b + c * cs);
+    i64 e = (i64)blockIdx.x * REDUCE_THREADS + threadIdx.x;
+    for (; e + 3 * stride < n2; e += 4 * stride) {
+      double2 bv[4], av[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) { bv[q] = bc[e + q * stride]; av[q] = ac[e + q * stride]; }
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const double d0 = fabs(av[q].x - bv[q].x), d1 = fabs(av[q].y - bv[q].y);
+        dmax = fmax(dmax, fmax(d0, d1));
+        dsum += d0;
+        dsum += d1;
+        if (COPY) ac[e + q * stride] = bv[q];
+      }
+    }
+    for (; e < n2; e += stride) {
+      const double2 bv = bc[e], av = ac[e];
+      const double d0 = fabs(av.x - bv.x), d1 = fabs(av.y - bv.y);
+      dmax = fmax(dmax, fmax(d0, d1));
+      dsum += d0;
+      dsum += d1;
       if (COPY) ac[e] = bv;
     }
   }
@@ -390,7 +439,7 @@ __global__ void __launch_bounds__(REDUCE_THREADS) k_diff_final(const double* __r
 void diff_reduce(double* a, const double* b, const Grid& g, bool copy, double* scratch, double* out,
                  cudaStream_t st) {
   const i64 n = (i64)g.nzl * g.ps;
-  const int nb = (int)std::min<i64>(REDUCE_BLOCKS, std::max<i64>(1, cdiv(n, REDUCE_THREADS)));
+  const int nb = (int)std::min<i64>(REDUCE_BLOCKS, std::max<i64>(1, cdiv(n / 8, REDUCE_THREADS)));
   if (copy)
     k_diff_partial<true><<<nb, REDUCE_THREADS, 0, st>>>(a, b, n, g.cs, scratch);
   else
@@ -631,6 +680,14 @@ k_solve_exact(double* __restrict__ u, const double* __restrict__ rhs, const Grid
   }
 }
 
+void solve_exact_prepare() {
+  static bool attr_set = false;
+  if (attr_set) return;
+  cudaFuncSetAttribute(k_solve_exact<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  cudaFuncSetAttribute(k_solve_exact<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  attr_set = true;
+}
+
 bool solve_exact_smem(int ndim, double* u, const double* rhs, const Grid& g, const Bounds& b, int first_colour,
                       const Weights& w, bool all_neumann, bool du_max, double ex_tol, int nmax, int* info,
                       cudaStream_t st) {
@@ -638,12 +695,7 @@ bool solve_exact_smem(int ndim, double* u, const double* rhs, const Grid& g, con
   const size_t bytes = (size_t)N * 3 * sizeof(double);
   if (bytes > 200 * 1024 || g.nzl != g.nz) return false;
   int threads = (int)std::min<i64>(1024, std::max<i64>(64, ((N / 2 + 31) / 32) * 32));
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaFuncSetAttribute(k_solve_exact<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    cudaFuncSetAttribute(k_solve_exact<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    attr_set = true;
-  }
+  solve_exact_prepare();
   if (ndim == 3)
     k_solve_exact<3><<<1, threads, bytes, st>>>(u, rhs, g, b, first_colour, w.wx, w.wy, w.wz, w.w1,
                                                 all_neumann ? 1 : 0, du_max ? 1 : 0, ex_tol, nmax, info);

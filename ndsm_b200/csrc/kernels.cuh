@@ -67,6 +67,7 @@ bool solve_exact_smem(int ndim, double* u, const double* rhs, const Grid& g, con
 // ndsm_multigrid_core.f90:1077-1122).  With copy=false it is du_metrics (:808-853) and leaves a untouched.
 void diff_reduce(double* a, const double* b, const Grid& g, bool copy, double* scratch, double* out, cudaStream_t st);
 size_t reduce_scratch_doubles();
+void solve_exact_prepare();  // one-time function attributes (call before stream capture)
 
 // layout conversion: dense (nx,ny,nzl) x-fastest <-> colour-split; split = dense - shift
 void split_from_dense(const double* dense, double* split, const Grid& g, double shift, cudaStream_t st);

@@ -1,8 +1,10 @@
 // mg.cu -- multigrid hierarchy, transfer tables and the V-cycle loop (host orchestration).
 // See mg.hpp for the reference functions this mirrors.
 #include "mg.hpp"
+#include "pool.hpp"
 
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 
 namespace ndsm {
@@ -135,14 +137,6 @@ std::vector<HostLevel> build_hierarchy(int ndim, const int* shape, int ngrids, c
   return lv;
 }
 
-template <typename T>
-static T* upload(const std::vector<T>& v, cudaStream_t st) {
-  T* d = nullptr;
-  CUDA_CHECK(cudaMalloc(&d, sizeof(T) * (v.empty() ? 1 : v.size())));
-  if (!v.empty()) CUDA_CHECK(cudaMemcpyAsync(d, v.data(), sizeof(T) * v.size(), cudaMemcpyHostToDevice, st));
-  return d;
-}
-
 MG::MG(int ndim, const int* shape, int ngrids, const double* const* mesh, cudaStream_t st) : ndim_(ndim), st_(st) {
   std::vector<HostLevel> hl = build_hierarchy(ndim, shape, ngrids, mesh);
   ngrids = (int)hl.size();
@@ -166,7 +160,7 @@ MG::MG(int ndim, const int* shape, int ngrids, const double* const* mesh, cudaSt
   const i64 off_sav = take(2 * lv_[ngrids - 1].g.cs);
   const i64 off_scr = take((i64)reduce_scratch_doubles());
   const i64 off_out = take(32);
-  CUDA_CHECK(cudaMalloc(&arena_, (size_t)total * sizeof(double)));
+  arena_ = static_cast<double*>(pool_alloc((size_t)total * sizeof(double)));
   CUDA_CHECK(cudaMemsetAsync(arena_, 0, (size_t)total * sizeof(double), st_));
   for (int g = 0; g < ngrids; ++g) {
     lv_[g].u = arena_ + off_u[g];
@@ -177,26 +171,41 @@ MG::MG(int ndim, const int* shape, int ngrids, const double* const* mesh, cudaSt
   scratch_ = arena_ + off_scr;
   d_out_ = arena_ + off_out;
   d_info_ = reinterpret_cast<int*>(arena_ + off_out + 8);
-  CUDA_CHECK(cudaMallocHost(&h_out_, 8 * sizeof(double)));
+  h_out_ = static_cast<double*>(pool_alloc_host(8 * sizeof(double)));
 
-  // --- upload the transfer tables
+  // --- pack every transfer table into one int and one double buffer: two uploads per hierarchy
+  std::vector<int> hi;
+  std::vector<double> hd;
+  struct Off { size_t lo, wl, wh, first, count, c2; };
+  std::vector<Off> offs((size_t)ngrids * 3);
+  auto pad = [](size_t n) { return (n + 31) / 32 * 32; };
   for (int g = 0; g + 1 < ngrids; ++g)
     for (int d = 0; d < 3; ++d) {
-      lv_[g].it[d] = InterpTab{upload(hl[g].lo[d], st_), upload(hl[g].wl[d], st_), upload(hl[g].wh[d], st_)};
-      lv_[g].rt[d] = RestrictTab{upload(hl[g].first[d], st_), upload(hl[g].count[d], st_), upload(hl[g].c2[d], st_), hl[g].w2[d]};
+      Off& o = offs[(size_t)g * 3 + d];
+      auto put_i = [&](const std::vector<int>& v) { size_t at = hi.size(); hi.insert(hi.end(), v.begin(), v.end()); hi.resize(pad(hi.size())); return at; };
+      auto put_d = [&](const std::vector<double>& v) { size_t at = hd.size(); hd.insert(hd.end(), v.begin(), v.end()); hd.resize(pad(hd.size())); return at; };
+      o.lo = put_i(hl[g].lo[d]); o.first = put_i(hl[g].first[d]); o.count = put_i(hl[g].count[d]);
+      o.wl = put_d(hl[g].wl[d]); o.wh = put_d(hl[g].wh[d]); o.c2 = put_d(hl[g].c2[d]);
     }
-  CUDA_CHECK(cudaStreamSynchronize(st_));  // host tables go out of scope
+  tab_i_ = static_cast<int*>(pool_alloc((hi.size() + 32) * sizeof(int)));
+  tab_d_ = static_cast<double*>(pool_alloc((hd.size() + 32) * sizeof(double)));
+  if (!hi.empty()) CUDA_CHECK(cudaMemcpyAsync(tab_i_, hi.data(), hi.size() * sizeof(int), cudaMemcpyHostToDevice, st_));
+  if (!hd.empty()) CUDA_CHECK(cudaMemcpyAsync(tab_d_, hd.data(), hd.size() * sizeof(double), cudaMemcpyHostToDevice, st_));
+  for (int g = 0; g + 1 < ngrids; ++g)
+    for (int d = 0; d < 3; ++d) {
+      const Off& o = offs[(size_t)g * 3 + d];
+      lv_[g].it[d] = InterpTab{tab_i_ + o.lo, tab_d_ + o.wl, tab_d_ + o.wh};
+      lv_[g].rt[d] = RestrictTab{tab_i_ + o.first, tab_i_ + o.count, tab_d_ + o.c2, hl[g].w2[d]};
+    }
+  CUDA_CHECK(cudaStreamSynchronize(st_));  // host staging vectors go out of scope
   set_options(5, 1e-13, "NNNNNN", true, 10000);
 }
 
 MG::~MG() {
-  for (size_t g = 0; g + 1 < lv_.size(); ++g)
-    for (int d = 0; d < 3; ++d) {
-      cudaFree((void*)lv_[g].it[d].lo); cudaFree((void*)lv_[g].it[d].wl); cudaFree((void*)lv_[g].it[d].wh);
-      cudaFree((void*)lv_[g].rt[d].first); cudaFree((void*)lv_[g].rt[d].count); cudaFree((void*)lv_[g].rt[d].c2);
-    }
-  cudaFree(arena_);
-  cudaFreeHost(h_out_);
+  pool_free(tab_i_);
+  pool_free(tab_d_);
+  pool_free(arena_);
+  pool_free_host(h_out_);
 }
 
 void MG::set_options(int ms, double ex_tol, const char* copt, bool du_max, int nmax_exact) {
@@ -318,52 +327,118 @@ int MG::last_nexact() {
   return info[0];
 }
 
-// solve_poisson_bvp (ndsm_poisson.f90:63-155)
-int MG::solve(double* u, const double* rhs, double vc_tol, int nmax, double* du_last, SolveTrace* tr) {
+// true when solve_exact() on level g will take the single-block shared-memory path (no host sync)
+bool MG::coarsest_in_smem(const double* rhs_coarsest) const {
+  const Grid& g = lv_.back().g;
+  return rhs_coarsest != nullptr && (size_t)g.nx * g.ny * g.nz * 3 * sizeof(double) <= 200 * 1024 && g.nzl == g.nz;
+}
+
+// one iteration of solve_poisson_bvp's loop body, enqueue only: V-cycle, update_u, results to pinned memory
+void MG::enqueue_cycle(double* u) {
+  Level& L0 = lv_[0];
+  v_cycle();
+  if (ndim_ == 3) prof_begin(PROF_DIFF0, st_);
+  diff_reduce(u, L0.u, L0.g, true, scratch_, d_out_, st_);  // update_u :122
+  if (ndim_ == 3) prof_end(PROF_DIFF0, st_);
+  CUDA_CHECK(cudaMemcpyAsync(h_out_, d_out_, 2 * sizeof(double), cudaMemcpyDeviceToHost, st_));
+  CUDA_CHECK(cudaMemcpyAsync(h_out_ + 2, d_info_, 2 * sizeof(int), cudaMemcpyDeviceToHost, st_));
+}
+
+// solve_poisson_bvp (ndsm_poisson.f90:63-155), split into begin / enqueue / poll / end so that several
+// independent solves (the six chi faces) can be interleaved on their own streams by one host thread.
+void MG::solve_begin(double* u, const double* rhs, double vc_tol, int nmax, SolveTrace* tr) {
   Level& L0 = lv_[0];
   const size_t bytes0 = (size_t)2 * L0.g.cs * sizeof(double);
-  double* zero_rhs = nullptr;
+  ss_ = SolveState();
+  ss_.u = u; ss_.vc_tol = vc_tol; ss_.nmax = nmax; ss_.tr = tr;
   if (!rhs && (ndim_ == 2 || lv_.size() == 1)) {  // kernels of those paths always read rhs
-    CUDA_CHECK(cudaMalloc(&zero_rhs, bytes0));
-    CUDA_CHECK(cudaMemsetAsync(zero_rhs, 0, bytes0, st_));
-    rhs = zero_rhs;
+    ss_.zero_rhs = static_cast<double*>(pool_alloc(bytes0));
+    CUDA_CHECK(cudaMemsetAsync(ss_.zero_rhs, 0, bytes0, st_));
+    rhs = ss_.zero_rhs;
   }
   rhs0_ = rhs;
   CUDA_CHECK(cudaMemcpyAsync(L0.u, u, bytes0, cudaMemcpyDeviceToDevice, st_));  // :100
-  double du = HUGE_VAL;
-  bool converged = false;
-  int ierr = 0;
-  const double N = (double)((i64)L0.g.nx * L0.g.ny * L0.g.nz);
-  if (g_debug) debug_msg("solve_poisson_bvp", "Performing V cycles...");
-  for (int i = 0; i < nmax; ++i) {
-    v_cycle();
-    if (ndim_ == 3) prof_begin(PROF_DIFF0, st_);
-    diff_reduce(u, L0.u, L0.g, true, scratch_, d_out_, st_);  // update_u :122
-    if (ndim_ == 3) prof_end(PROF_DIFF0, st_);
-    CUDA_CHECK(cudaMemcpyAsync(h_out_, d_out_, 2 * sizeof(double), cudaMemcpyDeviceToHost, st_));
-    CUDA_CHECK(cudaMemcpyAsync(h_out_ + 2, d_info_, 2 * sizeof(int), cudaMemcpyDeviceToHost, st_));
-    CUDA_CHECK(cudaStreamSynchronize(st_));
-    prof_collect();
-    du = du_max_ ? h_out_[0] : h_out_[1] / N;
-    const int* info = reinterpret_cast<const int*>(h_out_ + 2);
-    if (tr) { tr->du.push_back(du); tr->nexact.push_back(info[0]); }
-    if (!info[1]) printf(" Warning: IOPT_NMAXEX exceeded. Coarse-mesh solution may not have converged\n");
-    if (g_debug) {
-      char s[64];
-      snprintf(s, sizeof s, "Solution delta: %12.4E", du);
-      debug_msg("solve_poisson_bvp", s);
+
+  // The loop body is a static launch sequence (the coarsest solve iterates inside one kernel), so it is
+  // captured once into a CUDA graph and replayed every V-cycle: ~250-500 launches per cycle otherwise.
+  static const bool graphs_on = !(getenv("NDSM_B200_GRAPH") && atoi(getenv("NDSM_B200_GRAPH")) == 0);
+  const double* rhs_coarsest = (lv_.size() == 1) ? rhs0_ : lv_.back().rhs;
+  if (graphs_on && !prof_enabled() && nmax > 1 && coarsest_in_smem(rhs_coarsest)) {
+    solve_exact_prepare();
+    const unsigned long long l0 = g_launches;
+    cudaGraph_t graph = nullptr;
+    CUDA_CHECK(cudaStreamBeginCapture(st_, cudaStreamCaptureModeThreadLocal));
+    try {
+      enqueue_cycle(u);
+    } catch (...) {
+      cudaStreamEndCapture(st_, &graph);
+      if (graph) cudaGraphDestroy(graph);
+      throw;
     }
-    if (du < vc_tol) { converged = true; break; }  // :136 strict <
+    CUDA_CHECK(cudaStreamEndCapture(st_, &graph));
+    ss_.graph_launches = g_launches - l0;
+    g_launches = l0;  // nothing ran during capture
+    cudaError_t e = cudaGraphInstantiate(&ss_.gexec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (e != cudaSuccess) { ss_.gexec = nullptr; cudaGetLastError(); }
   }
-  if (du_last) *du_last = du;
-  if (!converged) {
+  if (g_debug) debug_msg("solve_poisson_bvp", "Performing V cycles...");
+  if (nmax <= 0) ss_.done = true;
+}
+
+void MG::solve_enqueue() {
+  if (ss_.done) return;
+  if (ss_.gexec) {
+    CUDA_CHECK(cudaGraphLaunch(ss_.gexec, st_));
+    g_launches += ss_.graph_launches;
+  } else {
+    enqueue_cycle(ss_.u);
+  }
+}
+
+bool MG::solve_poll() {
+  if (ss_.done) return true;
+  const Level& L0 = lv_[0];
+  const double N = (double)((i64)L0.g.nx * L0.g.ny * L0.g.nz);
+  CUDA_CHECK(cudaStreamSynchronize(st_));
+  prof_collect();
+  ss_.du = du_max_ ? h_out_[0] : h_out_[1] / N;
+  const int* info = reinterpret_cast<const int*>(h_out_ + 2);
+  if (ss_.tr) { ss_.tr->du.push_back(ss_.du); ss_.tr->nexact.push_back(info[0]); }
+  if (!info[1]) printf(" Warning: IOPT_NMAXEX exceeded. Coarse-mesh solution may not have converged\n");
+  if (g_debug) {
+    char s[64];
+    snprintf(s, sizeof s, "Solution delta: %12.4E", ss_.du);
+    debug_msg("solve_poisson_bvp", s);
+  }
+  ++ss_.it;
+  if (ss_.du < ss_.vc_tol) { ss_.converged = true; ss_.done = true; }  // :136 strict <
+  else if (ss_.it >= ss_.nmax) ss_.done = true;
+  return ss_.done;
+}
+
+int MG::solve_end(double* du_last) {
+  if (ss_.gexec) cudaGraphExecDestroy(ss_.gexec);
+  ss_.gexec = nullptr;
+  if (du_last) *du_last = ss_.du;
+  int ierr = 0;
+  if (!ss_.converged) {
     ierr = 1;
     printf(" Warning: IOPT_NCYCLES exceeded. V-cycle iteration may not have converged\n");
   }
-  if (tr) tr->ierr = ierr;
+  if (ss_.tr) ss_.tr->ierr = ierr;
   rhs0_ = nullptr;
-  if (zero_rhs) { CUDA_CHECK(cudaStreamSynchronize(st_)); cudaFree(zero_rhs); }
+  if (ss_.zero_rhs) { CUDA_CHECK(cudaStreamSynchronize(st_)); pool_free(ss_.zero_rhs); ss_.zero_rhs = nullptr; }
   return ierr;
+}
+
+int MG::solve(double* u, const double* rhs, double vc_tol, int nmax, double* du_last, SolveTrace* tr) {
+  solve_begin(u, rhs, vc_tol, nmax, tr);
+  while (!ss_.done) {
+    solve_enqueue();
+    solve_poll();
+  }
+  return solve_end(du_last);
 }
 
 }  // namespace ndsm

@@ -74,6 +74,14 @@ class MG {
   // solve_poisson_bvp: u (colour-split, level-0 layout) in/out; rhs colour-split or nullptr (== 0)
   int solve(double* u, const double* rhs, double vc_tol, int nmax, double* du_last, SolveTrace* tr);
   void set_level0_rhs(const double* rhs) { rhs0_ = rhs; }
+  // the same solve as a state machine (one outstanding solve per MG instance)
+  void solve_begin(double* u, const double* rhs, double vc_tol, int nmax, SolveTrace* tr);
+  void solve_enqueue();            // enqueue the next V-cycle (+ update_u) on the stream
+  bool solve_poll();               // wait for it, read du; true when converged or nmax reached
+  int solve_end(double* du_last);  // returns ierr
+  bool solve_done() const { return ss_.done; }
+  void enqueue_cycle(double* u);  // V-cycle + update_u + result copies (no sync)
+  bool coarsest_in_smem(const double* rhs_coarsest) const;
 
   cudaStream_t stream() const { return st_; }
   bool du_max() const { return du_max_; }
@@ -92,15 +100,25 @@ class MG {
   bool all_neumann_ = false;
   int first_colour_ = 0;
   const double* rhs0_ = nullptr;  // level-0 rhs for the current solve (nullptr == 0)
-  double* arena_ = nullptr;       // one allocation for all level arrays and tables
+  double* arena_ = nullptr;       // one allocation for all level arrays
+  int* tab_i_ = nullptr;          // packed transfer tables
+  double* tab_d_ = nullptr;
   double* r_ = nullptr;           // residual scratch (level-0 sized)
   double* usav_ = nullptr;        // coarsest u_sav for the fallback solve_exact
   double* scratch_ = nullptr;     // reduction scratch
   double* d_out_ = nullptr;       // [2] device result of reductions
   int* d_info_ = nullptr;         // [2] coarsest-solve iterations / converged
   double* h_out_ = nullptr;       // pinned [4]: du_max, du_sum, + info
-  int last_nexact_host_ = 0;
-  bool warned_exact_ = false;
+  struct SolveState {
+    double* u = nullptr;
+    double vc_tol = 0, du = 1.7976931348623157e308;
+    int nmax = 0, it = 0;
+    bool converged = false, done = false;
+    cudaGraphExec_t gexec = nullptr;
+    unsigned long long graph_launches = 0;
+    SolveTrace* tr = nullptr;
+    double* zero_rhs = nullptr;
+  } ss_;
 };
 
 }  // namespace ndsm

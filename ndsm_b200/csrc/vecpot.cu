@@ -3,6 +3,7 @@
 // solves -> flux-balance fields -> curl.  Everything between the face upload and the final
 // dense A/B arrays stays resident in HBM.
 #include "vecpot.hpp"
+#include "pool.hpp"
 
 #include <chrono>
 #include <cmath>
@@ -24,10 +25,8 @@ struct DevBuf {  // RAII device allocation
   double* p = nullptr;
   DevBuf() {}
   explicit DevBuf(size_t n) { alloc(n); }
-  void alloc(size_t n) {
-    if (cudaMalloc(&p, n * sizeof(double)) != cudaSuccess) { p = nullptr; throw NdsmError(3); }
-  }
-  ~DevBuf() { if (p) cudaFree(p); }
+  void alloc(size_t n) { p = static_cast<double*>(pool_alloc(n * sizeof(double))); }
+  ~DevBuf() { if (p) pool_free(p); }
   DevBuf(const DevBuf&) = delete;
   DevBuf& operator=(const DevBuf&) = delete;
 };
@@ -91,36 +90,72 @@ int vector_solve_core(const int* nshape, const long long* iopt, const double* ro
   DevBuf At[6][2];
   int ierr_last = 0;
   if (g_debug) debug_msg("compute_vector_potential", "Solve BVP on each boundary...");
-  for (int pair = 0; pair < 3; ++pair) {  // faces (1,2), (3,4), (5,6) share shape and mesh
-    const int f0 = 2 * pair;
-    const int sh2[3] = {n1[f0], n2[f0], 1};
-    const double* m2[2] = {mesh[imap_nc[f0][0]], mesh[imap_nc[f0][1]]};
-    MG mg(2, sh2, -1, m2, st);
-    mg.set_options((int)iopt[IOPT_MS], ropt[ROPT_CTOL], "NNNN", use_du_max, (int)iopt[IOPT_NMAXEX]);  // :355-357
-    const Grid g2 = mg.level(0).g;
-    DevBuf chi(2 * (size_t)g2.cs), rhs(2 * (size_t)g2.cs);
-    CUDA_CHECK(cudaMemsetAsync(rhs.p, 0, 2 * (size_t)g2.cs * sizeof(double), st));
-    for (int f = f0; f < f0 + 2; ++f) {
-      CUDA_CHECK(cudaMemsetAsync(chi.p, 0, 2 * (size_t)g2.cs * sizeof(double), st));  // :345
-      split_from_dense(bn[f], rhs.p, g2, phi[f] / Aq[f], st);                         // :348
-      double du_last;
-      ierr_last = mg.solve(chi.p, rhs.p, ropt[ROPT_VTOL], (int)iopt[IOPT_NCYCLES], &du_last, &rep.solves[f]);
+  {
+    // The six chi problems are independent (ndsm_vector_potential.f90:338-365) and each is a chain of tiny,
+    // latency-bound kernels, so they run concurrently: one hierarchy and one stream per face, V-cycles
+    // interleaved by this host thread.  (With the debug flag they run one after the other so that the
+    // reference's message order is kept.)
+    struct FaceSolve {
+      std::unique_ptr<MG> mg;
+      DevBuf chi, rhs;
+      cudaStream_t st = nullptr;
+      int ierr = 0;
+    } fs[6];
+    struct StreamGuard {
+      FaceSolve* f;
+      ~StreamGuard() { for (int i = 0; i < 6; ++i) if (f[i].st) cudaStreamDestroy(f[i].st); }
+    } guard{fs};
+    CUDA_CHECK(cudaStreamSynchronize(st));
+    for (int f = 0; f < 6; ++f) {
+      CUDA_CHECK(cudaStreamCreateWithFlags(&fs[f].st, cudaStreamNonBlocking));
+      const int sh2[3] = {n1[f], n2[f], 1};
+      const double* m2[2] = {mesh[imap_nc[f][0]], mesh[imap_nc[f][1]]};
+      fs[f].mg.reset(new MG(2, sh2, -1, m2, fs[f].st));
+      fs[f].mg->set_options((int)iopt[IOPT_MS], ropt[ROPT_CTOL], "NNNN", use_du_max, (int)iopt[IOPT_NMAXEX]);  // :355-357
+      const Grid g2 = fs[f].mg->level(0).g;
+      fs[f].chi.alloc(2 * (size_t)g2.cs);
+      fs[f].rhs.alloc(2 * (size_t)g2.cs);
+      CUDA_CHECK(cudaMemsetAsync(fs[f].rhs.p, 0, 2 * (size_t)g2.cs * sizeof(double), fs[f].st));
+      CUDA_CHECK(cudaMemsetAsync(fs[f].chi.p, 0, 2 * (size_t)g2.cs * sizeof(double), fs[f].st));  // :345
+      split_from_dense(bn[f], fs[f].rhs.p, g2, phi[f] / Aq[f], fs[f].st);                         // :348
       At[f][0].alloc((size_t)n1[f] * n2[f]);
       At[f][1].alloc((size_t)n1[f] * n2[f]);
-      compute_At(chi.p, g2, 1.0 / (2.0 * dq[imap_cp[f]]), f, At[f][0].p, At[f][1].p, st);  // :394-398 (dq of normal dir)
+    }
+    auto run_face_to_end = [&](int f) {
+      double du_last;
+      fs[f].ierr = fs[f].mg->solve(fs[f].chi.p, fs[f].rhs.p, ropt[ROPT_VTOL], (int)iopt[IOPT_NCYCLES], &du_last, &rep.solves[f]);
+    };
+    if (g_debug) {
+      for (int f = 0; f < 6; ++f) run_face_to_end(f);
+    } else {
+      for (int f = 0; f < 6; ++f)
+        fs[f].mg->solve_begin(fs[f].chi.p, fs[f].rhs.p, ropt[ROPT_VTOL], (int)iopt[IOPT_NCYCLES], &rep.solves[f]);
+      bool any = true;
+      while (any) {
+        any = false;
+        for (int f = 0; f < 6; ++f)
+          if (!fs[f].mg->solve_done()) fs[f].mg->solve_enqueue();
+        for (int f = 0; f < 6; ++f)
+          if (!fs[f].mg->solve_done()) { fs[f].mg->solve_poll(); any = true; }
+      }
+      for (int f = 0; f < 6; ++f) { double du_last; fs[f].ierr = fs[f].mg->solve_end(&du_last); }
+    }
+    ierr_last = fs[5].ierr;  // :360,480 -- only the last chi solve's ierr survives (reference quirk)
+    for (int f = 0; f < 6; ++f) {
+      const Grid g2 = fs[f].mg->level(0).g;
+      compute_At(fs[f].chi.p, g2, 1.0 / (2.0 * dq[imap_cp[f]]), f, At[f][0].p, At[f][1].p, fs[f].st);  // :394-398 (dq of normal dir)
       if (cap) {
         if (cap->chi[f]) {
           DevBuf dense((size_t)n1[f] * n2[f]);
-          dense_from_split(chi.p, dense.p, g2, st);
-          CUDA_CHECK(cudaMemcpyAsync(cap->chi[f], dense.p, sizeof(double) * n1[f] * n2[f], cudaMemcpyDeviceToHost, st));
-          CUDA_CHECK(cudaStreamSynchronize(st));
+          dense_from_split(fs[f].chi.p, dense.p, g2, fs[f].st);
+          CUDA_CHECK(cudaMemcpyAsync(cap->chi[f], dense.p, sizeof(double) * n1[f] * n2[f], cudaMemcpyDeviceToHost, fs[f].st));
+          CUDA_CHECK(cudaStreamSynchronize(fs[f].st));
         }
-        if (cap->At1[f]) CUDA_CHECK(cudaMemcpyAsync(cap->At1[f], At[f][0].p, sizeof(double) * n1[f] * n2[f], cudaMemcpyDeviceToHost, st));
-        if (cap->At2[f]) CUDA_CHECK(cudaMemcpyAsync(cap->At2[f], At[f][1].p, sizeof(double) * n1[f] * n2[f], cudaMemcpyDeviceToHost, st));
-        CUDA_CHECK(cudaStreamSynchronize(st));
+        if (cap->At1[f]) CUDA_CHECK(cudaMemcpyAsync(cap->At1[f], At[f][0].p, sizeof(double) * n1[f] * n2[f], cudaMemcpyDeviceToHost, fs[f].st));
+        if (cap->At2[f]) CUDA_CHECK(cudaMemcpyAsync(cap->At2[f], At[f][1].p, sizeof(double) * n1[f] * n2[f], cudaMemcpyDeviceToHost, fs[f].st));
       }
+      CUDA_CHECK(cudaStreamSynchronize(fs[f].st));
     }
-    CUDA_CHECK(cudaStreamSynchronize(st));
   }
   rep.ms_bc = tm.stop();
   if (stop_after_bc) {

@@ -68,6 +68,8 @@ def _declare(lib):
     lib.ndsm_b200_trace_nexact.argtypes = [c.c_int, c.c_int]
     lib.ndsm_b200_last_timing.argtypes = [vp]
     lib.ndsm_b200_version.restype = c.c_char_p
+    lib.ndsm_b200_release_workspace.restype = None
+    lib.ndsm_b200_workspace_bytes.restype = c.c_ulonglong
     lib.ndsm_b200_profile_enable.argtypes = [c.c_int]
     lib.ndsm_b200_profile_enable.restype = None
     lib.ndsm_b200_profile_get.argtypes = [c.c_int, vp, vp]
