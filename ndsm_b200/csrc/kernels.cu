@@ -128,32 +128,21 @@ __device__ __forceinline__ int x_other_offset(int s, int m, int i, int nx) {
   return (i == nx - 1) ? 0 : 1;
 }
 
+// ---- scalar column march: used for the first / last columns of a row, where mirrored ghosts, Dirichlet
+// ---- bounds and row padding need per-point care (loads of RELAX_UNROLL planes issued together)
 template <bool HAS_RHS>
-__global__ void __launch_bounds__(RELAX_THREADS)
-k_relax3d(double* __restrict__ u, const double* __restrict__ rhs, const Grid g, const Bounds b, const int colour,
-          const double wx, const double wy, const double wz, const double w1, const int klo, const int khi,
-          const int zchunk) {
-  const int t = blockIdx.x * RELAX_THREADS + threadIdx.x;
-  const int j = t / g.hp;
-  const int m = t - j * g.hp;
-  if (j < b.lb[1] || j > b.ub[1] || m >= g.mcnt) return;
-  const int kbeg = klo + blockIdx.y * zchunk;
-  const int kend = min(kbeg + zchunk - 1, khi);
-  if (kbeg > kend) return;
-
-  double* __restrict__ own = u + (i64)colour * g.cs;
-  const double* __restrict__ opp = u + (i64)(1 - colour) * g.cs;
-  const double* __restrict__ rh = HAS_RHS ? rhs + (i64)colour * g.cs : nullptr;
-
+__device__ __forceinline__ void relax_column(double* __restrict__ own, const double* __restrict__ opp,
+                                             const double* __restrict__ rh, const Grid& g, const Bounds& b,
+                                             const int colour, const int m, const int j, const int kbeg,
+                                             const int kend, const double wx, const double wy, const double wz,
+                                             const double w1) {
   const int jl = (j - 1 < 0) ? 1 : j - 1;                // mirrored Neumann ghost (:116-117)
   const int jh = (j + 1 > g.ny - 1) ? g.ny - 2 : j + 1;
   const i64 jo = (i64)j * g.hp + m, jlo = (i64)jl * g.hp + m, jho = (i64)jh * g.hp + m;
-
   const int kl0 = (kbeg - 1 < 0) ? 1 : kbeg - 1;
   double Zm = opp[(i64)(kl0 - g.k0) * g.ps + jo];
   double Zc = opp[(i64)(kbeg - g.k0) * g.ps + jo];
   for (int k0 = kbeg; k0 <= kend; k0 += RELAX_UNROLL) {
-    // phase 1: issue every load of the next RELAX_UNROLL planes (all independent)
     double Zn[RELAX_UNROLL], XO[RELAX_UNROLL], YL[RELAX_UNROLL], YH[RELAX_UNROLL], RH[RELAX_UNROLL];
 #pragma unroll
     for (int q = 0; q < RELAX_UNROLL; ++q) {
@@ -168,7 +157,6 @@ k_relax3d(double* __restrict__ u, const double* __restrict__ rhs, const Grid g, 
       YH[q] = opp[p + jho];
       RH[q] = HAS_RHS ? rh[p + jo] : 0.0;
     }
-    // phase 2: update
 #pragma unroll
     for (int q = 0; q < RELAX_UNROLL; ++q) {
       const int k = k0 + q;
@@ -177,7 +165,7 @@ k_relax3d(double* __restrict__ u, const double* __restrict__ rhs, const Grid g, 
         const int i = 2 * m + s;
         if (i >= b.lb[0] && i <= b.ub[0]) {
           // x neighbours i-1 / i+1 sit at compressed index m-1+s / m+s of the other colour, one of them
-          // being the in-column value Zc
+          // being the in-column value Zc; mirrored ghosts fold onto the opposite neighbour (:113-114)
           double xl, xh;
           if (s == 0) { xl = XO[q]; xh = (i == g.nx - 1) ? xl : Zc; }
           else        { xl = Zc;    xh = XO[q]; }
@@ -192,6 +180,96 @@ k_relax3d(double* __restrict__ u, const double* __restrict__ rhs, const Grid g, 
   }
 }
 
+// Columns handled by the scalar path: {0, 1} and the pair starting at the smallest even index >= mcnt-2.
+// Edge blocks (blockIdx.x == gridDim.x-1) give each (edge column, row) one thread.
+__device__ __forceinline__ int edge_column(int e, int mcnt) {
+  const int mE = (mcnt - 1) & ~1;  // smallest even >= mcnt-2
+  const int col = (e < 2) ? e : mE + (e - 2);
+  if (col >= mcnt) return -1;
+  if (e >= 2 && col < 2) return -1;  // already covered by e = 0,1
+  return col;
+}
+
+// ---- main kernel: one thread = two adjacent compressed columns (m0, m0+1) of the pass colour, 16-byte
+// ---- loads/stores, 32-bit element indices, 2D thread blocks so that y neighbours are L1 hits
+#define RELAX_BX 32  // pairs per block row  -> 64 compressed columns = 128 grid points in x
+#define RELAX_BY 8   // rows per block
+template <bool HAS_RHS>
+__global__ void __launch_bounds__(RELAX_BX * RELAX_BY, 3)
+k_relax3d(double* __restrict__ u, const double* __restrict__ rhs, const Grid g, const Bounds b, const int colour,
+          const double wx, const double wy, const double wz, const double w1, const int klo, const int khi,
+          const int zchunk) {
+  const int kbeg = klo + blockIdx.z * zchunk;
+  const int kend = min(kbeg + zchunk - 1, khi);
+  if (kbeg > kend) return;
+  double* __restrict__ own = u + (i64)colour * g.cs;
+  const double* __restrict__ opp = u + (i64)(1 - colour) * g.cs;
+  const double* __restrict__ rh = HAS_RHS ? rhs + (i64)colour * g.cs : nullptr;
+
+  if (blockIdx.x == gridDim.x - 1) {  // edge block: 4 edge columns x RELAX_BY rows
+    if (threadIdx.x >= 4 * RELAX_BY) return;
+    const int m = edge_column(threadIdx.x & 3, g.mcnt);
+    const int j = b.lb[1] + blockIdx.y * RELAX_BY + (threadIdx.x >> 2);
+    if (m < 0 || j > b.ub[1]) return;
+    relax_column<HAS_RHS>(own, opp, rh, g, b, colour, m, j, kbeg, kend, wx, wy, wz, w1);
+    return;
+  }
+  const int m0 = 2 + (blockIdx.x * RELAX_BX + (threadIdx.x & (RELAX_BX - 1))) * 2;
+  const int j = b.lb[1] + blockIdx.y * RELAX_BY + (threadIdx.x / RELAX_BX);
+  if (j > b.ub[1] || m0 + 2 >= g.mcnt) return;
+
+  // interior pair: every x neighbour exists, no Dirichlet point, no padding
+  const int jl = (j - 1 < 0) ? 1 : j - 1;
+  const int jh = (j + 1 > g.ny - 1) ? g.ny - 2 : j + 1;
+  const int ps = (int)g.ps;
+  const int io = j * g.hp + m0;  // element index inside a plane
+  const int dl = (jl - j) * g.hp, dh = (jh - j) * g.hp;
+  const int kl0 = (kbeg - 1 < 0) ? 1 : kbeg - 1;
+  const double* __restrict__ oppb = opp - (i64)g.k0 * ps;  // index with global k
+  double* __restrict__ ownb = own - (i64)g.k0 * ps;
+  const double* __restrict__ rhb = HAS_RHS ? rh - (i64)g.k0 * ps : nullptr;
+  double2 Zm = *reinterpret_cast<const double2*>(oppb + (i64)kl0 * ps + io);
+  double2 Zc = *reinterpret_cast<const double2*>(oppb + (i64)kbeg * ps + io);
+  int s = (j + kbeg + colour) & 1;
+  constexpr int U = HAS_RHS ? 2 : RELAX_UNROLL;  // planes in flight per thread (register budget: 3 blocks/SM)
+  for (int k0 = kbeg; k0 <= kend; k0 += U) {
+    double2 Zn[U], YL[U], YH[U], RH[U];
+    double XO[U];
+#pragma unroll
+    for (int q = 0; q < U; ++q) {  // phase 1: all loads of RELAX_UNROLL planes
+      const int k = min(k0 + q, kend);
+      const int kh = (k + 1 > g.nz - 1) ? g.nz - 2 : k + 1;
+      const double* __restrict__ pk = oppb + (i64)k * ps + io;
+      const int sq = s ^ (q & 1);
+      Zn[q] = *reinterpret_cast<const double2*>(oppb + (i64)kh * ps + io);
+      YL[q] = *reinterpret_cast<const double2*>(pk + dl);
+      YH[q] = *reinterpret_cast<const double2*>(pk + dh);
+      XO[q] = pk[sq ? 2 : -1];
+      if (HAS_RHS) RH[q] = *reinterpret_cast<const double2*>(rhb + (i64)k * ps + io);
+    }
+#pragma unroll
+    for (int q = 0; q < U; ++q) {  // phase 2: update
+      const int k = k0 + q;
+      if (k <= kend) {
+        const int sq = s ^ (q & 1);
+        // s == 0: point i = 2m has neighbours opp[m-1], opp[m];  s == 1: i = 2m+1 has opp[m], opp[m+1]
+        const double sx0 = sq ? (Zc.y + Zc.x) : (Zc.x + XO[q]);
+        const double sx1 = sq ? (XO[q] + Zc.y) : (Zc.y + Zc.x);
+        double un0 = (sx0 * wx + (YH[q].x + YL[q].x) * wy) + (Zn[q].x + Zm.x) * wz;  // (:123-125)
+        double un1 = (sx1 * wx + (YH[q].y + YL[q].y) * wy) + (Zn[q].y + Zm.y) * wz;
+        if (HAS_RHS) { un0 = un0 - RH[q].x; un1 = un1 - RH[q].y; }                   // (:126)
+        double2 o;
+        o.x = w1 * un0;                                                              // (:129)
+        o.y = w1 * un1;
+        *reinterpret_cast<double2*>(ownb + (i64)k * ps + io) = o;
+        Zm = Zc;
+        Zc = Zn[q];
+      }
+    }
+    if (U & 1) s ^= 1;
+  }
+}
+
 static int pick_zchunk(int nplanes, int blocks_per_plane) {
   // enough blocks to fill 148 SMs x 8 resident 256-thread blocks several times over
   int zc = 16;
@@ -202,14 +280,16 @@ static int pick_zchunk(int nplanes, int blocks_per_plane) {
 void relax3d_half(double* u, const double* rhs, const Grid& g, const Bounds& b, int colour, const Weights& w,
                   cudaStream_t st) {
   const int klo = max(b.lb[2], g.k0), khi = min(b.ub[2], g.k0 + g.nzl - 1);
-  if (klo > khi) return;
-  const int bpp = cdiv((i64)g.hp * g.ny, RELAX_THREADS);
-  const int zc = pick_zchunk(khi - klo + 1, bpp);
-  dim3 grid(bpp, cdiv(khi - klo + 1, zc));
+  const int nrows = b.ub[1] - b.lb[1] + 1;
+  if (klo > khi || nrows <= 0) return;
+  const int npairs = (g.mcnt > 4) ? (((g.mcnt - 1) & ~1) - 2) / 2 : 0;  // interior pairs m0 = 2, 4, ... < mE
+  const int bx = cdiv(npairs, RELAX_BX) + 1, by = cdiv(nrows, RELAX_BY);    // +1: edge blocks
+  const int zc = pick_zchunk(khi - klo + 1, bx * by);
+  dim3 grid(bx, by, cdiv(khi - klo + 1, zc));
   if (rhs)
-    k_relax3d<true><<<grid, RELAX_THREADS, 0, st>>>(u, rhs, g, b, colour, w.wx, w.wy, w.wz, w.w1, klo, khi, zc);
+    k_relax3d<true><<<grid, RELAX_BX * RELAX_BY, 0, st>>>(u, rhs, g, b, colour, w.wx, w.wy, w.wz, w.w1, klo, khi, zc);
   else
-    k_relax3d<false><<<grid, RELAX_THREADS, 0, st>>>(u, rhs, g, b, colour, w.wx, w.wy, w.wz, w.w1, klo, khi, zc);
+    k_relax3d<false><<<grid, RELAX_BX * RELAX_BY, 0, st>>>(u, rhs, g, b, colour, w.wx, w.wy, w.wz, w.w1, klo, khi, zc);
   LAUNCHED();
 }
 
@@ -219,28 +299,15 @@ void relax3d_half(double* u, const double* rhs, const Grid& g, const Bounds& b, 
 // Algorithmic traffic 24 B/pt (read u, read rhs, write r).
 // ---------------------------------------------------------------------------------------
 template <bool HAS_RHS>
-__global__ void __launch_bounds__(RELAX_THREADS)
-k_residual3d(const double* __restrict__ u, const double* __restrict__ rhs, double* __restrict__ r, const Grid g,
-             const Bounds b, const double wx, const double wy, const double wz, const double wc, const int zchunk) {
-  const int t = blockIdx.x * RELAX_THREADS + threadIdx.x;
-  const int j = t / g.hp;
-  const int m = t - j * g.hp;
-  if (j >= g.ny || m >= g.mcnt) return;
-  const int colour = blockIdx.z;
-  const int kbeg = g.k0 + blockIdx.y * zchunk;
-  const int kend = min(kbeg + zchunk - 1, g.k0 + g.nzl - 1);
-  if (kbeg > kend) return;
-
-  const double* __restrict__ own = u + (i64)colour * g.cs;
-  const double* __restrict__ opp = u + (i64)(1 - colour) * g.cs;
-  const double* __restrict__ rh = HAS_RHS ? rhs + (i64)colour * g.cs : nullptr;
-  double* __restrict__ ro = r + (i64)colour * g.cs;
-
+__device__ __forceinline__ void residual_column(const double* __restrict__ own, const double* __restrict__ opp,
+                                                const double* __restrict__ rh, double* __restrict__ ro,
+                                                const Grid& g, const Bounds& b, const int colour, const int m,
+                                                const int j, const int kbeg, const int kend, const double wx,
+                                                const double wy, const double wz, const double wc) {
   const int jl = (j - 1 < 0) ? 1 : j - 1;
   const int jh = (j + 1 > g.ny - 1) ? g.ny - 2 : j + 1;
   const i64 jo = (i64)j * g.hp + m, jlo = (i64)jl * g.hp + m, jho = (i64)jh * g.hp + m;
   const bool jin = (j >= b.lb[1] && j <= b.ub[1]);
-
   const int kl0 = (kbeg - 1 < 0) ? 1 : kbeg - 1;
   double Zm = opp[(i64)(kl0 - g.k0) * g.ps + jo];
   double Zc = opp[(i64)(kbeg - g.k0) * g.ps + jo];
@@ -286,15 +353,99 @@ k_residual3d(const double* __restrict__ u, const double* __restrict__ rhs, doubl
   }
 }
 
+template <bool HAS_RHS>
+__global__ void __launch_bounds__(RELAX_BX * RELAX_BY, 3)
+k_residual3d(const double* __restrict__ u, const double* __restrict__ rhs, double* __restrict__ r, const Grid g,
+             const Bounds b, const double wx, const double wy, const double wz, const double wc, const int zchunk) {
+  const int colour = blockIdx.z & 1;
+  const int kbeg = g.k0 + (blockIdx.z >> 1) * zchunk;
+  const int kend = min(kbeg + zchunk - 1, g.k0 + g.nzl - 1);
+  if (kbeg > kend) return;
+  const double* __restrict__ own = u + (i64)colour * g.cs;
+  const double* __restrict__ opp = u + (i64)(1 - colour) * g.cs;
+  const double* __restrict__ rh = HAS_RHS ? rhs + (i64)colour * g.cs : nullptr;
+  double* __restrict__ ro = r + (i64)colour * g.cs;
+
+  if (blockIdx.x == gridDim.x - 1) {  // edge block
+    if (threadIdx.x >= 4 * RELAX_BY) return;
+    const int m = edge_column(threadIdx.x & 3, g.mcnt);
+    const int j = blockIdx.y * RELAX_BY + (threadIdx.x >> 2);
+    if (m < 0 || j >= g.ny) return;
+    residual_column<HAS_RHS>(own, opp, rh, ro, g, b, colour, m, j, kbeg, kend, wx, wy, wz, wc);
+    return;
+  }
+  const int m0 = 2 + (blockIdx.x * RELAX_BX + (threadIdx.x & (RELAX_BX - 1))) * 2;
+  const int j = blockIdx.y * RELAX_BY + (threadIdx.x / RELAX_BX);
+  if (j >= g.ny || m0 + 2 >= g.mcnt) return;
+
+  const int jl = (j - 1 < 0) ? 1 : j - 1;
+  const int jh = (j + 1 > g.ny - 1) ? g.ny - 2 : j + 1;
+  const bool jin = (j >= b.lb[1] && j <= b.ub[1]);
+  const int ps = (int)g.ps;
+  const int io = j * g.hp + m0;
+  const int dl = (jl - j) * g.hp, dh = (jh - j) * g.hp;
+  const int kl0 = (kbeg - 1 < 0) ? 1 : kbeg - 1;
+  const double* __restrict__ oppb = opp - (i64)g.k0 * ps;
+  const double* __restrict__ ownb = own - (i64)g.k0 * ps;
+  const double* __restrict__ rhb = HAS_RHS ? rh - (i64)g.k0 * ps : nullptr;
+  double* __restrict__ rob = ro - (i64)g.k0 * ps;
+  double2 Zm = *reinterpret_cast<const double2*>(oppb + (i64)kl0 * ps + io);
+  double2 Zc = *reinterpret_cast<const double2*>(oppb + (i64)kbeg * ps + io);
+  int s = (j + kbeg + colour) & 1;
+  constexpr int U = 2;
+  for (int k0 = kbeg; k0 <= kend; k0 += U) {
+    double2 Zn[U], YL[U], YH[U], RH[U], UC[U];
+    double XO[U];
+#pragma unroll
+    for (int q = 0; q < U; ++q) {
+      const int k = min(k0 + q, kend);
+      const int kh = (k + 1 > g.nz - 1) ? g.nz - 2 : k + 1;
+      const double* __restrict__ pk = oppb + (i64)k * ps + io;
+      const int sq = s ^ (q & 1);
+      Zn[q] = *reinterpret_cast<const double2*>(oppb + (i64)kh * ps + io);
+      YL[q] = *reinterpret_cast<const double2*>(pk + dl);
+      YH[q] = *reinterpret_cast<const double2*>(pk + dh);
+      XO[q] = pk[sq ? 2 : -1];
+      UC[q] = *reinterpret_cast<const double2*>(ownb + (i64)k * ps + io);
+      if (HAS_RHS) RH[q] = *reinterpret_cast<const double2*>(rhb + (i64)k * ps + io);
+    }
+#pragma unroll
+    for (int q = 0; q < U; ++q) {
+      const int k = k0 + q;
+      if (k <= kend) {
+        const int sq = s ^ (q & 1);
+        double2 o;
+        o.x = 0.0;
+        o.y = 0.0;
+        if (jin && k >= b.lb[2] && k <= b.ub[2]) {
+          const double sx0 = sq ? (Zc.x + Zc.y) : (XO[q] + Zc.x);
+          const double sx1 = sq ? (Zc.y + XO[q]) : (Zc.x + Zc.y);
+          double t0 = (sx0 * wx + (YL[q].x + YH[q].x) * wy) + (Zm.x + Zn[q].x) * wz;  // (:424-426)
+          double t1 = (sx1 * wx + (YL[q].y + YH[q].y) * wy) + (Zm.y + Zn[q].y) * wz;
+          if (HAS_RHS) { t0 = t0 - RH[q].x; t1 = t1 - RH[q].y; }
+          t0 = t0 - UC[q].x * wc;                                                     // (:427)
+          t1 = t1 - UC[q].y * wc;
+          o.x = -t0;                                                                  // (:430)
+          o.y = -t1;
+        }
+        *reinterpret_cast<double2*>(rob + (i64)k * ps + io) = o;
+        Zm = Zc;
+        Zc = Zn[q];
+      }
+    }
+  }
+}
+
 void residual3d(const double* u, const double* rhs, double* r, const Grid& g, const Bounds& b, const Weights& w,
                 cudaStream_t st) {
-  const int bpp = cdiv((i64)g.hp * g.ny, RELAX_THREADS);
-  const int zc = pick_zchunk(g.nzl, bpp * 2);
-  dim3 grid(bpp, cdiv(g.nzl, zc), 2);
+  const int npairs = (g.mcnt > 4) ? (((g.mcnt - 1) & ~1) - 2) / 2 : 0;
+  const int bx = cdiv(npairs, RELAX_BX) + 1, by = cdiv(g.ny, RELAX_BY);
+  const int zc = pick_zchunk(g.nzl, bx * by * 2);
+  dim3 grid(bx, by, cdiv(g.nzl, zc) * 2);
   if (rhs)
-    k_residual3d<true><<<grid, RELAX_THREADS, 0, st>>>(u, rhs, r, g, b, w.wx, w.wy, w.wz, w.wc, zc);
+    k_residual3d<true><<<grid, RELAX_BX * RELAX_BY, 0, st>>>(u, rhs, r, g, b, w.wx, w.wy, w.wz, w.wc, zc);
   else
-    k_residual3d<false><<<grid, RELAX_THREADS, 0, st>>>(u, rhs, r, g, b, w.wx, w.wy, w.wz, w.wc, zc);
+    k_residual3d<false><<<grid, RELAX_BX * RELAX_BY, 0, st>>>(u, rhs, r, g, b, w.wx, w.wy, w.wz, w.wc, zc);
   LAUNCHED();
 }
 
