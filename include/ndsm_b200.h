@@ -120,6 +120,10 @@ int ndsm_b200_plan_interp(const ndsm_b200_plan* p, int level, int dim, int* lo, 
 int ndsm_b200_plan_restrict(const ndsm_b200_plan* p, int level, int dim, int* first, int* count, double* c2,
                             double* w2);
 int ndsm_b200_ngrids_for(int nmin); /* FLOOR(LOG(nmin/2.0)/LOG(2.0)), ndsm_vector_potential.f90:341-342 */
+/* z-slab partition of the hierarchy over `world` ranks: *ndist = number of partitioned levels; zs holds
+ * (ndist+1) rows of world+1 plane boundaries (row ndist = producers of the first replicated level).
+ * zs must have room for ngrids*(world+1) ints. */
+int ndsm_b200_plan_slab_partition(const ndsm_b200_plan* p, int world, int min_planes, int* ndist, int* zs);
 
 /* Stage hooks of the driver (host dense arrays) */
 int ndsm_b200_bc_setup(const int* nshape4, const int* ioptc, const double* ropt, const double* x, const double* y,

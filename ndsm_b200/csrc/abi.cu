@@ -2,6 +2,7 @@
 // BIND(C) surface (fortran/ndsm_python_wrapper.f90:56-234) with identical semantics.
 #include <chrono>
 #include <cstring>
+#include <memory>
 #include <thread>
 #include <vector>
 
@@ -118,6 +119,33 @@ struct DBuf {
   DBuf& operator=(const DBuf&) = delete;
 };
 
+// Full-array solve on the current device.  With NDSM_VIRTUAL_SLABS=G (> 1) the 3D solves run through the
+// z-slab code path with G "virtual ranks" on this one device (same arithmetic, halo copies instead of NVLink
+// traffic): the way to exercise the multi-GPU decomposition through the frozen ABI on a single GPU.
+static int run_core_full(const int* nshape4, const long long* iopt, const double* ropt, const double* x,
+                         const double* y, const double* z, double* const* bn, const double* dA0, double* dA,
+                         double* dB, cudaStream_t st) {
+  const int nz = nshape4[2];
+  const long long N = (long long)nshape4[0] * nshape4[1] * nz;
+  int world = 1;
+  if (const char* e = getenv("NDSM_VIRTUAL_SLABS")) world = atoi(e);
+  if (world < 1) world = 1;
+  DenseIn A0;
+  A0.p = dA0; A0.kfirst = 0; A0.cstride = N;
+  std::unique_ptr<Comm> comm;
+  std::vector<SlabOut> outs;
+  if (world > 1) comm = make_virtual_comm(world);
+  for (int r = 0; r < world; ++r) {
+    SlabOut o;
+    output_range(nz, world, r, &o.k0, &o.k1);
+    o.cstride = N;
+    o.A = dA + (long long)o.k0 * nshape4[0] * nshape4[1];
+    o.B = dB + (long long)o.k0 * nshape4[0] * nshape4[1];
+    outs.push_back(o);
+  }
+  return vector_solve_core(nshape4, iopt, ropt, x, y, z, bn, A0, comm.get(), outs, st, g_report, nullptr, false);
+}
+
 extern "C" {
 
 // ------------------------------------------------------------------------------------------
@@ -177,8 +205,7 @@ int ndsm_vector_solve(size_t nsize, const int* nshape4, int* ioptc, double* ropt
     pool_free_host(hfaces);
     g_report.ms_in = (now_s() - t1) * 1e3;
     if (g_debug) debug_msg(SUB, "Calling compute_vector_potential...");
-    int ierr = vector_solve_core(nshape4, iopt, ropt, x, y, z, bn, zero_guess ? nullptr : dA.p, dA.p, dB.p, st,
-                                 g_report, nullptr, false);
+    int ierr = run_core_full(nshape4, iopt, ropt, x, y, z, bn, zero_guess ? nullptr : dA.p, dA.p, dB.p, st);
     t1 = now_s();
     CUDA_CHECK(cudaMemcpyAsync(A, dA.p, 3 * N * sizeof(double), cudaMemcpyDeviceToHost, st));
     CUDA_CHECK(cudaMemcpyAsync(B, dB.p, 3 * N * sizeof(double), cudaMemcpyDeviceToHost, st));
@@ -240,7 +267,7 @@ int ndsm_b200_vector_solve_device(const int* nshape4, int* ioptc, double* ropt, 
       const int layer = (f % 2 == 0) ? 0 : nshape4[c] - 1;
       extract_face(dB + c * N, nx, ny, nz, c, layer, bn[f], st);  // ndsm_vector_potential.f90:283-293
     }
-    int ierr = vector_solve_core(nshape4, iopt, ropt, x, y, z, bn, dA, dA, dB, st, g_report, nullptr, false);
+    int ierr = run_core_full(nshape4, iopt, ropt, x, y, z, bn, dA, dA, dB, st);
     CUDA_CHECK(cudaStreamSynchronize(st));
     return finish(ierr);
   } catch (const NdsmError& e) {
@@ -308,6 +335,18 @@ int ndsm_b200_plan_restrict(const ndsm_b200_plan* p, int level, int dim, int* fi
   return 0;
 }
 int ndsm_b200_ngrids_for(int nmin) { return ngrids_for(nmin); }
+int ndsm_b200_plan_slab_partition(const ndsm_b200_plan* p, int world, int min_planes, int* ndist, int* zs) {
+  if (!p || !ndist || !zs || world < 1) return NDSM_B200_ERR_ARG;
+  try {
+    SlabPlan sp = plan_slabs(p->lv, p->ndim, world, min_planes);
+    *ndist = sp.ndist;
+    for (size_t l = 0; l < sp.zs.size(); ++l)
+      for (int r = 0; r <= world; ++r) zs[l * (world + 1) + r] = sp.zs[l][r];
+    return 0;
+  } catch (const NdsmError&) {
+    return NDSM_B200_ERR_ARG;
+  }
+}
 }  // extern "C"
 
 // ------------------------------------------------------------------------------------------
@@ -338,7 +377,7 @@ static double* handle_array(ndsm_b200_mg* h, int which, int level) {
   MG& mg = *h->mg;
   if (level < 0 || level >= mg.ngrids()) return nullptr;
   if (which == 0) return mg.level(level).u;
-  if (which == 2) return mg.r_scratch();
+  if (which == 2) return mg.r_scratch(level);
   if (which == 1) {
     if (level > 0) return mg.level(level).rhs;
     if (!h->rhs0) {
@@ -407,7 +446,7 @@ int ndsm_b200_mg_level_shape(const ndsm_b200_mg* h, int level, int* shape3) {
 }
 int ndsm_b200_mg_level_mesh(const ndsm_b200_mg* h, int level, int dim, double* out) {
   if (!h || !h->mg || level < 0 || level >= h->mg->ngrids() || dim < 0 || dim >= h->mg->ndim()) return NDSM_B200_ERR_ARG;
-  const auto& m = h->mg->level(level).mesh[dim];
+  const auto& m = h->mg->mesh(level, dim);
   memcpy(out, m.data(), m.size() * sizeof(double));
   return 0;
 }
@@ -555,7 +594,8 @@ int ndsm_b200_bc_setup(const int* nshape4, const int* ioptc, const double* ropt,
       cap.At2[f] = At2_6 ? At2_6[f] : nullptr;
     }
     g_report = Report();
-    int ierr = vector_solve_core(nshape4, iopt, ropt, x, y, z, bn, nullptr, nullptr, nullptr, st, g_report, &cap, true);
+    int ierr = vector_solve_core(nshape4, iopt, ropt, x, y, z, bn, DenseIn(), nullptr, std::vector<SlabOut>(), st,
+                                 g_report, &cap, true);
     if (phi6) for (int f = 0; f < 6; ++f) phi6[f] = g_report.phi[f];
     return ierr;
   } catch (const NdsmError& e) {
@@ -592,10 +632,11 @@ int ndsm_b200_flux_curl(const int* nshape4, int flxcrl, const double* x, const d
     for (int c = 0; c < 3; ++c) {
       CUDA_CHECK(cudaMemsetAsync(dAs.p, 0, 2 * (size_t)g.cs * sizeof(double), st));
       split_from_dense(dA.p + c * N, dAs.p, g, 0.0, st);
-      unsplit_A(dAs.p, g, c, dm.p, dm.p + nx, dm.p + nx + ny, phi6, Lq, flux_first, dA.p + c * N, st);
+      unsplit_A(dAs.p, g, c, dm.p, dm.p + nx, dm.p + nx + ny, phi6, Lq, flux_first, 0, nz, dA.p + c * N, st);
     }
-    curl_dense(dA.p, nx, ny, nz, dq[0], dq[1], dq[2], dB.p, st);
-    if (!flux_first) add_flux_dense(dA.p, dB.p, nx, ny, nz, dm.p, dm.p + nx, dm.p + nx + ny, phi6, Lq, st);
+    curl_dense(dA.p, 0, (long long)N, nx, ny, nz, dq[0], dq[1], dq[2], 0, nz, dB.p, (long long)N, st);
+    if (!flux_first)
+      add_flux_dense(dA.p, (long long)N, dB.p, (long long)N, nx, ny, 0, nz, dm.p, dm.p + nx, dm.p + nx + ny, phi6, Lq, st);
     CUDA_CHECK(cudaMemcpyAsync(A, dA.p, 3 * N * sizeof(double), cudaMemcpyDeviceToHost, st));
     CUDA_CHECK(cudaMemcpyAsync(B, dB.p, 3 * N * sizeof(double), cudaMemcpyDeviceToHost, st));
     CUDA_CHECK(cudaStreamSynchronize(st));

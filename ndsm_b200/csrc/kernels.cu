@@ -998,11 +998,11 @@ struct FluxPar { double phi[6]; double Lq[3]; };
 __global__ void __launch_bounds__(256)
 k_unsplit_A(const double* __restrict__ As, const Grid g, const int comp, const double* __restrict__ x,
             const double* __restrict__ y, const double* __restrict__ z, const FluxPar f, const int add_flux,
-            double* __restrict__ Ad) {
+            const int ka, double* __restrict__ Ad) {
   const int i = blockIdx.x * 256 + threadIdx.x;
   if (i >= g.nx) return;
-  const int j = blockIdx.y, kl = blockIdx.z, k = kl + g.k0;
-  double a = As[gidx(g, i, j, k)];
+  const int j = blockIdx.y, kl = blockIdx.z, k = ka + kl;
+  double a = As[gidx(g, i, j, k)];  // k may address a halo plane of the slab
   if (add_flux) {
     const double X = x[i], Y = y[j], Z = z[k];
     const double Vq = (f.Lq[0] * f.Lq[1]) * f.Lq[2];
@@ -1018,12 +1018,13 @@ k_unsplit_A(const double* __restrict__ As, const Grid g, const int comp, const d
 }
 
 void unsplit_A(const double* As, const Grid& g, int comp, const double* x, const double* y, const double* z,
-               const double* phi, const double* Lq, bool add_flux, double* A_dense, cudaStream_t st) {
+               const double* phi, const double* Lq, bool add_flux, int ka, int kb, double* A_dense, cudaStream_t st) {
   FluxPar f;
   for (int q = 0; q < 6; ++q) f.phi[q] = phi[q];
   for (int q = 0; q < 3; ++q) f.Lq[q] = Lq[q];
-  dim3 grid(cdiv(g.nx, 256), g.ny, g.nzl);
-  k_unsplit_A<<<grid, 256, 0, st>>>(As, g, comp, x, y, z, f, add_flux ? 1 : 0, A_dense);
+  if (kb <= ka) return;
+  dim3 grid(cdiv(g.nx, 256), g.ny, kb - ka);
+  k_unsplit_A<<<grid, 256, 0, st>>>(As, g, comp, x, y, z, f, add_flux ? 1 : 0, ka, A_dense);
   LAUNCHED();
 }
 
@@ -1044,44 +1045,46 @@ __device__ __forceinline__ double derivq(const double* __restrict__ u, i64 n, in
   }
   return d;
 }
+// A: dense planes starting at global plane ka, components csA apart; B: planes starting at k0, components csB apart
 __global__ void __launch_bounds__(256)
-k_curl(const double* __restrict__ A, const int nx, const int ny, const int nz, const double dqx, const double dqy,
-       const double dqz, double* __restrict__ B) {
+k_curl(const double* __restrict__ A, const int ka, const i64 csA, const int nx, const int ny, const int nz,
+       const double dqx, const double dqy, const double dqz, const int k0, double* __restrict__ B, const i64 csB) {
   const int i = blockIdx.x * 256 + threadIdx.x;
   if (i >= nx) return;
-  const int j = blockIdx.y, k = blockIdx.z;
-  const i64 N = (i64)nx * ny * nz, sy = nx, sz = (i64)nx * ny;
-  const i64 n = i + sy * j + sz * k;
+  const int j = blockIdx.y, k = k0 + blockIdx.z;
+  const i64 sy = nx, sz = (i64)nx * ny;
+  const i64 n = i + sy * j + sz * (k - ka);
   const double* __restrict__ Ax = A;
-  const double* __restrict__ Ay = A + N;
-  const double* __restrict__ Az = A + 2 * N;
+  const double* __restrict__ Ay = A + csA;
+  const double* __restrict__ Az = A + 2 * csA;
   const double dAx_dy = derivq(Ax, n, j, ny, sy, dqy);
   const double dAx_dz = derivq(Ax, n, k, nz, sz, dqz);
   const double dAy_dx = derivq(Ay, n, i, nx, 1, dqx);
   const double dAy_dz = derivq(Ay, n, k, nz, sz, dqz);
   const double dAz_dx = derivq(Az, n, i, nx, 1, dqx);
   const double dAz_dy = derivq(Az, n, j, ny, sy, dqy);
-  B[n] = dAz_dy - dAy_dz;          // (:802-804)
-  B[n + N] = dAx_dz - dAz_dx;
-  B[n + 2 * N] = dAy_dx - dAx_dy;
+  const i64 o = i + sy * j + sz * (k - k0);
+  B[o] = dAz_dy - dAy_dz;          // (:802-804)
+  B[o + csB] = dAx_dz - dAz_dx;
+  B[o + 2 * csB] = dAy_dx - dAx_dy;
 }
-void curl_dense(const double* A_dense, int nx, int ny, int nz, double dqx, double dqy, double dqz, double* B_dense,
-                cudaStream_t st) {
-  dim3 grid(cdiv(nx, 256), ny, nz);
-  k_curl<<<grid, 256, 0, st>>>(A_dense, nx, ny, nz, dqx, dqy, dqz, B_dense);
+void curl_dense(const double* A, int ka, i64 csA, int nx, int ny, int nz, double dqx, double dqy, double dqz, int k0,
+                int k1, double* B, i64 csB, cudaStream_t st) {
+  if (k1 <= k0) return;
+  dim3 grid(cdiv(nx, 256), ny, k1 - k0);
+  k_curl<<<grid, 256, 0, st>>>(A, ka, csA, nx, ny, nz, dqx, dqy, dqz, k0, B, csB);
   LAUNCHED();
 }
 
 // IOPT_FLXCRL = 1 order (:453-466): corrections added to both A and B after the curl
 __global__ void __launch_bounds__(256)
-k_add_flux_dense(double* __restrict__ A, double* __restrict__ B, const int nx, const int ny, const int nz,
-                 const double* __restrict__ x, const double* __restrict__ y, const double* __restrict__ z,
-                 const FluxPar f) {
+k_add_flux_dense(double* __restrict__ A, const i64 csA, double* __restrict__ B, const i64 csB, const int nx,
+                 const int ny, const int k0, const double* __restrict__ x, const double* __restrict__ y,
+                 const double* __restrict__ z, const FluxPar f) {
   const int i = blockIdx.x * 256 + threadIdx.x;
   if (i >= nx) return;
-  const int j = blockIdx.y, k = blockIdx.z;
-  const i64 N = (i64)nx * ny * nz;
-  const i64 n = i + (i64)nx * (j + (i64)ny * k);
+  const int j = blockIdx.y, kl = blockIdx.z, k = k0 + kl;
+  const i64 n = i + (i64)nx * (j + (i64)ny * kl);
   const double X = x[i], Y = y[j], Z = z[k];
   const double Vq = (f.Lq[0] * f.Lq[1]) * f.Lq[2];
   const double g1 = (f.phi[1] - f.phi[0]) / Vq, g2 = (f.phi[3] - f.phi[2]) / Vq, g3 = (f.phi[5] - f.phi[4]) / Vq;
@@ -1095,17 +1098,18 @@ k_add_flux_dense(double* __restrict__ A, double* __restrict__ B, const int nx, c
                         -((f.phi[2] * f.Lq[1]) * X) / Vq};
 #pragma unroll
   for (int c = 0; c < 3; ++c) {
-    B[n + c * N] = B[n + c * N] + bc[c];
-    A[n + c * N] = (A[n + c * N] + Ac[c]) + inv3 * ((A1[c] + A2[c]) + A3[c]);
+    B[n + c * csB] = B[n + c * csB] + bc[c];
+    A[n + c * csA] = (A[n + c * csA] + Ac[c]) + inv3 * ((A1[c] + A2[c]) + A3[c]);
   }
 }
-void add_flux_dense(double* A_dense, double* B_dense, int nx, int ny, int nz, const double* x, const double* y,
-                    const double* z, const double* phi, const double* Lq, cudaStream_t st) {
+void add_flux_dense(double* A, i64 csA, double* B, i64 csB, int nx, int ny, int k0, int k1, const double* x,
+                    const double* y, const double* z, const double* phi, const double* Lq, cudaStream_t st) {
   FluxPar f;
   for (int q = 0; q < 6; ++q) f.phi[q] = phi[q];
   for (int q = 0; q < 3; ++q) f.Lq[q] = Lq[q];
-  dim3 grid(cdiv(nx, 256), ny, nz);
-  k_add_flux_dense<<<grid, 256, 0, st>>>(A_dense, B_dense, nx, ny, nz, x, y, z, f);
+  if (k1 <= k0) return;
+  dim3 grid(cdiv(nx, 256), ny, k1 - k0);
+  k_add_flux_dense<<<grid, 256, 0, st>>>(A, csA, B, csB, nx, ny, k0, x, y, z, f);
   LAUNCHED();
 }
 

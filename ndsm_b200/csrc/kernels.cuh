@@ -81,13 +81,16 @@ void compute_At(const double* chi_split, const Grid& g2, double fac, int face_id
                 cudaStream_t st);
 void write_face(double* A_split, const Grid& g, int dim, int layer, const double* face, cudaStream_t st);
 
-// K8: flux-balance fields + curl (ndsm_vector_potential.f90:759-872,880-950)
-// A_dense[c] = unsplit(A_split[c]) (+ flux-balance potential when add_flux)
+// K8: flux-balance fields + curl (ndsm_vector_potential.f90:759-872,880-950).  Dense arrays are addressed as
+// "pointer to a first global plane + component stride" so that a z-slab can be written in place.
+// A_dense[planes ka..kb) = unsplit(A_split) (+ flux-balance potential of component comp when add_flux)
 void unsplit_A(const double* As, const Grid& g, int comp, const double* x, const double* y, const double* z,
-               const double* phi /*6*/, const double* Lq /*3*/, bool add_flux, double* A_dense, cudaStream_t st);
-void curl_dense(const double* A_dense /*3 comps*/, int nx, int ny, int nz, double dqx, double dqy, double dqz,
-                double* B_dense, cudaStream_t st);
-void add_flux_dense(double* A_dense, double* B_dense, int nx, int ny, int nz, const double* x, const double* y,
-                    const double* z, const double* phi, const double* Lq, cudaStream_t st);
+               const double* phi /*6*/, const double* Lq /*3*/, bool add_flux, int ka, int kb, double* A_dense,
+               cudaStream_t st);
+// B[planes k0..k1) = curl A; A holds planes from ka on (needs k-1,k+1 or the one-sided stencil planes)
+void curl_dense(const double* A, int ka, i64 csA, int nx, int ny, int nz, double dqx, double dqy, double dqz, int k0,
+                int k1, double* B, i64 csB, cudaStream_t st);
+void add_flux_dense(double* A, i64 csA, double* B, i64 csB, int nx, int ny, int k0, int k1, const double* x,
+                    const double* y, const double* z, const double* phi, const double* Lq, cudaStream_t st);
 
 }  // namespace ndsm

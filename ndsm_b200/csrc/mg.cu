@@ -3,6 +3,7 @@
 #include "mg.hpp"
 #include "pool.hpp"
 
+#include <algorithm>
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
@@ -137,41 +138,196 @@ std::vector<HostLevel> build_hierarchy(int ndim, const int* shape, int ngrids, c
   return lv;
 }
 
-MG::MG(int ndim, const int* shape, int ngrids, const double* const* mesh, cudaStream_t st) : ndim_(ndim), st_(st) {
+// ---------------------------------------------------------------------------------------------
+// z-slab partition (host only)
+// ---------------------------------------------------------------------------------------------
+SlabPlan plan_slabs(const std::vector<HostLevel>& hl, int ndim, int world, int min_planes) {
+  SlabPlan p;
+  p.world = world;
+  if (world <= 1 || ndim != 3) return p;
+  const int ng = (int)hl.size();
+  if (min_planes < NDSM_HALO) min_planes = NDSM_HALO;
+  std::vector<int> z(world + 1);
+  for (int r = 0; r <= world; ++r) z[r] = (int)((i64)hl[0].n[2] * r / world);  // balanced finest slabs
+  int g = 0;
+  while (true) {
+    bool ok = (g < ng - 1);  // the coarsest level is always replicated (solve_exact needs the whole grid)
+    for (int r = 0; r < world && ok; ++r) ok = (z[r + 1] - z[r] >= min_planes);
+    if (!ok) break;
+    p.zs.push_back(z);
+    p.ndist = g + 1;
+    // coarse plane kc belongs to the rank that owns its anchor fine plane (centre of its restriction stencil)
+    const std::vector<int>& first = hl[g].first[2];
+    const std::vector<int>& count = hl[g].count[2];
+    const int nc = hl[g + 1].n[2];
+    std::vector<int> zc(world + 1, 0);
+    zc[world] = nc;
+    for (int r = 1; r < world; ++r) {
+      int c = 0;
+      while (c < nc && first[c] + (count[c] - 1) / 2 < z[r]) ++c;
+      zc[r] = c;
+    }
+    z = zc;
+    ++g;
+  }
+  if (p.ndist == 0) return p;
+  p.zs.push_back(z);  // producer partition of the first replicated level
+  p.halo = NDSM_HALO;
+  // every stencil must stay inside owned planes + halo
+  for (int lv = 0; lv < p.ndist; ++lv) {
+    const int nzf = hl[lv].n[2], ncz = hl[lv + 1].n[2];
+    for (int r = 0; r < world; ++r) {
+      const int f0 = p.zs[lv][r] - p.halo, f1 = p.zs[lv][r + 1] + p.halo;
+      for (int c = p.zs[lv + 1][r]; c < p.zs[lv + 1][r + 1]; ++c) {
+        const int a = hl[lv].first[2][c], b = a + hl[lv].count[2][c];
+        if (a < (f0 < 0 ? 0 : f0) || b > (f1 > nzf ? nzf : f1)) throw NdsmError(6);
+      }
+      if (lv + 1 < p.ndist) {
+        const int c0 = p.zs[lv + 1][r] - p.halo, c1 = p.zs[lv + 1][r + 1] + p.halo;
+        for (int k = p.zs[lv][r]; k < p.zs[lv][r + 1]; ++k) {
+          const int lo = hl[lv].lo[2][k], hi = (lo + 1 < ncz) ? lo + 1 : ncz - 1;
+          if (lo < c0 || hi >= c1) throw NdsmError(6);
+        }
+      }
+    }
+  }
+  return p;
+}
+
+// ---------------------------------------------------------------------------------------------
+// virtual communication: every rank lives in this process on one device; messages are device copies
+// ---------------------------------------------------------------------------------------------
+namespace {
+struct VirtualComm : Comm {
+  struct Msg { int from, to; const double* src; double* dst; size_t n; bool used; };
+  int w;
+  std::vector<Msg> sends, recvs;
+  explicit VirtualComm(int world) : w(world) {}
+  int world() const override { return w; }
+  int first_rank() const override { return 0; }
+  int nlocal() const override { return w; }
+  void begin(cudaStream_t) override { sends.clear(); recvs.clear(); }
+  void send(int my_rank, int to_rank, const double* src, size_t n, cudaStream_t) override {
+    sends.push_back(Msg{my_rank, to_rank, src, nullptr, n, false});
+  }
+  void recv(int my_rank, int from_rank, double* dst, size_t n, cudaStream_t) override {
+    recvs.push_back(Msg{from_rank, my_rank, nullptr, dst, n, false});
+  }
+  void end(cudaStream_t st) override {
+    for (auto& r : recvs) {
+      bool found = false;
+      for (auto& s : sends)
+        if (!s.used && s.from == r.from && s.to == r.to) {
+          if (s.n != r.n) throw NdsmError(6);
+          CUDA_CHECK(cudaMemcpyAsync(r.dst, s.src, s.n * sizeof(double), cudaMemcpyDeviceToDevice, st));
+          s.used = true;
+          found = true;
+          break;
+        }
+      if (!found) throw NdsmError(6);
+    }
+  }
+  void gather2(int my_rank, const double* send2, double* recv_all, cudaStream_t st) override {
+    CUDA_CHECK(cudaMemcpyAsync(recv_all + 2 * my_rank, send2, 2 * sizeof(double), cudaMemcpyDeviceToDevice, st));
+  }
+  void bcast(int, double*, size_t, cudaStream_t) override {}
+};
+}  // namespace
+std::unique_ptr<Comm> make_virtual_comm(int world) { return std::unique_ptr<Comm>(new VirtualComm(world)); }
+
+// ---------------------------------------------------------------------------------------------
+// MG
+// ---------------------------------------------------------------------------------------------
+static Grid slab_grid(const Grid& full, int k0, int nzl, int H) {
+  Grid g = full;
+  g.k0 = k0;
+  g.nzl = nzl;
+  g.cs = full.ps * (nzl + 2 * H);
+  return g;
+}
+
+MG::MG(int ndim, const int* shape, int ngrids, const double* const* mesh, cudaStream_t st, Comm* comm)
+    : ndim_(ndim), comm_(comm), st_(st) {
   std::vector<HostLevel> hl = build_hierarchy(ndim, shape, ngrids, mesh);
   ngrids = (int)hl.size();
-  lv_.resize(ngrids);
   std::memset(copt_, 'N', sizeof copt_);
+  mesh_.resize(ngrids);
   for (int g = 0; g < ngrids; ++g) {
-    lv_[g].g = hl[g].g;
-    lv_[g].w = hl[g].w;
-    for (int d = 0; d < 3; ++d) lv_[g].mesh[d] = hl[g].mesh[d];
+    mesh_[g].resize(3);
+    for (int d = 0; d < 3; ++d) mesh_[g][d] = hl[g].mesh[d];
   }
+  const int world = comm_ ? comm_->world() : 1;
+  int min_planes = 16;
+  if (const char* e = getenv("NDSM_SLAB_MIN_PLANES")) min_planes = atoi(e);
+  plan_ = plan_slabs(hl, ndim, world, min_planes);
+  const int nd = plan_.ndist;
+  const int H = plan_.halo;
+  const int nlocal = (nd > 0 && comm_) ? comm_->nlocal() : 1;
+  slabs_.resize(nlocal);
+  rhs0_.assign(nlocal, nullptr);
 
-  // --- one arena for the level arrays
+  // --- shared arena: replicated levels, coarsest u_sav, reduction scratch, results
   i64 total = 0;
   auto take = [&](i64 n) { i64 o = total; total += round_up(n, 32); return o; };
-  std::vector<i64> off_u(ngrids), off_rhs(ngrids);
-  for (int g = 0; g < ngrids; ++g) {
-    off_u[g] = take(2 * lv_[g].g.cs);
-    off_rhs[g] = (g > 0) ? take(2 * lv_[g].g.cs) : -1;
+  std::vector<i64> off_u(ngrids, -1), off_rhs(ngrids, -1);
+  for (int g = nd; g < ngrids; ++g) {
+    off_u[g] = take(2 * hl[g].g.cs);
+    if (g > 0) off_rhs[g] = take(2 * hl[g].g.cs);
   }
-  const i64 off_r = take(2 * lv_[0].g.cs);
-  const i64 off_sav = take(2 * lv_[ngrids - 1].g.cs);
+  const i64 off_sav = take(2 * hl[ngrids - 1].g.cs);
   const i64 off_scr = take((i64)reduce_scratch_doubles());
-  const i64 off_out = take(32);
-  arena_ = static_cast<double*>(pool_alloc((size_t)total * sizeof(double)));
-  CUDA_CHECK(cudaMemsetAsync(arena_, 0, (size_t)total * sizeof(double), st_));
-  for (int g = 0; g < ngrids; ++g) {
-    lv_[g].u = arena_ + off_u[g];
-    lv_[g].rhs = (g > 0) ? arena_ + off_rhs[g] : nullptr;
+  const i64 off_all = take(2 * (i64)world + 8);
+  const i64 off_info = take(8);
+  shared_ = static_cast<double*>(pool_alloc((size_t)total * sizeof(double)));
+  CUDA_CHECK(cudaMemsetAsync(shared_, 0, (size_t)total * sizeof(double), st_));
+  usav_ = shared_ + off_sav;
+  scratch_ = shared_ + off_scr;
+  d_all_ = shared_ + off_all;
+  d_info_ = reinterpret_cast<int*>(shared_ + off_info);
+  h_out_ = static_cast<double*>(pool_alloc_host((2 * (size_t)world + 8) * sizeof(double)));
+
+  // --- per-slab arenas: partitioned levels (with halos), residual scratch, local reduction result
+  for (int s = 0; s < nlocal; ++s) {
+    Slab& S = slabs_[s];
+    S.rank = (comm_ ? comm_->first_rank() : 0) + s;
+    S.lv.resize(ngrids);
+    i64 tot = 0;
+    auto tk = [&](i64 n) { i64 o = tot; tot += round_up(n, 32); return o; };
+    std::vector<i64> ou(ngrids, -1), orh(ngrids, -1);
+    i64 rmax = 0;
+    for (int g = 0; g < ngrids; ++g) {
+      Level& L = S.lv[g];
+      L.w = hl[g].w;
+      if (g < nd) {
+        L.dist = true;
+        L.H = H;
+        L.g = slab_grid(hl[g].g, plan_.zs[g][S.rank], plan_.zs[g][S.rank + 1] - plan_.zs[g][S.rank], H);
+        ou[g] = tk(2 * L.g.cs);
+        if (g > 0) orh[g] = tk(2 * L.g.cs);
+      } else {
+        L.dist = false;
+        L.H = 0;
+        L.g = hl[g].g;
+      }
+      if (g < ngrids - 1 || ngrids == 1) rmax = std::max<i64>(rmax, 2 * L.g.cs);
+    }
+    const i64 orr = tk(rmax);
+    const i64 oout = tk(8);
+    S.arena = static_cast<double*>(pool_alloc((size_t)tot * sizeof(double)));
+    CUDA_CHECK(cudaMemsetAsync(S.arena, 0, (size_t)tot * sizeof(double), st_));
+    S.r = S.arena + orr;
+    S.d_out = S.arena + oout;
+    for (int g = 0; g < ngrids; ++g) {
+      Level& L = S.lv[g];
+      if (g < nd) {
+        L.u = S.arena + ou[g] + (i64)H * L.g.ps;
+        L.rhs = (g > 0) ? S.arena + orh[g] + (i64)H * L.g.ps : nullptr;
+      } else {
+        L.u = shared_ + off_u[g];
+        L.rhs = (g > 0) ? shared_ + off_rhs[g] : nullptr;
+      }
+    }
   }
-  r_ = arena_ + off_r;
-  usav_ = arena_ + off_sav;
-  scratch_ = arena_ + off_scr;
-  d_out_ = arena_ + off_out;
-  d_info_ = reinterpret_cast<int*>(arena_ + off_out + 8);
-  h_out_ = static_cast<double*>(pool_alloc_host(8 * sizeof(double)));
 
   // --- pack every transfer table into one int and one double buffer: two uploads per hierarchy
   std::vector<int> hi;
@@ -191,12 +347,13 @@ MG::MG(int ndim, const int* shape, int ngrids, const double* const* mesh, cudaSt
   tab_d_ = static_cast<double*>(pool_alloc((hd.size() + 32) * sizeof(double)));
   if (!hi.empty()) CUDA_CHECK(cudaMemcpyAsync(tab_i_, hi.data(), hi.size() * sizeof(int), cudaMemcpyHostToDevice, st_));
   if (!hd.empty()) CUDA_CHECK(cudaMemcpyAsync(tab_d_, hd.data(), hd.size() * sizeof(double), cudaMemcpyHostToDevice, st_));
-  for (int g = 0; g + 1 < ngrids; ++g)
-    for (int d = 0; d < 3; ++d) {
-      const Off& o = offs[(size_t)g * 3 + d];
-      lv_[g].it[d] = InterpTab{tab_i_ + o.lo, tab_d_ + o.wl, tab_d_ + o.wh};
-      lv_[g].rt[d] = RestrictTab{tab_i_ + o.first, tab_i_ + o.count, tab_d_ + o.c2, hl[g].w2[d]};
-    }
+  for (auto& S : slabs_)
+    for (int g = 0; g + 1 < ngrids; ++g)
+      for (int d = 0; d < 3; ++d) {
+        const Off& o = offs[(size_t)g * 3 + d];
+        S.lv[g].it[d] = InterpTab{tab_i_ + o.lo, tab_d_ + o.wl, tab_d_ + o.wh};
+        S.lv[g].rt[d] = RestrictTab{tab_i_ + o.first, tab_i_ + o.count, tab_d_ + o.c2, hl[g].w2[d]};
+      }
   CUDA_CHECK(cudaStreamSynchronize(st_));  // host staging vectors go out of scope
   set_options(5, 1e-13, "NNNNNN", true, 10000);
 }
@@ -204,8 +361,14 @@ MG::MG(int ndim, const int* shape, int ngrids, const double* const* mesh, cudaSt
 MG::~MG() {
   pool_free(tab_i_);
   pool_free(tab_d_);
-  pool_free(arena_);
+  for (auto& S : slabs_) pool_free(S.arena);
+  pool_free(shared_);
   pool_free_host(h_out_);
+}
+
+double* MG::r_scratch(int g, int s) {
+  const Level& L = slabs_[s].lv[g];
+  return slabs_[s].r + (i64)L.H * L.g.ps;
 }
 
 void MG::set_options(int ms, double ex_tol, const char* copt, bool du_max, int nmax_exact) {
@@ -219,69 +382,147 @@ void MG::set_options(int ms, double ex_tol, const char* copt, bool du_max, int n
     if (copt_[d] != 'N') all_neumann_ = false;
   // colour of the first pass: ndsm_optimized.f90:106 (3D, depends on the x-lower BC); ndsm_poisson.f90:499-501 (2D)
   first_colour_ = (ndim_ == 3 && copt_[0] == 'D') ? 1 : 0;
-  for (auto& L : lv_) {
-    const int n[3] = {L.g.nx, L.g.ny, L.g.nz};
-    for (int d = 0; d < 3; ++d) {
-      L.b.lb[d] = 0;
-      L.b.ub[d] = n[d] - 1;
-      if (d < ndim_) {
-        if (copt_[d] == 'D') L.b.lb[d] = 1;                 // bcs(d,1) = copt(d)
-        if (copt_[ndim_ + d] == 'D') L.b.ub[d] = n[d] - 2;  // bcs(d,2) = copt(ndim+d)
+  for (auto& S : slabs_)
+    for (auto& L : S.lv) {
+      const int n[3] = {L.g.nx, L.g.ny, L.g.nz};
+      for (int d = 0; d < 3; ++d) {
+        L.b.lb[d] = 0;
+        L.b.ub[d] = n[d] - 1;
+        if (d < ndim_) {
+          if (copt_[d] == 'D') L.b.lb[d] = 1;                 // bcs(d,1) = copt(d)
+          if (copt_[ndim_ + d] == 'D') L.b.ub[d] = n[d] - 2;  // bcs(d,2) = copt(ndim+d)
+        }
+      }
+    }
+}
+
+// halo planes with the z-neighbours (one grouped exchange)
+void MG::exchange(int g, int which, int colour_mask, int np, const std::vector<double*>* arr) {
+  if (g >= plan_.ndist || !comm_) return;
+  const int world = plan_.world;
+  comm_->begin(st_);
+  for (size_t s = 0; s < slabs_.size(); ++s) {
+    Slab& S = slabs_[s];
+    const Level& L = S.lv[g];
+    double* P = arr ? (*arr)[s] : (which == 0 ? L.u : r_scratch(g, (int)s));
+    const size_t n = (size_t)np * L.g.ps;
+    for (int c = 0; c < 2; ++c) {
+      if (!(colour_mask & (1 << c))) continue;
+      double* pc = P + (i64)c * L.g.cs;
+      if (S.rank + 1 < world) {
+        comm_->send(S.rank, S.rank + 1, pc + (i64)(L.g.nzl - np) * L.g.ps, n, st_);
+        comm_->recv(S.rank, S.rank + 1, pc + (i64)L.g.nzl * L.g.ps, n, st_);
+      }
+      if (S.rank > 0) {
+        comm_->send(S.rank, S.rank - 1, pc, n, st_);
+        comm_->recv(S.rank, S.rank - 1, pc - (i64)np * L.g.ps, n, st_);
       }
     }
   }
+  comm_->end(st_);
 }
 
 void MG::relax(int g) {
-  Level& L = lv_[g];
-  const double* rhs = (g == 0) ? rhs0_ : L.rhs;
+  const bool dist = g < plan_.ndist;
+  const size_t ns = dist ? slabs_.size() : 1;
   if (ndim_ == 3) {
-    // each colour pass is timed separately when profiling (PROF_RELAX0 = one k_relax3d launch on level 0)
-    if (g == 0) prof_begin(PROF_RELAX0, st_);
-    relax3d_half(L.u, rhs, L.g, L.b, first_colour_, L.w, st_);
-    if (g == 0) { prof_end(PROF_RELAX0, st_); prof_begin(PROF_RELAX0, st_); }
-    relax3d_half(L.u, rhs, L.g, L.b, first_colour_ ^ 1, L.w, st_);
-    if (g == 0) prof_end(PROF_RELAX0, st_);
+    for (int pass = 0; pass < 2; ++pass) {
+      const int colour = first_colour_ ^ pass;
+      // each colour pass is timed separately when profiling (PROF_RELAX0 = one k_relax3d launch on level 0)
+      if (g == 0 && ns == 1) prof_begin(PROF_RELAX0, st_);
+      for (size_t s = 0; s < ns; ++s) {
+        Level& L = slabs_[s].lv[g];
+        relax3d_half(L.u, (g == 0) ? rhs0_[s] : L.rhs, L.g, L.b, colour, L.w, st_);
+      }
+      if (g == 0 && ns == 1) prof_end(PROF_RELAX0, st_);
+      if (dist) exchange(g, 0, 1 << colour, 1);
+    }
   } else {
+    Level& L = slabs_[0].lv[g];
+    const double* rhs = (g == 0) ? rhs0_[0] : L.rhs;
     relax2d_half(L.u, rhs, L.g, L.b, 0, L.w, st_);
     relax2d_half(L.u, rhs, L.g, L.b, 1, L.w, st_);
   }
-  if (all_neumann_) subtract_mean(L.u, L.g, scratch_, st_);
+  if (all_neumann_) {
+    if (dist) throw NdsmError(6);  // pure-Neumann gauge on partitioned levels is not needed by this path
+    subtract_mean(slabs_[0].lv[g].u, slabs_[0].lv[g].g, scratch_, st_);
+  }
 }
 
 void MG::residual(int g) {
-  Level& L = lv_[g];
-  const double* rhs = (g == 0) ? rhs0_ : L.rhs;
-  const bool prof = (g == 0 && ndim_ == 3);
+  const size_t ns = (g < plan_.ndist) ? slabs_.size() : 1;
+  const bool prof = (g == 0 && ndim_ == 3 && ns == 1);
   if (prof) prof_begin(PROF_RESID0, st_);
-  if (ndim_ == 3) residual3d(L.u, rhs, r_, L.g, L.b, L.w, st_);
-  else residual2d(L.u, rhs, r_, L.g, L.b, L.w, st_);
+  for (size_t s = 0; s < ns; ++s) {
+    Level& L = slabs_[s].lv[g];
+    const double* rhs = (g == 0) ? rhs0_[s] : L.rhs;
+    if (ndim_ == 3) residual3d(L.u, rhs, r_scratch(g, (int)s), L.g, L.b, L.w, st_);
+    else residual2d(L.u, rhs, r_scratch(g, (int)s), L.g, L.b, L.w, st_);
+  }
   if (prof) prof_end(PROF_RESID0, st_);
 }
 
 void MG::restrict_to(int g) {
-  Level& F = lv_[g];
-  Level& C = lv_[g + 1];
-  const bool prof = (g == 0 && ndim_ == 3);
+  const int c = g + 1;
+  const bool fdist = g < plan_.ndist, cdist = c < plan_.ndist;
+  const size_t ns = fdist ? slabs_.size() : 1;
+  if (fdist) exchange(g, 2, 3, plan_.halo);
+  const bool prof = (g == 0 && ndim_ == 3 && ns == 1);
   if (prof) prof_begin(PROF_RESTRICT0, st_);
-  restrict_level(r_, F.g, C.rhs, C.g, F.rt[0], F.rt[1], F.rt[2], st_);
+  for (size_t s = 0; s < ns; ++s) {
+    Level& F = slabs_[s].lv[g];
+    Level& C = slabs_[s].lv[c];
+    if (!fdist || cdist) {
+      restrict_level(r_scratch(g, (int)s), F.g, C.rhs, C.g, F.rt[0], F.rt[1], F.rt[2], st_);
+    } else {  // partitioned -> replicated: this rank produces planes [zs[c][r], zs[c][r+1]) of the full array
+      const int r = slabs_[s].rank, k0 = plan_.zs[c][r], cnt = plan_.zs[c][r + 1] - k0;
+      if (cnt > 0) {
+        Grid gv = C.g;
+        gv.k0 = k0;
+        gv.nzl = cnt;
+        restrict_level(r_scratch(g, (int)s), F.g, C.rhs + (i64)k0 * C.g.ps, gv, F.rt[0], F.rt[1], F.rt[2], st_);
+      }
+    }
+  }
   if (prof) prof_end(PROF_RESTRICT0, st_);
-  CUDA_CHECK(cudaMemsetAsync(C.u, 0, (size_t)2 * C.g.cs * sizeof(double), st_));  // ndsm_multigrid_core.f90:557-558
+  if (fdist && !cdist && comm_) {  // all-gather the replicated rhs
+    Level& C = slabs_[0].lv[c];
+    comm_->begin(st_);
+    for (int q = 0; q < plan_.world; ++q) {
+      const int k0 = plan_.zs[c][q], cnt = plan_.zs[c][q + 1] - k0;
+      if (cnt <= 0) continue;
+      for (int col = 0; col < 2; ++col)
+        comm_->bcast(q, C.rhs + (i64)col * C.g.cs + (i64)k0 * C.g.ps, (size_t)cnt * C.g.ps, st_);
+    }
+    comm_->end(st_);
+  }
+  const size_t nc = cdist ? slabs_.size() : 1;
+  for (size_t s = 0; s < nc; ++s) {  // ndsm_multigrid_core.f90:557-558
+    Level& C = slabs_[s].lv[c];
+    CUDA_CHECK(cudaMemsetAsync(level_base(C.u, c, (int)s), 0, (size_t)2 * C.g.cs * sizeof(double), st_));
+  }
 }
 
 void MG::interp_add_from(int c) {
-  Level& C = lv_[c];
-  Level& F = lv_[c - 1];
-  const bool prof = (c == 1 && ndim_ == 3);
+  const int f = c - 1;
+  const bool fdist = f < plan_.ndist, cdist = c < plan_.ndist;
+  const size_t ns = fdist ? slabs_.size() : 1;
+  if (cdist) exchange(c, 0, 3, plan_.halo);
+  const bool prof = (c == 1 && ndim_ == 3 && ns == 1);
   if (prof) prof_begin(PROF_INTERP0, st_);
-  interp_add(C.u, C.g, F.u, F.g, F.it[0], F.it[1], F.it[2], st_);
+  for (size_t s = 0; s < ns; ++s) {
+    Level& C = slabs_[s].lv[c];
+    Level& F = slabs_[s].lv[f];
+    interp_add(C.u, C.g, F.u, F.g, F.it[0], F.it[1], F.it[2], st_);
+  }
   if (prof) prof_end(PROF_INTERP0, st_);
+  if (fdist) exchange(f, 0, 3, 1);
 }
 
-// solve_exact (ndsm_multigrid_core.f90:728-800)
+// solve_exact (ndsm_multigrid_core.f90:728-800) -- always on a replicated level
 int MG::solve_exact(int g) {
-  Level& L = lv_[g];
-  const double* rhs = (g == 0) ? rhs0_ : L.rhs;
+  Level& L = slabs_[0].lv[g];
+  const double* rhs = (g == 0) ? rhs0_[0] : L.rhs;
   if (rhs && solve_exact_smem(ndim_, L.u, rhs, L.g, L.b, first_colour_, L.w, all_neumann_, du_max_, ex_tol_,
                               nmax_exact_, d_info_, st_))
     return -1;  // result in d_info_
@@ -293,8 +534,8 @@ int MG::solve_exact(int g) {
   for (int i = 0; i < nmax_exact_; ++i) {
     if (du <= ex_tol_) { converged = 1; break; }
     relax(g);
-    diff_reduce(usav_, L.u, L.g, true, scratch_, d_out_, st_);
-    CUDA_CHECK(cudaMemcpyAsync(h_out_, d_out_, 2 * sizeof(double), cudaMemcpyDeviceToHost, st_));
+    diff_reduce(usav_, L.u, L.g, true, scratch_, slabs_[0].d_out, st_);
+    CUDA_CHECK(cudaMemcpyAsync(h_out_, slabs_[0].d_out, 2 * sizeof(double), cudaMemcpyDeviceToHost, st_));
     CUDA_CHECK(cudaStreamSynchronize(st_));
     du = du_max_ ? h_out_[0] : h_out_[1] / N;
     ++it;
@@ -306,7 +547,7 @@ int MG::solve_exact(int g) {
 }
 
 void MG::v_cycle() {  // ndsm_multigrid_core.f90:341-377
-  const int ng = (int)lv_.size();
+  const int ng = ngrids();
   for (int g = 0; g < ng - 1; ++g) {  // fine_to_coarse :482-560
     for (int s = 0; s < ms_; ++s) relax(g);
     residual(g);
@@ -327,49 +568,67 @@ int MG::last_nexact() {
   return info[0];
 }
 
-// true when solve_exact() on level g will take the single-block shared-memory path (no host sync)
+// true when solve_exact() on the coarsest level will take the single-block shared-memory path (no host sync)
 bool MG::coarsest_in_smem(const double* rhs_coarsest) const {
-  const Grid& g = lv_.back().g;
+  const Grid& g = slabs_[0].lv.back().g;
   return rhs_coarsest != nullptr && (size_t)g.nx * g.ny * g.nz * 3 * sizeof(double) <= 200 * 1024 && g.nzl == g.nz;
 }
 
 // one iteration of solve_poisson_bvp's loop body, enqueue only: V-cycle, update_u, results to pinned memory
-void MG::enqueue_cycle(double* u) {
-  Level& L0 = lv_[0];
+void MG::enqueue_cycle() {
   v_cycle();
-  if (ndim_ == 3) prof_begin(PROF_DIFF0, st_);
-  diff_reduce(u, L0.u, L0.g, true, scratch_, d_out_, st_);  // update_u :122
-  if (ndim_ == 3) prof_end(PROF_DIFF0, st_);
-  CUDA_CHECK(cudaMemcpyAsync(h_out_, d_out_, 2 * sizeof(double), cudaMemcpyDeviceToHost, st_));
-  CUDA_CHECK(cudaMemcpyAsync(h_out_ + 2, d_info_, 2 * sizeof(int), cudaMemcpyDeviceToHost, st_));
+  const bool dist = plan_.ndist > 0 && comm_;
+  const bool prof = (ndim_ == 3 && slabs_.size() == 1);
+  if (prof) prof_begin(PROF_DIFF0, st_);
+  for (size_t s = 0; s < slabs_.size(); ++s) {
+    Level& L0 = slabs_[s].lv[0];
+    diff_reduce(ss_.u[s], L0.u, L0.g, true, scratch_, slabs_[s].d_out, st_);  // update_u :122
+  }
+  if (prof) prof_end(PROF_DIFF0, st_);
+  const int npairs = dist ? plan_.world : 1;
+  if (dist) {
+    for (auto& S : slabs_) comm_->gather2(S.rank, S.d_out, d_all_, st_);
+    CUDA_CHECK(cudaMemcpyAsync(h_out_, d_all_, 2 * npairs * sizeof(double), cudaMemcpyDeviceToHost, st_));
+  } else {
+    CUDA_CHECK(cudaMemcpyAsync(h_out_, slabs_[0].d_out, 2 * sizeof(double), cudaMemcpyDeviceToHost, st_));
+  }
+  CUDA_CHECK(cudaMemcpyAsync(h_out_ + 2 * npairs, d_info_, 2 * sizeof(int), cudaMemcpyDeviceToHost, st_));
 }
 
 // solve_poisson_bvp (ndsm_poisson.f90:63-155), split into begin / enqueue / poll / end so that several
 // independent solves (the six chi faces) can be interleaved on their own streams by one host thread.
-void MG::solve_begin(double* u, const double* rhs, double vc_tol, int nmax, SolveTrace* tr) {
-  Level& L0 = lv_[0];
-  const size_t bytes0 = (size_t)2 * L0.g.cs * sizeof(double);
+void MG::solve_begin(const std::vector<double*>& u, const std::vector<const double*>& rhs, double vc_tol, int nmax,
+                     SolveTrace* tr) {
+  if (u.size() != slabs_.size() || rhs.size() != slabs_.size()) throw NdsmError(6);
   ss_ = SolveState();
   ss_.u = u; ss_.vc_tol = vc_tol; ss_.nmax = nmax; ss_.tr = tr;
-  if (!rhs && (ndim_ == 2 || lv_.size() == 1)) {  // kernels of those paths always read rhs
-    ss_.zero_rhs = static_cast<double*>(pool_alloc(bytes0));
-    CUDA_CHECK(cudaMemsetAsync(ss_.zero_rhs, 0, bytes0, st_));
-    rhs = ss_.zero_rhs;
+  ss_.zero_rhs.assign(slabs_.size(), nullptr);
+  for (size_t s = 0; s < slabs_.size(); ++s) {
+    Level& L0 = slabs_[s].lv[0];
+    const size_t bytes0 = (size_t)2 * L0.g.cs * sizeof(double);
+    const double* r = rhs[s];
+    if (!r && (ndim_ == 2 || ngrids() == 1)) {  // kernels of those paths always read rhs
+      ss_.zero_rhs[s] = static_cast<double*>(pool_alloc(bytes0));
+      CUDA_CHECK(cudaMemsetAsync(ss_.zero_rhs[s], 0, bytes0, st_));
+      r = ss_.zero_rhs[s] + (i64)L0.H * L0.g.ps;
+    }
+    rhs0_[s] = r;
+    CUDA_CHECK(cudaMemcpyAsync(level_base(L0.u, 0, (int)s), level_base(u[s], 0, (int)s), bytes0,
+                               cudaMemcpyDeviceToDevice, st_));  // :100
   }
-  rhs0_ = rhs;
-  CUDA_CHECK(cudaMemcpyAsync(L0.u, u, bytes0, cudaMemcpyDeviceToDevice, st_));  // :100
+  exchange(0, 0, 3, 1);  // the caller's halo planes are not trusted
 
   // The loop body is a static launch sequence (the coarsest solve iterates inside one kernel), so it is
   // captured once into a CUDA graph and replayed every V-cycle: ~250-500 launches per cycle otherwise.
   static const bool graphs_on = !(getenv("NDSM_B200_GRAPH") && atoi(getenv("NDSM_B200_GRAPH")) == 0);
-  const double* rhs_coarsest = (lv_.size() == 1) ? rhs0_ : lv_.back().rhs;
+  const double* rhs_coarsest = (ngrids() == 1) ? rhs0_[0] : slabs_[0].lv.back().rhs;
   if (graphs_on && !prof_enabled() && nmax > 1 && coarsest_in_smem(rhs_coarsest)) {
     solve_exact_prepare();
     const unsigned long long l0 = g_launches;
     cudaGraph_t graph = nullptr;
     CUDA_CHECK(cudaStreamBeginCapture(st_, cudaStreamCaptureModeThreadLocal));
     try {
-      enqueue_cycle(u);
+      enqueue_cycle();
     } catch (...) {
       cudaStreamEndCapture(st_, &graph);
       if (graph) cudaGraphDestroy(graph);
@@ -386,24 +645,34 @@ void MG::solve_begin(double* u, const double* rhs, double vc_tol, int nmax, Solv
   if (nmax <= 0) ss_.done = true;
 }
 
+void MG::solve_begin(double* u, const double* rhs, double vc_tol, int nmax, SolveTrace* tr) {
+  solve_begin(std::vector<double*>{u}, std::vector<const double*>{rhs}, vc_tol, nmax, tr);
+}
+
 void MG::solve_enqueue() {
   if (ss_.done) return;
   if (ss_.gexec) {
     CUDA_CHECK(cudaGraphLaunch(ss_.gexec, st_));
     g_launches += ss_.graph_launches;
   } else {
-    enqueue_cycle(ss_.u);
+    enqueue_cycle();
   }
 }
 
 bool MG::solve_poll() {
   if (ss_.done) return true;
-  const Level& L0 = lv_[0];
-  const double N = (double)((i64)L0.g.nx * L0.g.ny * L0.g.nz);
+  const Grid& g0 = slabs_[0].lv[0].g;
+  const double N = (double)((i64)g0.nx * g0.ny * g0.nz);
   CUDA_CHECK(cudaStreamSynchronize(st_));
   prof_collect();
-  ss_.du = du_max_ ? h_out_[0] : h_out_[1] / N;
-  const int* info = reinterpret_cast<const int*>(h_out_ + 2);
+  const int npairs = (plan_.ndist > 0 && comm_) ? plan_.world : 1;
+  double dmax = 0.0, dsum = 0.0;
+  for (int q = 0; q < npairs; ++q) {  // fixed rank order: every rank takes the same decision
+    dmax = h_out_[2 * q] > dmax ? h_out_[2 * q] : dmax;
+    dsum += h_out_[2 * q + 1];
+  }
+  ss_.du = du_max_ ? dmax : dsum / N;
+  const int* info = reinterpret_cast<const int*>(h_out_ + 2 * npairs);
   if (ss_.tr) { ss_.tr->du.push_back(ss_.du); ss_.tr->nexact.push_back(info[0]); }
   if (!info[1]) printf(" Warning: IOPT_NMAXEX exceeded. Coarse-mesh solution may not have converged\n");
   if (g_debug) {
@@ -427,18 +696,30 @@ int MG::solve_end(double* du_last) {
     printf(" Warning: IOPT_NCYCLES exceeded. V-cycle iteration may not have converged\n");
   }
   if (ss_.tr) ss_.tr->ierr = ierr;
-  rhs0_ = nullptr;
-  if (ss_.zero_rhs) { CUDA_CHECK(cudaStreamSynchronize(st_)); pool_free(ss_.zero_rhs); ss_.zero_rhs = nullptr; }
+  bool freed = false;
+  for (size_t s = 0; s < slabs_.size(); ++s) {
+    rhs0_[s] = nullptr;
+    if (ss_.zero_rhs[s]) {
+      if (!freed) { CUDA_CHECK(cudaStreamSynchronize(st_)); freed = true; }
+      pool_free(ss_.zero_rhs[s]);
+      ss_.zero_rhs[s] = nullptr;
+    }
+  }
   return ierr;
 }
 
-int MG::solve(double* u, const double* rhs, double vc_tol, int nmax, double* du_last, SolveTrace* tr) {
+int MG::solve(const std::vector<double*>& u, const std::vector<const double*>& rhs, double vc_tol, int nmax,
+              double* du_last, SolveTrace* tr) {
   solve_begin(u, rhs, vc_tol, nmax, tr);
   while (!ss_.done) {
     solve_enqueue();
     solve_poll();
   }
   return solve_end(du_last);
+}
+
+int MG::solve(double* u, const double* rhs, double vc_tol, int nmax, double* du_last, SolveTrace* tr) {
+  return solve(std::vector<double*>{u}, std::vector<const double*>{rhs}, vc_tol, nmax, du_last, tr);
 }
 
 }  // namespace ndsm

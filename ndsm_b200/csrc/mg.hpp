@@ -2,7 +2,13 @@
 // Mirrors the reference's MG_HANDLE (ndsm_multigrid_core.f90:86-101), new_mg_handle (:165-270),
 // v_cycle (:341-377) and solve_poisson_bvp (ndsm_poisson.f90:63-155); relax/residual are the
 // CUDA operators of kernels.cu sitting behind the reference's MG_RELAX / MG_RESIDUAL seam.
+//
+// Multi-GPU: the finest levels are partitioned into z-slabs (one per rank) with halo planes; levels
+// below a size threshold are replicated on every rank (all-gather of the restricted rhs once per
+// V-cycle, no scatter on the way up).  A process holds one slab (NCCL mode, one process per GPU) or all
+// slabs (virtual mode: every rank on one device, used to test the slab logic on a single GPU).
 #pragma once
+#include <memory>
 #include <vector>
 #include "kernels.cuh"
 
@@ -29,6 +35,37 @@ struct HostLevel {
 // throws NdsmError(2) for shapes the reference cannot handle, NdsmError(4) if a stencil exceeds NDSM_RMAX
 std::vector<HostLevel> build_hierarchy(int ndim, const int* shape, int ngrids, const double* const* mesh);
 
+// z-slab partition of the hierarchy over `world` ranks (host-only).
+struct SlabPlan {
+  int world = 1;
+  int ndist = 0;                     // levels [0, ndist) are partitioned; the rest are replicated
+  int halo = 0;                      // halo planes on each side of a partitioned array
+  std::vector<std::vector<int>> zs;  // zs[level][r] .. zs[level][r+1]: planes owned by rank r; the entry for
+                                     // level ndist says who PRODUCES which planes of the first replicated level
+};
+#define NDSM_HALO 4
+// min_planes: a level is partitioned only while every rank keeps at least that many planes
+SlabPlan plan_slabs(const std::vector<HostLevel>& hl, int ndim, int world, int min_planes);
+
+// Communication between slabs.  Two-sided, matched in call order per (from,to) pair; all calls are
+// enqueued on the stream and may be captured into a CUDA graph.
+struct Comm {
+  virtual ~Comm() {}
+  virtual int world() const = 0;
+  virtual int first_rank() const = 0;  // first global rank held by this process
+  virtual int nlocal() const = 0;      // consecutive ranks held by this process
+  virtual void begin(cudaStream_t st) = 0;
+  virtual void send(int my_rank, int to_rank, const double* src, size_t n, cudaStream_t st) = 0;
+  virtual void recv(int my_rank, int from_rank, double* dst, size_t n, cudaStream_t st) = 0;
+  virtual void end(cudaStream_t st) = 0;
+  // every rank contributes 2 doubles; result [2*world] on every process, ordered by rank
+  virtual void gather2(int my_rank, const double* send2, double* recv_all, cudaStream_t st) = 0;
+  // in-place broadcast of buf[0..n) from root_rank into every rank's own copy of the same array; when all
+  // local ranks share one copy (virtual mode) this is a no-op
+  virtual void bcast(int root_rank, double* buf, size_t n, cudaStream_t st) = 0;
+};
+std::unique_ptr<Comm> make_virtual_comm(int world);  // all ranks in this process, on the current device
+
 struct SolveTrace {
   std::vector<double> du;      // du after each V-cycle
   std::vector<int> nexact;     // coarsest-solve iterations in each V-cycle
@@ -36,51 +73,76 @@ struct SolveTrace {
 };
 
 struct Level {
-  Grid g;
+  Grid g;               // local view: k0/nzl = owned planes, cs includes the halo planes
   Bounds b;
   Weights w;
-  std::vector<double> mesh[3];
+  int H = 0;            // halo planes on each side (0 for replicated levels)
+  bool dist = false;    // partitioned level
   double* u = nullptr;    // colour-split, local plane 0
-  double* rhs = nullptr;  // colour-split (level 0: may alias caller data or be null)
+  double* rhs = nullptr;  // colour-split (level 0: supplied per solve, may be null)
   // transfer tables between this level (fine) and the next (coarse); device pointers
   InterpTab it[3];
   RestrictTab rt[3];
 };
 
+struct Slab {
+  int rank = 0;
+  std::vector<Level> lv;
+  double* r = nullptr;      // residual scratch base (sized for the largest level incl. halos)
+  double* arena = nullptr;
+  double* d_out = nullptr;  // [2] local max / sum of |du|
+};
+
 class MG {
  public:
   // shape: (nx,ny,nz) with nz == 1 for ndim == 2.  ngrids < 0 => reference rule from min(shape).
-  MG(int ndim, const int* shape, int ngrids, const double* const* mesh, cudaStream_t st);
+  // comm == nullptr: one slab covering the whole grid.
+  MG(int ndim, const int* shape, int ngrids, const double* const* mesh, cudaStream_t st, Comm* comm = nullptr);
   ~MG();
   MG(const MG&) = delete;
   MG& operator=(const MG&) = delete;
 
   void set_options(int ms, double ex_tol, const char* copt, bool du_max, int nmax_exact);
-  int ngrids() const { return (int)lv_.size(); }
+  int ngrids() const { return (int)mesh_.size(); }
   int ndim() const { return ndim_; }
-  const Level& level(int g) const { return lv_[g]; }
-  Level& level(int g) { return lv_[g]; }
-  double* r_scratch() { return r_; }
-  size_t level_doubles(int g) const { return (size_t)2 * lv_[g].g.cs; }
+  int nslabs() const { return (int)slabs_.size(); }
+  const Level& level(int g, int s = 0) const { return slabs_[s].lv[g]; }
+  Level& level(int g, int s = 0) { return slabs_[s].lv[g]; }
+  const std::vector<double>& mesh(int g, int d) const { return mesh_[g][d]; }
+  int slab_rank(int s) const { return slabs_[s].rank; }
+  double* r_scratch(int g, int s = 0);  // local plane 0 of the residual scratch laid out like level g
+  size_t level_doubles(int g, int s = 0) const { return (size_t)2 * slabs_[s].lv[g].g.cs; }
+  double* level_base(double* plane0, int g, int s = 0) const {  // allocation start (first halo plane)
+    const Level& L = slabs_[s].lv[g];
+    return plane0 - (i64)L.H * L.g.ps;
+  }
+  const SlabPlan& plan() const { return plan_; }
 
   // operators on a level (enqueue only)
-  void relax(int g);          // one full red+black sweep (+ pure-Neumann mean subtraction)
-  void residual(int g);       // r_scratch <- rhs - L u
-  void restrict_to(int g);    // rhs[g+1] <- R r_scratch (fine level g)
+  void relax(int g);            // one full red+black sweep (+ pure-Neumann mean subtraction)
+  void residual(int g);         // r_scratch <- rhs - L u
+  void restrict_to(int g);      // rhs[g+1] <- R r_scratch (fine level g); u[g+1] <- 0
   void interp_add_from(int c);  // u[c-1] += P u[c]
-  int solve_exact(int g);     // returns iterations (synchronises only in the fallback path)
-  void v_cycle();             // from the finest grid; leaves coarsest info in d_info_
+  int solve_exact(int g);       // coarsest level (synchronises only in the fallback path)
+  void v_cycle();               // from the finest grid; leaves coarsest info in d_info_
+  // halo planes with the z-neighbours: which = 0 (u) or 2 (r scratch); arr overrides the array (per slab)
+  void exchange(int g, int which, int colour_mask, int nplanes, const std::vector<double*>* arr = nullptr);
 
-  // solve_poisson_bvp: u (colour-split, level-0 layout) in/out; rhs colour-split or nullptr (== 0)
+  // solve_poisson_bvp: u[s] (colour-split, level-0 layout of slab s incl. halos, pointer to local plane 0)
+  // in/out; rhs[s] colour-split or nullptr (== 0)
+  int solve(const std::vector<double*>& u, const std::vector<const double*>& rhs, double vc_tol, int nmax,
+            double* du_last, SolveTrace* tr);
   int solve(double* u, const double* rhs, double vc_tol, int nmax, double* du_last, SolveTrace* tr);
-  void set_level0_rhs(const double* rhs) { rhs0_ = rhs; }
+  void set_level0_rhs(const double* rhs, int s = 0) { rhs0_[s] = rhs; }
   // the same solve as a state machine (one outstanding solve per MG instance)
+  void solve_begin(const std::vector<double*>& u, const std::vector<const double*>& rhs, double vc_tol, int nmax,
+                   SolveTrace* tr);
   void solve_begin(double* u, const double* rhs, double vc_tol, int nmax, SolveTrace* tr);
   void solve_enqueue();            // enqueue the next V-cycle (+ update_u) on the stream
   bool solve_poll();               // wait for it, read du; true when converged or nmax reached
   int solve_end(double* du_last);  // returns ierr
   bool solve_done() const { return ss_.done; }
-  void enqueue_cycle(double* u);  // V-cycle + update_u + result copies (no sync)
+  void enqueue_cycle();            // V-cycle + update_u + result copies (no sync)
   bool coarsest_in_smem(const double* rhs_coarsest) const;
 
   cudaStream_t stream() const { return st_; }
@@ -90,7 +152,10 @@ class MG {
 
  private:
   int ndim_;
-  std::vector<Level> lv_;
+  std::vector<std::vector<std::vector<double>>> mesh_;  // [level][dim]
+  std::vector<Slab> slabs_;
+  SlabPlan plan_;
+  Comm* comm_ = nullptr;
   cudaStream_t st_;
   int ms_ = -1;
   double ex_tol_ = -1;
@@ -99,25 +164,24 @@ class MG {
   int nmax_exact_ = 0;
   bool all_neumann_ = false;
   int first_colour_ = 0;
-  const double* rhs0_ = nullptr;  // level-0 rhs for the current solve (nullptr == 0)
-  double* arena_ = nullptr;       // one allocation for all level arrays
-  int* tab_i_ = nullptr;          // packed transfer tables
+  std::vector<const double*> rhs0_;  // level-0 rhs per slab for the current solve (nullptr == 0)
+  int* tab_i_ = nullptr;             // packed transfer tables
   double* tab_d_ = nullptr;
-  double* r_ = nullptr;           // residual scratch (level-0 sized)
-  double* usav_ = nullptr;        // coarsest u_sav for the fallback solve_exact
-  double* scratch_ = nullptr;     // reduction scratch
-  double* d_out_ = nullptr;       // [2] device result of reductions
-  int* d_info_ = nullptr;         // [2] coarsest-solve iterations / converged
-  double* h_out_ = nullptr;       // pinned [4]: du_max, du_sum, + info
+  double* shared_ = nullptr;         // replicated levels, usav, reduction scratch, results
+  double* usav_ = nullptr;           // coarsest u_sav for the fallback solve_exact
+  double* scratch_ = nullptr;        // reduction scratch
+  double* d_all_ = nullptr;          // [2*world] gathered (max,sum) pairs
+  int* d_info_ = nullptr;            // [2] coarsest-solve iterations / converged
+  double* h_out_ = nullptr;          // pinned: [2*world] pairs + 2 ints
   struct SolveState {
-    double* u = nullptr;
+    std::vector<double*> u;
     double vc_tol = 0, du = 1.7976931348623157e308;
     int nmax = 0, it = 0;
     bool converged = false, done = false;
     cudaGraphExec_t gexec = nullptr;
     unsigned long long graph_launches = 0;
     SolveTrace* tr = nullptr;
-    double* zero_rhs = nullptr;
+    std::vector<double*> zero_rhs;
   } ss_;
 };
 

@@ -6,6 +6,7 @@
 #include "pool.hpp"
 
 #include <chrono>
+#include <algorithm>
 #include <cmath>
 #include <memory>
 
@@ -47,7 +48,7 @@ struct EvTimer {
 };
 
 int vector_solve_core(const int* nshape, const long long* iopt, const double* ropt, const double* x, const double* y,
-                      const double* z, double* const* bn, const double* A0, double* A_out, double* B_out,
+                      const double* z, double* const* bn, const DenseIn& A0, Comm* comm, const std::vector<SlabOut>& outs_in,
                       cudaStream_t st, Report& rep, BcCapture* cap, bool stop_after_bc) {
   const int nx = nshape[0], ny = nshape[1], nz = nshape[2];
   const i64 N = (i64)nx * ny * nz;
@@ -167,33 +168,47 @@ int vector_solve_core(const int* nshape, const long long* iopt, const double* ro
   tm.start();
   if (g_debug) debug_msg("compute_vector_potential", "Solve BVP 3D...");
   const int sh3[3] = {nx, ny, nz};
-  std::unique_ptr<MG> mg3(new MG(3, sh3, -1, mesh, st));
-  const Grid g3 = mg3->level(0).g;
-  const size_t lvl = 2 * (size_t)g3.cs;
-  DevBuf As(3 * lvl);
-  if (A0) {
+  std::unique_ptr<MG> mg3(new MG(3, sh3, -1, mesh, st, comm));
+  const int ns = mg3->nslabs();
+  std::vector<SlabOut> outs = outs_in;
+  if (ns == 1 && outs.size() > 1) {  // every virtual rank shares one undivided solve: one contiguous output
+    SlabOut o = outs.front();
+    o.k1 = outs.back().k1;
+    outs.assign(1, o);
+  }
+  if ((int)outs.size() != ns) throw NdsmError(6);
+  rep.ndist = mg3->plan().ndist;
+  std::vector<DevBuf> As(ns);
+  std::vector<size_t> lvl(ns);
+  std::vector<double*> Ap[3];  // per component: local plane 0 of every slab
+  for (int s = 0; s < ns; ++s) {
+    const Level& L0 = mg3->level(0, s);
+    lvl[s] = mg3->level_doubles(0, s);
+    As[s].alloc(3 * lvl[s]);
+    CUDA_CHECK(cudaMemsetAsync(As[s].p, 0, 3 * lvl[s] * sizeof(double), st));
     for (int c = 0; c < 3; ++c) {
-      CUDA_CHECK(cudaMemsetAsync(As.p + c * lvl, 0, lvl * sizeof(double), st));
-      split_from_dense(A0 + c * N, As.p + c * lvl, g3, 0.0, st);
+      double* p0 = As[s].p + c * lvl[s] + (i64)L0.H * L0.g.ps;
+      Ap[c].push_back(p0);
+      if (A0.p)  // initial guess as received (reference never zeroes A)
+        split_from_dense(A0.p + c * A0.cstride + (i64)(L0.g.k0 - A0.kfirst) * nx * ny, p0, L0.g, 0.0, st);
     }
-  } else {
-    CUDA_CHECK(cudaMemsetAsync(As.p, 0, 3 * lvl * sizeof(double), st));
   }
   static const int wf[3][4] = {{2, 3, 4, 5}, {0, 1, 4, 5}, {0, 1, 2, 3}};  // face write order :647-650,663-666,679-682
   static const int wa[3][4] = {{0, 0, 0, 0}, {0, 0, 1, 1}, {1, 1, 1, 1}};  // At(1,.) or At(2,.)
   static const char* cop[3] = {"NDDNDD", "DNDDND", "DDNDDN"};              // :655,671,687
+  const std::vector<const double*> norhs(ns, nullptr);                     // rhs = 0 (:640-641)
   for (int c = 0; c < 3; ++c) {
-    double* Ac = As.p + c * lvl;
-    for (int w = 0; w < 4; ++w) {
-      const int f = wf[c][w];
-      const int layer = (f % 2 == 0) ? 0 : nshape[imap_cp[f]] - 1;
-      write_face(Ac, g3, imap_cp[f], layer, At[f][wa[c][w]].p, st);
-    }
+    for (int s = 0; s < ns; ++s)
+      for (int w = 0; w < 4; ++w) {
+        const int f = wf[c][w];
+        const int layer = (f % 2 == 0) ? 0 : nshape[imap_cp[f]] - 1;
+        write_face(Ap[c][s], mg3->level(0, s).g, imap_cp[f], layer, At[f][wa[c][w]].p, st);
+      }
     mg3->set_options(c == 2 ? 5 : (int)iopt[IOPT_MS], ropt[ROPT_CTOL], cop[c], use_du_max, (int)iopt[IOPT_NMAXEX]);  // :685
     double du_last;
-    mg3->solve(Ac, nullptr, ropt[ROPT_VTOL], (int)iopt[IOPT_NCYCLES], &du_last, &rep.solves[6 + c]);  // rhs = 0 (:640-641)
+    mg3->solve(Ap[c], norhs, ropt[ROPT_VTOL], (int)iopt[IOPT_NCYCLES], &du_last, &rep.solves[6 + c]);
+    mg3->exchange(0, 0, 3, 1, &Ap[c]);  // halo planes of the converged component (curl needs k-1, k+1)
   }
-  mg3.reset();  // release the hierarchy before the dense outputs are touched
   rep.ms_solve3d = tm.stop();
 
   // ---------------- flux-balance fields + curl (K8) ----------------
@@ -201,14 +216,48 @@ int vector_solve_core(const int* nshape, const long long* iopt, const double* ro
   if (g_debug) debug_msg("compute_vector_potential", "Compute B = curl(B) and flux correction...");
   const bool flux_first = (iopt[IOPT_FLXCRL] != 1);  // :453-477
   if (!flux_first) printf(" FLAG SET: FLXCRL\n");
-  for (int c = 0; c < 3; ++c)
-    unsplit_A(As.p + c * lvl, g3, c, dx_, dy_, dz_, phi, Lq, flux_first, A_out + c * N, st);
-  curl_dense(A_out, nx, ny, nz, dq[0], dq[1], dq[2], B_out, st);
-  if (!flux_first) add_flux_dense(A_out, B_out, nx, ny, nz, dx_, dy_, dz_, phi, Lq, st);
+  const i64 pl = (i64)nx * ny;
+  for (int s = 0; s < ns; ++s) {
+    const Grid& g3 = mg3->level(0, s).g;
+    // planes this slab has to deliver, and the planes of A the curl stencil touches
+    int k0 = g3.k0, k1 = g3.k0 + g3.nzl;
+    if (ns == 1 && mg3->plan().ndist == 0) { k0 = outs[0].k0; k1 = outs[0].k1; }  // replicated solve: own output range
+    const SlabOut& o = outs[s];
+    if (o.k0 != k0 || o.k1 != k1) throw NdsmError(6);
+    const int glo = g3.k0 - mg3->level(0, s).H, ghi = g3.k0 + g3.nzl + mg3->level(0, s).H;
+    int ka = (k0 == 0) ? 0 : k0 - 1, kb = (k1 == nz) ? nz : k1 + 1;
+    if (k0 == 0 && kb < 3) kb = 3 < nz ? 3 : nz;       // one-sided stencil at the lower face needs planes 0,1,2
+    if (k1 == nz && ka > nz - 3) ka = nz - 3 > 0 ? nz - 3 : 0;
+    if (ka < (glo < 0 ? 0 : glo) || kb > (ghi > nz ? nz : ghi)) throw NdsmError(6);
+    const bool in_place = (ka == k0 && kb == k1);
+    DevBuf tmp;
+    double* Ad = o.A;
+    i64 csA = o.cstride;
+    if (!in_place) {
+      tmp.alloc((size_t)3 * (kb - ka) * pl);
+      Ad = tmp.p;
+      csA = (i64)(kb - ka) * pl;
+    }
+    for (int c = 0; c < 3; ++c)
+      unsplit_A(Ap[c][s], g3, c, dx_, dy_, dz_, phi, Lq, flux_first, ka, kb, Ad + c * csA, st);
+    curl_dense(Ad, ka, csA, nx, ny, nz, dq[0], dq[1], dq[2], k0, k1, o.B, o.cstride, st);
+    if (!in_place)
+      for (int c = 0; c < 3; ++c)
+        CUDA_CHECK(cudaMemcpyAsync(o.A + c * o.cstride, Ad + c * csA + (i64)(k0 - ka) * pl, (size_t)(k1 - k0) * pl * sizeof(double),
+                                   cudaMemcpyDeviceToDevice, st));
+    if (!flux_first) add_flux_dense(o.A, o.cstride, o.B, o.cstride, nx, ny, k0, k1, dx_, dy_, dz_, phi, Lq, st);
+    CUDA_CHECK(cudaStreamSynchronize(st));  // tmp goes out of scope
+  }
+  mg3.reset();
   rep.ms_post = tm.stop();
   rep.ms_device = tall.stop();
   rep.launches = g_launches - launches0;
   return ierr_last;  // :480 -- ierr of the LAST chi solve (reference quirk)
+}
+
+void output_range(int nz, int world, int rank, int* k0, int* k1) {
+  *k0 = (int)((i64)nz * rank / world);
+  *k1 = (int)((i64)nz * (rank + 1) / world);
 }
 
 }  // namespace ndsm

@@ -17,6 +17,7 @@ struct Report {
   // milliseconds
   double ms_total = 0, ms_in = 0, ms_bc = 0, ms_solve3d = 0, ms_post = 0, ms_out = 0, ms_device = 0;
   unsigned long long launches = 0;
+  int ndist = 0;  // number of z-partitioned multigrid levels in the 3D solves
 };
 extern Report g_report;
 
@@ -27,11 +28,26 @@ struct BcCapture {
   double* At2[6] = {nullptr};
 };
 
-// bn[f]: dense device faces (face f has shape (n1,n2) per ndsm_vector_potential.f90:225-246).
-// A0: dense device initial guess (3N) or nullptr for zeros.  A_out/B_out: dense device (3N).
+// Dense device arrays are described as "pointer to a first global z-plane + component stride".
+struct DenseIn {   // initial guess A0: p == nullptr means zeros
+  const double* p = nullptr;
+  int kfirst = 0;       // global index of the first plane stored
+  long long cstride = 0;
+};
+struct SlabOut {   // where one slab delivers A and B: planes [k0,k1), components cstride apart
+  double* A = nullptr;
+  double* B = nullptr;
+  long long cstride = 0;
+  int k0 = 0, k1 = 0;
+};
+// balanced z-range of rank `rank` (identical to the finest-level slab partition)
+void output_range(int nz, int world, int rank, int* k0, int* k1);
+
+// bn[f]: dense device faces (face f has shape (n1,n2) per ndsm_vector_potential.f90:225-246), all six on every
+// rank.  comm == nullptr: single slab.  outs: one entry per slab held by this process.
 // stop_after_bc: only run the BC setup (tests).  Returns iopt(IOPT_IERR).
 int vector_solve_core(const int* nshape, const long long* iopt, const double* ropt, const double* x, const double* y,
-                      const double* z, double* const* bn, const double* A0, double* A_out, double* B_out,
+                      const double* z, double* const* bn, const DenseIn& A0, Comm* comm, const std::vector<SlabOut>& outs,
                       cudaStream_t st, Report& rep, BcCapture* cap, bool stop_after_bc);
 
 }  // namespace ndsm

@@ -165,6 +165,14 @@ class Plan:
         assert self.lib.ndsm_b200_plan_interp(self.p, g, d, _ptr(lo), _ptr(wl), _ptr(wh)) == 0
         return lo, wl, wh
 
+    def slab_partition(self, world, min_planes=16):
+        """Returns (ndist, zs) with zs[level][rank] plane boundaries (ndist+1 rows when ndist > 0)."""
+        nd = ctypes.c_int(0)
+        zs = np.zeros((self.ngrids, world + 1), dtype=np.intc)
+        assert self.lib.ndsm_b200_plan_slab_partition(self.p, world, min_planes, ctypes.byref(nd), _ptr(zs)) == 0
+        n = nd.value
+        return n, (zs[: n + 1].copy() if n > 0 else zs[:0])
+
     def restrict_table(self, g, d):
         nc = self.level(g + 1)["shape"][d]
         first = np.zeros(nc, dtype=np.intc)

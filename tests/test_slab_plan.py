@@ -1,0 +1,54 @@
+"""Host-side logic of the multi-GPU z-slab decomposition (no GPU needed): partition of every partitioned
+level, replication threshold, and the halo property that restriction / prolongation stencils of the
+planes a rank produces stay inside its owned planes + NDSM_HALO halo planes."""
+import numpy as np
+import pytest
+
+from conftest import aniso_mesh
+
+HALO = 4
+
+
+@pytest.mark.parametrize("shape,world,min_planes", [((513, 513, 513), 8, 16), ((513, 513, 513), 2, 16),
+                                                    ((1025, 1025, 257), 8, 16), ((129, 129, 129), 4, 16),
+                                                    ((44, 44, 44), 3, 4), ((40, 33, 52), 2, 4), ((257, 257, 257), 8, 8)])
+def test_partition_tiles_and_respects_halo(shape, world, min_planes):
+    from ndsm_b200.mg import Plan
+    p = Plan(aniso_mesh(shape))
+    ndist, zs = p.slab_partition(world, min_planes)
+    assert 0 <= ndist <= p.ngrids - 1  # the coarsest level is never partitioned
+    if ndist == 0:
+        return
+    assert zs.shape == (ndist + 1, world + 1)
+    for lv in range(ndist + 1):
+        nz = p.level(lv)["shape"][2]
+        assert zs[lv][0] == 0 and zs[lv][-1] == nz
+        assert np.all(np.diff(zs[lv]) >= (min_planes if lv < ndist else 0))
+    # finest level is the balanced split used for the output ranges
+    assert list(zs[0]) == [shape[2] * r // world for r in range(world + 1)]
+    for lv in range(ndist):
+        first, count, _, _ = p.restrict_table(lv, 2)
+        lo, _, _ = p.interp_table(lv, 2)
+        nzf, nzc = p.level(lv)["shape"][2], p.level(lv + 1)["shape"][2]
+        for r in range(world):
+            f0, f1 = max(zs[lv][r] - HALO, 0), min(zs[lv][r + 1] + HALO, nzf)
+            for c in range(zs[lv + 1][r], zs[lv + 1][r + 1]):
+                assert f0 <= first[c] and first[c] + count[c] <= f1
+            if lv + 1 < ndist:
+                c0, c1 = zs[lv + 1][r] - HALO, zs[lv + 1][r + 1] + HALO
+                for k in range(zs[lv][r], zs[lv][r + 1]):
+                    assert c0 <= lo[k] and min(lo[k] + 1, nzc - 1) < c1
+    p.close()
+
+
+def test_expected_depth_for_headline_config():
+    """513^3 on 8 GPUs: 513 -> 256 -> 128 planes are partitioned (>= 16 planes per rank), 64^3 and below replicated."""
+    from ndsm_b200.mg import Plan
+    p = Plan(aniso_mesh((513, 513, 513)))
+    ndist, zs = p.slab_partition(8, 16)
+    assert ndist == 3
+    ndist2, _ = p.slab_partition(2, 16)
+    assert ndist2 == 5
+    ndist1, zs1 = p.slab_partition(1, 16)
+    assert ndist1 == 0 and len(zs1) == 0
+    p.close()
