@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bench.py -- headline benchmark of the NDSM vector-potential hot path on B200.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--n 513]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--size 513]
 
 A "step" is one complete vector-potential solve (BC setup: 6 chi solves -> 3 multigrid solves to
 vc_tol -> flux-balance fields -> curl) of the synthetic sub-surface dipole on an n^3 mesh (default
@@ -175,43 +175,98 @@ def run_reference(args, rank, world):
 # ------------------------------------------------------------------------------------------------
 # GPU arm
 # ------------------------------------------------------------------------------------------------
+def kernel_report(lib, npoints, dev_ms):
+    """Per-kernel-class CUDA-event timings gathered by the library (finest level of this rank's slab)."""
+    cnt, tot = ctypes.c_ulonglong(0), ctypes.c_double(0)
+    peak, peak_src = measured_peak()
+    kern = {}
+    names = ["k_relax3d<rhs=0> colour pass", "k_residual3d", "k_restrict", "k_interp_add", "update_u (k_diff_partial+final)"]
+    bytes_per_pt = [8.0, 16.0, 9.0, 17.0, 24.0]  # SURVEY 8d / DESIGN.md (level 0, rhs == 0)
+    for cls in range(5):
+        lib.ndsm_b200_profile_get(cls, ctypes.byref(cnt), ctypes.byref(tot))
+        if cnt.value:
+            avg_ms = tot.value / cnt.value
+            kern[names[cls]] = {"launches": cnt.value, "avg_ms": avg_ms, "total_ms": tot.value,
+                                "achieved_gbs": bytes_per_pt[cls] * npoints / (avg_ms * 1e-3) / 1e9}
+    k0 = kern.get(names[0], {"achieved_gbs": 0.0, "total_ms": 0.0})
+    return {"bound": "hbm", "kernel": names[0], "achieved": k0["achieved_gbs"], "peak": peak, "unit": "GB/s",
+            "frac": k0["achieved_gbs"] / peak, "traffic": NCU_TRAFFIC_BYTES.get(npoints), "peak_source": peak_src,
+            "algorithmic_bytes_per_launch": 8.0 * npoints, "share_of_step": k0["total_ms"] / (dev_ms if dev_ms else 1.0),
+            "measured_in": "second pass of the same K steps with per-launch CUDA events (graphs off)",
+            "kernels": kern}
+
+
+# dram__bytes_read.sum + dram__bytes_write.sum per launch of the finest-level colour pass from the committed
+# `ncu --set full` capture (profiles/), keyed by points per launch
+NCU_TRAFFIC_BYTES = {513 ** 3: 559.7e6 + 503.3e6}
+
+
 def run_ours(args, rank, world):
     import torch
     from ndsm_b200 import load_library
     from ndsm_b200.ndsm import _options
-    if world > 1:
-        import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=torch.device("cuda", int(os.environ.get("LOCAL_RANK", rank))))
     local = int(os.environ.get("LOCAL_RANK", 0))
     torch.cuda.set_device(local)
     os.environ["NDSM_DEVICE"] = str(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     lib = load_library()
     if lib.ndsm_b200_device_count() <= 0:
         raise RuntimeError("bench.py: no CUDA device -- the product has no CPU fallback")
-    if world > 1:
-        raise SystemExit("bench.py: z-slab multi-GPU path not built yet (DESIGN.md, SURVEY 8e)")
 
     n = args.n
     N = n ** 3
     x, y, z, b = workload(n)
     nshape = np.array([n, n, n, 3], dtype=np.intc)
     p = lambda a: a.ctypes.data_as(ctypes.c_void_p)
-    barrier = (lambda: None)
-
-    # ---------------- device-resident arm: inputs already in HBM --------------------------------
-    dB0 = torch.from_numpy(b).cuda()       # pristine boundary data
-    dB = torch.empty_like(dB0)
-    dA = torch.empty_like(dB0)
     ioptc, ropt = _options(lib, 10000, 1024, 1e-13, 1e-10, 5, False, False)
 
-    def device_step():
-        dA.zero_()                          # initial guess (reference passes zeros)
-        dB.copy_(dB0)                       # B is overwritten by curl A every step
-        torch.cuda.current_stream().synchronize()
-        rc = lib.ndsm_b200_vector_solve_device(p(nshape), p(ioptc), p(ropt), p(x), p(y), p(z),
-                                               ctypes.c_void_p(dA.data_ptr()), ctypes.c_void_p(dB.data_ptr()))
-        if rc != 0:
-            raise RuntimeError("ndsm_b200_vector_solve_device returned %d" % rc)
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+
+    def maxr(v):
+        if dist is None:
+            return v
+        t = torch.tensor([v], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    if world == 1:
+        # ---------------- device-resident arm: inputs already in HBM ------------------------------
+        dB0 = torch.from_numpy(b).cuda()       # pristine boundary data
+        dB = torch.empty_like(dB0)
+        dA = torch.empty_like(dB0)
+        npts_local = N
+
+        def device_step():
+            dA.zero_()                          # initial guess (reference passes zeros)
+            dB.copy_(dB0)                       # B is overwritten by curl A every step
+            torch.cuda.current_stream().synchronize()
+            rc = lib.ndsm_b200_vector_solve_device(p(nshape), p(ioptc), p(ropt), p(x), p(y), p(z),
+                                                   ctypes.c_void_p(dA.data_ptr()), ctypes.c_void_p(dB.data_ptr()))
+            if rc != 0:
+                raise RuntimeError("ndsm_b200_vector_solve_device returned %d" % rc)
+        timed = "K x (zero A, restore B faces, ndsm_b200_vector_solve_device)"
+    else:
+        from ndsm_b200 import dist as ndist
+        ndist.init_from_torch(local)
+        k0, k1 = ndist.slab_range(n, world, rank)
+        faces_h = ndist.extract_faces(b)
+        faces_d = [torch.from_numpy(f).cuda() for f in faces_h]
+        fptr = [f.data_ptr() for f in faces_d]
+        dA = torch.empty((3, k1 - k0, n, n), dtype=torch.float64, device="cuda")
+        dB = torch.empty_like(dA)
+        npts_local = (k1 - k0) * n * n
+
+        def device_step():
+            rc, _, _, _ = ndist.vector_potential_rank(x, y, z, fptr, out=(dA.data_ptr(), dB.data_ptr()),
+                                                      faces_on_device=True)
+            if rc != 0:
+                raise RuntimeError("ndsm_b200_vector_solve_rank returned %d" % rc)
+        timed = "K x ndsm_b200_vector_solve_rank (six faces resident in HBM on every rank, z-slab outputs in HBM)"
 
     for _ in range(args.warmup):
         device_step()
@@ -233,7 +288,7 @@ def run_ours(args, rank, world):
         stage = {"bc_ms": tim[2], "solve3d_ms": tim[3], "post_ms": tim[4]}
     ev1.record()
     torch.cuda.synchronize(); barrier()
-    wall = time.perf_counter() - t0
+    wall = maxr(time.perf_counter() - t0)
     launches = lib.ndsm_b200_launch_count() - l0
     clk = clocks.stop()
     value = upd_total / wall / 1e9
@@ -246,80 +301,84 @@ def run_ours(args, rank, world):
         device_step()
         lib.ndsm_b200_last_timing(p(tim))
         prof_ms += tim[6]
+    roofline = kernel_report(lib, npts_local, prof_ms)
     lib.ndsm_b200_profile_enable(0)
 
-    # roofline of the dominant kernel: finest-level colour pass, rhs == 0
-    cnt, tot = ctypes.c_ulonglong(0), ctypes.c_double(0)
-    peak, peak_src = measured_peak()
-    kern = {}
-    names = ["k_relax3d<rhs=0> colour pass", "k_residual3d", "k_restrict", "k_interp_add", "update_u (k_diff_partial+final)"]
-    bytes_per_pt = [8.0, 16.0, 9.0, 17.0, 24.0]  # SURVEY 8d / DESIGN.md (level 0, rhs == 0)
-    for cls in range(5):
-        lib.ndsm_b200_profile_get(cls, ctypes.byref(cnt), ctypes.byref(tot))
-        if cnt.value:
-            avg_ms = tot.value / cnt.value
-            kern[names[cls]] = {"launches": cnt.value, "avg_ms": avg_ms, "total_ms": tot.value,
-                                "achieved_gbs": bytes_per_pt[cls] * N / (avg_ms * 1e-3) / 1e9}
-    k0 = kern.get(names[0], {"achieved_gbs": 0.0, "total_ms": 0.0})
-    roofline = {"bound": "hbm", "kernel": names[0], "achieved": k0["achieved_gbs"], "peak": peak, "unit": "GB/s",
-                "frac": k0["achieved_gbs"] / peak, "traffic": None, "peak_source": peak_src,
-                "algorithmic_bytes_per_launch": 8.0 * N, "share_of_step": k0["total_ms"] / (prof_ms if prof_ms else 1.0),
-                "measured_in": "second pass of the same K steps with per-launch CUDA events (graphs off)",
-                "kernels": kern}
-
-    # ---------------- end-to-end arm: host buffers through the frozen C ABI -----------------------
-    hA = torch.zeros(3 * N, dtype=torch.float64).pin_memory()
-    hB = torch.empty(3 * N, dtype=torch.float64).pin_memory()
-    hb0 = torch.from_numpy(b.reshape(-1))
-    A_np, B_np = hA.numpy(), hB.numpy()
+    # ---------------- end-to-end arm: host buffers, H2D and D2H inside the timed region -------------
     faces_bytes = 8 * 6 * n * n + 8 * 3 * n
     e2e_upd, e2e_t = 0, 0.0
+    if world == 1:   # the frozen reference-facing C ABI
+        hA = torch.zeros(3 * N, dtype=torch.float64).pin_memory()
+        hB = torch.empty(3 * N, dtype=torch.float64).pin_memory()
+        hb0 = torch.from_numpy(b.reshape(-1))
+        A_np, B_np = hA.numpy(), hB.numpy()
+        d2h = 8 * 6 * N
+        api = "ndsm_vector_solve (frozen reference ABI), pinned host buffers"
+    else:
+        hA = torch.zeros(3 * npts_local, dtype=torch.float64).pin_memory()
+        hB = torch.zeros(3 * npts_local, dtype=torch.float64).pin_memory()
+        A_np, B_np = hA.numpy(), hB.numpy()
+        fpin = [torch.from_numpy(f).pin_memory().numpy() for f in faces_h]
+        d2h = 8 * 6 * N
+        api = "ndsm_b200_vector_solve_rank with host faces and host z-slab outputs (pinned)"
     for i in range(args.warmup + args.steps):
-        A_np[:] = 0.0
-        hB.copy_(hb0)
-        torch.cuda.synchronize()
+        if world == 1:
+            A_np[:] = 0.0
+            hB.copy_(hb0)
+        torch.cuda.synchronize(); barrier()
         t1 = time.perf_counter()
-        rc = lib.ndsm_vector_solve(ctypes.c_size_t(3 * N), p(nshape), p(ioptc), p(ropt), p(x), p(y), p(z), p(A_np), p(B_np))
-        torch.cuda.synchronize()
-        dt = time.perf_counter() - t1
+        if world == 1:
+            rc = lib.ndsm_vector_solve(ctypes.c_size_t(3 * N), p(nshape), p(ioptc), p(ropt), p(x), p(y), p(z), p(A_np), p(B_np))
+        else:
+            fp = (ctypes.c_void_p * 6)(*[f.ctypes.data for f in fpin])
+            rc = lib.ndsm_b200_vector_solve_rank(p(nshape), p(ioptc), p(ropt), p(x), p(y), p(z), fp, 0, p(A_np), p(B_np), 0)
+        torch.cuda.synchronize(); barrier()
+        dt = maxr(time.perf_counter() - t1)
         if rc != 0:
-            raise RuntimeError("ndsm_vector_solve returned %d" % rc)
+            raise RuntimeError("end-to-end solve returned %d" % rc)
         if i >= args.warmup:
             e2e_upd += updates_from_trace(lib, N)[0]
             e2e_t += dt
             lib.ndsm_b200_last_timing(p(tim))
             e2e_stage = {"in_ms": tim[1], "bc_ms": tim[2], "solve3d_ms": tim[3], "post_ms": tim[4], "d2h_ms": tim[5]}
-    e2e = {"value": e2e_upd / e2e_t / 1e9, "unit": "Gpoint-updates/s", "h2d_bytes_per_step": faces_bytes,
-           "d2h_bytes_per_step": 8 * 6 * N, "ms_per_step": e2e_t / args.steps * 1e3, "stages_ms": e2e_stage,
-           "host_memory": "pinned"}
+    e2e = {"value": e2e_upd / e2e_t / 1e9, "unit": "Gpoint-updates/s", "h2d_bytes_per_step": faces_bytes * world,
+           "d2h_bytes_per_step": d2h, "ms_per_step": e2e_t / args.steps * 1e3, "stages_ms": e2e_stage,
+           "host_memory": "pinned", "api": api}
 
-    # analytic sanity of the last result (B against the exact dipole field on the six faces)
-    err = float(np.abs(B_np.reshape(3, n, n, n)[:, 0] - b[:, 0]).max())
+    # analytic sanity of the last result (B against the exact dipole field on the z = 0 face, rank 0's slab)
+    err = float(np.abs(B_np.reshape(3, -1, n, n)[:, 0] - b[:, 0]).max()) if rank == 0 else None
 
-    # ---------------- CPU baseline: bounded sample on the host cores -------------------------------
+    # ---------------- CPU baseline: bounded sample on the host cores (rank 0, N = 1 only) -----------
     cpu = None
-    if not args.no_cpu_baseline:
+    if not args.no_cpu_baseline and world == 1:
         sample_n = n if n <= 257 else 257
         v, dt, thr, desc = cpu_sample(sample_n, 1)
         if n > sample_n and dt * (n / sample_n) ** 3 < 30.0:
             v, dt, thr, desc = cpu_sample(n, 1)
         cpu = {"value": v, "unit": "Gpoint-updates/s", "cores": thr, "kind": "port", "sample": desc, "seconds": dt}
 
-    line = {
-        "metric": "fine-grid Gpoint-updates/s (time-to-vc_tol in ms_per_step)", "value": value,
-        "unit": "Gpoint-updates/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": wall / args.steps * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-        "dtype": "f64", "data": "synthetic",
-        "config": {"workload": workload_name(n),
-                   "l2": "inputs larger than L2 (each %d^3 fp64 array = %.2f GB)" % (n, 8 * N / 1e9),
-                   "v_cycles": {"chi": cyc[:6], "Ax": cyc[6], "Ay": cyc[7], "Az": cyc[8]},
-                   "timed_region": "K x (zero A, restore B faces, ndsm_b200_vector_solve_device)"},
-        "time_to_vc_tol_ms": {"device_events": dev_ms / args.steps, "wall": wall / args.steps * 1e3, **stage,
-                              "torch_events": ev0.elapsed_time(ev1) / args.steps},
-        "clocks": clk, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
-        "check": {"max_abs_B_error_on_z0_face": err},
-    }
-    print(json.dumps(line), flush=True)
+    if rank == 0:
+        line = {
+            "metric": "fine-grid Gpoint-updates/s (time-to-vc_tol in ms_per_step)", "value": value,
+            "unit": "Gpoint-updates/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": wall / args.steps * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": workload_name(n),
+                       "l2": "inputs larger than L2 (each %d^3 fp64 array = %.2f GB)" % (n, 8 * N / 1e9),
+                       "v_cycles": {"chi": cyc[:6], "Ax": cyc[6], "Ay": cyc[7], "Az": cyc[8]},
+                       "decomposition": "z-slabs, %d rank(s), one-plane halo exchange per colour pass over NCCL" % world
+                                        if world > 1 else "single GPU",
+                       "timed_region": timed},
+            "time_to_vc_tol_ms": {"device_events": dev_ms / args.steps, "wall": wall / args.steps * 1e3, **stage,
+                                  "torch_events_rank0": ev0.elapsed_time(ev1) / args.steps},
+            "clocks": clk, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
+            "check": {"max_abs_B_error_on_z0_face": err},
+        }
+        print(json.dumps(line), flush=True)
+    if dist is not None:
+        lib.ndsm_b200_dist_finalize()
+        dist.barrier()
+        dist.destroy_process_group()
 
 
 def main():
@@ -328,7 +387,7 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--n", type=int, default=513)
+    ap.add_argument("--size", dest="n", type=int, default=513, help="mesh points per dimension")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", 0))

@@ -65,6 +65,24 @@ int get_ropt_ctol(void);        /* :230-234  -> 1 */
 int ndsm_b200_vector_solve_device(const int* nshape4, int* ioptc, double* ropt, const double* x,
                                   const double* y, const double* z, double* dA, double* dB);
 
+/* Multi-GPU (one process per GPU, z-slab domain decomposition with one-plane halo exchange per colour pass over
+ * NCCL / NVLink; levels with fewer than NDSM_SLAB_MIN_PLANES (default 16) planes per rank are replicated).
+ * Bootstrap: rank 0 calls dist_unique_id, the 128 bytes are distributed by the caller (MPI, torch.distributed,
+ * a file ...), every rank calls dist_init on its own device (NDSM_DEVICE or the current device).
+ * vector_solve_rank: every rank passes all six boundary faces as dense arrays (face f of shape (n1,n2) with the
+ * lower-numbered axis fastest: x-faces (ny,nz), y-faces (nx,nz), z-faces (nx,ny); ndsm_vector_potential.f90:225-246)
+ * and receives planes [k0,k1) = slab_range(nz, world, rank) of A and B, laid out (nx,ny,k1-k0,3).  Faces and
+ * outputs may be host or device pointers (flags).  The initial guess is zero (what ndsm.py always passes). */
+int ndsm_b200_dist_unique_id(void* out128);
+int ndsm_b200_dist_init(int rank, int world, const void* id128);
+int ndsm_b200_dist_finalize(void);
+int ndsm_b200_dist_world(void);
+int ndsm_b200_dist_rank(void);
+int ndsm_b200_slab_range(int nz, int world, int rank, int* k0, int* k1);
+int ndsm_b200_vector_solve_rank(const int* nshape4, int* ioptc, double* ropt, const double* x, const double* y,
+                                const double* z, const double* const* faces6, int faces_on_device, double* A_slab,
+                                double* B_slab, int out_on_device);
+
 /* solve_poisson_bvp for a caller-defined scalar problem (ndsm_poisson.f90:63-155 with
  * new_mg_handle, ndsm_multigrid_core.f90:165): ndim = 2 or 3; copt = 2*ndim chars 'N'/'D' in the
  * reference order [lo_1..lo_ndim, hi_1..hi_ndim]; u: initial guess in / solution out (Dirichlet

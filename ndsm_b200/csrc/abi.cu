@@ -647,6 +647,106 @@ int ndsm_b200_flux_curl(const int* nshape4, int flxcrl, const double* x, const d
 }
 
 // ------------------------------------------------------------------------------------------
+// multi-GPU: one process per GPU, z-slabs over NCCL
+// ------------------------------------------------------------------------------------------
+static std::unique_ptr<Comm> g_dist;
+
+int ndsm_b200_dist_unique_id(void* out128) {
+  if (!out128) return NDSM_B200_ERR_ARG;
+  return nccl_unique_id(out128) ? 0 : NDSM_B200_ERR_CUDA;
+}
+int ndsm_b200_dist_init(int rank, int world, const void* id128) {
+  static const char* SUB = "ndsm_b200_dist_init";
+  if (!id128 || world < 1 || rank < 0 || rank >= world) return NDSM_B200_ERR_ARG;
+  if (int e = ensure_device(SUB)) return e;
+  try {
+    g_dist.reset();
+    g_dist = make_nccl_comm(rank, world, id128);
+    return 0;
+  } catch (const NdsmError& e) {
+    return fail(e, SUB);
+  }
+}
+int ndsm_b200_dist_finalize(void) {
+  cudaDeviceSynchronize();
+  g_dist.reset();
+  return 0;
+}
+int ndsm_b200_dist_world(void) { return g_dist ? g_dist->world() : 1; }
+int ndsm_b200_dist_rank(void) { return g_dist ? g_dist->first_rank() : 0; }
+int ndsm_b200_slab_range(int nz, int world, int rank, int* k0, int* k1) {
+  if (!k0 || !k1 || world < 1 || rank < 0 || rank >= world) return NDSM_B200_ERR_ARG;
+  output_range(nz, world, rank, k0, k1);
+  return 0;
+}
+
+int ndsm_b200_vector_solve_rank(const int* nshape4, int* ioptc, double* ropt, const double* x, const double* y,
+                                const double* z, const double* const* faces6, int faces_on_device, double* A_slab,
+                                double* B_slab, int out_on_device) {
+  static const char* SUB = "ndsm_b200_vector_solve_rank";
+  const double t0 = now_s();
+  if (!nshape4 || !ioptc || !ropt || !x || !y || !z || !faces6 || !A_slab || !B_slab) return NDSM_B200_ERR_ARG;
+  long long iopt[IOPT_LEN];
+  for (int i = 0; i < IOPT_LEN; ++i) iopt[i] = ioptc[i];
+  g_debug = (iopt[IOPT_DEBUG] == IOPT_TRUE);
+  const int nx = nshape4[0], ny = nshape4[1], nz = nshape4[2];
+  auto finish = [&](int ierr) {
+    iopt[IOPT_IERR] = ierr;
+    ropt[ROPT_TIM] = now_s() - t0;
+    for (int i = 0; i < IOPT_LEN; ++i) ioptc[i] = (int)iopt[i];
+    g_report.ms_total = ropt[ROPT_TIM] * 1e3;
+    return ierr;
+  };
+  if (nx < 2 || ny < 2 || nz < 2) return finish(NDSM_B200_ERR_NOT_CONVERGED);
+  if (int e = ensure_device(SUB)) return finish(e);
+  g_report = Report();
+  const int world = g_dist ? g_dist->world() : 1, rank = g_dist ? g_dist->first_rank() : 0;
+  try {
+    cudaStream_t st = g_stream;
+    double t1 = now_s();
+    size_t fsz[6], ftot = 0;
+    for (int f = 0; f < 6; ++f) { fsz[f] = (size_t)nshape4[imap_nc[f][0]] * nshape4[imap_nc[f][1]]; ftot += fsz[f]; }
+    DBuf dfaces(ftot);
+    double* bn[6];
+    size_t o = 0;
+    for (int f = 0; f < 6; ++f) {
+      bn[f] = dfaces.p + o;
+      CUDA_CHECK(cudaMemcpyAsync(bn[f], faces6[f], fsz[f] * sizeof(double),
+                                 faces_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, st));
+      o += fsz[f];
+    }
+    SlabOut so;
+    output_range(nz, world, rank, &so.k0, &so.k1);
+    const size_t nslab = (size_t)(so.k1 - so.k0) * nx * ny;
+    so.cstride = (long long)nslab;
+    std::unique_ptr<DBuf> dA, dB;
+    if (out_on_device) {
+      so.A = A_slab;
+      so.B = B_slab;
+    } else {
+      dA.reset(new DBuf(3 * nslab));
+      dB.reset(new DBuf(3 * nslab));
+      so.A = dA->p;
+      so.B = dB->p;
+    }
+    CUDA_CHECK(cudaStreamSynchronize(st));
+    g_report.ms_in = (now_s() - t1) * 1e3;
+    int ierr = vector_solve_core(nshape4, iopt, ropt, x, y, z, bn, DenseIn(), g_dist.get(), std::vector<SlabOut>{so}, st,
+                                 g_report, nullptr, false);
+    t1 = now_s();
+    if (!out_on_device) {
+      CUDA_CHECK(cudaMemcpyAsync(A_slab, so.A, 3 * nslab * sizeof(double), cudaMemcpyDeviceToHost, st));
+      CUDA_CHECK(cudaMemcpyAsync(B_slab, so.B, 3 * nslab * sizeof(double), cudaMemcpyDeviceToHost, st));
+    }
+    CUDA_CHECK(cudaStreamSynchronize(st));
+    g_report.ms_out = (now_s() - t1) * 1e3;
+    return finish(ierr);
+  } catch (const NdsmError& e) {
+    return finish(fail(e, SUB));
+  }
+}
+
+// ------------------------------------------------------------------------------------------
 // 4. Introspection
 // ------------------------------------------------------------------------------------------
 int ndsm_b200_device_count(void) {

@@ -65,6 +65,8 @@ struct Comm {
   virtual void bcast(int root_rank, double* buf, size_t n, cudaStream_t st) = 0;
 };
 std::unique_ptr<Comm> make_virtual_comm(int world);  // all ranks in this process, on the current device
+bool nccl_unique_id(void* out128);                    // ncclGetUniqueId (rank 0)
+std::unique_ptr<Comm> make_nccl_comm(int rank, int world, const void* id128);  // one rank per process / GPU
 
 struct SolveTrace {
   std::vector<double> du;      // du after each V-cycle

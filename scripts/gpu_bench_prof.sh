@@ -2,10 +2,10 @@
 # bench at 129/257/513 + ncu launch list and one full capture of the dominant kernel (after a plain run exited 0)
 mkdir -p gpurun_out
 N=${1:-513}
-timeout 600 python bench.py --n 129 --steps 3 --warmup 3 > gpurun_out/bench129.json 2> gpurun_out/bench129.err
-timeout 600 python bench.py --n 257 --steps 3 --warmup 3 > gpurun_out/bench257.json 2> gpurun_out/bench257.err
-timeout 900 python bench.py --n 513 --steps 3 --warmup 3 > gpurun_out/bench513.json 2> gpurun_out/bench513.err
-timeout 900 python bench.py --impl reference --n 513 --steps 2 --warmup 1 > gpurun_out/bench513_ref.json 2> gpurun_out/bench513_ref.err
+timeout 600 python bench.py --size 129 --steps 3 --warmup 3 > gpurun_out/bench129.json 2> gpurun_out/bench129.err
+timeout 600 python bench.py --size 257 --steps 3 --warmup 3 > gpurun_out/bench257.json 2> gpurun_out/bench257.err
+timeout 900 python bench.py --size 513 --steps 3 --warmup 3 > gpurun_out/bench513.json 2> gpurun_out/bench513.err
+timeout 900 python bench.py --impl reference --size 513 --steps 2 --warmup 1 > gpurun_out/bench513_ref.json 2> gpurun_out/bench513_ref.err
 # profile target: one device-resident 257^3 solve (short enough for ncu)
 timeout 300 python scripts/prof_target.py 257 > gpurun_out/plain.log 2>&1 && \
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 6000 --csv --log-file gpurun_out/launches_257.csv python scripts/prof_target.py 257 > gpurun_out/ncu_launch.log 2>&1

@@ -4,7 +4,7 @@ mkdir -p gpurun_out
 timeout 1500 python -m pytest tests -m gpu -q --timeout=900 -x > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?" >> gpurun_out/pytest_gpu.log
 tail -n 4 gpurun_out/pytest_gpu.log
 for n in 129 257 513; do
-  timeout 900 python bench.py --n $n --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/bench$n.json 2> gpurun_out/bench$n.err || tail -n 5 gpurun_out/bench$n.err
+  timeout 900 python bench.py --size $n --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/bench$n.json 2> gpurun_out/bench$n.err || tail -n 5 gpurun_out/bench$n.err
 done
 if [ "$1" = "ncu" ]; then
   timeout 300 python scripts/prof_target.py 129 > gpurun_out/plain129.log 2>&1 && \
