@@ -278,8 +278,9 @@ static int pick_zchunk(int nplanes, int blocks_per_plane) {
 }
 
 void relax3d_half(double* u, const double* rhs, const Grid& g, const Bounds& b, int colour, const Weights& w,
-                  cudaStream_t st) {
-  const int klo = max(b.lb[2], g.k0), khi = min(b.ub[2], g.k0 + g.nzl - 1);
+                  int ext, cudaStream_t st) {
+  // ext > 0: also update `ext` halo planes on each side of the slab (communication-avoiding smoothing)
+  const int klo = max(b.lb[2], g.k0 - ext), khi = min(b.ub[2], g.k0 + g.nzl - 1 + ext);
   const int nrows = b.ub[1] - b.lb[1] + 1;
   if (klo > khi || nrows <= 0) return;
   const int npairs = (g.mcnt > 4) ? (((g.mcnt - 1) & ~1) - 2) / 2 : 0;  // interior pairs m0 = 2, 4, ... < mE

@@ -141,7 +141,7 @@ std::vector<HostLevel> build_hierarchy(int ndim, const int* shape, int ngrids, c
 // ---------------------------------------------------------------------------------------------
 // z-slab partition (host only)
 // ---------------------------------------------------------------------------------------------
-SlabPlan plan_slabs(const std::vector<HostLevel>& hl, int ndim, int world, int min_planes) {
+SlabPlan plan_slabs(const std::vector<HostLevel>& hl, int ndim, int world, int min_planes, long long min_points) {
   SlabPlan p;
   p.world = world;
   if (world <= 1 || ndim != 3) return p;
@@ -152,6 +152,8 @@ SlabPlan plan_slabs(const std::vector<HostLevel>& hl, int ndim, int world, int m
   int g = 0;
   while (true) {
     bool ok = (g < ng - 1);  // the coarsest level is always replicated (solve_exact needs the whole grid)
+    // small levels are cheaper to solve redundantly on every rank than to exchange halos for
+    if ((long long)hl[g].n[0] * hl[g].n[1] * hl[g].n[2] < min_points) ok = false;
     for (int r = 0; r < world && ok; ++r) ok = (z[r + 1] - z[r] >= min_planes);
     if (!ok) break;
     p.zs.push_back(z);
@@ -258,8 +260,11 @@ MG::MG(int ndim, const int* shape, int ngrids, const double* const* mesh, cudaSt
   }
   const int world = comm_ ? comm_->world() : 1;
   int min_planes = 16;
+  long long min_points = 8000000;  // 256^3 is partitioned, 128^3 is replicated
   if (const char* e = getenv("NDSM_SLAB_MIN_PLANES")) min_planes = atoi(e);
-  plan_ = plan_slabs(hl, ndim, world, min_planes);
+  if (const char* e = getenv("NDSM_SLAB_MIN_POINTS")) min_points = atoll(e);
+  plan_ = plan_slabs(hl, ndim, world, min_planes, min_points);
+  valid_.assign(ngrids, std::array<int, 2>{{0, 0}});
   const int nd = plan_.ndist;
   const int H = plan_.halo;
   const int nlocal = (nd > 0 && comm_) ? comm_->nlocal() : 1;
@@ -422,20 +427,35 @@ void MG::exchange(int g, int which, int colour_mask, int np, const std::vector<d
   comm_->end(st_);
 }
 
+void MG::need_halo(int g, int depth) {
+  if (g >= plan_.ndist || !comm_) return;
+  if (valid_[g][0] >= depth && valid_[g][1] >= depth) return;
+  exchange(g, 0, 3, plan_.halo);
+  valid_[g][0] = valid_[g][1] = plan_.halo;
+}
+
 void MG::relax(int g) {
-  const bool dist = g < plan_.ndist;
+  const bool dist = g < plan_.ndist && comm_;
   const size_t ns = dist ? slabs_.size() : 1;
   if (ndim_ == 3) {
     for (int pass = 0; pass < 2; ++pass) {
       const int colour = first_colour_ ^ pass;
+      int ext = 0;
+      if (dist) {  // the pass needs the other colour one plane beyond the planes it updates
+        need_halo_colour(g, 1 - colour);
+        // extended passes read rhs in the halo planes: exchanged for g > 0, identically zero for the
+        // vector-potential solves on g == 0; a caller-supplied level-0 rhs has no trusted halo
+        const bool rhs_halo_ok = (g > 0) || rhs0_[0] == nullptr;
+        ext = rhs_halo_ok ? valid_[g][1 - colour] - 1 : 0;
+      }
       // each colour pass is timed separately when profiling (PROF_RELAX0 = one k_relax3d launch on level 0)
       if (g == 0 && ns == 1) prof_begin(PROF_RELAX0, st_);
       for (size_t s = 0; s < ns; ++s) {
         Level& L = slabs_[s].lv[g];
-        relax3d_half(L.u, (g == 0) ? rhs0_[s] : L.rhs, L.g, L.b, colour, L.w, st_);
+        relax3d_half(L.u, (g == 0) ? rhs0_[s] : L.rhs, L.g, L.b, colour, L.w, ext, st_);
       }
       if (g == 0 && ns == 1) prof_end(PROF_RELAX0, st_);
-      if (dist) exchange(g, 0, 1 << colour, 1);
+      if (dist) valid_[g][colour] = ext;
     }
   } else {
     Level& L = slabs_[0].lv[g];
@@ -449,7 +469,15 @@ void MG::relax(int g) {
   }
 }
 
+// the other colour must be valid at least one plane deep before a pass; refresh both colours when it is not
+void MG::need_halo_colour(int g, int colour) {
+  if (valid_[g][colour] >= 1) return;
+  exchange(g, 0, 3, plan_.halo);
+  valid_[g][0] = valid_[g][1] = plan_.halo;
+}
+
 void MG::residual(int g) {
+  need_halo(g, 1);
   const size_t ns = (g < plan_.ndist) ? slabs_.size() : 1;
   const bool prof = (g == 0 && ndim_ == 3 && ns == 1);
   if (prof) prof_begin(PROF_RESID0, st_);
@@ -496,6 +524,12 @@ void MG::restrict_to(int g) {
     }
     comm_->end(st_);
   }
+  if (cdist) {  // extended colour passes read rhs in the halo planes
+    std::vector<double*> rp;
+    for (auto& S : slabs_) rp.push_back(S.lv[c].rhs);
+    exchange(c, 0, 3, plan_.halo, &rp);
+    valid_[c][0] = valid_[c][1] = plan_.halo;  // u[c] = 0 everywhere, halos included
+  }
   const size_t nc = cdist ? slabs_.size() : 1;
   for (size_t s = 0; s < nc; ++s) {  // ndsm_multigrid_core.f90:557-558
     Level& C = slabs_[s].lv[c];
@@ -507,7 +541,7 @@ void MG::interp_add_from(int c) {
   const int f = c - 1;
   const bool fdist = f < plan_.ndist, cdist = c < plan_.ndist;
   const size_t ns = fdist ? slabs_.size() : 1;
-  if (cdist) exchange(c, 0, 3, plan_.halo);
+  if (cdist) { exchange(c, 0, 3, plan_.halo); valid_[c][0] = valid_[c][1] = plan_.halo; }
   const bool prof = (c == 1 && ndim_ == 3 && ns == 1);
   if (prof) prof_begin(PROF_INTERP0, st_);
   for (size_t s = 0; s < ns; ++s) {
@@ -516,7 +550,7 @@ void MG::interp_add_from(int c) {
     interp_add(C.u, C.g, F.u, F.g, F.it[0], F.it[1], F.it[2], st_);
   }
   if (prof) prof_end(PROF_INTERP0, st_);
-  if (fdist) exchange(f, 0, 3, 1);
+  if (fdist) valid_[f][0] = valid_[f][1] = 0;  // owned planes changed; halos are refreshed by the next consumer
 }
 
 // solve_exact (ndsm_multigrid_core.f90:728-800) -- always on a replicated level
@@ -616,7 +650,7 @@ void MG::solve_begin(const std::vector<double*>& u, const std::vector<const doub
     CUDA_CHECK(cudaMemcpyAsync(level_base(L0.u, 0, (int)s), level_base(u[s], 0, (int)s), bytes0,
                                cudaMemcpyDeviceToDevice, st_));  // :100
   }
-  exchange(0, 0, 3, 1);  // the caller's halo planes are not trusted
+  for (auto& v : valid_) v = {{0, 0}};  // the caller's halo planes are not trusted; refreshed on first use
 
   // The loop body is a static launch sequence (the coarsest solve iterates inside one kernel), so it is
   // captured once into a CUDA graph and replayed every V-cycle: ~250-500 launches per cycle otherwise.

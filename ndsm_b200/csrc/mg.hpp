@@ -8,6 +8,7 @@
 // V-cycle, no scatter on the way up).  A process holds one slab (NCCL mode, one process per GPU) or all
 // slabs (virtual mode: every rank on one device, used to test the slab logic on a single GPU).
 #pragma once
+#include <array>
 #include <memory>
 #include <vector>
 #include "kernels.cuh"
@@ -44,8 +45,9 @@ struct SlabPlan {
                                      // level ndist says who PRODUCES which planes of the first replicated level
 };
 #define NDSM_HALO 4
-// min_planes: a level is partitioned only while every rank keeps at least that many planes
-SlabPlan plan_slabs(const std::vector<HostLevel>& hl, int ndim, int world, int min_planes);
+// a level is partitioned only while every rank keeps at least min_planes planes and the level has at least
+// min_points points (smaller levels are replicated)
+SlabPlan plan_slabs(const std::vector<HostLevel>& hl, int ndim, int world, int min_planes, long long min_points = 0);
 
 // Communication between slabs.  Two-sided, matched in call order per (from,to) pair; all calls are
 // enqueued on the stream and may be captured into a CUDA graph.
@@ -167,6 +169,12 @@ class MG {
   bool all_neumann_ = false;
   int first_colour_ = 0;
   std::vector<const double*> rhs0_;  // level-0 rhs per slab for the current solve (nullptr == 0)
+  // communication-avoiding smoothing on partitioned levels: valid_[g][c] = number of halo planes (each side)
+  // that currently hold up-to-date values of colour c.  A colour pass may also update `e` halo planes if the
+  // other colour is valid to depth e+1, so one 4-plane exchange feeds four passes (bit-identical values).
+  std::vector<std::array<int, 2>> valid_;
+  void need_halo(int g, int depth);  // make both colours of u[g] valid to at least `depth` planes
+  void need_halo_colour(int g, int colour);
   int* tab_i_ = nullptr;             // packed transfer tables
   double* tab_d_ = nullptr;
   double* shared_ = nullptr;         // replicated levels, usav, reduction scratch, results
