@@ -700,6 +700,301 @@ void restrict_level(const double* rf, const Grid& gf, double* rhsc, const Grid& 
 }
 
 // ---------------------------------------------------------------------------------------
+// K3 tiled: the same restriction as k_restrict (same weights, same summation order -> same bits), for
+// stencils of at most 5 points in x and y (every level of the 2:1-like hierarchies; wider stencils of very
+// coarse odd-sized levels take k_restrict).  A block owns a 32x8 tile of coarse (x,y) points and marches
+// over coarse planes; the fine residual planes stream through a rolling window of RR_WZ planes in shared
+// memory (x de-interleaved by parity so that neighbouring coarse points read neighbouring banks).  The
+// per-thread products ((1*c2x)*w2x*c2y)*w2y do not depend on z and are hoisted out of the march.
+// Algorithmic traffic: 8 B per fine point + 8 B per coarse point.
+// ---------------------------------------------------------------------------------------
+#define RR_CX 32
+#define RR_CY 8
+#define RR_WZ 8  // >= NDSM_RMAX
+#define RR_SM 5  // max stencil width in x and y handled by the tiled kernel
+
+__global__ void __launch_bounds__(RR_CX * RR_CY, 2)
+k_restrict_tiled(const double* __restrict__ rf, const Grid gf, double* __restrict__ rc, const Grid gc,
+                 const RestrictTab tx, const RestrictTab ty, const RestrictTab tz, const int hwp, const int fyw,
+                 const int kchunk) {
+  extern __shared__ double sr[];  // [RR_WZ][fyw][2*hwp]
+  const int txi = threadIdx.x & (RR_CX - 1), tyi = threadIdx.x / RR_CX;
+  const int ic0 = blockIdx.x * RR_CX, jc0 = blockIdx.y * RR_CY;
+  const int ic = ic0 + txi, jc = jc0 + tyi;
+  const bool active = (ic < gc.nx && jc < gc.ny);
+  const int icl = min(ic0 + RR_CX, gc.nx) - 1, jcl = min(jc0 + RR_CY, gc.ny) - 1;
+  // fine window of the tile (x start rounded down to even so that parity == global parity)
+  const int fx0 = tx.first[ic0] & ~1, fx1 = tx.first[icl] + tx.count[icl];
+  const int fy0 = ty.first[jc0], fy1 = ty.first[jcl] + ty.count[jcl];
+  const int FXW = fx1 - fx0, FYW = fy1 - fy0;
+  const int xp = 2 * hwp, pl = fyw * xp;
+  const int kc_beg = gc.k0 + blockIdx.z * kchunk;
+  const int kc_end = min(kc_beg + kchunk, gc.k0 + gc.nzl) - 1;
+  if (kc_beg > kc_end) return;
+
+  // per-thread x weights (1*c2x)*w2x, y weights and shared-memory offsets (all independent of z)
+  double px[RR_SM], wy[RR_SM];
+  int xoff[RR_SM];
+  int cx = 0, cy = 0, yrow = 0;
+  if (active) {
+    const int ax = tx.first[ic], ay = ty.first[jc];
+    cx = tx.count[ic];
+    cy = ty.count[jc];
+    yrow = (ay - fy0) * xp;
+    const double* __restrict__ wxv = tx.c2 + (i64)ic * NDSM_RMAX;
+    const double* __restrict__ wyv = ty.c2 + (i64)jc * NDSM_RMAX;
+#pragma unroll
+    for (int ii = 0; ii < RR_SM; ++ii) {
+      const int xo = ax + ii - fx0;
+      xoff[ii] = (xo & 1) * hwp + (xo >> 1);
+      px[ii] = (ii < cx) ? (wxv[ii] * tx.w2) : 0.0;
+      wy[ii] = (ii < cy) ? wyv[ii] : 0.0;
+    }
+  }
+  const int colour_base = (ic + jc) & 1;
+  int next_plane = tz.first[kc_beg];
+  // two coarse planes per iteration: two independent accumulation chains per thread hide the latency of the
+  // serial (reference-ordered) sum; the window holds the union of both stencils (<= RR_WZ planes)
+  for (int kc = kc_beg; kc <= kc_end; kc += 2) {
+    const bool two = (kc + 1 <= kc_end) &&
+                     (tz.first[kc + 1] + tz.count[kc + 1] - tz.first[kc] <= RR_WZ);
+    const int kcB = two ? kc + 1 : kc;
+    const int azA = tz.first[kc], czA = tz.count[kc];
+    const int azB = tz.first[kcB], czB = tz.count[kcB];
+    const int last = azB + czB - 1;
+    __syncthreads();  // the previous stencil loops have finished with the slots about to be overwritten
+    for (int kf = max(next_plane, azA); kf <= last; ++kf) {
+      double* __restrict__ dst = sr + (kf & (RR_WZ - 1)) * pl;
+      const i64 pz = (i64)(kf - gf.k0) * gf.ps;
+      for (int yo = tyi; yo < FYW; yo += RR_CY) {
+        const int j_f = fy0 + yo;
+        const i64 prow = pz + (i64)j_f * gf.hp;
+        const int par = (j_f + kf) & 1;
+        for (int xo = txi; xo < FXW; xo += RR_CX) {
+          const int i_f = fx0 + xo;
+          dst[yo * xp + (xo & 1) * hwp + (xo >> 1)] = rf[(i64)((i_f + par) & 1) * gf.cs + prow + (i_f >> 1)];
+        }
+      }
+    }
+    next_plane = max(next_plane, last + 1);
+    __syncthreads();
+    if (active) {
+      const double* __restrict__ wzA = tz.c2 + (i64)kc * NDSM_RMAX;
+      const double* __restrict__ wzB = tz.c2 + (i64)kcB * NDSM_RMAX;
+      double fa = 0.0, fb = 0.0;
+      const int cz = max(czA, czB);
+      for (int kk = 0; kk < cz; ++kk) {  // reference order: z outermost, x fastest (ndsm_interp.f90:263-290)
+        const bool doA = kk < czA, doB = two && kk < czB;
+        const double* __restrict__ sa = sr + ((azA + kk) & (RR_WZ - 1)) * pl + yrow;
+        const double* __restrict__ sb = sr + ((azB + kk) & (RR_WZ - 1)) * pl + yrow;
+        const double wza = doA ? wzA[kk] : 0.0, wzb = doB ? wzB[kk] : 0.0;
+#pragma unroll
+        for (int jj = 0; jj < RR_SM; ++jj) {
+          if (jj < cy) {
+#pragma unroll
+            for (int ii = 0; ii < RR_SM; ++ii) {
+              if (ii < cx) {
+                const double pxy = (px[ii] * wy[jj]) * ty.w2;
+                if (doA) fa = fa + ((pxy * wza) * tz.w2) * sa[jj * xp + xoff[ii]];
+                if (doB) fb = fb + ((pxy * wzb) * tz.w2) * sb[jj * xp + xoff[ii]];
+              }
+            }
+          }
+        }
+      }
+      const i64 o = (i64)jc * gc.hp + (ic >> 1);
+      rc[(i64)((colour_base + kc) & 1) * gc.cs + (i64)(kc - gc.k0) * gc.ps + o] = fa;
+      if (two) rc[(i64)((colour_base + kcB) & 1) * gc.cs + (i64)(kcB - gc.k0) * gc.ps + o] = fb;
+    }
+    if (!two) kc -= 1;  // only one plane was consumed
+  }
+}
+
+// host: largest fine window of any tile and the widest x/y stencil (computed once per level pair)
+bool restrict_tiled_fits(const int* first_x, const int* count_x, int ncx, const int* first_y, const int* count_y,
+                         int ncy, int* hwp, int* fyw) {
+  int fxw = 0, fy = 0, wmax = 0;
+  for (int c = 0; c < ncx; ++c) wmax = std::max(wmax, count_x[c]);
+  for (int c = 0; c < ncy; ++c) wmax = std::max(wmax, count_y[c]);
+  if (wmax > RR_SM) return false;
+  for (int c0 = 0; c0 < ncx; c0 += RR_CX) {
+    const int cl = std::min(c0 + RR_CX, ncx) - 1;
+    fxw = std::max(fxw, first_x[cl] + count_x[cl] - (first_x[c0] & ~1));
+  }
+  for (int c0 = 0; c0 < ncy; c0 += RR_CY) {
+    const int cl = std::min(c0 + RR_CY, ncy) - 1;
+    fy = std::max(fy, first_y[cl] + count_y[cl] - first_y[c0]);
+  }
+  *hwp = (fxw + 1) / 2 + 1;
+  if ((*hwp & 1) == 0) *hwp += 1;  // odd half-row pitch: even/odd halves start in different banks
+  *fyw = fy;
+  return (size_t)RR_WZ * fy * 2 * (*hwp) * sizeof(double) <= 100 * 1024;
+}
+
+void restrict_tiled(const double* rf, const Grid& gf, double* rhsc, const Grid& gc, const RestrictTab& tx,
+                    const RestrictTab& ty, const RestrictTab& tz, int hwp, int fyw, cudaStream_t st) {
+  static bool attr = false;
+  if (!attr) {
+    cudaFuncSetAttribute(k_restrict_tiled, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+    attr = true;
+  }
+  const size_t smem = (size_t)RR_WZ * fyw * 2 * hwp * sizeof(double);
+  const int bx = cdiv(gc.nx, RR_CX), by = cdiv(gc.ny, RR_CY);
+  int kchunk = 16;
+  while (kchunk > 2 && (i64)bx * by * cdiv(gc.nzl, kchunk) < 148 * 4) kchunk >>= 1;
+  dim3 grid(bx, by, cdiv(gc.nzl, kchunk));
+  k_restrict_tiled<<<grid, RR_CX * RR_CY, smem, st>>>(rf, gf, rhsc, gc, tx, ty, tz, hwp, fyw, kchunk);
+  LAUNCHED();
+}
+
+// ---------------------------------------------------------------------------------------
+// K3 separable (default): rhs_c = Rz Ry Rx r_f with the SAME 1-D weights c2*w2 of the reference, applied one
+// dimension at a time instead of as a 125-term triple product.  Mathematically identical; rounding differs at
+// the 1e-16 level (tests: <= 1e-14 relative against the oracle; NDSM_B200_EXACT_RESTRICT=1 selects the
+// bit-identical kernels above).  A block owns 32x8 coarse (x,y) points and marches over FINE planes: each
+// plane tile is loaded once, restricted in x then y through shared memory, and the xy-restricted value enters
+// an 8-deep register ring per thread; a coarse plane is emitted when its last fine plane has passed.
+// Algorithmic traffic: 8 B per fine point + 8 B per coarse point; ~25 instructions per fine point.
+// ---------------------------------------------------------------------------------------
+#define RS_CX 32
+#define RS_CY 8
+#define RS_FXW 72  // >= 2*RS_CX + 6
+#define RS_FYW 24  // >= 2*RS_CY + 6
+
+__global__ void __launch_bounds__(RS_CX * RS_CY, 2)
+k_restrict_sep(const double* __restrict__ rf, const Grid gf, double* __restrict__ rc, const Grid gc,
+               const RestrictTab tx, const RestrictTab ty, const RestrictTab tz, const int kchunk) {
+  __shared__ double sA[RS_FYW][RS_FXW + 1];  // fine plane tile, natural order
+  __shared__ double sB[RS_FYW][RS_CX + 1];   // x-restricted rows
+  const int txi = threadIdx.x & (RS_CX - 1), tyi = threadIdx.x / RS_CX;
+  const int ic0 = blockIdx.x * RS_CX, jc0 = blockIdx.y * RS_CY;
+  const int ic = ic0 + txi, jc = jc0 + tyi;
+  const bool xact = ic < gc.nx, active = xact && jc < gc.ny;
+  const int icl = min(ic0 + RS_CX, gc.nx) - 1, jcl = min(jc0 + RS_CY, gc.ny) - 1;
+  const int fx0 = tx.first[ic0], fx1 = tx.first[icl] + tx.count[icl];
+  const int fy0 = ty.first[jc0], fy1 = ty.first[jcl] + ty.count[jcl];
+  const int FXW = fx1 - fx0, FYW = fy1 - fy0;
+  const int kc_beg = gc.k0 + blockIdx.z * kchunk;
+  const int kc_end = min(kc_beg + kchunk, gc.k0 + gc.nzl) - 1;
+  if (kc_beg > kc_end) return;
+
+  // 1-D weights of this thread's coarse column: c2*w2 (ndsm_interp.f90:277-282)
+  double wxr[NDSM_RMAX], wyr[NDSM_RMAX];
+  int axl = 0, ayl = 0, cx = 0, cy = 0;
+  {
+    const int icc = xact ? ic : icl, jcc = (jc < gc.ny) ? jc : jcl;
+    axl = tx.first[icc] - fx0;
+    ayl = ty.first[jcc] - fy0;
+    cx = tx.count[icc];
+    cy = ty.count[jcc];
+#pragma unroll
+    for (int q = 0; q < NDSM_RMAX; ++q) {
+      wxr[q] = (q < cx) ? tx.c2[(i64)icc * NDSM_RMAX + q] * tx.w2 : 0.0;
+      wyr[q] = (q < cy) ? ty.c2[(i64)jcc * NDSM_RMAX + q] * ty.w2 : 0.0;
+    }
+  }
+  const int colour_base = (ic + jc) & 1;
+  double ring[NDSM_RMAX];  // xy-restricted values of the last NDSM_RMAX fine planes (ring[7] = newest)
+#pragma unroll
+  for (int q = 0; q < NDSM_RMAX; ++q) ring[q] = 0.0;
+
+  int kc = kc_beg;
+  const int kf_beg = tz.first[kc_beg], kf_end = tz.first[kc_end] + tz.count[kc_end] - 1;
+  // software pipeline: the tile of plane kf+1 is fetched into registers while plane kf is being reduced
+  constexpr int NPF = (RS_FYW * RS_FXW + RS_CX * RS_CY - 1) / (RS_CX * RS_CY);
+  int gofs[NPF], sofs[NPF], gpar[NPF];
+  double nxt[NPF];
+  double* __restrict__ sAflat = &sA[0][0];
+#pragma unroll
+  for (int q = 0; q < NPF; ++q) {
+    const int e = threadIdx.x + q * (RS_CX * RS_CY);
+    const int yo = e / FXW, xo = e - yo * FXW;
+    if (yo < FYW) {
+      const int i_f = fx0 + xo, j_f = fy0 + yo;
+      gofs[q] = j_f * gf.hp + (i_f >> 1);
+      gpar[q] = (i_f + j_f) & 1;
+      sofs[q] = yo * (RS_FXW + 1) + xo;
+    } else {
+      gofs[q] = -1;
+      gpar[q] = 0;
+      sofs[q] = 0;
+    }
+  }
+  auto fetch = [&](int kf) {
+    const double* __restrict__ p0 = rf + (i64)(kf - gf.k0) * gf.ps;
+#pragma unroll
+    for (int q = 0; q < NPF; ++q)
+      if (gofs[q] >= 0) nxt[q] = p0[(i64)((gpar[q] + kf) & 1) * gf.cs + gofs[q]];
+  };
+  fetch(kf_beg);
+  for (int kf = kf_beg; kf <= kf_end; ++kf) {
+    __syncthreads();  // previous plane's x/y passes have finished with sA and sB
+#pragma unroll
+    for (int q = 0; q < NPF; ++q)
+      if (gofs[q] >= 0) sAflat[sofs[q]] = nxt[q];
+    if (kf < kf_end) fetch(kf + 1);
+    __syncthreads();
+    // ---- x pass: every thread restricts its coarse column on rows tyi, tyi+8, tyi+16
+    for (int yo = tyi; yo < FYW; yo += RS_CY) {
+      double s = 0.0;
+#pragma unroll
+      for (int q = 0; q < NDSM_RMAX; ++q)
+        if (q < cx) s += wxr[q] * sA[yo][axl + q];  // predicated: shared memory beyond the window is uninitialised
+      sB[yo][txi] = s;
+    }
+    __syncthreads();
+    // ---- y pass into the register ring
+    double p = 0.0;
+#pragma unroll
+    for (int q = 0; q < NDSM_RMAX; ++q)
+      if (q < cy) p += wyr[q] * sB[ayl + q][txi];
+#pragma unroll
+    for (int q = 0; q < NDSM_RMAX - 1; ++q) ring[q] = ring[q + 1];
+    ring[NDSM_RMAX - 1] = p;
+    // ---- z pass: emit every coarse plane whose stencil ends at this fine plane
+    while (kc <= kc_end && tz.first[kc] + tz.count[kc] - 1 == kf) {
+      const int cz = tz.count[kc];
+      const double* __restrict__ wzv = tz.c2 + (i64)kc * NDSM_RMAX;
+      double out = 0.0;
+#pragma unroll
+      for (int q = 0; q < NDSM_RMAX; ++q) {  // stencil plane q sits at ring[NDSM_RMAX - cz + q]
+        const int slot = NDSM_RMAX - cz + q;
+        double v = 0.0;
+#pragma unroll
+        for (int r = 0; r < NDSM_RMAX; ++r) v = (r == slot) ? ring[r] : v;
+        if (q < cz) out += (wzv[q] * tz.w2) * v;
+      }
+      if (active)
+        rc[(i64)((colour_base + kc) & 1) * gc.cs + (i64)(kc - gc.k0) * gc.ps + (i64)jc * gc.hp + (ic >> 1)] = out;
+      ++kc;
+    }
+  }
+}
+
+bool restrict_sep_fits(const int* first_x, const int* count_x, int ncx, const int* first_y, const int* count_y,
+                       int ncy) {
+  for (int c0 = 0; c0 < ncx; c0 += RS_CX) {
+    const int cl = std::min(c0 + RS_CX, ncx) - 1;
+    if (first_x[cl] + count_x[cl] - first_x[c0] > RS_FXW) return false;
+  }
+  for (int c0 = 0; c0 < ncy; c0 += RS_CY) {
+    const int cl = std::min(c0 + RS_CY, ncy) - 1;
+    if (first_y[cl] + count_y[cl] - first_y[c0] > RS_FYW) return false;
+  }
+  return true;
+}
+
+void restrict_sep(const double* rf, const Grid& gf, double* rhsc, const Grid& gc, const RestrictTab& tx,
+                  const RestrictTab& ty, const RestrictTab& tz, cudaStream_t st) {
+  const int bx = cdiv(gc.nx, RS_CX), by = cdiv(gc.ny, RS_CY);
+  int kchunk = 32;
+  while (kchunk > 2 && (i64)bx * by * cdiv(gc.nzl, kchunk) < 148 * 8) kchunk >>= 1;
+  dim3 grid(bx, by, cdiv(gc.nzl, kchunk));
+  k_restrict_sep<<<grid, RS_CX * RS_CY, 0, st>>>(rf, gf, rhsc, gc, tx, ty, tz, kchunk);
+  LAUNCHED();
+}
+
+// ---------------------------------------------------------------------------------------
 // K4  prolongation + correction add   u_f += P u_c
 //     (ndsm_multigrid_core.f90:900-919,706-710 ; ndsm_interp.f90:120-156)
 // 8 coarse corners, reduced z -> y -> x as fs(j) = wh*fs(j) + wl*fs(j+NC).
@@ -734,6 +1029,99 @@ k_interp_add(const double* __restrict__ uc, const Grid gc, double* __restrict__ 
   f0 = whx * f0 + wlx * f1;
   const i64 o = (i64)colour * gf.cs + (i64)(k - gf.k0) * gf.ps + (i64)j * gf.hp + m;
   uf[o] = uf[o] + f0;
+}
+
+// K4 tiled (3D): the coarse values a 64x8 fine tile needs (<= 40x8 per plane) stream through a rolling window of
+// coarse planes in shared memory in natural (un-split) order, so the 8 corner reads are shared-memory loads at
+// constant offsets from one base index; x and y tables are hoisted per thread.  Same lerp order -> same bits.
+#define IP_FX 64
+#define IP_TY 4    // thread rows; every thread updates rows j and j + IP_TY
+#define IP_CXW 40
+#define IP_CYW 8
+#define IP_CZW 4
+__global__ void __launch_bounds__(IP_FX * IP_TY)
+k_interp_add_tiled(const double* __restrict__ uc, const Grid gc, double* __restrict__ uf, const Grid gf,
+                   const InterpTab tx, const InterpTab ty, const InterpTab tz, const int zchunk) {
+  __shared__ double sc[IP_CZW * IP_CYW * IP_CXW];
+  const int txi = threadIdx.x & (IP_FX - 1), tyi = threadIdx.x / IP_FX;
+  const int i0 = blockIdx.x * IP_FX, j0 = blockIdx.y * (2 * IP_TY);
+  const int kbeg = gf.k0 + blockIdx.z * zchunk;
+  const int kend = min(kbeg + zchunk, gf.k0 + gf.nzl) - 1;
+  if (kbeg > kend) return;
+  const int cx0 = tx.lo[i0], cy0 = ty.lo[j0];
+  const int i = i0 + txi;
+  const bool xin = i < gf.nx;
+  const int ic = xin ? i : gf.nx - 1;
+  const int x0l = tx.lo[ic] - cx0;
+  const double whx = tx.wh[ic], wlx = tx.wl[ic];
+  int jrow[2], y0l[2];
+  double why[2], wly[2];
+  bool yin[2];
+#pragma unroll
+  for (int q = 0; q < 2; ++q) {
+    jrow[q] = j0 + tyi + q * IP_TY;
+    yin[q] = jrow[q] < gf.ny;
+    const int jc = yin[q] ? jrow[q] : gf.ny - 1;
+    y0l[q] = ty.lo[jc] - cy0;
+    why[q] = ty.wh[jc];
+    wly[q] = ty.wl[jc];
+  }
+  int next_c = tz.lo[kbeg];  // first coarse plane not yet in the window
+  for (int k = kbeg; k <= kend; ++k) {
+    const int z0 = tz.lo[k], z1 = min(z0 + 1, gc.nz - 1);
+    if (z1 >= next_c) {  // uniform over the block
+      __syncthreads();
+      for (int zc = max(next_c, z0); zc <= z1; ++zc) {
+        double* __restrict__ dst = sc + (zc & (IP_CZW - 1)) * (IP_CYW * IP_CXW);
+        for (int e = threadIdx.x; e < IP_CYW * IP_CXW; e += IP_FX * IP_TY) {
+          const int cyo = e / IP_CXW, cxo = e - cyo * IP_CXW;
+          const int xc = cx0 + cxo, yc = cy0 + cyo;
+          dst[e] = (xc < gc.nx && yc < gc.ny) ? uc[gidx(gc, xc, yc, zc)] : 0.0;
+        }
+      }
+      next_c = z1 + 1;
+      __syncthreads();
+    }
+    if (!xin) continue;
+    const double whz = tz.wh[k], wlz = tz.wl[k];
+    const double* __restrict__ s0 = sc + (z0 & (IP_CZW - 1)) * (IP_CYW * IP_CXW) + x0l;
+    const double* __restrict__ s1 = sc + (z1 & (IP_CZW - 1)) * (IP_CYW * IP_CXW) + x0l;
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+      if (!yin[q]) continue;
+      const int b0 = y0l[q] * IP_CXW;
+      // ndsm_interp.f90:128-154: reduce z, then y, then x
+      double f0 = whz * s0[b0] + wlz * s1[b0];
+      double f1 = whz * s0[b0 + 1] + wlz * s1[b0 + 1];
+      double f2 = whz * s0[b0 + IP_CXW] + wlz * s1[b0 + IP_CXW];
+      double f3 = whz * s0[b0 + IP_CXW + 1] + wlz * s1[b0 + IP_CXW + 1];
+      f0 = why[q] * f0 + wly[q] * f2;
+      f1 = why[q] * f1 + wly[q] * f3;
+      f0 = whx * f0 + wlx * f1;
+      const int j = jrow[q];
+      const i64 o = (i64)((i + j + k) & 1) * gf.cs + (i64)(k - gf.k0) * gf.ps + (i64)j * gf.hp + (i >> 1);
+      uf[o] = uf[o] + f0;  // add_correction, ndsm_multigrid_core.f90:706-710
+    }
+  }
+}
+
+// host check: every fine tile's coarse footprint fits the fixed shared-memory window
+bool interp_tiled_fits(const int* lo_x, int nfx, int ncx, const int* lo_y, int nfy, int ncy) {
+  if (ncx < 2 || ncy < 2) return false;
+  for (int i0 = 0; i0 < nfx; i0 += IP_FX)
+    if (lo_x[std::min(i0 + IP_FX, nfx) - 1] + 1 - lo_x[i0] + 1 > IP_CXW) return false;
+  for (int j0 = 0; j0 < nfy; j0 += 2 * IP_TY)
+    if (lo_y[std::min(j0 + 2 * IP_TY, nfy) - 1] + 1 - lo_y[j0] + 1 > IP_CYW) return false;
+  return true;
+}
+
+void interp_add_tiled(const double* uc, const Grid& gc, double* uf, const Grid& gf, const InterpTab& tx,
+                      const InterpTab& ty, const InterpTab& tz, cudaStream_t st) {
+  const int bx = cdiv(gf.nx, IP_FX), by = cdiv(gf.ny, 2 * IP_TY);
+  const int zc = pick_zchunk(gf.nzl, bx * by);
+  dim3 grid(bx, by, cdiv(gf.nzl, zc));
+  k_interp_add_tiled<<<grid, IP_FX * IP_TY, 0, st>>>(uc, gc, uf, gf, tx, ty, tz, zc);
+  LAUNCHED();
 }
 
 void interp_add(const double* uc, const Grid& gc, double* uf, const Grid& gf, const InterpTab& tx,

@@ -55,9 +55,26 @@ void subtract_mean(double* u, const Grid& g, double* scratch, cudaStream_t st);
 // K3: rhs_c = R r_f (ndsm_multigrid_core.f90:1010-1065 + ndsm_interp.f90:186-292), exact reference summation order.
 void restrict_level(const double* rf, const Grid& gf, double* rhsc, const Grid& gc, const RestrictTab& tx,
                     const RestrictTab& ty, const RestrictTab& tz, cudaStream_t st);
+// K3 tiled: same arithmetic as restrict_level (bit-identical) through a shared-memory window; for stencils of
+// at most 5 points in x and y.  restrict_tiled_fits computes the window from the host tables and says
+// whether the level pair qualifies (the caller uses restrict_level otherwise).
+bool restrict_tiled_fits(const int* first_x, const int* count_x, int ncx, const int* first_y, const int* count_y,
+                         int ncy, int* hwp, int* fyw);
+void restrict_tiled(const double* rf, const Grid& gf, double* rhsc, const Grid& gc, const RestrictTab& tx,
+                    const RestrictTab& ty, const RestrictTab& tz, int hwp, int fyw, cudaStream_t st);
 // K4: u_f += P u_c on every fine point (ndsm_multigrid_core.f90:865-921,692-712 + ndsm_interp.f90:85-158).
 void interp_add(const double* uc, const Grid& gc, double* uf, const Grid& gf, const InterpTab& tx,
                 const InterpTab& ty, const InterpTab& tz, cudaStream_t st);
+// K3 separable (3D, default): same 1-D weights applied one dimension at a time (HBM-bound; rounding differs from
+// the reference's triple product at the 1e-16 level)
+bool restrict_sep_fits(const int* first_x, const int* count_x, int ncx, const int* first_y, const int* count_y,
+                       int ncy);
+void restrict_sep(const double* rf, const Grid& gf, double* rhsc, const Grid& gc, const RestrictTab& tx,
+                  const RestrictTab& ty, const RestrictTab& tz, cudaStream_t st);
+// K4 tiled (3D): same arithmetic through a shared-memory window of coarse planes
+bool interp_tiled_fits(const int* lo_x, int nfx, int ncx, const int* lo_y, int nfy, int ncy);
+void interp_add_tiled(const double* uc, const Grid& gc, double* uf, const Grid& gf, const InterpTab& tx,
+                      const InterpTab& ty, const InterpTab& tz, cudaStream_t st);
 // K5: coarsest-level relaxation solve to ex_tol inside ONE thread block (ndsm_multigrid_core.f90:728-800).
 // info[0] = iterations done, info[1] = converged flag.  Returns false if the level does not fit in shared memory.
 bool solve_exact_smem(int ndim, double* u, const double* rhs, const Grid& g, const Bounds& b, int first_colour,

@@ -179,7 +179,9 @@ SlabPlan plan_slabs(const std::vector<HostLevel>& hl, int ndim, int world, int m
   for (int lv = 0; lv < p.ndist; ++lv) {
     const int nzf = hl[lv].n[2], ncz = hl[lv + 1].n[2];
     for (int r = 0; r < world; ++r) {
-      const int f0 = p.zs[lv][r] - p.halo, f1 = p.zs[lv][r + 1] + p.halo;
+      // one plane less than the halo: the fused residual+restriction evaluates the residual on every fine
+      // plane of the stencil, which reads u one plane further out
+      const int f0 = p.zs[lv][r] - (p.halo - 1), f1 = p.zs[lv][r + 1] + (p.halo - 1);
       for (int c = p.zs[lv + 1][r]; c < p.zs[lv + 1][r + 1]; ++c) {
         const int a = hl[lv].first[2][c], b = a + hl[lv].count[2][c];
         if (a < (f0 < 0 ? 0 : f0) || b > (f1 > nzf ? nzf : f1)) throw NdsmError(6);
@@ -352,13 +354,27 @@ MG::MG(int ndim, const int* shape, int ngrids, const double* const* mesh, cudaSt
   tab_d_ = static_cast<double*>(pool_alloc((hd.size() + 32) * sizeof(double)));
   if (!hi.empty()) CUDA_CHECK(cudaMemcpyAsync(tab_i_, hi.data(), hi.size() * sizeof(int), cudaMemcpyHostToDevice, st_));
   if (!hd.empty()) CUDA_CHECK(cudaMemcpyAsync(tab_d_, hd.data(), hd.size() * sizeof(double), cudaMemcpyHostToDevice, st_));
+  static const bool fuse_on = !(getenv("NDSM_B200_TILED") && atoi(getenv("NDSM_B200_TILED")) == 0);
+  // read per hierarchy (not cached): tests toggle it between solves
+  const bool exact_restrict = getenv("NDSM_B200_EXACT_RESTRICT") && atoi(getenv("NDSM_B200_EXACT_RESTRICT")) != 0;
   for (auto& S : slabs_)
-    for (int g = 0; g + 1 < ngrids; ++g)
+    for (int g = 0; g + 1 < ngrids; ++g) {
       for (int d = 0; d < 3; ++d) {
         const Off& o = offs[(size_t)g * 3 + d];
         S.lv[g].it[d] = InterpTab{tab_i_ + o.lo, tab_d_ + o.wl, tab_d_ + o.wh};
         S.lv[g].rt[d] = RestrictTab{tab_i_ + o.first, tab_i_ + o.count, tab_d_ + o.c2, hl[g].w2[d]};
       }
+      if (ndim == 3 && fuse_on && hl[g].n[0] >= 64 && hl[g].n[2] >= 8)
+        S.lv[g].itiled = interp_tiled_fits(hl[g].lo[0].data(), hl[g].n[0], hl[g + 1].n[0], hl[g].lo[1].data(),
+                                           hl[g].n[1], hl[g + 1].n[1]);
+      if (ndim == 3 && !exact_restrict && hl[g + 1].n[0] >= 16 && hl[g + 1].n[1] >= 8 && hl[g + 1].n[2] >= 8)
+        S.lv[g].rsep = restrict_sep_fits(hl[g].first[0].data(), hl[g].count[0].data(), hl[g + 1].n[0],
+                                         hl[g].first[1].data(), hl[g].count[1].data(), hl[g + 1].n[1]);
+      if (ndim == 3 && fuse_on && hl[g + 1].n[0] >= 16 && hl[g + 1].n[1] >= 8)
+        S.lv[g].fused = restrict_tiled_fits(hl[g].first[0].data(), hl[g].count[0].data(), hl[g + 1].n[0],
+                                            hl[g].first[1].data(), hl[g].count[1].data(), hl[g + 1].n[1],
+                                            &S.lv[g].rr_hwp, &S.lv[g].rr_fyw);
+    }
   CUDA_CHECK(cudaStreamSynchronize(st_));  // host staging vectors go out of scope
   set_options(5, 1e-13, "NNNNNN", true, 10000);
 }
@@ -500,19 +516,30 @@ void MG::restrict_to(int g) {
   for (size_t s = 0; s < ns; ++s) {
     Level& F = slabs_[s].lv[g];
     Level& C = slabs_[s].lv[c];
-    if (!fdist || cdist) {
-      restrict_level(r_scratch(g, (int)s), F.g, C.rhs, C.g, F.rt[0], F.rt[1], F.rt[2], st_);
-    } else {  // partitioned -> replicated: this rank produces planes [zs[c][r], zs[c][r+1]) of the full array
-      const int r = slabs_[s].rank, k0 = plan_.zs[c][r], cnt = plan_.zs[c][r + 1] - k0;
-      if (cnt > 0) {
-        Grid gv = C.g;
-        gv.k0 = k0;
-        gv.nzl = cnt;
-        restrict_level(r_scratch(g, (int)s), F.g, C.rhs + (i64)k0 * C.g.ps, gv, F.rt[0], F.rt[1], F.rt[2], st_);
-      }
+    Grid gv = C.g;
+    double* out = C.rhs;
+    if (fdist && !cdist) {  // partitioned -> replicated: this rank produces planes [zs[c][r], zs[c][r+1]) of the full array
+      const int r = slabs_[s].rank;
+      gv.k0 = plan_.zs[c][r];
+      gv.nzl = plan_.zs[c][r + 1] - gv.k0;
+      out = C.rhs + (i64)gv.k0 * C.g.ps;
     }
+    if (gv.nzl <= 0) continue;
+    if (F.rsep)
+      restrict_sep(r_scratch(g, (int)s), F.g, out, gv, F.rt[0], F.rt[1], F.rt[2], st_);
+    else if (F.fused)
+      restrict_tiled(r_scratch(g, (int)s), F.g, out, gv, F.rt[0], F.rt[1], F.rt[2], F.rr_hwp, F.rr_fyw, st_);
+    else
+      restrict_level(r_scratch(g, (int)s), F.g, out, gv, F.rt[0], F.rt[1], F.rt[2], st_);
   }
   if (prof) prof_end(PROF_RESTRICT0, st_);
+  finish_restrict(g);
+}
+
+// all-gather of a replicated coarse rhs, halo planes of a partitioned one, u[c] = 0
+void MG::finish_restrict(int g) {
+  const int c = g + 1;
+  const bool fdist = g < plan_.ndist, cdist = c < plan_.ndist;
   if (fdist && !cdist && comm_) {  // all-gather the replicated rhs
     Level& C = slabs_[0].lv[c];
     comm_->begin(st_);
@@ -524,7 +551,7 @@ void MG::restrict_to(int g) {
     }
     comm_->end(st_);
   }
-  if (cdist) {  // extended colour passes read rhs in the halo planes
+  if (cdist) {  // extended colour passes and the fused residual read rhs in the halo planes
     std::vector<double*> rp;
     for (auto& S : slabs_) rp.push_back(S.lv[c].rhs);
     exchange(c, 0, 3, plan_.halo, &rp);
@@ -547,7 +574,8 @@ void MG::interp_add_from(int c) {
   for (size_t s = 0; s < ns; ++s) {
     Level& C = slabs_[s].lv[c];
     Level& F = slabs_[s].lv[f];
-    interp_add(C.u, C.g, F.u, F.g, F.it[0], F.it[1], F.it[2], st_);
+    if (F.itiled) interp_add_tiled(C.u, C.g, F.u, F.g, F.it[0], F.it[1], F.it[2], st_);
+    else interp_add(C.u, C.g, F.u, F.g, F.it[0], F.it[1], F.it[2], st_);
   }
   if (prof) prof_end(PROF_INTERP0, st_);
   if (fdist) valid_[f][0] = valid_[f][1] = 0;  // owned planes changed; halos are refreshed by the next consumer

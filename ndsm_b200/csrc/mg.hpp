@@ -44,7 +44,7 @@ struct SlabPlan {
   std::vector<std::vector<int>> zs;  // zs[level][r] .. zs[level][r+1]: planes owned by rank r; the entry for
                                      // level ndist says who PRODUCES which planes of the first replicated level
 };
-#define NDSM_HALO 4
+#define NDSM_HALO 6
 // a level is partitioned only while every rank keeps at least min_planes planes and the level has at least
 // min_points points (smaller levels are replicated)
 SlabPlan plan_slabs(const std::vector<HostLevel>& hl, int ndim, int world, int min_planes, long long min_points = 0);
@@ -87,6 +87,11 @@ struct Level {
   // transfer tables between this level (fine) and the next (coarse); device pointers
   InterpTab it[3];
   RestrictTab rt[3];
+  // tiled restriction towards the next level: shared-memory window, or fused == false (plain kernel)
+  bool fused = false;
+  int rr_hwp = 0, rr_fyw = 0;
+  bool itiled = false;  // tiled prolongation from the next level
+  bool rsep = false;    // separable restriction towards the next level (default; not bit-identical)
 };
 
 struct Slab {
@@ -173,6 +178,7 @@ class MG {
   // that currently hold up-to-date values of colour c.  A colour pass may also update `e` halo planes if the
   // other colour is valid to depth e+1, so one 4-plane exchange feeds four passes (bit-identical values).
   std::vector<std::array<int, 2>> valid_;
+  void finish_restrict(int g);
   void need_halo(int g, int depth);  // make both colours of u[g] valid to at least `depth` planes
   void need_halo_colour(int g, int colour);
   int* tab_i_ = nullptr;             // packed transfer tables

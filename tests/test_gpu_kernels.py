@@ -25,6 +25,21 @@ def rand(shape, seed):
     return np.random.default_rng(seed).standard_normal(shape[::-1])
 
 
+@pytest.fixture(params=["separable", "exact"])
+def restrict_mode(request):
+    """The production restriction applies the reference's 1-D weights one dimension at a time (HBM-bound; rounding
+    differs from the 125-term triple product at the 1e-16 level).  NDSM_B200_EXACT_RESTRICT=1 selects the kernels
+    that keep the reference's summation order and are bit-identical."""
+    import os
+    old = os.environ.get("NDSM_B200_EXACT_RESTRICT")
+    os.environ["NDSM_B200_EXACT_RESTRICT"] = "1" if request.param == "exact" else "0"
+    yield request.param
+    if old is None:
+        os.environ.pop("NDSM_B200_EXACT_RESTRICT", None)
+    else:
+        os.environ["NDSM_B200_EXACT_RESTRICT"] = old
+
+
 def mg(gpu_lib, mesh, copt, **kw):
     from ndsm_b200.mg import MGHandle
     return MGHandle(mesh, copt, **kw)
@@ -119,8 +134,8 @@ def test_relax2d_residual2d_match_oracle(gpu_lib, oracle, shape, copt):
     h.close()
 
 
-@pytest.mark.parametrize("shape", SHAPES3 + [(45, 27, 13), (9, 9, 9)])
-def test_restrict_matches_oracle(gpu_lib, oracle, shape):
+@pytest.mark.parametrize("shape", SHAPES3 + [(45, 27, 13), (9, 9, 9), (96, 80, 72)])
+def test_restrict_matches_oracle(gpu_lib, oracle, shape, restrict_mode):
     mesh = aniso_mesh(shape)
     h = mg(gpu_lib, mesh, "NDDNDD")
     for g in range(h.ngrids - 1):
@@ -131,8 +146,9 @@ def test_restrict_matches_oracle(gpu_lib, oracle, shape):
         want_lit = oracle.mg_restrict(h.level_mesh(g), h.level_mesh(g + 1), r, mode=0)
         want_tab = oracle.mg_restrict(h.level_mesh(g), h.level_mesh(g + 1), r, mode=1)
         assert np.array_equal(want_lit, want_tab)
-        assert rel_err(got, want_lit) <= TOL
-        assert np.array_equal(got, want_lit)
+        assert rel_err(got, want_lit) <= 1e-14
+        if restrict_mode == "exact":
+            assert np.array_equal(got, want_lit)
         assert not h.get(h.U, g + 1).any()  # u_c zeroed (ndsm_multigrid_core.f90:557-558)
     h.close()
 
@@ -254,8 +270,9 @@ def test_update_u_matches_oracle(gpu_lib, oracle, du_max):
     h.close()
 
 
-@pytest.mark.parametrize("shape,copt", [((22, 22, 22), "NDDNDD"), ((33, 18, 25), "DNDDND"), ((40, 24, 17), "DDNDDN")])
-def test_v_cycle_matches_oracle(gpu_lib, oracle, shape, copt):
+@pytest.mark.parametrize("shape,copt", [((22, 22, 22), "NDDNDD"), ((33, 18, 25), "DNDDND"), ((40, 24, 17), "DDNDDN"),
+                                        ((72, 64, 80), "NDDNDD")])
+def test_v_cycle_matches_oracle(gpu_lib, oracle, shape, copt, restrict_mode):
     mesh = aniso_mesh(shape)
     u0 = rand(shape, 11)
     rhs = rand(shape, 12)
@@ -269,14 +286,15 @@ def test_v_cycle_matches_oracle(gpu_lib, oracle, shape, copt):
         o.v_cycle()
         got, want = h.get(h.U, 0), o.u(0)
         assert rel_err(got, want) <= TOL
-        assert np.array_equal(got, want)
+        if restrict_mode == "exact":
+            assert np.array_equal(got, want)
     h.close()
 
 
 @pytest.mark.parametrize("mean", [False, True])
-def test_poisson_solve_3d_matches_oracle(gpu_lib, oracle, mean):
+def test_poisson_solve_3d_matches_oracle(gpu_lib, oracle, mean, restrict_mode):
     """solve_poisson_bvp on config-5 style data: u = cos(pi x) sin(pi y) sin(pi z), copt = NDDNDD."""
-    n = 33
+    n = 65
     x = np.linspace(0, 1, n)
     mesh = [x, x.copy(), x.copy()]
     Z, Y, X = np.meshgrid(x, x, x, indexing="ij")
@@ -290,7 +308,7 @@ def test_poisson_solve_3d_matches_oracle(gpu_lib, oracle, mean):
     assert ierr == oierr == 0
     assert abs(nc - onc) <= 1
     assert rel_err(u, ou) <= 1e-10
-    if not mean:
+    if not mean and restrict_mode == "exact":
         assert nc == onc and np.array_equal(u, ou)
     assert np.abs(u - uex).max() < 5e-3  # O(h^2) truncation error
     h.close()

@@ -6,7 +6,7 @@ import pytest
 
 from conftest import aniso_mesh
 
-HALO = 4
+HALO = 6
 
 
 @pytest.mark.parametrize("shape,world,min_planes", [((513, 513, 513), 8, 16), ((513, 513, 513), 2, 16),
@@ -31,7 +31,7 @@ def test_partition_tiles_and_respects_halo(shape, world, min_planes):
         lo, _, _ = p.interp_table(lv, 2)
         nzf, nzc = p.level(lv)["shape"][2], p.level(lv + 1)["shape"][2]
         for r in range(world):
-            f0, f1 = max(zs[lv][r] - HALO, 0), min(zs[lv][r + 1] + HALO, nzf)
+            f0, f1 = max(zs[lv][r] - (HALO - 1), 0), min(zs[lv][r + 1] + (HALO - 1), nzf)
             for c in range(zs[lv + 1][r], zs[lv + 1][r + 1]):
                 assert f0 <= first[c] and first[c] + count[c] <= f1
             if lv + 1 < ndist:
