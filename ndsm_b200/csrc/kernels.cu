@@ -1038,7 +1038,8 @@ k_interp_add(const double* __restrict__ uc, const Grid gc, double* __restrict__ 
 #define IP_TY 4    // thread rows; every thread updates rows j and j + IP_TY
 #define IP_CXW 40
 #define IP_CYW 8
-#define IP_CZW 4
+#define IP_CZW 8
+#define IP_UN 4   // fine planes per iteration
 __global__ void __launch_bounds__(IP_FX * IP_TY)
 k_interp_add_tiled(const double* __restrict__ uc, const Grid gc, double* __restrict__ uf, const Grid gf,
                    const InterpTab tx, const InterpTab ty, const InterpTab tz, const int zchunk) {
@@ -1067,11 +1068,14 @@ k_interp_add_tiled(const double* __restrict__ uc, const Grid gc, double* __restr
     wly[q] = ty.wl[jc];
   }
   int next_c = tz.lo[kbeg];  // first coarse plane not yet in the window
-  for (int k = kbeg; k <= kend; ++k) {
-    const int z0 = tz.lo[k], z1 = min(z0 + 1, gc.nz - 1);
-    if (z1 >= next_c) {  // uniform over the block
+  for (int kb = kbeg; kb <= kend; kb += IP_UN) {
+    // IP_UN fine planes per iteration: their coarse planes (at most IP_UN/2 + 2) are staged together and all
+    // u_f loads are issued before the arithmetic
+    const int klast = min(kb + IP_UN - 1, kend);
+    const int zlast = min(tz.lo[klast] + 1, gc.nz - 1);
+    if (zlast >= next_c) {  // uniform over the block
       __syncthreads();
-      for (int zc = max(next_c, z0); zc <= z1; ++zc) {
+      for (int zc = max(next_c, tz.lo[kb]); zc <= zlast; ++zc) {
         double* __restrict__ dst = sc + (zc & (IP_CZW - 1)) * (IP_CYW * IP_CXW);
         for (int e = threadIdx.x; e < IP_CYW * IP_CXW; e += IP_FX * IP_TY) {
           const int cyo = e / IP_CXW, cxo = e - cyo * IP_CXW;
@@ -1079,28 +1083,44 @@ k_interp_add_tiled(const double* __restrict__ uc, const Grid gc, double* __restr
           dst[e] = (xc < gc.nx && yc < gc.ny) ? uc[gidx(gc, xc, yc, zc)] : 0.0;
         }
       }
-      next_c = z1 + 1;
+      next_c = zlast + 1;
       __syncthreads();
     }
     if (!xin) continue;
-    const double whz = tz.wh[k], wlz = tz.wl[k];
-    const double* __restrict__ s0 = sc + (z0 & (IP_CZW - 1)) * (IP_CYW * IP_CXW) + x0l;
-    const double* __restrict__ s1 = sc + (z1 & (IP_CZW - 1)) * (IP_CYW * IP_CXW) + x0l;
+    double uold[IP_UN][2];
+    i64 off[IP_UN][2];
 #pragma unroll
-    for (int q = 0; q < 2; ++q) {
-      if (!yin[q]) continue;
-      const int b0 = y0l[q] * IP_CXW;
-      // ndsm_interp.f90:128-154: reduce z, then y, then x
-      double f0 = whz * s0[b0] + wlz * s1[b0];
-      double f1 = whz * s0[b0 + 1] + wlz * s1[b0 + 1];
-      double f2 = whz * s0[b0 + IP_CXW] + wlz * s1[b0 + IP_CXW];
-      double f3 = whz * s0[b0 + IP_CXW + 1] + wlz * s1[b0 + IP_CXW + 1];
-      f0 = why[q] * f0 + wly[q] * f2;
-      f1 = why[q] * f1 + wly[q] * f3;
-      f0 = whx * f0 + wlx * f1;
-      const int j = jrow[q];
-      const i64 o = (i64)((i + j + k) & 1) * gf.cs + (i64)(k - gf.k0) * gf.ps + (i64)j * gf.hp + (i >> 1);
-      uf[o] = uf[o] + f0;  // add_correction, ndsm_multigrid_core.f90:706-710
+    for (int p = 0; p < IP_UN; ++p) {
+      const int k = min(kb + p, kend);
+#pragma unroll
+      for (int q = 0; q < 2; ++q) {
+        const int j = yin[q] ? jrow[q] : gf.ny - 1;
+        off[p][q] = (i64)((i + j + k) & 1) * gf.cs + (i64)(k - gf.k0) * gf.ps + (i64)j * gf.hp + (i >> 1);
+        uold[p][q] = uf[off[p][q]];
+      }
+    }
+#pragma unroll
+    for (int p = 0; p < IP_UN; ++p) {
+      const int k = kb + p;
+      if (k > kend) break;
+      const int z0 = tz.lo[k], z1 = min(z0 + 1, gc.nz - 1);
+      const double whz = tz.wh[k], wlz = tz.wl[k];
+      const double* __restrict__ s0 = sc + (z0 & (IP_CZW - 1)) * (IP_CYW * IP_CXW) + x0l;
+      const double* __restrict__ s1 = sc + (z1 & (IP_CZW - 1)) * (IP_CYW * IP_CXW) + x0l;
+#pragma unroll
+      for (int q = 0; q < 2; ++q) {
+        if (!yin[q]) continue;
+        const int b0 = y0l[q] * IP_CXW;
+        // ndsm_interp.f90:128-154: reduce z, then y, then x
+        double f0 = whz * s0[b0] + wlz * s1[b0];
+        double f1 = whz * s0[b0 + 1] + wlz * s1[b0 + 1];
+        double f2 = whz * s0[b0 + IP_CXW] + wlz * s1[b0 + IP_CXW];
+        double f3 = whz * s0[b0 + IP_CXW + 1] + wlz * s1[b0 + IP_CXW + 1];
+        f0 = why[q] * f0 + wly[q] * f2;
+        f1 = why[q] * f1 + wly[q] * f3;
+        f0 = whx * f0 + wlx * f1;
+        uf[off[p][q]] = uold[p][q] + f0;  // add_correction, ndsm_multigrid_core.f90:706-710
+      }
     }
   }
 }
