@@ -180,10 +180,11 @@ def kernel_report(lib, npoints, dev_ms):
     cnt, tot = ctypes.c_ulonglong(0), ctypes.c_double(0)
     peak, peak_src = measured_peak()
     kern = {}
-    names = ["k_relax3d<rhs=0> colour pass", "k_residual3d", "k_restrict_tiled", "k_interp_add",
-             "update_u (k_diff_partial+final)"]
-    bytes_per_pt = [8.0, 16.0, 9.0, 17.0, 24.0]  # SURVEY 8d / DESIGN.md (level 0, rhs == 0)
-    for cls in range(5):
+    names = ["k_relax3d<rhs=0> colour pass", "k_residual3d", "k_restrict_sep", "k_interp_add_tiled",
+             "update_u (k_diff_partial+final)", "halo exchange (one NCCL group)", "levels >= 2 of one V-cycle",
+             "level 1 of one V-cycle (2 brackets per cycle)"]
+    bytes_per_pt = [8.0, 16.0, 9.0, 17.0, 24.0, 0.0, 0.0, 0.0]  # SURVEY 8d / DESIGN.md (level 0, rhs == 0)
+    for cls in range(8):
         lib.ndsm_b200_profile_get(cls, ctypes.byref(cnt), ctypes.byref(tot))
         if cnt.value:
             avg_ms = tot.value / cnt.value

@@ -165,7 +165,8 @@ int ndsm_b200_trace_nexact(int solve, int cycle);
  * [3] 3D solves, [4] flux+curl, [5] D2H, [6] device-resident total (CUDA events), [7] kernel launches */
 int ndsm_b200_last_timing(double* out8);
 /* CUDA-event timing of the finest-level 3D kernels (off by default).  cls: 0 = k_relax3d colour pass,
- * 1 = k_residual3d, 2 = k_restrict, 3 = k_interp_add, 4 = update_u reduction (2 launches). */
+ * 1 = k_residual3d, 2 = restriction, 3 = prolongation, 4 = update_u reduction (2 launches), 5 = one halo exchange,
+ * 6 = all work on levels >= 2 of one V-cycle, 7 = all work on level 1 of one V-cycle (two brackets per cycle). */
 void ndsm_b200_profile_enable(int on);
 int ndsm_b200_profile_get(int cls, unsigned long long* count, double* total_ms);
 /* Device and pinned staging buffers are cached between calls (a 513^3 solve needs ~15 GB and cudaMalloc/cudaFree

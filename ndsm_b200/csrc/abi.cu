@@ -124,7 +124,7 @@ struct DBuf {
 // traffic): the way to exercise the multi-GPU decomposition through the frozen ABI on a single GPU.
 static int run_core_full(const int* nshape4, const long long* iopt, const double* ropt, const double* x,
                          const double* y, const double* z, double* const* bn, const double* dA0, double* dA,
-                         double* dB, cudaStream_t st) {
+                         double* dB, cudaStream_t st, const CoreHooks* hooks = nullptr) {
   const int nz = nshape4[2];
   const long long N = (long long)nshape4[0] * nshape4[1] * nz;
   int world = 1;
@@ -143,7 +143,7 @@ static int run_core_full(const int* nshape4, const long long* iopt, const double
     o.B = dB + (long long)o.k0 * nshape4[0] * nshape4[1];
     outs.push_back(o);
   }
-  return vector_solve_core(nshape4, iopt, ropt, x, y, z, bn, A0, comm.get(), outs, st, g_report, nullptr, false);
+  return vector_solve_core(nshape4, iopt, ropt, x, y, z, bn, A0, comm.get(), outs, st, g_report, nullptr, false, hooks);
 }
 
 extern "C" {
@@ -197,19 +197,58 @@ int ndsm_vector_solve(size_t nsize, const int* nshape4, int* ioptc, double* ropt
       }
     }
     CUDA_CHECK(cudaMemcpyAsync(dfaces.p, hfaces, ftot * sizeof(double), cudaMemcpyHostToDevice, st));
-    // --- A is the initial guess as received (reference never zeroes it); ndsm.py passes zeros
+    // --- A is the initial guess as received (reference never zeroes it); ndsm.py passes zeros.  Scanning
+    // 3N doubles on the host (and uploading them when they are not all zero) overlaps the chi solves.
     DBuf dA(3 * N), dB(3 * N);
-    const bool zero_guess = all_zero_host(A, 3 * N);
-    if (!zero_guess) CUDA_CHECK(cudaMemcpyAsync(dA.p, A, 3 * N * sizeof(double), cudaMemcpyHostToDevice, st));
     CUDA_CHECK(cudaStreamSynchronize(st));
     pool_free_host(hfaces);
     g_report.ms_in = (now_s() - t1) * 1e3;
+    bool zero_guess = true;
+    std::thread scan([&] { zero_guess = all_zero_host(A, 3 * N); });
+    struct Joiner { std::thread& t; ~Joiner() { if (t.joinable()) t.join(); } } joiner{scan};
+    cudaStream_t cst = nullptr;  // copy stream for the early device-to-host copies of A
+    CUDA_CHECK(cudaStreamCreateWithFlags(&cst, cudaStreamNonBlocking));
+    struct StreamDel { cudaStream_t s; ~StreamDel() { cudaStreamDestroy(s); } } sdel{cst};
+    cudaEvent_t ev;
+    CUDA_CHECK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    struct EvDel { cudaEvent_t e; ~EvDel() { cudaEventDestroy(e); } } edel{ev};
+    bool copied[3] = {false, false, false};
+    // the early copies run in helper threads: a device-to-host copy into PAGEABLE memory (what numpy hands us)
+    // blocks the calling thread, and the main thread has to keep launching the next solve
+    std::vector<std::thread> copiers;
+    struct JoinAll { std::vector<std::thread>& v; ~JoinAll() { for (auto& t : v) if (t.joinable()) t.join(); } } jall{copiers};
+    const int dev = g_device;
+    CoreHooks hooks;
+    hooks.guess = [&]() {
+      scan.join();
+      DenseIn g;
+      if (!zero_guess) {
+        CUDA_CHECK(cudaMemcpyAsync(dA.p, A, 3 * N * sizeof(double), cudaMemcpyHostToDevice, st));
+        g.p = dA.p; g.kfirst = 0; g.cstride = (long long)N;
+      }
+      return g;
+    };
+    hooks.component_ready = [&](int c) {
+      CUDA_CHECK(cudaEventRecord(ev, st));
+      CUDA_CHECK(cudaStreamWaitEvent(cst, ev, 0));
+      double* dst = A + (size_t)c * N;
+      const double* src = dA.p + (size_t)c * N;
+      copiers.emplace_back([=] {
+        cudaSetDevice(dev);
+        cudaMemcpyAsync(dst, src, N * sizeof(double), cudaMemcpyDeviceToHost, cst);
+      });
+      copied[c] = true;
+    };
     if (g_debug) debug_msg(SUB, "Calling compute_vector_potential...");
-    int ierr = run_core_full(nshape4, iopt, ropt, x, y, z, bn, zero_guess ? nullptr : dA.p, dA.p, dB.p, st);
+    int ierr = run_core_full(nshape4, iopt, ropt, x, y, z, bn, nullptr, dA.p, dB.p, st, &hooks);
     t1 = now_s();
-    CUDA_CHECK(cudaMemcpyAsync(A, dA.p, 3 * N * sizeof(double), cudaMemcpyDeviceToHost, st));
+    for (int c = 0; c < 3; ++c)
+      if (!copied[c])
+        CUDA_CHECK(cudaMemcpyAsync(A + (size_t)c * N, dA.p + (size_t)c * N, N * sizeof(double), cudaMemcpyDeviceToHost, st));
     CUDA_CHECK(cudaMemcpyAsync(B, dB.p, 3 * N * sizeof(double), cudaMemcpyDeviceToHost, st));
     CUDA_CHECK(cudaStreamSynchronize(st));
+    for (auto& t : copiers) t.join();
+    CUDA_CHECK(cudaStreamSynchronize(cst));
     g_report.ms_out = (now_s() - t1) * 1e3;
     return finish(ierr);
   } catch (const NdsmError& e) {

@@ -10,7 +10,7 @@ extern unsigned long long g_launches;  // number of kernels this library has lau
 
 // Optional per-kernel-class timing with CUDA events on the launching stream (bench.py roofline numbers).
 // Classes are recorded only for level-0 launches (tagged by the MG driver through prof_scope()).
-enum ProfClass { PROF_RELAX0 = 0, PROF_RESID0, PROF_RESTRICT0, PROF_INTERP0, PROF_DIFF0, PROF_NCLASS };
+enum ProfClass { PROF_RELAX0 = 0, PROF_RESID0, PROF_RESTRICT0, PROF_INTERP0, PROF_DIFF0, PROF_EXCH, PROF_TAIL, PROF_LEVEL1, PROF_NCLASS };
 void prof_enable(bool on);
 bool prof_enabled();
 void prof_begin(int cls, cudaStream_t st);  // record start event (no-op when disabled)

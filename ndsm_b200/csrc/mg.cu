@@ -235,6 +235,7 @@ struct VirtualComm : Comm {
     CUDA_CHECK(cudaMemcpyAsync(recv_all + 2 * my_rank, send2, 2 * sizeof(double), cudaMemcpyDeviceToDevice, st));
   }
   void bcast(int, double*, size_t, cudaStream_t) override {}
+  std::unique_ptr<Comm> clone(cudaStream_t) override { return std::unique_ptr<Comm>(new VirtualComm(w)); }
 };
 }  // namespace
 std::unique_ptr<Comm> make_virtual_comm(int world) { return std::unique_ptr<Comm>(new VirtualComm(world)); }
@@ -421,6 +422,7 @@ void MG::set_options(int ms, double ex_tol, const char* copt, bool du_max, int n
 void MG::exchange(int g, int which, int colour_mask, int np, const std::vector<double*>* arr) {
   if (g >= plan_.ndist || !comm_) return;
   const int world = plan_.world;
+  prof_begin(PROF_EXCH, st_);
   comm_->begin(st_);
   for (size_t s = 0; s < slabs_.size(); ++s) {
     Slab& S = slabs_[s];
@@ -441,6 +443,7 @@ void MG::exchange(int g, int which, int colour_mask, int np, const std::vector<d
     }
   }
   comm_->end(st_);
+  prof_end(PROF_EXCH, st_);
 }
 
 void MG::need_halo(int g, int depth) {
@@ -610,7 +613,11 @@ int MG::solve_exact(int g) {
 
 void MG::v_cycle() {  // ndsm_multigrid_core.f90:341-377
   const int ng = ngrids();
+  // profiling brackets (3D only): PROF_LEVEL1 = all work on level 1, PROF_TAIL = all work on levels >= 2
+  const bool pr = (ndim_ == 3 && ng > 3);
   for (int g = 0; g < ng - 1; ++g) {  // fine_to_coarse :482-560
+    if (pr && g == 1) prof_begin(PROF_LEVEL1, st_);
+    if (pr && g == 2) { prof_end(PROF_LEVEL1, st_); prof_begin(PROF_TAIL, st_); }
     for (int s = 0; s < ms_; ++s) relax(g);
     residual(g);
     restrict_to(g);
@@ -618,6 +625,8 @@ void MG::v_cycle() {  // ndsm_multigrid_core.f90:341-377
   solve_exact(ng - 1);
   for (int c = ng - 1; c >= 1; --c) {  // coarse_to_fine :593-684
     for (int s = 0; s < ms_; ++s) relax(c);
+    if (pr && c == 2) { prof_end(PROF_TAIL, st_); prof_begin(PROF_LEVEL1, st_); }
+    if (pr && c == 1) prof_end(PROF_LEVEL1, st_);
     interp_add_from(c);
     for (int s = 0; s < ms_; ++s) relax(c - 1);
   }

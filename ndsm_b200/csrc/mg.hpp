@@ -65,6 +65,9 @@ struct Comm {
   // in-place broadcast of buf[0..n) from root_rank into every rank's own copy of the same array; when all
   // local ranks share one copy (virtual mode) this is a no-op
   virtual void bcast(int root_rank, double* buf, size_t n, cudaStream_t st) = 0;
+  // an independent communicator over the same ranks (collective: every rank calls it in the same order);
+  // lets independent solves overlap their exchanges on different streams
+  virtual std::unique_ptr<Comm> clone(cudaStream_t st) = 0;
 };
 std::unique_ptr<Comm> make_virtual_comm(int world);  // all ranks in this process, on the current device
 bool nccl_unique_id(void* out128);                    // ncclGetUniqueId (rank 0)

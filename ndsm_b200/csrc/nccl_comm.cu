@@ -5,6 +5,8 @@
 #include <dlfcn.h>
 #include <nccl.h>
 
+#include <cstring>
+
 #include "mg.hpp"
 
 namespace ndsm {
@@ -84,6 +86,20 @@ struct NcclComm : Comm {
   }
   void bcast(int root_rank, double* buf, size_t n, cudaStream_t st) override {
     NCCL_CHECK(g_nccl.Broadcast(buf, buf, n, ncclDouble, root_rank, comm, st));
+  }
+  std::unique_ptr<Comm> clone(cudaStream_t st) override {
+    // rank 0 draws a fresh unique id and hands it to the others through this communicator
+    ncclUniqueId id;
+    memset(&id, 0, sizeof id);
+    if (rank_ == 0) NCCL_CHECK(g_nccl.GetUniqueId(&id));
+    char* d = nullptr;
+    CUDA_CHECK(cudaMalloc(&d, sizeof id));
+    CUDA_CHECK(cudaMemcpyAsync(d, &id, sizeof id, cudaMemcpyHostToDevice, st));
+    NCCL_CHECK(g_nccl.Broadcast(d, d, sizeof id, ncclChar, 0, comm, st));
+    CUDA_CHECK(cudaMemcpyAsync(&id, d, sizeof id, cudaMemcpyDeviceToHost, st));
+    CUDA_CHECK(cudaStreamSynchronize(st));
+    cudaFree(d);
+    return std::unique_ptr<Comm>(new NcclComm(rank_, world_, id));
   }
 };
 }  // namespace

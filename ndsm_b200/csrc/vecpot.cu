@@ -48,8 +48,8 @@ struct EvTimer {
 };
 
 int vector_solve_core(const int* nshape, const long long* iopt, const double* ropt, const double* x, const double* y,
-                      const double* z, double* const* bn, const DenseIn& A0, Comm* comm, const std::vector<SlabOut>& outs_in,
-                      cudaStream_t st, Report& rep, BcCapture* cap, bool stop_after_bc) {
+                      const double* z, double* const* bn, const DenseIn& A0_in, Comm* comm, const std::vector<SlabOut>& outs_in,
+                      cudaStream_t st, Report& rep, BcCapture* cap, bool stop_after_bc, const CoreHooks* hooks) {
   const int nx = nshape[0], ny = nshape[1], nz = nshape[2];
   const i64 N = (i64)nx * ny * nz;
   const double* mesh[3] = {x, y, z};
@@ -165,10 +165,43 @@ int vector_solve_core(const int* nshape, const long long* iopt, const double* ro
   }
 
   // ---------------- three 3D solves (solve, :598-691) ----------------
+  const DenseIn A0 = (hooks && hooks->guess) ? hooks->guess() : A0_in;
   tm.start();
   if (g_debug) debug_msg("compute_vector_potential", "Solve BVP 3D...");
   const int sh3[3] = {nx, ny, nz};
-  std::unique_ptr<MG> mg3(new MG(3, sh3, -1, mesh, st, comm));
+  // Multi-GPU: the three component solves are independent (ndsm_vector_potential.f90:647-689), so they run
+  // concurrently on three streams with three communicators: the halo-exchange latency of one solve is hidden
+  // behind the kernels of the other two.  On one GPU the solves are bandwidth-bound and run one after another
+  // on one hierarchy (a third of the memory).
+  // opt-in: fine with virtual ranks, but NCCL serialises kernels of concurrently used communicators badly
+  // (measured 10x slower on 2 GPUs), so the default is one solve at a time
+  static const bool conc_env = getenv("NDSM_CONCURRENT_COMPONENTS") && atoi(getenv("NDSM_CONCURRENT_COMPONENTS")) != 0;
+  const bool concurrent = comm && comm->world() > 1 && conc_env && !prof_enabled() && !g_debug;
+  struct Ctx {
+    std::unique_ptr<MG> mg;
+    std::unique_ptr<Comm> own_comm;
+    cudaStream_t st = nullptr;
+    bool own_stream = false;
+    ~Ctx() {
+      mg.reset();
+      own_comm.reset();
+      if (own_stream && st) cudaStreamDestroy(st);
+    }
+  } ctx[3];
+  const int nctx = concurrent ? 3 : 1;
+  for (int q = 0; q < nctx; ++q) {
+    Comm* cq = comm;
+    ctx[q].st = st;
+    if (q > 0) {
+      CUDA_CHECK(cudaStreamCreateWithFlags(&ctx[q].st, cudaStreamNonBlocking));
+      ctx[q].own_stream = true;
+      ctx[q].own_comm = comm->clone(st);
+      cq = ctx[q].own_comm.get();
+    }
+    ctx[q].mg.reset(new MG(3, sh3, -1, mesh, ctx[q].st, cq));
+  }
+  MG* mg3 = ctx[0].mg.get();
+  auto mgc = [&](int c) { return ctx[concurrent ? c : 0].mg.get(); };
   const int ns = mg3->nslabs();
   std::vector<SlabOut> outs = outs_in;
   if (ns == 1 && outs.size() > 1) {  // every virtual rank shares one undivided solve: one contiguous output
@@ -197,24 +230,58 @@ int vector_solve_core(const int* nshape, const long long* iopt, const double* ro
   static const int wa[3][4] = {{0, 0, 0, 0}, {0, 0, 1, 1}, {1, 1, 1, 1}};  // At(1,.) or At(2,.)
   static const char* cop[3] = {"NDDNDD", "DNDDND", "DDNDDN"};              // :655,671,687
   const std::vector<const double*> norhs(ns, nullptr);                     // rhs = 0 (:640-641)
-  for (int c = 0; c < 3; ++c) {
+  for (int c = 0; c < 3; ++c)
     for (int s = 0; s < ns; ++s)
       for (int w = 0; w < 4; ++w) {
         const int f = wf[c][w];
         const int layer = (f % 2 == 0) ? 0 : nshape[imap_cp[f]] - 1;
         write_face(Ap[c][s], mg3->level(0, s).g, imap_cp[f], layer, At[f][wa[c][w]].p, st);
       }
-    mg3->set_options(c == 2 ? 5 : (int)iopt[IOPT_MS], ropt[ROPT_CTOL], cop[c], use_du_max, (int)iopt[IOPT_NMAXEX]);  // :685
-    double du_last;
-    mg3->solve(Ap[c], norhs, ropt[ROPT_VTOL], (int)iopt[IOPT_NCYCLES], &du_last, &rep.solves[6 + c]);
-    mg3->exchange(0, 0, 3, 1, &Ap[c]);  // halo planes of the converged component (curl needs k-1, k+1)
+  CUDA_CHECK(cudaStreamSynchronize(st));
+  auto set_opts = [&](int c) {
+    mgc(c)->set_options(c == 2 ? 5 : (int)iopt[IOPT_MS], ropt[ROPT_CTOL], cop[c], use_du_max, (int)iopt[IOPT_NMAXEX]);  // :685
+  };
+  // single slab writing the whole array in the default (flux first) order: a component of A is final as soon
+  // as its solve has converged, so it is converted and handed out early
+  const bool flux_first = (iopt[IOPT_FLXCRL] != 1);  // :453-477
+  const bool early_out = !concurrent && ns == 1 && flux_first && outs[0].k0 == 0 && outs[0].k1 == nz &&
+                         mg3->plan().ndist == 0;
+  if (!concurrent) {
+    for (int c = 0; c < 3; ++c) {
+      set_opts(c);
+      double du_last;
+      mg3->solve(Ap[c], norhs, ropt[ROPT_VTOL], (int)iopt[IOPT_NCYCLES], &du_last, &rep.solves[6 + c]);
+      mg3->exchange(0, 0, 3, 1, &Ap[c]);  // halo planes of the converged component (curl needs k-1, k+1)
+      if (early_out) {
+        unsplit_A(Ap[c][0], mg3->level(0, 0).g, c, dx_, dy_, dz_, phi, Lq, true, 0, nz, outs[0].A + c * outs[0].cstride, st);
+        if (hooks && hooks->component_ready) hooks->component_ready(c);
+      }
+    }
+  } else {
+    for (int c = 0; c < 3; ++c) {
+      set_opts(c);
+      mgc(c)->solve_begin(Ap[c], norhs, ropt[ROPT_VTOL], (int)iopt[IOPT_NCYCLES], &rep.solves[6 + c]);
+    }
+    bool any = true;
+    while (any) {
+      any = false;
+      for (int c = 0; c < 3; ++c)
+        if (!mgc(c)->solve_done()) mgc(c)->solve_enqueue();
+      for (int c = 0; c < 3; ++c)
+        if (!mgc(c)->solve_done()) { mgc(c)->solve_poll(); any = true; }
+    }
+    for (int c = 0; c < 3; ++c) {
+      double du_last;
+      mgc(c)->solve_end(&du_last);
+      mgc(c)->exchange(0, 0, 3, 1, &Ap[c]);
+      CUDA_CHECK(cudaStreamSynchronize(ctx[c].st));
+    }
   }
   rep.ms_solve3d = tm.stop();
 
   // ---------------- flux-balance fields + curl (K8) ----------------
   tm.start();
   if (g_debug) debug_msg("compute_vector_potential", "Compute B = curl(B) and flux correction...");
-  const bool flux_first = (iopt[IOPT_FLXCRL] != 1);  // :453-477
   if (!flux_first) printf(" FLAG SET: FLXCRL\n");
   const i64 pl = (i64)nx * ny;
   for (int s = 0; s < ns; ++s) {
@@ -238,8 +305,9 @@ int vector_solve_core(const int* nshape, const long long* iopt, const double* ro
       Ad = tmp.p;
       csA = (i64)(kb - ka) * pl;
     }
-    for (int c = 0; c < 3; ++c)
-      unsplit_A(Ap[c][s], g3, c, dx_, dy_, dz_, phi, Lq, flux_first, ka, kb, Ad + c * csA, st);
+    if (!early_out)
+      for (int c = 0; c < 3; ++c)
+        unsplit_A(Ap[c][s], g3, c, dx_, dy_, dz_, phi, Lq, flux_first, ka, kb, Ad + c * csA, st);
     curl_dense(Ad, ka, csA, nx, ny, nz, dq[0], dq[1], dq[2], k0, k1, o.B, o.cstride, st);
     if (!in_place)
       for (int c = 0; c < 3; ++c)
@@ -248,7 +316,6 @@ int vector_solve_core(const int* nshape, const long long* iopt, const double* ro
     if (!flux_first) add_flux_dense(o.A, o.cstride, o.B, o.cstride, nx, ny, k0, k1, dx_, dy_, dz_, phi, Lq, st);
     CUDA_CHECK(cudaStreamSynchronize(st));  // tmp goes out of scope
   }
-  mg3.reset();
   rep.ms_post = tm.stop();
   rep.ms_device = tall.stop();
   rep.launches = g_launches - launches0;

@@ -1,6 +1,7 @@
 // vecpot.hpp -- device-resident vector-potential driver (compute_vector_potential,
 // ndsm_vector_potential.f90:130-497) on top of the MG class.
 #pragma once
+#include <functional>
 #include <vector>
 #include "mg.hpp"
 
@@ -43,11 +44,21 @@ struct SlabOut {   // where one slab delivers A and B: planes [k0,k1), component
 // balanced z-range of rank `rank` (identical to the finest-level slab partition)
 void output_range(int nz, int world, int rank, int* k0, int* k1);
 
+// Optional hooks of the core (single-slab host entry): `guess` is called after the BC setup and returns the
+// initial guess (lets the host check / upload of A overlap the chi solves); `component_ready(c)` is called
+// as soon as component c of A is final in the output array (flux-balance field included), on stream st,
+// so that its device-to-host copy can overlap the remaining solves.
+struct CoreHooks {
+  std::function<DenseIn()> guess;
+  std::function<void(int)> component_ready;
+};
+
 // bn[f]: dense device faces (face f has shape (n1,n2) per ndsm_vector_potential.f90:225-246), all six on every
 // rank.  comm == nullptr: single slab.  outs: one entry per slab held by this process.
 // stop_after_bc: only run the BC setup (tests).  Returns iopt(IOPT_IERR).
 int vector_solve_core(const int* nshape, const long long* iopt, const double* ropt, const double* x, const double* y,
                       const double* z, double* const* bn, const DenseIn& A0, Comm* comm, const std::vector<SlabOut>& outs,
-                      cudaStream_t st, Report& rep, BcCapture* cap, bool stop_after_bc);
+                      cudaStream_t st, Report& rep, BcCapture* cap, bool stop_after_bc,
+                      const CoreHooks* hooks = nullptr);
 
 }  // namespace ndsm
