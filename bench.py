@@ -200,7 +200,7 @@ def kernel_report(lib, npoints, dev_ms):
 
 # dram__bytes_read.sum + dram__bytes_write.sum per launch of the finest-level colour pass from the committed
 # `ncu --set full` capture (profiles/), keyed by points per launch
-NCU_TRAFFIC_BYTES = {513 ** 3: 559.7e6 + 503.3e6}
+NCU_TRAFFIC_BYTES = {513 ** 3: 560.1e6 + 505.3e6}  # profiles/r01_ncu_full_finest_level_kernels_513.json
 
 
 def run_ours(args, rank, world):
