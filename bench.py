@@ -102,9 +102,15 @@ def workload(n, faces_only=True):
     return x, y, z, b
 
 
-def updates_from_trace(lib, n_points, ms=5):
-    """sum over Ax,Ay,Az of V-cycles * 2*ms * N.  Az always uses ms=5 (reference quirk)."""
+def updates_from_trace(lib, n_points, ms=5, dist=None):
+    """sum over Ax,Ay,Az of V-cycles * 2*ms * N.  Az always uses ms=5 (reference quirk).
+    With >= 3 ranks every rank only traces the component its group solved: take the max over ranks."""
     cyc = [lib.ndsm_b200_trace_ncycles(s) for s in range(9)]
+    if dist is not None:
+        import torch
+        t = torch.tensor(cyc, dtype=torch.int64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        cyc = [int(v) for v in t.tolist()]
     upd = sum(cyc[6 + c] * 2 * (5 if c == 2 else ms) * n_points for c in range(3))
     return upd, cyc
 
@@ -281,9 +287,12 @@ def run_ours(args, rank, world):
     ev0.record()
     upd_total, dev_ms = 0, 0.0
     tim = np.zeros(8)
+    step_ms = []
     for _ in range(args.steps):
+        ts = time.perf_counter()
         device_step()
-        upd, cyc = updates_from_trace(lib, N)
+        step_ms.append((time.perf_counter() - ts) * 1e3)
+        upd, cyc = updates_from_trace(lib, N, dist=dist)
         upd_total += upd
         lib.ndsm_b200_last_timing(p(tim))
         dev_ms += tim[6]
@@ -339,7 +348,7 @@ def run_ours(args, rank, world):
         if rc != 0:
             raise RuntimeError("end-to-end solve returned %d" % rc)
         if i >= args.warmup:
-            e2e_upd += updates_from_trace(lib, N)[0]
+            e2e_upd += updates_from_trace(lib, N, dist=dist)[0]
             e2e_t += dt
             lib.ndsm_b200_last_timing(p(tim))
             e2e_stage = {"in_ms": tim[1], "bc_ms": tim[2], "solve3d_ms": tim[3], "post_ms": tim[4], "d2h_ms": tim[5]}
@@ -368,8 +377,11 @@ def run_ours(args, rank, world):
             "config": {"workload": workload_name(n),
                        "l2": "inputs larger than L2 (each %d^3 fp64 array = %.2f GB)" % (n, 8 * N / 1e9),
                        "v_cycles": {"chi": cyc[:6], "Ax": cyc[6], "Ay": cyc[7], "Az": cyc[8]},
-                       "decomposition": "z-slabs, %d rank(s), one-plane halo exchange per colour pass over NCCL" % world
-                                        if world > 1 else "single GPU",
+                       "decomposition": ("single GPU" if world == 1 else
+                                         "2 ranks: z-slabs, communication-avoiding halo exchange over NCCL" if world == 2 else
+                                         "%d ranks: three component groups (Ax|Ay|Az) x z-slabs inside each group, "
+                                         "NCCL halo exchange + all-to-all of A before the curl" % world),
+                       "steps_ms": step_ms,
                        "timed_region": timed},
             "time_to_vc_tol_ms": {"device_events": dev_ms / args.steps, "wall": wall / args.steps * 1e3, **stage,
                                   "torch_events_rank0": ev0.elapsed_time(ev1) / args.steps},

@@ -72,7 +72,10 @@ int ndsm_b200_vector_solve_device(const int* nshape4, int* ioptc, double* ropt, 
  * vector_solve_rank: every rank passes all six boundary faces as dense arrays (face f of shape (n1,n2) with the
  * lower-numbered axis fastest: x-faces (ny,nz), y-faces (nx,nz), z-faces (nx,ny); ndsm_vector_potential.f90:225-246)
  * and receives planes [k0,k1) = slab_range(nz, world, rank) of A and B, laid out (nx,ny,k1-k0,3).  Faces and
- * outputs may be host or device pointers (flags).  The initial guess is zero (what ndsm.py always passes). */
+ * outputs may be host or device pointers (flags).  The initial guess is zero (what ndsm.py always passes).
+ * With 3 or more ranks the three component solves run concurrently on three disjoint groups of ranks (z-slabs
+ * inside each group) and A is redistributed for the curl; NDSM_HYBRID=0 (set before dist_init) keeps all ranks
+ * on one component at a time.  The V-cycle trace of a rank then only covers the component its group solved. */
 int ndsm_b200_dist_unique_id(void* out128);
 int ndsm_b200_dist_init(int rank, int world, const void* id128);
 int ndsm_b200_dist_finalize(void);

@@ -689,6 +689,7 @@ int ndsm_b200_flux_curl(const int* nshape4, int flxcrl, const double* x, const d
 // multi-GPU: one process per GPU, z-slabs over NCCL
 // ------------------------------------------------------------------------------------------
 static std::unique_ptr<Comm> g_dist;
+static std::unique_ptr<Comm> g_dist_group;  // my group of the hybrid decomposition (>= 3 ranks)
 
 int ndsm_b200_dist_unique_id(void* out128) {
   if (!out128) return NDSM_B200_ERR_ARG;
@@ -699,8 +700,16 @@ int ndsm_b200_dist_init(int rank, int world, const void* id128) {
   if (!id128 || world < 1 || rank < 0 || rank >= world) return NDSM_B200_ERR_ARG;
   if (int e = ensure_device(SUB)) return e;
   try {
+    g_dist_group.reset();
     g_dist.reset();
     g_dist = make_nccl_comm(rank, world, id128);
+    const bool hybrid_on = !(getenv("NDSM_HYBRID") && atoi(getenv("NDSM_HYBRID")) == 0);
+    if (world >= 3 && hybrid_on) {
+      int gf[3], gs[3];
+      hybrid_groups(world, gf, gs);
+      const int colour = (rank >= gf[2]) ? 2 : (rank >= gf[1]) ? 1 : 0;
+      g_dist_group = g_dist->split(colour);
+    }
     return 0;
   } catch (const NdsmError& e) {
     return fail(e, SUB);
@@ -708,6 +717,7 @@ int ndsm_b200_dist_init(int rank, int world, const void* id128) {
 }
 int ndsm_b200_dist_finalize(void) {
   cudaDeviceSynchronize();
+  g_dist_group.reset();
   g_dist.reset();
   return 0;
 }
@@ -770,8 +780,16 @@ int ndsm_b200_vector_solve_rank(const int* nshape4, int* ioptc, double* ropt, co
     }
     CUDA_CHECK(cudaStreamSynchronize(st));
     g_report.ms_in = (now_s() - t1) * 1e3;
+    Hybrid hyb;
+    const bool use_hybrid = g_dist && g_dist_group && world >= 3;
+    if (use_hybrid) {
+      hyb.world = g_dist.get();
+      hyb.group = g_dist_group.get();
+      hybrid_groups(world, hyb.gfirst, hyb.gsize);
+      hyb.comp = (rank >= hyb.gfirst[2]) ? 2 : (rank >= hyb.gfirst[1]) ? 1 : 0;
+    }
     int ierr = vector_solve_core(nshape4, iopt, ropt, x, y, z, bn, DenseIn(), g_dist.get(), std::vector<SlabOut>{so}, st,
-                                 g_report, nullptr, false);
+                                 g_report, nullptr, false, nullptr, use_hybrid ? &hyb : nullptr);
     t1 = now_s();
     if (!out_on_device) {
       CUDA_CHECK(cudaMemcpyAsync(A_slab, so.A, 3 * nslab * sizeof(double), cudaMemcpyDeviceToHost, st));

@@ -236,6 +236,7 @@ struct VirtualComm : Comm {
   }
   void bcast(int, double*, size_t, cudaStream_t) override {}
   std::unique_ptr<Comm> clone(cudaStream_t) override { return std::unique_ptr<Comm>(new VirtualComm(w)); }
+  std::unique_ptr<Comm> split(int) override { return nullptr; }
 };
 }  // namespace
 std::unique_ptr<Comm> make_virtual_comm(int world) { return std::unique_ptr<Comm>(new VirtualComm(world)); }

@@ -68,6 +68,9 @@ struct Comm {
   // an independent communicator over the same ranks (collective: every rank calls it in the same order);
   // lets independent solves overlap their exchanges on different streams
   virtual std::unique_ptr<Comm> clone(cudaStream_t st) = 0;
+  // sub-communicator of the ranks that pass the same colour (collective); ranks keep their relative order.
+  // Not available for virtual ranks (returns nullptr).
+  virtual std::unique_ptr<Comm> split(int colour) = 0;
 };
 std::unique_ptr<Comm> make_virtual_comm(int world);  // all ranks in this process, on the current device
 bool nccl_unique_id(void* out128);                    // ncclGetUniqueId (rank 0)

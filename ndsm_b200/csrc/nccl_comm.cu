@@ -23,6 +23,9 @@ struct NcclApi {
   ncclResult_t (*Broadcast)(const void*, void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
   ncclResult_t (*GroupStart)() = nullptr;
   ncclResult_t (*GroupEnd)() = nullptr;
+  ncclResult_t (*CommSplit)(ncclComm_t, int, int, ncclComm_t*, ncclConfig_t*) = nullptr;
+  ncclResult_t (*CommCount)(const ncclComm_t, int*) = nullptr;
+  ncclResult_t (*CommUserRank)(const ncclComm_t, int*) = nullptr;
   const char* (*GetErrorString)(ncclResult_t) = nullptr;
   bool ok = false;
 };
@@ -49,6 +52,9 @@ bool load_nccl() {
   NDSM_SYM(GroupStart, "ncclGroupStart")
   NDSM_SYM(GroupEnd, "ncclGroupEnd")
   NDSM_SYM(GetErrorString, "ncclGetErrorString")
+  NDSM_SYM(CommSplit, "ncclCommSplit")
+  NDSM_SYM(CommCount, "ncclCommCount")
+  NDSM_SYM(CommUserRank, "ncclCommUserRank")
 #undef NDSM_SYM
   g_nccl.ok = true;
   return true;
@@ -68,6 +74,15 @@ struct NcclComm : Comm {
   ncclComm_t comm = nullptr;
   NcclComm(int rank, int world, const ncclUniqueId& id) : rank_(rank), world_(world) {
     NCCL_CHECK(g_nccl.CommInitRank(&comm, world, id, rank));
+  }
+  explicit NcclComm(ncclComm_t c) : rank_(0), world_(1), comm(c) {
+    NCCL_CHECK(g_nccl.CommCount(comm, &world_));
+    NCCL_CHECK(g_nccl.CommUserRank(comm, &rank_));
+  }
+  std::unique_ptr<Comm> split(int colour) override {
+    ncclComm_t nc = nullptr;
+    NCCL_CHECK(g_nccl.CommSplit(comm, colour, rank_, &nc, nullptr));
+    return std::unique_ptr<Comm>(new NcclComm(nc));
   }
   ~NcclComm() override { if (comm) g_nccl.CommDestroy(comm); }
   int world() const override { return world_; }

@@ -49,7 +49,8 @@ struct EvTimer {
 
 int vector_solve_core(const int* nshape, const long long* iopt, const double* ropt, const double* x, const double* y,
                       const double* z, double* const* bn, const DenseIn& A0_in, Comm* comm, const std::vector<SlabOut>& outs_in,
-                      cudaStream_t st, Report& rep, BcCapture* cap, bool stop_after_bc, const CoreHooks* hooks) {
+                      cudaStream_t st, Report& rep, BcCapture* cap, bool stop_after_bc, const CoreHooks* hooks,
+                      const Hybrid* hyb) {
   const int nx = nshape[0], ny = nshape[1], nz = nshape[2];
   const i64 N = (i64)nx * ny * nz;
   const double* mesh[3] = {x, y, z};
@@ -160,6 +161,90 @@ int vector_solve_core(const int* nshape, const long long* iopt, const double* ro
   }
   rep.ms_bc = tm.stop();
   if (stop_after_bc) {
+    rep.launches = g_launches - launches0;
+    return ierr_last;
+  }
+
+  // ---------------- hybrid: my group solves ONE component, then all-to-all of dense A planes ------------
+  if (hyb) {
+    tm.start();
+    const int c = hyb->comp, me = hyb->world->first_rank(), W = hyb->world->world();
+    const int sh3h[3] = {nx, ny, nz};
+    const i64 plh = (i64)nx * ny;
+    static const int wf[3][4] = {{2, 3, 4, 5}, {0, 1, 4, 5}, {0, 1, 2, 3}};
+    static const int wa[3][4] = {{0, 0, 0, 0}, {0, 0, 1, 1}, {1, 1, 1, 1}};
+    static const char* cop[3] = {"NDDNDD", "DNDDND", "DDNDDN"};
+    const bool flux_first = (iopt[IOPT_FLXCRL] != 1);
+    if (!flux_first && me == 0) printf(" FLAG SET: FLXCRL\n");
+    int a0, a1;  // planes of component c this rank converts and sends out
+    output_range(nz, hyb->gsize[c], me - hyb->gfirst[c], &a0, &a1);
+    DevBuf mine((size_t)std::max(a1 - a0, 1) * plh);
+    {
+      MG mg(3, sh3h, -1, mesh, st, hyb->gsize[c] > 1 ? hyb->group : nullptr);
+      rep.ndist = mg.plan().ndist;
+      const Level& L0 = mg.level(0, 0);
+      const size_t lv0 = mg.level_doubles(0, 0);
+      DevBuf As1(lv0);
+      CUDA_CHECK(cudaMemsetAsync(As1.p, 0, lv0 * sizeof(double), st));
+      double* p0 = As1.p + (i64)L0.H * L0.g.ps;
+      for (int w = 0; w < 4; ++w) {
+        const int f = wf[c][w];
+        write_face(p0, L0.g, imap_cp[f], (f % 2 == 0) ? 0 : nshape[imap_cp[f]] - 1, At[f][wa[c][w]].p, st);
+      }
+      mg.set_options(c == 2 ? 5 : (int)iopt[IOPT_MS], ropt[ROPT_CTOL], cop[c], use_du_max, (int)iopt[IOPT_NMAXEX]);
+      double du_last;
+      mg.solve(p0, nullptr, ropt[ROPT_VTOL], (int)iopt[IOPT_NCYCLES], &du_last, &rep.solves[6 + c]);
+      if (L0.g.k0 > a0 || L0.g.k0 + L0.g.nzl < a1) throw NdsmError(6);
+      unsplit_A(p0, L0.g, c, dx_, dy_, dz_, phi, Lq, flux_first, a0, a1, mine.p, st);
+      CUDA_CHECK(cudaStreamSynchronize(st));
+    }
+    rep.ms_solve3d = tm.stop();
+    tm.start();
+    // planes every rank needs: its output range plus the planes the curl stencil touches
+    auto need = [&](int d, int* ka, int* kb, int* k0, int* k1) {
+      output_range(nz, W, d, k0, k1);
+      *ka = (*k0 == 0) ? 0 : *k0 - 1;
+      *kb = (*k1 == nz) ? nz : *k1 + 1;
+      if (*k0 == 0 && *kb < 3) *kb = 3 < nz ? 3 : nz;
+      if (*k1 == nz && *ka > nz - 3) *ka = nz - 3 > 0 ? nz - 3 : 0;
+    };
+    if (outs_in.size() != 1) throw NdsmError(6);
+    const SlabOut& o = outs_in[0];
+    int ka, kb, k0, k1;
+    need(me, &ka, &kb, &k0, &k1);
+    if (o.k0 != k0 || o.k1 != k1) throw NdsmError(6);
+    const i64 csA = (i64)(kb - ka) * plh;
+    DevBuf tmp((size_t)3 * csA);
+    hyb->world->begin(st);
+    for (int cc = 0; cc < 3; ++cc)
+      for (int q = hyb->gfirst[cc]; q < hyb->gfirst[cc] + hyb->gsize[cc]; ++q) {
+        int qa0, qa1;
+        output_range(nz, hyb->gsize[cc], q - hyb->gfirst[cc], &qa0, &qa1);
+        for (int d = 0; d < W; ++d) {
+          int dka, dkb, dk0, dk1;
+          need(d, &dka, &dkb, &dk0, &dk1);
+          const int v0 = std::max(qa0, dka), v1 = std::min(qa1, dkb);
+          if (v1 <= v0) continue;
+          const size_t n = (size_t)(v1 - v0) * plh;
+          if (q == me && d == me) {
+            CUDA_CHECK(cudaMemcpyAsync(tmp.p + cc * csA + (i64)(v0 - ka) * plh, mine.p + (i64)(v0 - a0) * plh,
+                                       n * sizeof(double), cudaMemcpyDeviceToDevice, st));
+          } else if (q == me) {
+            hyb->world->send(me, d, mine.p + (i64)(v0 - a0) * plh, n, st);
+          } else if (d == me) {
+            hyb->world->recv(me, q, tmp.p + cc * csA + (i64)(v0 - ka) * plh, n, st);
+          }
+        }
+      }
+    hyb->world->end(st);
+    curl_dense(tmp.p, ka, csA, nx, ny, nz, dq[0], dq[1], dq[2], k0, k1, o.B, o.cstride, st);
+    for (int cc = 0; cc < 3; ++cc)
+      CUDA_CHECK(cudaMemcpyAsync(o.A + cc * o.cstride, tmp.p + cc * csA + (i64)(k0 - ka) * plh,
+                                 (size_t)(k1 - k0) * plh * sizeof(double), cudaMemcpyDeviceToDevice, st));
+    if (!flux_first) add_flux_dense(o.A, o.cstride, o.B, o.cstride, nx, ny, k0, k1, dx_, dy_, dz_, phi, Lq, st);
+    CUDA_CHECK(cudaStreamSynchronize(st));
+    rep.ms_post = tm.stop();
+    rep.ms_device = tall.stop();
     rep.launches = g_launches - launches0;
     return ierr_last;
   }
@@ -320,6 +405,16 @@ int vector_solve_core(const int* nshape, const long long* iopt, const double* ro
   rep.ms_device = tall.stop();
   rep.launches = g_launches - launches0;
   return ierr_last;  // :480 -- ierr of the LAST chi solve (reference quirk)
+}
+
+// contiguous groups of ranks, sizes as equal as possible (larger groups first)
+void hybrid_groups(int world, int* gfirst3, int* gsize3) {
+  int at = 0;
+  for (int c = 0; c < 3; ++c) {
+    gsize3[c] = world / 3 + (c < world % 3 ? 1 : 0);
+    gfirst3[c] = at;
+    at += gsize3[c];
+  }
 }
 
 void output_range(int nz, int world, int rank, int* k0, int* k1) {
