@@ -65,7 +65,13 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append((time.perf_counter(), [c.strip() for c in line.split(",")]))
+
+    def mark_begin(self):
+        self.t0 = time.perf_counter()
+
+    def mark_end(self):
+        self.t1 = time.perf_counter()
 
     def stop(self):
         if not self.proc:
@@ -78,7 +84,10 @@ class ClockSampler:
             self.proc.kill()
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        t0, t1 = getattr(self, "t0", 0.0), getattr(self, "t1", float("inf"))
+        for ts, r in self.rows:
+            if ts < t0 or ts > t1 + 0.3:
+                continue  # the sampler runs from before the warm-up; only samples of the timed region count
             try:
                 sm.append(float(r[0]))
                 mx.append(float(r[1]))
@@ -276,11 +285,12 @@ def run_ours(args, rank, world):
                 raise RuntimeError("ndsm_b200_vector_solve_rank returned %d" % rc)
         timed = "K x ndsm_b200_vector_solve_rank (six faces resident in HBM on every rank, z-slab outputs in HBM)"
 
+    clocks = ClockSampler(local)
+    clocks.start()   # started before the warm-up: spawning nvidia-smi stalls the driver for a moment
     for _ in range(args.warmup):
         device_step()
-    clocks = ClockSampler(local)
     torch.cuda.synchronize(); barrier()
-    clocks.start()
+    clocks.mark_begin()
     l0 = lib.ndsm_b200_launch_count()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t0 = time.perf_counter()
@@ -300,6 +310,7 @@ def run_ours(args, rank, world):
     ev1.record()
     torch.cuda.synchronize(); barrier()
     wall = maxr(time.perf_counter() - t0)
+    clocks.mark_end()
     launches = lib.ndsm_b200_launch_count() - l0
     clk = clocks.stop()
     value = upd_total / wall / 1e9
@@ -312,7 +323,7 @@ def run_ours(args, rank, world):
         device_step()
         lib.ndsm_b200_last_timing(p(tim))
         prof_ms += tim[6]
-    roofline = kernel_report(lib, npts_local, prof_ms)
+    roofline = kernel_report(lib, int(lib.ndsm_b200_last_slab_points()) or npts_local, prof_ms)
     lib.ndsm_b200_profile_enable(0)
 
     # ---------------- end-to-end arm: host buffers, H2D and D2H inside the timed region -------------

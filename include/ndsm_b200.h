@@ -167,6 +167,8 @@ int ndsm_b200_trace_nexact(int solve, int cycle);
 /* milliseconds of the last vector solve: [0] total wall, [1] input staging + H2D, [2] BC setup,
  * [3] 3D solves, [4] flux+curl, [5] D2H, [6] device-resident total (CUDA events), [7] kernel launches */
 int ndsm_b200_last_timing(double* out8);
+/* finest-level points this process smoothed per component solve in the last call (its z-slab) */
+unsigned long long ndsm_b200_last_slab_points(void);
 /* CUDA-event timing of the finest-level 3D kernels (off by default).  cls: 0 = k_relax3d colour pass,
  * 1 = k_residual3d, 2 = restriction, 3 = prolongation, 4 = update_u reduction (2 launches), 5 = one halo exchange,
  * 6 = all work on levels >= 2 of one V-cycle, 7 = all work on level 1 of one V-cycle (two brackets per cycle). */

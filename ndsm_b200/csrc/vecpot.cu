@@ -183,6 +183,7 @@ int vector_solve_core(const int* nshape, const long long* iopt, const double* ro
       MG mg(3, sh3h, -1, mesh, st, hyb->gsize[c] > 1 ? hyb->group : nullptr);
       rep.ndist = mg.plan().ndist;
       const Level& L0 = mg.level(0, 0);
+      rep.slab_points = (unsigned long long)nx * ny * L0.g.nzl;
       const size_t lv0 = mg.level_doubles(0, 0);
       DevBuf As1(lv0);
       CUDA_CHECK(cudaMemsetAsync(As1.p, 0, lv0 * sizeof(double), st));
@@ -296,6 +297,8 @@ int vector_solve_core(const int* nshape, const long long* iopt, const double* ro
   }
   if ((int)outs.size() != ns) throw NdsmError(6);
   rep.ndist = mg3->plan().ndist;
+  rep.slab_points = 0;
+  for (int s = 0; s < ns; ++s) rep.slab_points += (unsigned long long)nx * ny * mg3->level(0, s).g.nzl;
   std::vector<DevBuf> As(ns);
   std::vector<size_t> lvl(ns);
   std::vector<double*> Ap[3];  // per component: local plane 0 of every slab
