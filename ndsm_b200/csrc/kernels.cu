@@ -1267,6 +1267,256 @@ bool solve_exact_smem(int ndim, double* u, const double* rhs, const Grid& g, con
 }
 
 // ---------------------------------------------------------------------------------------
+// Small-level sub-V-cycle in ONE thread block.
+// Levels of at most SMALL_MAX_POINTS points are latency-bound: every colour pass, mean subtraction, residual,
+// transfer ... is a dependent launch of a few microseconds.  This kernel keeps u and rhs of all those levels
+// dense in shared memory and runs, with the same arithmetic as the per-level kernels,
+//     for g = ls .. ng-2 : ms x relax(g); r = residual(g); rhs[g+1] = R r; u[g+1] = 0      (fine_to_coarse)
+//     solve_exact(ng-1)
+//     for c = ng-1 .. ls+1 : ms x relax(c); u[c-1] += P u[c]; ms x relax(c-1)              (coarse_to_fine)
+//     ms x relax(ls)                                     (the pre-smooth that opens coarse_to_fine(ls))
+// (ndsm_multigrid_core.f90:341-377,482-560,593-684,728-800).  Input rhs[ls] (u[ls] = 0), output u[ls].
+// The 3D arithmetic is bit-identical to the per-level kernels (restriction in the reference's summation order);
+// in 2D only the pure-Neumann mean uses a different (block-strided) summation order.
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ void sm_decode(const SmallLevel& L, int p, int& i, int& j, int& k) {
+  const int sxy = L.nx * L.ny;
+  k = p / sxy;
+  const int rem = p - k * sxy;
+  j = rem / L.nx;
+  i = rem - j * L.nx;
+}
+
+template <int NDIM>
+__device__ void sm_relax(double* __restrict__ u, const double* __restrict__ rhs, const SmallLevel& L,
+                         const int first_colour, const int all_neumann, double* red) {
+  const int N = L.nx * L.ny * L.nz, sxy = L.nx * L.ny;
+  for (int pass = 0; pass < 2; ++pass) {
+    const int colour = first_colour ^ pass;
+    for (int p = threadIdx.x; p < N; p += blockDim.x) {
+      int i, j, k;
+      sm_decode(L, p, i, j, k);
+      if (((i + j + k) & 1) != colour) continue;
+      if (i < L.b.lb[0] || i > L.b.ub[0] || j < L.b.lb[1] || j > L.b.ub[1]) continue;
+      if (NDIM == 3) {
+        if (k < L.b.lb[2] || k > L.b.ub[2]) continue;
+        const int xl = (i - 1 < 0) ? 1 : i - 1, xh = (i + 1 > L.nx - 1) ? L.nx - 2 : i + 1;
+        const int yl = (j - 1 < 0) ? 1 : j - 1, yh = (j + 1 > L.ny - 1) ? L.ny - 2 : j + 1;
+        const int zl = (k - 1 < 0) ? 1 : k - 1, zh = (k + 1 > L.nz - 1) ? L.nz - 2 : k + 1;
+        double unew = ((u[xh + j * L.nx + k * sxy] + u[xl + j * L.nx + k * sxy]) * L.w.wx +
+                       (u[i + yh * L.nx + k * sxy] + u[i + yl * L.nx + k * sxy]) * L.w.wy) +
+                      (u[i + j * L.nx + zh * sxy] + u[i + j * L.nx + zl * sxy]) * L.w.wz;
+        unew = unew - rhs[p];
+        u[p] = L.w.w1 * unew;
+      } else {
+        const int x1 = (i == 0) ? i + 1 : i - 1, x2 = (i == L.nx - 1) ? i - 1 : i + 1;
+        const int y1 = (j == 0) ? j + 1 : j - 1, y2 = (j == L.ny - 1) ? j - 1 : j + 1;
+        double un = u[x1 + j * L.nx] * L.w.wx + u[x2 + j * L.nx] * L.w.wx;
+        un = (un + u[i + y1 * L.nx] * L.w.wy) + u[i + y2 * L.nx] * L.w.wy;
+        u[p] = (un - rhs[p]) * L.w.w1;
+      }
+    }
+    __syncthreads();
+  }
+  if (all_neumann) {
+    double s = 0.0;
+    for (int p = threadIdx.x; p < N; p += blockDim.x) s += u[p];
+    s = block_sum(s, red);
+    const double mean = s / (double)N;
+    for (int p = threadIdx.x; p < N; p += blockDim.x) u[p] = u[p] - mean;
+    __syncthreads();
+  }
+}
+
+template <int NDIM>
+__device__ void sm_residual(const double* __restrict__ u, const double* __restrict__ rhs, double* __restrict__ r,
+                            const SmallLevel& L) {
+  const int N = L.nx * L.ny * L.nz, sxy = L.nx * L.ny;
+  for (int p = threadIdx.x; p < N; p += blockDim.x) {
+    int i, j, k;
+    sm_decode(L, p, i, j, k);
+    double res = 0.0;
+    const bool in = !(i < L.b.lb[0] || i > L.b.ub[0] || j < L.b.lb[1] || j > L.b.ub[1] ||
+                      (NDIM == 3 && (k < L.b.lb[2] || k > L.b.ub[2])));
+    if (in) {
+      if (NDIM == 3) {
+        const int xl = (i - 1 < 0) ? 1 : i - 1, xh = (i + 1 > L.nx - 1) ? L.nx - 2 : i + 1;
+        const int yl = (j - 1 < 0) ? 1 : j - 1, yh = (j + 1 > L.ny - 1) ? L.ny - 2 : j + 1;
+        const int zl = (k - 1 < 0) ? 1 : k - 1, zh = (k + 1 > L.nz - 1) ? L.nz - 2 : k + 1;
+        double tt = ((u[xl + j * L.nx + k * sxy] + u[xh + j * L.nx + k * sxy]) * L.w.wx +
+                     (u[i + yl * L.nx + k * sxy] + u[i + yh * L.nx + k * sxy]) * L.w.wy) +
+                    (u[i + j * L.nx + zl * sxy] + u[i + j * L.nx + zh * sxy]) * L.w.wz;
+        tt = tt - rhs[p];
+        tt = tt - u[p] * L.w.wc;
+        res = -tt;
+      } else {
+        const int x1 = (i == 0) ? i + 1 : i - 1, x2 = (i == L.nx - 1) ? i - 1 : i + 1;
+        const int y1 = (j == 0) ? j + 1 : j - 1, y2 = (j == L.ny - 1) ? j - 1 : j + 1;
+        const double uc = u[p];
+        double lap = ((u[x1 + j * L.nx] - 2 * uc) + u[x2 + j * L.nx]) * L.w.wx;
+        lap = lap + ((u[i + y1 * L.nx] - 2 * uc) + u[i + y2 * L.nx]) * L.w.wy;
+        res = rhs[p] - lap;
+      }
+    }
+    r[p] = res;
+  }
+  __syncthreads();
+}
+
+// rhs_c = R r_f in the reference's order (same as k_restrict); also u_c = 0
+__device__ void sm_restrict(const double* __restrict__ rf, const SmallLevel& F, double* __restrict__ rc,
+                            double* __restrict__ uc, const SmallLevel& C) {
+  const int NC = C.nx * C.ny * C.nz, fxy = F.nx * F.ny;
+  for (int p = threadIdx.x; p < NC; p += blockDim.x) {
+    int ic, jc, kc;
+    sm_decode(C, p, ic, jc, kc);
+    const int ax = F.rt[0].first[ic], cx = F.rt[0].count[ic];
+    const int ay = F.rt[1].first[jc], cy = F.rt[1].count[jc];
+    const int az = F.rt[2].first[kc], cz = F.rt[2].count[kc];
+    const double* __restrict__ wxv = F.rt[0].c2 + (i64)ic * NDSM_RMAX;
+    const double* __restrict__ wyv = F.rt[1].c2 + (i64)jc * NDSM_RMAX;
+    const double* __restrict__ wzv = F.rt[2].c2 + (i64)kc * NDSM_RMAX;
+    double fc = 0.0;
+    for (int kk = 0; kk < cz; ++kk)
+      for (int jj = 0; jj < cy; ++jj) {
+        const double* __restrict__ row = rf + (az + kk) * fxy + (ay + jj) * F.nx + ax;
+        for (int ii = 0; ii < cx; ++ii) {
+          double w = (wxv[ii] * F.rt[0].w2);
+          w = (w * wyv[jj]) * F.rt[1].w2;
+          w = (w * wzv[kk]) * F.rt[2].w2;
+          fc = fc + w * row[ii];
+        }
+      }
+    rc[p] = fc;
+    uc[p] = 0.0;
+  }
+  __syncthreads();
+}
+
+// u_f += P u_c (same lerp order as k_interp_add)
+__device__ void sm_interp_add(const double* __restrict__ ucv, const SmallLevel& C, double* __restrict__ uf,
+                              const SmallLevel& F) {
+  const int NF = F.nx * F.ny * F.nz, cxy = C.nx * C.ny;
+  for (int p = threadIdx.x; p < NF; p += blockDim.x) {
+    int i, j, k;
+    sm_decode(F, p, i, j, k);
+    const int x0 = F.it[0].lo[i], y0 = F.it[1].lo[j], z0 = F.it[2].lo[k];
+    const int x1 = min(x0 + 1, C.nx - 1), y1 = min(y0 + 1, C.ny - 1), z1 = min(z0 + 1, C.nz - 1);
+    double f0 = ucv[x0 + y0 * C.nx + z0 * cxy], f1 = ucv[x1 + y0 * C.nx + z0 * cxy];
+    double f2 = ucv[x0 + y1 * C.nx + z0 * cxy], f3 = ucv[x1 + y1 * C.nx + z0 * cxy];
+    const double f4 = ucv[x0 + y0 * C.nx + z1 * cxy], f5 = ucv[x1 + y0 * C.nx + z1 * cxy];
+    const double f6 = ucv[x0 + y1 * C.nx + z1 * cxy], f7 = ucv[x1 + y1 * C.nx + z1 * cxy];
+    const double whz = F.it[2].wh[k], wlz = F.it[2].wl[k];
+    f0 = whz * f0 + wlz * f4;
+    f1 = whz * f1 + wlz * f5;
+    f2 = whz * f2 + wlz * f6;
+    f3 = whz * f3 + wlz * f7;
+    const double why = F.it[1].wh[j], wly = F.it[1].wl[j];
+    f0 = why * f0 + wly * f2;
+    f1 = why * f1 + wly * f3;
+    const double whx = F.it[0].wh[i], wlx = F.it[0].wl[i];
+    f0 = whx * f0 + wlx * f1;
+    uf[p] = uf[p] + f0;
+  }
+  __syncthreads();
+}
+
+template <int NDIM>
+__global__ void __launch_bounds__(1024)
+k_vcycle_small(const double* __restrict__ rhs_in, double* __restrict__ u_out, const Grid g0, const SmallArgs a,
+               int* __restrict__ info) {
+  extern __shared__ double sm[];
+  __shared__ double red[40];
+  const int nl = a.nlev;
+  // ---- load rhs of the first small level, u = 0
+  {
+    const SmallLevel& L = a.lv[0];
+    const int N = L.nx * L.ny * L.nz;
+    for (int p = threadIdx.x; p < N; p += blockDim.x) {
+      int i, j, k;
+      sm_decode(L, p, i, j, k);
+      sm[L.off_rhs + p] = rhs_in[gidx(g0, i, j, k)];
+      sm[L.off_u + p] = 0.0;
+    }
+    __syncthreads();
+  }
+  // ---- fine_to_coarse
+  for (int l = 0; l + 1 < nl; ++l) {
+    const SmallLevel& F = a.lv[l];
+    const SmallLevel& C = a.lv[l + 1];
+    for (int s = 0; s < a.ms; ++s) sm_relax<NDIM>(sm + F.off_u, sm + F.off_rhs, F, a.first_colour, a.all_neumann, red);
+    sm_residual<NDIM>(sm + F.off_u, sm + F.off_rhs, sm + a.off_r, F);
+    sm_restrict(sm + a.off_r, F, sm + C.off_rhs, sm + C.off_u, C);
+  }
+  // ---- solve_exact on the coarsest level (ndsm_multigrid_core.f90:728-800)
+  {
+    const SmallLevel& L = a.lv[nl - 1];
+    const int N = L.nx * L.ny * L.nz;
+    double* su = sm + L.off_u;
+    double* ss = sm + a.off_sav;
+    for (int p = threadIdx.x; p < N; p += blockDim.x) ss[p] = 0.0;
+    __syncthreads();
+    double du = 1.7976931348623157e308;
+    int iters = 0, converged = 0;
+    for (int it = 0; it < a.nmax_exact; ++it) {
+      if (du <= a.ex_tol) { converged = 1; break; }
+      sm_relax<NDIM>(su, sm + L.off_rhs, L, a.first_colour, a.all_neumann, red);
+      double dmax = 0.0, dsum = 0.0;
+      for (int p = threadIdx.x; p < N; p += blockDim.x) {
+        const double v = su[p];
+        const double d = fabs(ss[p] - v);
+        dmax = fmax(dmax, d);
+        dsum += d;
+        ss[p] = v;
+      }
+      if (a.du_max) du = block_max(dmax, red);
+      else du = block_sum(dsum, red) / (double)N;
+      ++iters;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) { info[0] = iters; info[1] = converged; }
+  }
+  // ---- coarse_to_fine
+  for (int l = nl - 1; l >= 1; --l) {
+    const SmallLevel& C = a.lv[l];
+    const SmallLevel& F = a.lv[l - 1];
+    for (int s = 0; s < a.ms; ++s) sm_relax<NDIM>(sm + C.off_u, sm + C.off_rhs, C, a.first_colour, a.all_neumann, red);
+    sm_interp_add(sm + C.off_u, C, sm + F.off_u, F);
+    for (int s = 0; s < a.ms; ++s) sm_relax<NDIM>(sm + F.off_u, sm + F.off_rhs, F, a.first_colour, a.all_neumann, red);
+  }
+  // ---- the pre-smooth that opens coarse_to_fine(ls), then write u[ls] back
+  {
+    const SmallLevel& L = a.lv[0];
+    for (int s = 0; s < a.ms; ++s) sm_relax<NDIM>(sm + L.off_u, sm + L.off_rhs, L, a.first_colour, a.all_neumann, red);
+    const int N = L.nx * L.ny * L.nz;
+    for (int p = threadIdx.x; p < N; p += blockDim.x) {
+      int i, j, k;
+      sm_decode(L, p, i, j, k);
+      u_out[gidx(g0, i, j, k)] = sm[L.off_u + p];
+    }
+  }
+}
+
+void vcycle_small_prepare() {
+  static bool done = false;
+  if (done) return;
+  cudaFuncSetAttribute(k_vcycle_small<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  cudaFuncSetAttribute(k_vcycle_small<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  done = true;
+}
+
+void vcycle_small(int ndim, const double* rhs_in, double* u_out, const Grid& g0, const SmallArgs& a, int* info,
+                  cudaStream_t st) {
+  vcycle_small_prepare();
+  const size_t bytes = (size_t)a.smem_doubles * sizeof(double);
+  const int n0 = a.lv[0].nx * a.lv[0].ny * a.lv[0].nz;
+  const int threads = std::min(1024, std::max(64, ((n0 / 2 + 31) / 32) * 32));
+  if (ndim == 3) k_vcycle_small<3><<<1, threads, bytes, st>>>(rhs_in, u_out, g0, a, info);
+  else k_vcycle_small<2><<<1, threads, bytes, st>>>(rhs_in, u_out, g0, a, info);
+  LAUNCHED();
+}
+
+// ---------------------------------------------------------------------------------------
 // layout conversion
 // ---------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)

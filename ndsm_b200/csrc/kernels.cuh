@@ -80,6 +80,27 @@ void interp_add_tiled(const double* uc, const Grid& gc, double* uf, const Grid& 
 bool solve_exact_smem(int ndim, double* u, const double* rhs, const Grid& g, const Bounds& b, int first_colour,
                       const Weights& w, bool all_neumann, bool du_max, double ex_tol, int nmax, int* info,
                       cudaStream_t st);
+// Small-level sub-V-cycle in one thread block (levels of at most SMALL_MAX_POINTS points, dense in shared memory)
+#define SMALL_MAX_POINTS 4096
+#define SMALL_MAX_LEVELS 6
+struct SmallLevel {
+  int nx, ny, nz;
+  Weights w;
+  Bounds b;
+  InterpTab it[3];    // towards the next coarser level
+  RestrictTab rt[3];
+  int off_u, off_rhs;  // shared-memory offsets (doubles)
+};
+struct SmallArgs {
+  int nlev;
+  SmallLevel lv[SMALL_MAX_LEVELS];
+  int first_colour, all_neumann, du_max, nmax_exact, ms;
+  double ex_tol;
+  int off_r, off_sav, smem_doubles;
+};
+void vcycle_small_prepare();
+void vcycle_small(int ndim, const double* rhs_in, double* u_out, const Grid& g0, const SmallArgs& a, int* info,
+                  cudaStream_t st);
 // K6: out[0] = max|a-b|, out[1] = sum|a-b| over owned planes; then a := b  (update_u: a=caller's u, b=V-cycled u;
 // ndsm_multigrid_core.f90:1077-1122).  With copy=false it is du_metrics (:808-853) and leaves a untouched.
 void diff_reduce(double* a, const double* b, const Grid& g, bool copy, double* scratch, double* out, cudaStream_t st);

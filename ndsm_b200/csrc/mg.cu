@@ -378,7 +378,46 @@ MG::MG(int ndim, const int* shape, int ngrids, const double* const* mesh, cudaSt
                                             &S.lv[g].rr_hwp, &S.lv[g].rr_fyw);
     }
   CUDA_CHECK(cudaStreamSynchronize(st_));  // host staging vectors go out of scope
+  // --- which levels run inside the single-block small-level kernel
+  static const bool small_on = !(getenv("NDSM_B200_SMALL") && atoi(getenv("NDSM_B200_SMALL")) == 0);
+  small_from_ = 0;
+  if (small_on && ngrids >= 2) {
+    int ls = ngrids;
+    while (ls - 1 >= 1 && ls - 1 >= nd && (i64)hl[ls - 1].n[0] * hl[ls - 1].n[1] * hl[ls - 1].n[2] <= SMALL_MAX_POINTS &&
+           ngrids - (ls - 1) <= SMALL_MAX_LEVELS)
+      --ls;
+    if (ls < ngrids) small_from_ = ls;
+  }
   set_options(5, 1e-13, "NNNNNN", true, 10000);
+}
+
+void MG::build_small_args() {
+  if (small_from_ <= 0) return;
+  SmallArgs& a = small_args_;
+  const int ng = ngrids();
+  a.nlev = ng - small_from_;
+  int off = 0;
+  for (int l = 0; l < a.nlev; ++l) {
+    const Level& L = slabs_[0].lv[small_from_ + l];
+    SmallLevel& S = a.lv[l];
+    S.nx = L.g.nx; S.ny = L.g.ny; S.nz = L.g.nz;
+    S.w = L.w;
+    S.b = L.b;
+    for (int d = 0; d < 3; ++d) { S.it[d] = L.it[d]; S.rt[d] = L.rt[d]; }
+    const int N = S.nx * S.ny * S.nz;
+    S.off_u = off; off += N;
+    S.off_rhs = off; off += N;
+  }
+  a.off_r = off; off += a.lv[0].nx * a.lv[0].ny * a.lv[0].nz;
+  a.off_sav = off; off += a.lv[a.nlev - 1].nx * a.lv[a.nlev - 1].ny * a.lv[a.nlev - 1].nz;
+  a.smem_doubles = off;
+  a.first_colour = first_colour_;
+  a.all_neumann = all_neumann_ ? 1 : 0;
+  a.du_max = du_max_ ? 1 : 0;
+  a.nmax_exact = nmax_exact_;
+  a.ms = ms_;
+  a.ex_tol = ex_tol_;
+  if ((size_t)off * sizeof(double) > 200 * 1024) small_from_ = 0;
 }
 
 MG::~MG() {
@@ -417,6 +456,7 @@ void MG::set_options(int ms, double ex_tol, const char* copt, bool du_max, int n
         }
       }
     }
+  build_small_args();
 }
 
 // halo planes with the z-neighbours (one grouped exchange)
@@ -615,17 +655,28 @@ int MG::solve_exact(int g) {
 void MG::v_cycle() {  // ndsm_multigrid_core.f90:341-377
   const int ng = ngrids();
   // profiling brackets (3D only): PROF_LEVEL1 = all work on level 1, PROF_TAIL = all work on levels >= 2
-  const bool pr = (ndim_ == 3 && ng > 3);
-  for (int g = 0; g < ng - 1; ++g) {  // fine_to_coarse :482-560
+  const bool pr = (ndim_ == 3 && ng > 3 && (small_from_ == 0 || small_from_ > 2));
+  const int gend = (small_from_ > 0) ? small_from_ : ng - 1;
+  for (int g = 0; g < gend; ++g) {  // fine_to_coarse :482-560
     if (pr && g == 1) prof_begin(PROF_LEVEL1, st_);
     if (pr && g == 2) { prof_end(PROF_LEVEL1, st_); prof_begin(PROF_TAIL, st_); }
     for (int s = 0; s < ms_; ++s) relax(g);
     residual(g);
     restrict_to(g);
   }
-  solve_exact(ng - 1);
-  for (int c = ng - 1; c >= 1; --c) {  // coarse_to_fine :593-684
-    for (int s = 0; s < ms_; ++s) relax(c);
+  const int ls = small_from_;
+  int cstart = ng - 1;
+  if (ls > 0) {
+    // levels >= ls: the whole sub-V-cycle (and the pre-smooth of level ls) in one thread block
+    Level& L = slabs_[0].lv[ls];
+    vcycle_small(ndim_, L.rhs, L.u, L.g, small_args_, d_info_, st_);
+    cstart = ls;
+  } else {
+    solve_exact(ng - 1);
+  }
+  for (int c = cstart; c >= 1; --c) {  // coarse_to_fine :593-684
+    if (!(ls > 0 && c == ls))
+      for (int s = 0; s < ms_; ++s) relax(c);
     if (pr && c == 2) { prof_end(PROF_TAIL, st_); prof_begin(PROF_LEVEL1, st_); }
     if (pr && c == 1) prof_end(PROF_LEVEL1, st_);
     interp_add_from(c);
@@ -694,8 +745,9 @@ void MG::solve_begin(const std::vector<double*>& u, const std::vector<const doub
   // captured once into a CUDA graph and replayed every V-cycle: ~250-500 launches per cycle otherwise.
   static const bool graphs_on = !(getenv("NDSM_B200_GRAPH") && atoi(getenv("NDSM_B200_GRAPH")) == 0);
   const double* rhs_coarsest = (ngrids() == 1) ? rhs0_[0] : slabs_[0].lv.back().rhs;
-  if (graphs_on && !prof_enabled() && nmax > 1 && coarsest_in_smem(rhs_coarsest)) {
+  if (graphs_on && !prof_enabled() && nmax > 1 && (small_from_ > 0 || coarsest_in_smem(rhs_coarsest))) {
     solve_exact_prepare();
+    vcycle_small_prepare();
     const unsigned long long l0 = g_launches;
     cudaGraph_t graph = nullptr;
     CUDA_CHECK(cudaStreamBeginCapture(st_, cudaStreamCaptureModeThreadLocal));

@@ -159,6 +159,7 @@ class MG {
   bool solve_done() const { return ss_.done; }
   void enqueue_cycle();            // V-cycle + update_u + result copies (no sync)
   bool coarsest_in_smem(const double* rhs_coarsest) const;
+  int small_from() const { return small_from_; }
 
   cudaStream_t stream() const { return st_; }
   bool du_max() const { return du_max_; }
@@ -195,6 +196,10 @@ class MG {
   double* d_all_ = nullptr;          // [2*world] gathered (max,sum) pairs
   int* d_info_ = nullptr;            // [2] coarsest-solve iterations / converged
   double* h_out_ = nullptr;          // pinned: [2*world] pairs + 2 ints
+  // levels >= small_from_ (each <= SMALL_MAX_POINTS points) run as one single-block kernel; 0 = disabled
+  int small_from_ = 0;
+  SmallArgs small_args_;
+  void build_small_args();
   struct SolveState {
     std::vector<double*> u;
     double vc_tol = 0, du = 1.7976931348623157e308;
