@@ -8,6 +8,7 @@
 #include "kernels.cuh"
 
 #include <algorithm>
+#include <cstdlib>
 #include <vector>
 
 namespace ndsm {
@@ -270,6 +271,128 @@ k_relax3d(double* __restrict__ u, const double* __restrict__ rhs, const Grid g, 
   }
 }
 
+// ---- shared-memory z-plane staging (cp.async ring): the interior path for levels large enough to fill it.
+// A block owns a tile of 64 compressed columns x 8 rows and marches in z.  Each plane of the OTHER colour is
+// copied once, asynchronously, into a ring of RS3 stages in shared memory (tile + one halo row/column on each
+// side, y/z mirroring resolved when the copy is issued), NST-2 planes ahead of the plane being updated, so that
+// ~10 planes of loads per block are in flight without holding registers.  One __syncthreads per plane.
+#define RS3_PITCH 68  // doubles per staged row: [1] = column -1, [2..65] = columns 0..63, [66] = column 64
+#define RS3_ROWS 10   // row slots -1 .. 8
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async8(void* smem_dst, const void* gsrc) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(d), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
+
+template <bool HAS_RHS>
+__global__ void __launch_bounds__(RELAX_BX * RELAX_BY, HAS_RHS ? 2 : 3)
+k_relax3d_staged(double* __restrict__ u, const double* __restrict__ rhs, const Grid g, const Bounds b,
+                 const int colour, const double wx, const double wy, const double wz, const double w1,
+                 const int klo, const int khi, const int zchunk) {
+  constexpr int NST = HAS_RHS ? 8 : 12;
+  extern __shared__ __align__(16) double smem[];
+  const int kbeg = klo + blockIdx.z * zchunk;
+  const int kend = min(kbeg + zchunk - 1, khi);
+  if (kbeg > kend) return;
+  double* __restrict__ own = u + (i64)colour * g.cs;
+  const double* __restrict__ opp = u + (i64)(1 - colour) * g.cs;
+  const double* __restrict__ rh = HAS_RHS ? rhs + (i64)colour * g.cs : nullptr;
+
+  if (blockIdx.x == gridDim.x - 1) {  // edge block: 4 edge columns x RELAX_BY rows, scalar path
+    if (threadIdx.x >= 4 * RELAX_BY) return;
+    const int m = edge_column(threadIdx.x & 3, g.mcnt);
+    const int j = b.lb[1] + blockIdx.y * RELAX_BY + (threadIdx.x >> 2);
+    if (m < 0 || j > b.ub[1]) return;
+    relax_column<HAS_RHS>(own, opp, rh, g, b, colour, m, j, kbeg, kend, wx, wy, wz, w1);
+    return;
+  }
+  const int tx = threadIdx.x & (RELAX_BX - 1), ty = threadIdx.x / RELAX_BX;
+  const int c0 = 2 + blockIdx.x * (2 * RELAX_BX);
+  const int m0 = c0 + 2 * tx;
+  const int r0 = b.lb[1] + blockIdx.y * RELAX_BY;
+  const int j = r0 + ty;
+  const bool active = (j <= b.ub[1]) && (m0 + 2 < g.mcnt);
+  const int ps = (int)g.ps;
+  // global row of a row slot t = -1..8 (mirrored Neumann ghosts, ndsm_optimized.f90:116-117; rows past the
+  // domain belong to inactive threads and are clamped)
+  auto grow = [&](int t) {
+    int jj = r0 + t;
+    if (jj < 0) jj = 1;
+    else if (jj == g.ny) jj = g.ny - 2;
+    else if (jj > g.ny) jj = g.ny - 1;
+    return jj;
+  };
+  const int m0c = min(m0, g.hp - 2);
+  const int row_own = grow(ty) * g.hp, row_lo = grow(-1) * g.hp, row_hi = grow(RELAX_BY) * g.hp;
+  const int col_l = max(c0 - 1, 0), col_r = min(c0 + 2 * RELAX_BX, g.hp - 1);
+  double* __restrict__ S = smem;                                   // [NST][RS3_ROWS][RS3_PITCH]
+  double* __restrict__ R = smem + NST * RS3_ROWS * RS3_PITCH;      // [NST][RELAX_BY][2*RELAX_BX] (HAS_RHS)
+  const int np = kend - kbeg + 3;                                  // planes kbeg-1 .. kend+1
+  auto issue = [&](int q) {                                        // q = index in the plane sequence
+    if (q < np) {
+      int kp = kbeg - 1 + q;
+      kp = (kp < 0) ? 1 : ((kp > g.nz - 1) ? g.nz - 2 : kp);       // mirrored z ghosts (:119-120)
+      const double* __restrict__ base = opp + (i64)(kp - g.k0) * ps;
+      double* __restrict__ st = S + (q % NST) * (RS3_ROWS * RS3_PITCH);
+      cp_async16(st + (ty + 1) * RS3_PITCH + 2 + 2 * tx, base + row_own + m0c);
+      if (ty == 0) cp_async16(st + 2 + 2 * tx, base + row_lo + m0c);
+      if (ty == RELAX_BY - 1) cp_async16(st + (RELAX_BY + 1) * RS3_PITCH + 2 + 2 * tx, base + row_hi + m0c);
+      if (tx == 0) cp_async8(st + (ty + 1) * RS3_PITCH + 1, base + row_own + col_l);
+      if (tx == RELAX_BX - 1) cp_async8(st + (ty + 1) * RS3_PITCH + 2 + 2 * RELAX_BX, base + row_own + col_r);
+      if (HAS_RHS)
+        cp_async16(R + (q % NST) * (RELAX_BY * 2 * RELAX_BX) + ty * (2 * RELAX_BX) + 2 * tx,
+                   rh + (i64)(kp - g.k0) * ps + row_own + m0c);
+    }
+    cp_async_commit();  // one group per plane index, empty past the end, keeps the wait count constant
+  };
+  for (int q = 0; q < NST - 1; ++q) issue(q);
+
+  double2 Zm = make_double2(0.0, 0.0), Zc = make_double2(0.0, 0.0);
+  const int mine = (ty + 1) * RS3_PITCH + 2 + 2 * tx;
+  double* __restrict__ ownb = own - (i64)g.k0 * ps + (i64)j * g.hp + m0;
+  int s = (j + kbeg + colour) & 1;
+  for (int t = 0; t <= kend - kbeg; ++t, s ^= 1) {
+    cp_async_wait<NST - 4>();  // my copies of planes <= t+2 have landed
+    __syncthreads();           // ... and everybody else's; everybody has finished reading plane t
+    if (t == 0) {
+      Zm = *reinterpret_cast<const double2*>(S + mine);
+      Zc = *reinterpret_cast<const double2*>(S + (RS3_ROWS * RS3_PITCH) + mine);
+    }
+    issue(t + NST - 1);        // refill the stage of plane t-1
+    const double* __restrict__ sk = S + ((t + 1) % NST) * (RS3_ROWS * RS3_PITCH);
+    const double2 Zn = *reinterpret_cast<const double2*>(S + ((t + 2) % NST) * (RS3_ROWS * RS3_PITCH) + mine);
+    if (active) {
+      const double XO = sk[mine + (s ? 2 : -1)];
+      const double2 YL = *reinterpret_cast<const double2*>(sk + mine - RS3_PITCH);
+      const double2 YH = *reinterpret_cast<const double2*>(sk + mine + RS3_PITCH);
+      // s == 0: point i = 2m has neighbours opp[m-1], opp[m];  s == 1: i = 2m+1 has opp[m], opp[m+1]
+      const double sx0 = s ? (Zc.y + Zc.x) : (Zc.x + XO);
+      const double sx1 = s ? (XO + Zc.y) : (Zc.y + Zc.x);
+      double un0 = (sx0 * wx + (YH.x + YL.x) * wy) + (Zn.x + Zm.x) * wz;  // (:123-125)
+      double un1 = (sx1 * wx + (YH.y + YL.y) * wy) + (Zn.y + Zm.y) * wz;
+      if (HAS_RHS) {
+        const double2 RH = *reinterpret_cast<const double2*>(R + ((t + 1) % NST) * (RELAX_BY * 2 * RELAX_BX) +
+                                                              ty * (2 * RELAX_BX) + 2 * tx);
+        un0 = un0 - RH.x;                                                  // (:126)
+        un1 = un1 - RH.y;
+      }
+      double2 o;
+      o.x = w1 * un0;                                                      // (:129)
+      o.y = w1 * un1;
+      *reinterpret_cast<double2*>(ownb + (i64)(kbeg + t) * ps) = o;
+    }
+    Zm = Zc;
+    Zc = Zn;
+  }
+  cp_async_wait<0>();
+}
+
 static int pick_zchunk(int nplanes, int blocks_per_plane) {
   // enough blocks to fill 148 SMs x 8 resident 256-thread blocks several times over
   int zc = 16;
@@ -285,6 +408,32 @@ void relax3d_half(double* u, const double* rhs, const Grid& g, const Bounds& b, 
   if (klo > khi || nrows <= 0) return;
   const int npairs = (g.mcnt > 4) ? (((g.mcnt - 1) & ~1) - 2) / 2 : 0;  // interior pairs m0 = 2, 4, ... < mE
   const int bx = cdiv(npairs, RELAX_BX) + 1, by = cdiv(nrows, RELAX_BY);    // +1: edge blocks
+  // opt-in: measured on B200 at 513^3 it is SLOWER than the register-ring kernel (0.239 vs 0.215 ms per colour
+  // pass): every staged value is read ~3.5 times from shared memory (own column, two y neighbours, x neighbour)
+  // on top of the cp.async writes, which makes the kernel shared-memory-bandwidth-bound before HBM saturates
+  static const bool staged_on = getenv("NDSM_B200_STAGED") && atoi(getenv("NDSM_B200_STAGED")) != 0;
+  if (staged_on && npairs >= RELAX_BX && khi - klo + 1 >= 16 && nrows >= RELAX_BY) {
+    // shared-memory staged path: long z-chunks amortise the pipeline fill
+    static bool attr = false;
+    if (!attr) {
+      cudaFuncSetAttribute(k_relax3d_staged<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 80 * 1024);
+      cudaFuncSetAttribute(k_relax3d_staged<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 80 * 1024);
+      attr = true;
+    }
+    int zc = 64;
+    while (zc > 16 && (i64)bx * by * cdiv(khi - klo + 1, zc) < 148 * 3 * 4) zc >>= 1;
+    dim3 grid(bx, by, cdiv(khi - klo + 1, zc));
+    const size_t sm_norhs = (size_t)12 * RS3_ROWS * RS3_PITCH * sizeof(double);
+    const size_t sm_rhs = (size_t)8 * (RS3_ROWS * RS3_PITCH + RELAX_BY * 2 * RELAX_BX) * sizeof(double);
+    if (rhs)
+      k_relax3d_staged<true><<<grid, RELAX_BX * RELAX_BY, sm_rhs, st>>>(u, rhs, g, b, colour, w.wx, w.wy, w.wz, w.w1,
+                                                                        klo, khi, zc);
+    else
+      k_relax3d_staged<false><<<grid, RELAX_BX * RELAX_BY, sm_norhs, st>>>(u, rhs, g, b, colour, w.wx, w.wy, w.wz,
+                                                                          w.w1, klo, khi, zc);
+    LAUNCHED();
+    return;
+  }
   const int zc = pick_zchunk(khi - klo + 1, bx * by);
   dim3 grid(bx, by, cdiv(khi - klo + 1, zc));
   if (rhs)

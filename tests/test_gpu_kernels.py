@@ -62,6 +62,33 @@ def test_relax3d_matches_oracle(gpu_lib, oracle, shape, copt):
     h.close()
 
 
+def test_relax3d_staged_variant_is_bit_identical(gpu_lib, oracle):
+    """The opt-in cp.async shared-memory staged smoother (NDSM_B200_STAGED=1 is read once per process, so it is
+    exercised in a subprocess) gives the same bits as the oracle."""
+    import os
+    import subprocess
+    import sys
+    code = (
+        "import sys, numpy as np\n"
+        "sys.path.insert(0, %r); sys.path.insert(0, %r)\n"
+        "from conftest import aniso_mesh\n"
+        "from ndsm_b200.mg import MGHandle\n"
+        "from oracle import pyoracle as O\n"
+        "shape = (150, 40, 36)\n"
+        "mesh = aniso_mesh(shape)\n"
+        "rng = np.random.default_rng(1)\n"
+        "u0, rhs = rng.standard_normal(shape[::-1]), rng.standard_normal(shape[::-1])\n"
+        "for copt in ('NDDNDD', 'DNDDND', 'DDNDDN'):\n"
+        "    h = MGHandle(mesh, copt); h.put(h.U, 0, u0); h.put(h.RHS, 0, rhs); h.relax(0, 2)\n"
+        "    assert np.array_equal(h.get(h.U, 0), O.relax3d(copt, mesh, rhs, u0, nsweeps=2)), copt\n"
+        "print('STAGED_OK')\n") % (os.path.dirname(os.path.abspath(__file__)),
+                                   os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    env = dict(os.environ)
+    env["NDSM_B200_STAGED"] = "1"
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, timeout=600)
+    assert out.returncode == 0 and "STAGED_OK" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
+
+
 def test_relax3d_all_neumann_mean_subtraction(gpu_lib, oracle):
     shape = (20, 14, 12)
     mesh = aniso_mesh(shape)

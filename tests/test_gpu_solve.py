@@ -57,7 +57,7 @@ def test_case1_matches_oracle(gpu_lib, oracle, mean):
             np.testing.assert_allclose(gpu[3][name]["du"][:6], ora[3][name]["du"][:6], rtol=1e-9)
 
 
-@pytest.mark.parametrize("shape", [(65, 65, 65), (40, 33, 20), (33, 48, 64)])
+@pytest.mark.parametrize("shape", [(65, 65, 65), (40, 33, 20), (33, 48, 64), (129, 97, 33)])
 def test_dipole_matches_oracle(gpu_lib, oracle, shape):
     """Sub-surface dipole (BASELINE configs 0-2), cubic and non-cubic boxes; all six faces carry flux."""
     from ndsm_b200 import synthetic, vector_potential
@@ -90,6 +90,18 @@ def test_exact_restriction_mode_is_bit_identical_to_oracle_3d_solves(gpu_lib, or
     for name in ("Ax", "Ay", "Az"):
         assert gpu[3][name]["nexact"] == ora[3][name]["nexact"]
         np.testing.assert_allclose(gpu[3][name]["du"], ora[3][name]["du"], rtol=1e-4, atol=1e-14)
+
+
+def test_charges_magnetogram_non_cubic_matches_oracle(gpu_lib, oracle):
+    """Active-region-like bipolar magnetogram on a 4:1 box (scaled-down BASELINE config 3): anisotropic coarsest
+    levels (16x16x4 in 3D, 16x4 on the side faces) need hundreds of coarsest-level iterations per V-cycle."""
+    from ndsm_b200 import synthetic, vector_potential
+    x, y, z = synthetic.mesh(129, 129, 33)
+    b = synthetic.charges(x, y, z)
+    gpu = vector_potential(x, y, z, b, mean=True, trace=True)
+    ora = oracle.vector_potential(x, y, z, b, mean=True, trace=True)
+    check_against_oracle(gpu, ora, rel=1e-9)
+    assert max(gpu[3]["Az"]["nexact"]) > 100
 
 
 def test_dipole_faces_only_input_is_equivalent(gpu_lib):

@@ -42,7 +42,7 @@ def test_partition_tiles_and_respects_halo(shape, world, min_planes):
 
 
 def test_expected_depth_for_headline_config():
-    """513^3 on 8 GPUs: 513 -> 256 -> 128 planes are partitioned (>= 16 planes per rank), 64^3 and below replicated."""
+    """513^3 with the plane-count rule only: on 8 ranks 513 -> 256 -> 128 planes keep >= 16 planes per rank."""
     from ndsm_b200.mg import Plan
     p = Plan(aniso_mesh((513, 513, 513)))
     ndist, zs = p.slab_partition(8, 16)
