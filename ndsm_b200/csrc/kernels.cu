@@ -394,9 +394,10 @@ k_relax3d_staged(double* __restrict__ u, const double* __restrict__ rhs, const G
 }
 
 static int pick_zchunk(int nplanes, int blocks_per_plane) {
-  // enough blocks to fill 148 SMs x 8 resident 256-thread blocks several times over
+  // every z-chunk re-reads two warm-up planes, so chunks should be long; two to three waves of the resident
+  // blocks (148 SMs x 3 blocks of 256 threads) are enough to balance the SMs
   int zc = 16;
-  while (zc > 1 && (i64)blocks_per_plane * cdiv(nplanes, zc) < 148 * 8 * 4) zc >>= 1;
+  while (zc > 2 && (i64)blocks_per_plane * cdiv(nplanes, zc) < 148 * 3 * 2) zc >>= 1;
   return zc;
 }
 

@@ -264,9 +264,9 @@ MG::MG(int ndim, const int* shape, int ngrids, const double* const* mesh, cudaSt
   }
   const int world = comm_ ? comm_->world() : 1;
   int min_planes = 16;
-  // measured on 2 GPUs at 513^3: level 1 (256^3) costs 1.5 ms per V-cycle partitioned (8 halo exchanges) but
-  // ~1.0 ms replicated, so only levels of at least 3e7 points are partitioned
-  long long min_points = 30000000;
+  // measured at 513^3: level 1 (256^3) costs 1.66 ms per V-cycle replicated and 1.52 ms partitioned over two
+  // ranks (8 halo exchanges included); 128^3 and below are cheaper replicated than exchanged
+  long long min_points = 8000000;
   if (const char* e = getenv("NDSM_SLAB_MIN_PLANES")) min_planes = atoi(e);
   if (const char* e = getenv("NDSM_SLAB_MIN_POINTS")) min_points = atoll(e);
   plan_ = plan_slabs(hl, ndim, world, min_planes, min_points);
