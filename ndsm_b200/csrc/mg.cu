@@ -146,7 +146,11 @@ SlabPlan plan_slabs(const std::vector<HostLevel>& hl, int ndim, int world, int m
   p.world = world;
   if (world <= 1 || ndim != 3) return p;
   const int ng = (int)hl.size();
-  if (min_planes < NDSM_HALO) min_planes = NDSM_HALO;
+  // halo depth: a deeper halo trades redundant smoothing of halo planes for fewer exchanges (one exchange
+  // buys about halo-1 colour passes); NDSM_HALO_PLANES overrides the default
+  int halo = NDSM_HALO;
+  if (const char* e = std::getenv("NDSM_HALO_PLANES")) halo = std::max(4, std::min(64, std::atoi(e)));
+  if (min_planes < halo) min_planes = halo;
   std::vector<int> z(world + 1);
   for (int r = 0; r <= world; ++r) z[r] = (int)((i64)hl[0].n[2] * r / world);  // balanced finest slabs
   int g = 0;
@@ -174,7 +178,7 @@ SlabPlan plan_slabs(const std::vector<HostLevel>& hl, int ndim, int world, int m
   }
   if (p.ndist == 0) return p;
   p.zs.push_back(z);  // producer partition of the first replicated level
-  p.halo = NDSM_HALO;
+  p.halo = halo;
   // every stencil must stay inside owned planes + halo
   for (int lv = 0; lv < p.ndist; ++lv) {
     const int nzf = hl[lv].n[2], ncz = hl[lv + 1].n[2];

@@ -13,7 +13,8 @@ pytestmark = pytest.mark.gpu
 
 @pytest.fixture
 def slab_env():
-    saved = {k: os.environ.get(k) for k in ("NDSM_VIRTUAL_SLABS", "NDSM_SLAB_MIN_PLANES")}
+    saved = {k: os.environ.get(k) for k in ("NDSM_VIRTUAL_SLABS", "NDSM_SLAB_MIN_PLANES", "NDSM_SLAB_MIN_POINTS",
+                                            "NDSM_HALO_PLANES")}
     yield
     for k, v in saved.items():
         if v is None:
@@ -22,13 +23,23 @@ def slab_env():
             os.environ[k] = v
 
 
-def solve(shape, world, min_planes, **kw):
-    from ndsm_b200 import synthetic, vector_potential
+def solve(shape, world, min_planes, halo=None, **kw):
+    """Solve with `world` virtual ranks; the size threshold that keeps small levels replicated in production
+    is switched off so that these small grids really are partitioned (asserted)."""
+    from ndsm_b200 import load_library, synthetic, vector_potential
     os.environ["NDSM_VIRTUAL_SLABS"] = str(world)
     os.environ["NDSM_SLAB_MIN_PLANES"] = str(min_planes)
+    os.environ["NDSM_SLAB_MIN_POINTS"] = "0"
+    if halo is None:
+        os.environ.pop("NDSM_HALO_PLANES", None)
+    else:
+        os.environ["NDSM_HALO_PLANES"] = str(halo)
     x, y, z = synthetic.mesh(*shape)
     b = synthetic.dipole(x, y, z)
-    return vector_potential(x, y, z, b, trace=True, **kw)
+    out = vector_potential(x, y, z, b, trace=True, **kw)
+    nd = load_library().ndsm_b200_last_partitioned_levels()
+    assert (nd > 0) == (world > 1), (world, nd)
+    return out
 
 
 @pytest.mark.parametrize("shape", [(44, 44, 44), (40, 33, 52), (65, 65, 65)])
@@ -40,6 +51,17 @@ def test_virtual_slabs_reproduce_single_slab(gpu_lib, slab_env, shape, world, mi
     for name in ("Ax", "Ay", "Az"):
         assert got[3][name]["du"] == ref[3][name]["du"], name      # identical du history (max metric)
         assert got[3][name]["nexact"] == ref[3][name]["nexact"], name
+    assert np.array_equal(got[1], ref[1])
+    assert np.array_equal(got[2], ref[2])
+
+
+@pytest.mark.parametrize("halo", [4, 5, 9, 12])
+def test_halo_depth_does_not_change_the_result(gpu_lib, slab_env, halo):
+    shape = (48, 40, 80)
+    ref = solve(shape, 1, 16)
+    got = solve(shape, 3, halo, halo=halo)
+    for name in ("Ax", "Ay", "Az"):
+        assert got[3][name]["du"] == ref[3][name]["du"], name
     assert np.array_equal(got[1], ref[1])
     assert np.array_equal(got[2], ref[2])
 
@@ -62,5 +84,8 @@ def test_virtual_slabs_with_initial_guess(gpu_lib, slab_env):
     ref = vector_potential(x, y, z, b, A0=A0)
     os.environ["NDSM_VIRTUAL_SLABS"] = "2"
     os.environ["NDSM_SLAB_MIN_PLANES"] = "4"
+    os.environ["NDSM_SLAB_MIN_POINTS"] = "0"
     got = vector_potential(x, y, z, b, A0=A0)
+    from ndsm_b200 import load_library
+    assert load_library().ndsm_b200_last_partitioned_levels() > 0
     assert np.array_equal(got[1], ref[1]) and np.array_equal(got[2], ref[2])
