@@ -1,0 +1,125 @@
+"""Full-size checks at BASELINE.json's headline size (513^3 dipole, config 1), where the CPU oracle would take
+minutes: size-independent properties of the result instead of a point-by-point comparison, plus a direct oracle
+comparison at 257^3 (the largest size the oracle finishes in seconds on the GPU box's host cores).
+
+Properties (each follows from the reference's algorithm, not from this implementation):
+ * the z-slab decomposition reproduces the single-slab solve bit for bit (max metric) -- here with two virtual
+   ranks on one device, same kernels and halo logic as the NCCL path;
+ * B = curl A uses centred differences in the interior (ndsm_vector_potential.f90 curl), and centred difference
+   operators of different axes commute, so the centred discrete divergence of B vanishes to rounding there;
+ * every A component solves the 7-point Laplace equation: the interior residual is small against |A|/h^2;
+ * the truncation error of B against the analytic dipole is second order: it drops ~4x from 257^3 to 513^3;
+ * the interior of the input b is never read (ndsm.py:82-83): a faces-only input gives identical output.
+"""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import rel_err
+
+pytestmark = pytest.mark.gpu
+
+N_FULL = 513
+
+
+@pytest.fixture(scope="module")
+def full(gpu_lib):
+    from ndsm_b200 import synthetic, vector_potential
+    x, y, z = synthetic.mesh(N_FULL)
+    b = synthetic.dipole(x, y, z)
+    ierr, A, B, tr = vector_potential(x, y, z, b, trace=True)
+    assert ierr == 0
+    return dict(x=x, y=y, z=z, b=b, A=A, B=B, tr=tr)
+
+
+def test_full_size_cycle_counts_and_contraction(full):
+    tr = full["tr"]
+    for name in ("Ax", "Ay", "Az"):
+        du = np.array(tr[name]["du"])
+        assert 10 <= len(du) <= 20, (name, len(du))
+        assert du[-1] <= 1e-10 and np.all(du[:-1] > 1e-10)          # stops at the first cycle under vc_tol
+        rate = du[4:] / du[3:-1]
+        assert np.all(rate < 0.35), (name, rate)                     # multigrid contraction, size independent
+    for f in range(1, 7):
+        assert len(tr["chi%d" % f]["du"]) <= 25
+
+
+def test_full_size_interior_divergence_of_B_vanishes(full):
+    x, y, z, B = full["x"], full["y"], full["z"], full["B"]
+    k0, k1 = 200, 232   # a band of planes keeps the numpy temporaries small
+    s = (slice(k0, k1), slice(3, -3), slice(3, -3))
+    dBx = (B[0][k0:k1, 3:-3, 4:-2] - B[0][k0:k1, 3:-3, 2:-4]) / (x[4:-2] - x[2:-4])[None, None, :]
+    dBy = (B[1][k0:k1, 4:-2, 3:-3] - B[1][k0:k1, 2:-4, 3:-3]) / (y[4:-2] - y[2:-4])[None, :, None]
+    dBz = (B[2][k0 + 1:k1 + 1, 3:-3, 3:-3] - B[2][k0 - 1:k1 - 1, 3:-3, 3:-3]) / (z[k0 + 1:k1 + 1] - z[k0 - 1:k1 - 1])[:, None, None]
+    div = dBx + dBy + dBz
+    scale = np.abs(B[:, k0:k1]).max() / (x[1] - x[0])
+    assert np.abs(div).max() <= 1e-9 * scale, (np.abs(div).max(), scale)
+    assert np.abs(B[2][s]).max() > 0
+
+
+def test_full_size_laplace_residual_is_small(full):
+    x, A = full["x"], full["A"]
+    h2 = (x[1] - x[0]) ** 2
+    k0, k1 = 240, 272
+    for c in range(3):
+        u = A[c]
+        lap = (u[k0:k1, 1:-1, 2:] + u[k0:k1, 1:-1, :-2] + u[k0:k1, 2:, 1:-1] + u[k0:k1, :-2, 1:-1]
+               + u[k0 + 1:k1 + 1, 1:-1, 1:-1] + u[k0 - 1:k1 - 1, 1:-1, 1:-1] - 6.0 * u[k0:k1, 1:-1, 1:-1]) / h2
+        scale = np.abs(u).max() / h2
+        assert np.abs(lap).max() <= 1e-7 * scale, (c, np.abs(lap).max(), scale)
+
+
+def test_full_size_second_order_against_analytic_dipole(full, gpu_lib):
+    from ndsm_b200 import synthetic, vector_potential
+    e_full = np.linalg.norm(full["B"] - full["b"], axis=0).mean()
+    x, y, z = synthetic.mesh(257)
+    b = synthetic.dipole(x, y, z)
+    ierr, _, B = vector_potential(x, y, z, b)
+    assert ierr == 0
+    e_half = np.linalg.norm(B - b, axis=0).mean()
+    order = np.log2(e_half / e_full)
+    assert 1.7 < order < 2.4, (e_half, e_full, order)
+
+
+def test_full_size_virtual_slabs_bit_identical(full, gpu_lib):
+    from ndsm_b200 import vector_potential
+    saved = os.environ.get("NDSM_VIRTUAL_SLABS")
+    os.environ["NDSM_VIRTUAL_SLABS"] = "2"
+    try:
+        ierr, A, B, tr = vector_potential(full["x"], full["y"], full["z"], full["b"], trace=True)
+        nd = gpu_lib.ndsm_b200_last_partitioned_levels()
+    finally:
+        if saved is None:
+            os.environ.pop("NDSM_VIRTUAL_SLABS", None)
+        else:
+            os.environ["NDSM_VIRTUAL_SLABS"] = saved
+    assert ierr == 0 and nd >= 1            # production thresholds: the finest levels are partitioned
+    for name in ("Ax", "Ay", "Az"):
+        assert tr[name]["du"] == full["tr"][name]["du"], name
+    assert np.array_equal(A, full["A"])
+    assert np.array_equal(B, full["B"])
+
+
+def test_full_size_faces_only_input(full, gpu_lib):
+    from ndsm_b200 import synthetic, vector_potential
+    faces = synthetic.dipole(full["x"], full["y"], full["z"], faces_only=True)
+    ierr, A, B = vector_potential(full["x"], full["y"], full["z"], faces)
+    assert ierr == 0
+    assert np.array_equal(A, full["A"]) and np.array_equal(B, full["B"])
+
+
+def test_257_matches_oracle(gpu_lib, oracle):
+    """Point-by-point parity at 257^3 (BASELINE config 1 halved): V-cycle counts +-1, A and B within 1e-10."""
+    from ndsm_b200 import synthetic, vector_potential
+    x, y, z = synthetic.mesh(257)
+    b = synthetic.dipole(x, y, z, faces_only=True)
+    gpu = vector_potential(x, y, z, b, trace=True)
+    ora = oracle.vector_potential(x, y, z, b, trace=True)
+    assert gpu[0] == ora[0] == 0
+    for name in ["chi%d" % f for f in range(1, 7)] + ["Ax", "Ay", "Az"]:
+        assert abs(len(gpu[3][name]["du"]) - len(ora[3][name]["du"])) <= 1, name
+    for name in ("Ax", "Ay", "Az"):
+        assert len(gpu[3][name]["du"]) == len(ora[3][name]["du"])
+    assert rel_err(gpu[1], ora[1]) <= 1e-10
+    assert rel_err(gpu[2], ora[2]) <= 1e-10
