@@ -9,6 +9,7 @@
 #include "../../include/ndsm_b200.h"
 #include "pool.hpp"
 #include "vecpot.hpp"
+#include "hostsink.hpp"
 
 using namespace ndsm;
 
@@ -206,18 +207,10 @@ int ndsm_vector_solve(size_t nsize, const int* nshape4, int* ioptc, double* ropt
     bool zero_guess = true;
     std::thread scan([&] { zero_guess = all_zero_host(A, 3 * N); });
     struct Joiner { std::thread& t; ~Joiner() { if (t.joinable()) t.join(); } } joiner{scan};
-    cudaStream_t cst = nullptr;  // copy stream for the early device-to-host copies of A
-    CUDA_CHECK(cudaStreamCreateWithFlags(&cst, cudaStreamNonBlocking));
-    struct StreamDel { cudaStream_t s; ~StreamDel() { cudaStreamDestroy(s); } } sdel{cst};
-    cudaEvent_t ev;
-    CUDA_CHECK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
-    struct EvDel { cudaEvent_t e; ~EvDel() { cudaEventDestroy(e); } } edel{ev};
+    // result delivery: page-locked destinations are copied directly, pageable ones (what numpy hands us)
+    // through the sink's own pinned staging so that the main thread keeps launching the next solve
+    HostSink sink(g_device);
     bool copied[3] = {false, false, false};
-    // the early copies run in helper threads: a device-to-host copy into PAGEABLE memory (what numpy hands us)
-    // blocks the calling thread, and the main thread has to keep launching the next solve
-    std::vector<std::thread> copiers;
-    struct JoinAll { std::vector<std::thread>& v; ~JoinAll() { for (auto& t : v) if (t.joinable()) t.join(); } } jall{copiers};
-    const int dev = g_device;
     CoreHooks hooks;
     hooks.guess = [&]() {
       scan.join();
@@ -229,26 +222,17 @@ int ndsm_vector_solve(size_t nsize, const int* nshape4, int* ioptc, double* ropt
       return g;
     };
     hooks.component_ready = [&](int c) {
-      CUDA_CHECK(cudaEventRecord(ev, st));
-      CUDA_CHECK(cudaStreamWaitEvent(cst, ev, 0));
-      double* dst = A + (size_t)c * N;
-      const double* src = dA.p + (size_t)c * N;
-      copiers.emplace_back([=] {
-        cudaSetDevice(dev);
-        cudaMemcpyAsync(dst, src, N * sizeof(double), cudaMemcpyDeviceToHost, cst);
-      });
+      sink.push(A + (size_t)c * N, dA.p + (size_t)c * N, N, st);
       copied[c] = true;
     };
     if (g_debug) debug_msg(SUB, "Calling compute_vector_potential...");
     int ierr = run_core_full(nshape4, iopt, ropt, x, y, z, bn, nullptr, dA.p, dB.p, st, &hooks);
     t1 = now_s();
     for (int c = 0; c < 3; ++c)
-      if (!copied[c])
-        CUDA_CHECK(cudaMemcpyAsync(A + (size_t)c * N, dA.p + (size_t)c * N, N * sizeof(double), cudaMemcpyDeviceToHost, st));
-    CUDA_CHECK(cudaMemcpyAsync(B, dB.p, 3 * N * sizeof(double), cudaMemcpyDeviceToHost, st));
+      if (!copied[c]) sink.push(A + (size_t)c * N, dA.p + (size_t)c * N, N, st);
+    sink.push(B, dB.p, 3 * N, st);
+    sink.wait();
     CUDA_CHECK(cudaStreamSynchronize(st));
-    for (auto& t : copiers) t.join();
-    CUDA_CHECK(cudaStreamSynchronize(cst));
     g_report.ms_out = (now_s() - t1) * 1e3;
     return finish(ierr);
   } catch (const NdsmError& e) {

@@ -2,6 +2,7 @@
 #include "pool.hpp"
 
 #include <map>
+#include <mutex>
 #include <unordered_map>
 #include <vector>
 
@@ -60,13 +61,15 @@ struct Pool {
   }
 };
 Pool g_dev{false}, g_host{true};
+std::mutex g_mu;  // the copy workers of HostSink allocate their pinned slots from their own threads
+using Lock = std::lock_guard<std::mutex>;
 }  // namespace
 
-void* pool_alloc(size_t bytes) { return g_dev.alloc(bytes); }
-void pool_free(void* p) { g_dev.free(p); }
-void* pool_alloc_host(size_t bytes) { return g_host.alloc(bytes); }
-void pool_free_host(void* p) { g_host.free(p); }
-void pool_release() { g_dev.release(); g_host.release(); }
-size_t pool_cached_bytes() { return g_dev.cached; }
+void* pool_alloc(size_t bytes) { Lock l(g_mu); return g_dev.alloc(bytes); }
+void pool_free(void* p) { Lock l(g_mu); g_dev.free(p); }
+void* pool_alloc_host(size_t bytes) { Lock l(g_mu); return g_host.alloc(bytes); }
+void pool_free_host(void* p) { Lock l(g_mu); g_host.free(p); }
+void pool_release() { Lock l(g_mu); g_dev.release(); g_host.release(); }
+size_t pool_cached_bytes() { Lock l(g_mu); return g_dev.cached; }
 
 }  // namespace ndsm
