@@ -438,8 +438,11 @@ ndsm_b200_mg* ndsm_b200_new_mg_handle(int ndim, const int* nshape, int ngrids, c
     ndsm_b200_mg* h = new ndsm_b200_mg();
     h->mg = new MG(ndim, sh, ngrids, mesh, g_stream);
     h->mg->set_options(5, 1e-13, "NNNNNN", du_max != 0, nmax_exact);
-    // the handle always owns a (zero) level-0 rhs so every operator can be called standalone
-    handle_array(h, 1, 0);
+    // the handle owns a (zero) level-0 rhs so every operator can be called standalone; NDSM_B200_HANDLE_RHS0=0
+    // leaves it unset until mg_put(1, 0, ...) so that the rhs == 0 kernel specialisations of the vector-potential
+    // solves can be driven (and timed) through the handle
+    const char* r0 = getenv("NDSM_B200_HANDLE_RHS0");
+    if (!r0 || atoi(r0) != 0) handle_array(h, 1, 0);
     CUDA_CHECK(cudaStreamSynchronize(g_stream));
     return h;
   } catch (const NdsmError& e) {
@@ -492,6 +495,7 @@ int ndsm_b200_mg_relax(ndsm_b200_mg* h, int level, int nsweeps) {
   if (level < 0 || level >= h->mg->ngrids()) return NDSM_B200_ERR_ARG;
   for (int s = 0; s < nsweeps; ++s) h->mg->relax(level);
   CUDA_CHECK(cudaStreamSynchronize(h->mg->stream()));
+  prof_collect();
   HANDLE_END("ndsm_b200_mg_relax")
 }
 int ndsm_b200_mg_residual(ndsm_b200_mg* h, int level) {

@@ -120,6 +120,9 @@ __device__ double block_max(double v, double* red) {
 // ---------------------------------------------------------------------------------------
 #define RELAX_THREADS 256
 #define RELAX_UNROLL 4  // z-planes whose loads are issued together (memory-level parallelism)
+#ifndef RELAX_EDGE_UNROLL
+#define RELAX_EDGE_UNROLL 1  // the scalar edge-column path shares the kernel, hence its register budget
+#endif
 
 // offset (in compressed elements, relative to the thread's own column) of the x neighbour that is not
 // the in-column value Zc; 0 means "coincides with Zc" (mirrored Neumann ghost, ndsm_optimized.f90:113-114)
@@ -131,7 +134,7 @@ __device__ __forceinline__ int x_other_offset(int s, int m, int i, int nx) {
 
 // ---- scalar column march: used for the first / last columns of a row, where mirrored ghosts, Dirichlet
 // ---- bounds and row padding need per-point care (loads of RELAX_UNROLL planes issued together)
-template <bool HAS_RHS>
+template <bool HAS_RHS, int EU = RELAX_UNROLL>
 __device__ __forceinline__ void relax_column(double* __restrict__ own, const double* __restrict__ opp,
                                              const double* __restrict__ rh, const Grid& g, const Bounds& b,
                                              const int colour, const int m, const int j, const int kbeg,
@@ -143,10 +146,10 @@ __device__ __forceinline__ void relax_column(double* __restrict__ own, const dou
   const int kl0 = (kbeg - 1 < 0) ? 1 : kbeg - 1;
   double Zm = opp[(i64)(kl0 - g.k0) * g.ps + jo];
   double Zc = opp[(i64)(kbeg - g.k0) * g.ps + jo];
-  for (int k0 = kbeg; k0 <= kend; k0 += RELAX_UNROLL) {
-    double Zn[RELAX_UNROLL], XO[RELAX_UNROLL], YL[RELAX_UNROLL], YH[RELAX_UNROLL], RH[RELAX_UNROLL];
+  for (int k0 = kbeg; k0 <= kend; k0 += EU) {
+    double Zn[EU], XO[EU], YL[EU], YH[EU], RH[EU];
 #pragma unroll
-    for (int q = 0; q < RELAX_UNROLL; ++q) {
+    for (int q = 0; q < EU; ++q) {
       const int k = min(k0 + q, kend);
       const int kh = (k + 1 > g.nz - 1) ? g.nz - 2 : k + 1;  // (:119-120)
       const i64 p = (i64)(k - g.k0) * g.ps;
@@ -159,7 +162,7 @@ __device__ __forceinline__ void relax_column(double* __restrict__ own, const dou
       RH[q] = HAS_RHS ? rh[p + jo] : 0.0;
     }
 #pragma unroll
-    for (int q = 0; q < RELAX_UNROLL; ++q) {
+    for (int q = 0; q < EU; ++q) {
       const int k = k0 + q;
       if (k <= kend) {
         const int s = (j + k + colour) & 1;
@@ -195,8 +198,86 @@ __device__ __forceinline__ int edge_column(int e, int mcnt) {
 // ---- loads/stores, 32-bit element indices, 2D thread blocks so that y neighbours are L1 hits
 #define RELAX_BX 32  // pairs per block row  -> 64 compressed columns = 128 grid points in x
 #define RELAX_BY 8   // rows per block
+#define RELAX_EDGE_ROWS (RELAX_BX * RELAX_BY / 4)  // rows per edge block: 4 edge columns x 64 rows
+
+// one updated pair: s == 0: point i = 2m has x neighbours opp[m-1], opp[m];  s == 1: i = 2m+1 has opp[m], opp[m+1]
 template <bool HAS_RHS>
-__global__ void __launch_bounds__(RELAX_BX * RELAX_BY, 3)
+__device__ __forceinline__ double2 relax_pair(const bool sq, const double2 Zm, const double2 Zc, const double2 Zn,
+                                              const double2 YL, const double2 YH, const double XO, const double2 RH,
+                                              const double wx, const double wy, const double wz, const double w1) {
+  const double sx0 = sq ? (Zc.y + Zc.x) : (Zc.x + XO);
+  const double sx1 = sq ? (XO + Zc.y) : (Zc.y + Zc.x);
+  double un0 = (sx0 * wx + (YH.x + YL.x) * wy) + (Zn.x + Zm.x) * wz;  // (:123-125)
+  double un1 = (sx1 * wx + (YH.y + YL.y) * wy) + (Zn.y + Zm.y) * wz;
+  if (HAS_RHS) { un0 = un0 - RH.x; un1 = un1 - RH.y; }                // (:126)
+  double2 o;
+  o.x = w1 * un0;                                                     // (:129)
+  o.y = w1 * un1;
+  return o;
+}
+
+// z-march of one interior pair over planes t = 0 .. n-1 of its chunk.  po / pw / pr point at the pair in plane 0
+// (other colour, own colour, rhs).  S = (i+j+k) parity offset of plane 0, a template parameter so that the x
+// neighbour offset of every unrolled plane is an immediate; batches of U planes issue all their loads first.
+// The last plane of the grid (mirror_top) takes its upper z neighbour from the plane below (:119-120).
+template <bool HAS_RHS, int U, int S>
+__device__ __forceinline__ void relax_pair_march(const double* __restrict__ po, double* __restrict__ pw,
+                                                 const double* __restrict__ pr, const int ps, const int dl,
+                                                 const int dh, const int n_main, const bool mirror_top, double2 Zm,
+                                                 double2 Zc, const double wx, const double wy, const double wz,
+                                                 const double w1) {
+  static_assert(U % 2 == 0, "the parity of a batch must not depend on the batch index");
+  const double2 zero2 = make_double2(0.0, 0.0);
+  int t = 0;
+  for (; t + U <= n_main; t += U) {
+    double2 Zn[U], YL[U], YH[U], RH[U];
+    double XO[U];
+#pragma unroll
+    for (int q = 0; q < U; ++q) {  // phase 1: all loads of U planes
+      const double* __restrict__ p = po + q * ps;
+      Zn[q] = *reinterpret_cast<const double2*>(p + ps);
+      YL[q] = *reinterpret_cast<const double2*>(p + dl);
+      YH[q] = *reinterpret_cast<const double2*>(p + dh);
+      XO[q] = p[((S ^ q) & 1) ? 2 : -1];
+      RH[q] = HAS_RHS ? *reinterpret_cast<const double2*>(pr + q * ps) : zero2;
+    }
+#pragma unroll
+    for (int q = 0; q < U; ++q) {  // phase 2: update
+      *reinterpret_cast<double2*>(pw + q * ps) =
+          relax_pair<HAS_RHS>(((S ^ q) & 1) != 0, Zm, Zc, Zn[q], YL[q], YH[q], XO[q], RH[q], wx, wy, wz, w1);
+      Zm = Zc;
+      Zc = Zn[q];
+    }
+    po += U * ps;
+    pw += U * ps;
+    if (HAS_RHS) pr += U * ps;
+  }
+  for (; t < n_main; ++t) {  // fewer than U planes left
+    const bool sq = ((S ^ t) & 1) != 0;
+    const double2 Zn = *reinterpret_cast<const double2*>(po + ps);
+    const double2 YL = *reinterpret_cast<const double2*>(po + dl);
+    const double2 YH = *reinterpret_cast<const double2*>(po + dh);
+    const double XO = po[sq ? 2 : -1];
+    const double2 RH = HAS_RHS ? *reinterpret_cast<const double2*>(pr) : zero2;
+    *reinterpret_cast<double2*>(pw) = relax_pair<HAS_RHS>(sq, Zm, Zc, Zn, YL, YH, XO, RH, wx, wy, wz, w1);
+    Zm = Zc;
+    Zc = Zn;
+    po += ps;
+    pw += ps;
+    if (HAS_RHS) pr += ps;
+  }
+  if (mirror_top) {
+    const bool sq = ((S ^ t) & 1) != 0;
+    const double2 YL = *reinterpret_cast<const double2*>(po + dl);
+    const double2 YH = *reinterpret_cast<const double2*>(po + dh);
+    const double XO = po[sq ? 2 : -1];
+    const double2 RH = HAS_RHS ? *reinterpret_cast<const double2*>(pr) : zero2;
+    *reinterpret_cast<double2*>(pw) = relax_pair<HAS_RHS>(sq, Zm, Zc, Zm, YL, YH, XO, RH, wx, wy, wz, w1);
+  }
+}
+
+template <bool HAS_RHS, int U = 2, int MINB = 4>
+__global__ void __launch_bounds__(RELAX_BX * RELAX_BY, MINB)
 k_relax3d(double* __restrict__ u, const double* __restrict__ rhs, const Grid g, const Bounds b, const int colour,
           const double wx, const double wy, const double wz, const double w1, const int klo, const int khi,
           const int zchunk) {
@@ -207,12 +288,11 @@ k_relax3d(double* __restrict__ u, const double* __restrict__ rhs, const Grid g, 
   const double* __restrict__ opp = u + (i64)(1 - colour) * g.cs;
   const double* __restrict__ rh = HAS_RHS ? rhs + (i64)colour * g.cs : nullptr;
 
-  if (blockIdx.x == gridDim.x - 1) {  // edge block: 4 edge columns x RELAX_BY rows
-    if (threadIdx.x >= 4 * RELAX_BY) return;
+  if (blockIdx.x == gridDim.x - 1) {  // edge blocks: 4 edge columns x RELAX_EDGE_ROWS rows, scalar path
     const int m = edge_column(threadIdx.x & 3, g.mcnt);
-    const int j = b.lb[1] + blockIdx.y * RELAX_BY + (threadIdx.x >> 2);
+    const int j = b.lb[1] + blockIdx.y * RELAX_EDGE_ROWS + (threadIdx.x >> 2);
     if (m < 0 || j > b.ub[1]) return;
-    relax_column<HAS_RHS>(own, opp, rh, g, b, colour, m, j, kbeg, kend, wx, wy, wz, w1);
+    relax_column<HAS_RHS, RELAX_EDGE_UNROLL>(own, opp, rh, g, b, colour, m, j, kbeg, kend, wx, wy, wz, w1);
     return;
   }
   const int m0 = 2 + (blockIdx.x * RELAX_BX + (threadIdx.x & (RELAX_BX - 1))) * 2;
@@ -220,55 +300,21 @@ k_relax3d(double* __restrict__ u, const double* __restrict__ rhs, const Grid g, 
   if (j > b.ub[1] || m0 + 2 >= g.mcnt) return;
 
   // interior pair: every x neighbour exists, no Dirichlet point, no padding
-  const int jl = (j - 1 < 0) ? 1 : j - 1;
+  const int jl = (j - 1 < 0) ? 1 : j - 1;                  // mirrored Neumann ghosts (:116-117)
   const int jh = (j + 1 > g.ny - 1) ? g.ny - 2 : j + 1;
   const int ps = (int)g.ps;
-  const int io = j * g.hp + m0;  // element index inside a plane
   const int dl = (jl - j) * g.hp, dh = (jh - j) * g.hp;
-  const int kl0 = (kbeg - 1 < 0) ? 1 : kbeg - 1;
-  const double* __restrict__ oppb = opp - (i64)g.k0 * ps;  // index with global k
-  double* __restrict__ ownb = own - (i64)g.k0 * ps;
-  const double* __restrict__ rhb = HAS_RHS ? rh - (i64)g.k0 * ps : nullptr;
-  double2 Zm = *reinterpret_cast<const double2*>(oppb + (i64)kl0 * ps + io);
-  double2 Zc = *reinterpret_cast<const double2*>(oppb + (i64)kbeg * ps + io);
-  int s = (j + kbeg + colour) & 1;
-  constexpr int U = HAS_RHS ? 2 : RELAX_UNROLL;  // planes in flight per thread (register budget: 3 blocks/SM)
-  for (int k0 = kbeg; k0 <= kend; k0 += U) {
-    double2 Zn[U], YL[U], YH[U], RH[U];
-    double XO[U];
-#pragma unroll
-    for (int q = 0; q < U; ++q) {  // phase 1: all loads of RELAX_UNROLL planes
-      const int k = min(k0 + q, kend);
-      const int kh = (k + 1 > g.nz - 1) ? g.nz - 2 : k + 1;
-      const double* __restrict__ pk = oppb + (i64)k * ps + io;
-      const int sq = s ^ (q & 1);
-      Zn[q] = *reinterpret_cast<const double2*>(oppb + (i64)kh * ps + io);
-      YL[q] = *reinterpret_cast<const double2*>(pk + dl);
-      YH[q] = *reinterpret_cast<const double2*>(pk + dh);
-      XO[q] = pk[sq ? 2 : -1];
-      if (HAS_RHS) RH[q] = *reinterpret_cast<const double2*>(rhb + (i64)k * ps + io);
-    }
-#pragma unroll
-    for (int q = 0; q < U; ++q) {  // phase 2: update
-      const int k = k0 + q;
-      if (k <= kend) {
-        const int sq = s ^ (q & 1);
-        // s == 0: point i = 2m has neighbours opp[m-1], opp[m];  s == 1: i = 2m+1 has opp[m], opp[m+1]
-        const double sx0 = sq ? (Zc.y + Zc.x) : (Zc.x + XO[q]);
-        const double sx1 = sq ? (XO[q] + Zc.y) : (Zc.y + Zc.x);
-        double un0 = (sx0 * wx + (YH[q].x + YL[q].x) * wy) + (Zn[q].x + Zm.x) * wz;  // (:123-125)
-        double un1 = (sx1 * wx + (YH[q].y + YL[q].y) * wy) + (Zn[q].y + Zm.y) * wz;
-        if (HAS_RHS) { un0 = un0 - RH[q].x; un1 = un1 - RH[q].y; }                   // (:126)
-        double2 o;
-        o.x = w1 * un0;                                                              // (:129)
-        o.y = w1 * un1;
-        *reinterpret_cast<double2*>(ownb + (i64)k * ps + io) = o;
-        Zm = Zc;
-        Zc = Zn[q];
-      }
-    }
-    if (U & 1) s ^= 1;
-  }
+  const i64 o0 = (i64)(kbeg - g.k0) * ps + (j * g.hp + m0);  // the pair in plane kbeg
+  const double* __restrict__ po = opp + o0;
+  const double2 Zm = *reinterpret_cast<const double2*>(kbeg - 1 < 0 ? po + ps : po - ps);  // (:119-120)
+  const double2 Zc = *reinterpret_cast<const double2*>(po);
+  const bool mirror_top = (kend == g.nz - 1);
+  const int n_main = kend - kbeg + (mirror_top ? 0 : 1);
+  const double* __restrict__ pr = HAS_RHS ? rh + o0 : nullptr;
+  if ((j + kbeg + colour) & 1)
+    relax_pair_march<HAS_RHS, U, 1>(po, own + o0, pr, ps, dl, dh, n_main, mirror_top, Zm, Zc, wx, wy, wz, w1);
+  else
+    relax_pair_march<HAS_RHS, U, 0>(po, own + o0, pr, ps, dl, dh, n_main, mirror_top, Zm, Zc, wx, wy, wz, w1);
 }
 
 // ---- shared-memory z-plane staging (cp.async ring): the interior path for levels large enough to fill it.
@@ -393,10 +439,10 @@ k_relax3d_staged(double* __restrict__ u, const double* __restrict__ rhs, const G
   cp_async_wait<0>();
 }
 
-static int pick_zchunk(int nplanes, int blocks_per_plane) {
+static int pick_zchunk(int nplanes, int blocks_per_plane, int zc_max = 16) {
   // every z-chunk re-reads two warm-up planes, so chunks should be long; two to three waves of the resident
   // blocks (148 SMs x 3 blocks of 256 threads) are enough to balance the SMs
-  int zc = 16;
+  int zc = zc_max;
   while (zc > 2 && (i64)blocks_per_plane * cdiv(nplanes, zc) < 148 * 3 * 2) zc >>= 1;
   return zc;
 }
@@ -435,12 +481,22 @@ void relax3d_half(double* u, const double* rhs, const Grid& g, const Bounds& b, 
     LAUNCHED();
     return;
   }
-  const int zc = pick_zchunk(khi - klo + 1, bx * by);
+  static const int zc_max = getenv("NDSM_B200_ZCHUNK") ? atoi(getenv("NDSM_B200_ZCHUNK")) : 16;
+  static const int variant = getenv("NDSM_B200_RELAX_VARIANT") ? atoi(getenv("NDSM_B200_RELAX_VARIANT")) : 0;
+  const int zc = pick_zchunk(khi - klo + 1, bx * by, zc_max);
   dim3 grid(bx, by, cdiv(khi - klo + 1, zc));
-  if (rhs)
-    k_relax3d<true><<<grid, RELAX_BX * RELAX_BY, 0, st>>>(u, rhs, g, b, colour, w.wx, w.wy, w.wz, w.w1, klo, khi, zc);
-  else
-    k_relax3d<false><<<grid, RELAX_BX * RELAX_BY, 0, st>>>(u, rhs, g, b, colour, w.wx, w.wy, w.wz, w.w1, klo, khi, zc);
+#define RELAX_LAUNCH(R, UU, MB) \
+  k_relax3d<R, UU, MB><<<grid, RELAX_BX * RELAX_BY, 0, st>>>(u, rhs, g, b, colour, w.wx, w.wy, w.wz, w.w1, klo, khi, zc)
+  // measured at 513^3 (B200): rhs == 0: U=4 at 4 blocks/SM 186 us per colour pass (U=2: 188, U=4 at 3 blocks: 190);
+  // with rhs: U=2 at 4 blocks/SM 254 us (U=4 at 3 blocks: 260)
+  if (rhs) {
+    if (variant == 1) RELAX_LAUNCH(true, 4, 3);
+    else RELAX_LAUNCH(true, 2, 4);
+  } else {
+    if (variant == 1) RELAX_LAUNCH(false, 2, 4);
+    else RELAX_LAUNCH(false, 4, 4);
+  }
+#undef RELAX_LAUNCH
   LAUNCHED();
 }
 
@@ -449,7 +505,7 @@ void relax3d_half(double* u, const double* rhs, const Grid& g, const Bounds& b, 
 // Same z-march as K1, both colours (blockIdx.z), writes r = 0 on Dirichlet faces.
 // Algorithmic traffic 24 B/pt (read u, read rhs, write r).
 // ---------------------------------------------------------------------------------------
-template <bool HAS_RHS>
+template <bool HAS_RHS, int EU = RELAX_UNROLL>
 __device__ __forceinline__ void residual_column(const double* __restrict__ own, const double* __restrict__ opp,
                                                 const double* __restrict__ rh, double* __restrict__ ro,
                                                 const Grid& g, const Bounds& b, const int colour, const int m,
@@ -462,10 +518,10 @@ __device__ __forceinline__ void residual_column(const double* __restrict__ own, 
   const int kl0 = (kbeg - 1 < 0) ? 1 : kbeg - 1;
   double Zm = opp[(i64)(kl0 - g.k0) * g.ps + jo];
   double Zc = opp[(i64)(kbeg - g.k0) * g.ps + jo];
-  for (int k0 = kbeg; k0 <= kend; k0 += RELAX_UNROLL) {
-    double Zn[RELAX_UNROLL], XO[RELAX_UNROLL], YL[RELAX_UNROLL], YH[RELAX_UNROLL], RH[RELAX_UNROLL], UC[RELAX_UNROLL];
+  for (int k0 = kbeg; k0 <= kend; k0 += EU) {
+    double Zn[EU], XO[EU], YL[EU], YH[EU], RH[EU], UC[EU];
 #pragma unroll
-    for (int q = 0; q < RELAX_UNROLL; ++q) {
+    for (int q = 0; q < EU; ++q) {
       const int k = min(k0 + q, kend);
       const int kh = (k + 1 > g.nz - 1) ? g.nz - 2 : k + 1;
       const i64 p = (i64)(k - g.k0) * g.ps;
@@ -479,7 +535,7 @@ __device__ __forceinline__ void residual_column(const double* __restrict__ own, 
       RH[q] = HAS_RHS ? rh[p + jo] : 0.0;
     }
 #pragma unroll
-    for (int q = 0; q < RELAX_UNROLL; ++q) {
+    for (int q = 0; q < EU; ++q) {
       const int k = k0 + q;
       if (k <= kend) {
         const int s = (j + k + colour) & 1;
@@ -504,6 +560,78 @@ __device__ __forceinline__ void residual_column(const double* __restrict__ own, 
   }
 }
 
+// one pair of residual values; same evaluation order as the reference (:424-430)
+template <bool HAS_RHS>
+__device__ __forceinline__ double2 residual_pair(const bool sq, const double2 Zm, const double2 Zc, const double2 Zn,
+                                                 const double2 YL, const double2 YH, const double XO, const double2 UC,
+                                                 const double2 RH, const double wx, const double wy, const double wz,
+                                                 const double wc) {
+  const double sx0 = sq ? (Zc.x + Zc.y) : (XO + Zc.x);
+  const double sx1 = sq ? (Zc.y + XO) : (Zc.x + Zc.y);
+  double t0 = (sx0 * wx + (YL.x + YH.x) * wy) + (Zm.x + Zn.x) * wz;  // (:424-426)
+  double t1 = (sx1 * wx + (YL.y + YH.y) * wy) + (Zm.y + Zn.y) * wz;
+  if (HAS_RHS) { t0 = t0 - RH.x; t1 = t1 - RH.y; }
+  t0 = t0 - UC.x * wc;                                               // (:427)
+  t1 = t1 - UC.y * wc;
+  double2 o;
+  o.x = -t0;                                                         // (:430)
+  o.y = -t1;
+  return o;
+}
+
+// z-march of one interior pair over the non-Dirichlet planes of its chunk (same structure as relax_pair_march)
+template <bool HAS_RHS, int U, int S>
+__device__ __forceinline__ void residual_pair_march(const double* __restrict__ po, const double* __restrict__ pu,
+                                                    const double* __restrict__ pr, double* __restrict__ pw,
+                                                    const int ps, const int dl, const int dh, const int n_main,
+                                                    const bool mirror_top, double2 Zm, double2 Zc, const double wx,
+                                                    const double wy, const double wz, const double wc) {
+  static_assert(U % 2 == 0, "the parity of a batch must not depend on the batch index");
+  const double2 zero2 = make_double2(0.0, 0.0);
+  int t = 0;
+  for (; t + U <= n_main; t += U) {
+    double2 Zn[U], YL[U], YH[U], RH[U], UC[U];
+    double XO[U];
+#pragma unroll
+    for (int q = 0; q < U; ++q) {
+      const double* __restrict__ p = po + q * ps;
+      Zn[q] = *reinterpret_cast<const double2*>(p + ps);
+      YL[q] = *reinterpret_cast<const double2*>(p + dl);
+      YH[q] = *reinterpret_cast<const double2*>(p + dh);
+      XO[q] = p[((S ^ q) & 1) ? 2 : -1];
+      UC[q] = *reinterpret_cast<const double2*>(pu + q * ps);
+      RH[q] = HAS_RHS ? *reinterpret_cast<const double2*>(pr + q * ps) : zero2;
+    }
+#pragma unroll
+    for (int q = 0; q < U; ++q) {
+      *reinterpret_cast<double2*>(pw + q * ps) =
+          residual_pair<HAS_RHS>(((S ^ q) & 1) != 0, Zm, Zc, Zn[q], YL[q], YH[q], XO[q], UC[q], RH[q], wx, wy, wz, wc);
+      Zm = Zc;
+      Zc = Zn[q];
+    }
+    po += U * ps;
+    pu += U * ps;
+    pw += U * ps;
+    if (HAS_RHS) pr += U * ps;
+  }
+  for (; t < n_main + (mirror_top ? 1 : 0); ++t) {  // fewer than U planes left, and the mirrored top plane
+    const bool sq = ((S ^ t) & 1) != 0;
+    const double2 Zn = (t < n_main) ? *reinterpret_cast<const double2*>(po + ps) : Zm;  // (:119-120 mirror)
+    const double2 YL = *reinterpret_cast<const double2*>(po + dl);
+    const double2 YH = *reinterpret_cast<const double2*>(po + dh);
+    const double XO = po[sq ? 2 : -1];
+    const double2 UC = *reinterpret_cast<const double2*>(pu);
+    const double2 RH = HAS_RHS ? *reinterpret_cast<const double2*>(pr) : zero2;
+    *reinterpret_cast<double2*>(pw) = residual_pair<HAS_RHS>(sq, Zm, Zc, Zn, YL, YH, XO, UC, RH, wx, wy, wz, wc);
+    Zm = Zc;
+    Zc = Zn;
+    po += ps;
+    pu += ps;
+    pw += ps;
+    if (HAS_RHS) pr += ps;
+  }
+}
+
 template <bool HAS_RHS>
 __global__ void __launch_bounds__(RELAX_BX * RELAX_BY, 3)
 k_residual3d(const double* __restrict__ u, const double* __restrict__ rhs, double* __restrict__ r, const Grid g,
@@ -517,74 +645,41 @@ k_residual3d(const double* __restrict__ u, const double* __restrict__ rhs, doubl
   const double* __restrict__ rh = HAS_RHS ? rhs + (i64)colour * g.cs : nullptr;
   double* __restrict__ ro = r + (i64)colour * g.cs;
 
-  if (blockIdx.x == gridDim.x - 1) {  // edge block
-    if (threadIdx.x >= 4 * RELAX_BY) return;
+  if (blockIdx.x == gridDim.x - 1) {  // edge blocks: 4 edge columns x RELAX_EDGE_ROWS rows, scalar path
     const int m = edge_column(threadIdx.x & 3, g.mcnt);
-    const int j = blockIdx.y * RELAX_BY + (threadIdx.x >> 2);
+    const int j = blockIdx.y * RELAX_EDGE_ROWS + (threadIdx.x >> 2);
     if (m < 0 || j >= g.ny) return;
-    residual_column<HAS_RHS>(own, opp, rh, ro, g, b, colour, m, j, kbeg, kend, wx, wy, wz, wc);
+    residual_column<HAS_RHS, RELAX_EDGE_UNROLL>(own, opp, rh, ro, g, b, colour, m, j, kbeg, kend, wx, wy, wz, wc);
     return;
   }
   const int m0 = 2 + (blockIdx.x * RELAX_BX + (threadIdx.x & (RELAX_BX - 1))) * 2;
   const int j = blockIdx.y * RELAX_BY + (threadIdx.x / RELAX_BX);
   if (j >= g.ny || m0 + 2 >= g.mcnt) return;
 
+  const int ps = (int)g.ps;
+  const i64 oj = (i64)j * g.hp + m0;
+  // planes of the chunk that hold residuals; Dirichlet planes and rows get r = 0 (:389-397, :439-445)
+  const bool jin = (j >= b.lb[1] && j <= b.ub[1]);
+  const int kb = jin ? max(kbeg, b.lb[2]) : kend + 1, ke = min(kend, b.ub[2]);
+  const double2 zero2 = make_double2(0.0, 0.0);
+  for (int k = kbeg; k <= min(kb - 1, kend); ++k) *reinterpret_cast<double2*>(ro + (i64)(k - g.k0) * ps + oj) = zero2;
+  for (int k = max(ke + 1, kb); k <= kend; ++k) *reinterpret_cast<double2*>(ro + (i64)(k - g.k0) * ps + oj) = zero2;
+  if (kb > ke) return;
+
   const int jl = (j - 1 < 0) ? 1 : j - 1;
   const int jh = (j + 1 > g.ny - 1) ? g.ny - 2 : j + 1;
-  const bool jin = (j >= b.lb[1] && j <= b.ub[1]);
-  const int ps = (int)g.ps;
-  const int io = j * g.hp + m0;
   const int dl = (jl - j) * g.hp, dh = (jh - j) * g.hp;
-  const int kl0 = (kbeg - 1 < 0) ? 1 : kbeg - 1;
-  const double* __restrict__ oppb = opp - (i64)g.k0 * ps;
-  const double* __restrict__ ownb = own - (i64)g.k0 * ps;
-  const double* __restrict__ rhb = HAS_RHS ? rh - (i64)g.k0 * ps : nullptr;
-  double* __restrict__ rob = ro - (i64)g.k0 * ps;
-  double2 Zm = *reinterpret_cast<const double2*>(oppb + (i64)kl0 * ps + io);
-  double2 Zc = *reinterpret_cast<const double2*>(oppb + (i64)kbeg * ps + io);
-  int s = (j + kbeg + colour) & 1;
-  constexpr int U = 2;
-  for (int k0 = kbeg; k0 <= kend; k0 += U) {
-    double2 Zn[U], YL[U], YH[U], RH[U], UC[U];
-    double XO[U];
-#pragma unroll
-    for (int q = 0; q < U; ++q) {
-      const int k = min(k0 + q, kend);
-      const int kh = (k + 1 > g.nz - 1) ? g.nz - 2 : k + 1;
-      const double* __restrict__ pk = oppb + (i64)k * ps + io;
-      const int sq = s ^ (q & 1);
-      Zn[q] = *reinterpret_cast<const double2*>(oppb + (i64)kh * ps + io);
-      YL[q] = *reinterpret_cast<const double2*>(pk + dl);
-      YH[q] = *reinterpret_cast<const double2*>(pk + dh);
-      XO[q] = pk[sq ? 2 : -1];
-      UC[q] = *reinterpret_cast<const double2*>(ownb + (i64)k * ps + io);
-      if (HAS_RHS) RH[q] = *reinterpret_cast<const double2*>(rhb + (i64)k * ps + io);
-    }
-#pragma unroll
-    for (int q = 0; q < U; ++q) {
-      const int k = k0 + q;
-      if (k <= kend) {
-        const int sq = s ^ (q & 1);
-        double2 o;
-        o.x = 0.0;
-        o.y = 0.0;
-        if (jin && k >= b.lb[2] && k <= b.ub[2]) {
-          const double sx0 = sq ? (Zc.x + Zc.y) : (XO[q] + Zc.x);
-          const double sx1 = sq ? (Zc.y + XO[q]) : (Zc.x + Zc.y);
-          double t0 = (sx0 * wx + (YL[q].x + YH[q].x) * wy) + (Zm.x + Zn[q].x) * wz;  // (:424-426)
-          double t1 = (sx1 * wx + (YL[q].y + YH[q].y) * wy) + (Zm.y + Zn[q].y) * wz;
-          if (HAS_RHS) { t0 = t0 - RH[q].x; t1 = t1 - RH[q].y; }
-          t0 = t0 - UC[q].x * wc;                                                     // (:427)
-          t1 = t1 - UC[q].y * wc;
-          o.x = -t0;                                                                  // (:430)
-          o.y = -t1;
-        }
-        *reinterpret_cast<double2*>(rob + (i64)k * ps + io) = o;
-        Zm = Zc;
-        Zc = Zn[q];
-      }
-    }
-  }
+  const i64 o0 = (i64)(kb - g.k0) * ps + oj;  // the pair in plane kb
+  const double* __restrict__ po = opp + o0;
+  const double2 Zm = *reinterpret_cast<const double2*>(kb - 1 < 0 ? po + ps : po - ps);
+  const double2 Zc = *reinterpret_cast<const double2*>(po);
+  const bool mirror_top = (ke == g.nz - 1);
+  const int n_main = ke - kb + (mirror_top ? 0 : 1);
+  const double* __restrict__ pr = HAS_RHS ? rh + o0 : nullptr;
+  if ((j + kb + colour) & 1)
+    residual_pair_march<HAS_RHS, 2, 1>(po, own + o0, pr, ro + o0, ps, dl, dh, n_main, mirror_top, Zm, Zc, wx, wy, wz, wc);
+  else
+    residual_pair_march<HAS_RHS, 2, 0>(po, own + o0, pr, ro + o0, ps, dl, dh, n_main, mirror_top, Zm, Zc, wx, wy, wz, wc);
 }
 
 void residual3d(const double* u, const double* rhs, double* r, const Grid& g, const Bounds& b, const Weights& w,
