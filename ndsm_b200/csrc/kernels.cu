@@ -1370,6 +1370,124 @@ k_interp_add_tiled(const double* __restrict__ uc, const Grid gc, double* __restr
   }
 }
 
+// K4 z-lerped tile (3D, default): a block owns 64 x 8 fine columns and marches in z, two planes per step.
+// Thread e < IZ_CXW*IZ_CYW keeps ONE coarse column of the block's coarse footprint (<= 36 x 7) in registers for
+// the two bracketing coarse planes and writes its z-lerp  whz*c(z0) + wlz*c(z1)  for each of the two fine planes
+// into shared memory (every z-lerp is computed once per block instead of once per fine point); after one barrier
+// every thread finishes two fine columns (i0, i0+2), i0 = 4a + b -- neighbours in the colour-split layout, one
+// 16-byte load and store per plane -- with the y and x lerps from four shared-memory values each.
+// Same lerp order as the reference (z, then y, then x; ndsm_interp.f90:128-154) -> same bits as the other
+// prolongation kernels.  Double-buffered tile: one barrier per two fine planes.
+#define IZ_BX 32   // threads per row: 16 values of a, two column parities b
+#define IZ_BY 8
+#define IZ_FX 64   // fine columns per block
+#define IZ_CXW 36
+#define IZ_CYW 7
+__global__ void __launch_bounds__(IZ_BX * IZ_BY, 4)
+k_interp_add_zt(const double* __restrict__ uc, const Grid gc, double* __restrict__ uf, const Grid gf,
+                const InterpTab tx, const InterpTab ty, const InterpTab tz, const int zchunk) {
+  __shared__ double zt[2][2][IZ_CYW * IZ_CXW];  // [buffer][plane of the step][coarse tile]
+  const int e = threadIdx.x;
+  const int txi = e & (IZ_BX - 1), tyi = e / IZ_BX;
+  const int ib = blockIdx.x * IZ_FX, j0 = blockIdx.y * IZ_BY;
+  const int kbeg = gf.k0 + blockIdx.z * zchunk;
+  const int kend = min(kbeg + zchunk, gf.k0 + gf.nzl) - 1;
+  if (kbeg > kend) return;
+  const int cx0 = tx.lo[ib], cy0 = ty.lo[j0];
+  // --- my coarse column of the footprint
+  const bool cact = e < IZ_CXW * IZ_CYW;
+  const int cyo = e / IZ_CXW, cxo = e - cyo * IZ_CXW;
+  const int xc = min(cx0 + cxo, gc.nx - 1), yc = min(cy0 + cyo, gc.ny - 1);
+  const int coff = yc * gc.hp + (xc >> 1);
+  const bool cpar = ((xc + yc) & 1) != 0;
+  auto coarse = [&](const int zc) {
+    const i64 c0 = (((zc & 1) != 0) != cpar) ? gc.cs : 0;  // colour (xc + yc + zc) & 1
+    return uc[c0 + (i64)(zc - gc.k0) * gc.ps + coff];
+  };
+  int za = tz.lo[kbeg], zb = min(za + 1, gc.nz - 1);
+  double ca = 0.0, cb = 0.0;
+  if (cact) { ca = coarse(za); cb = coarse(zb); }
+  auto zlerp = [&](const int k) {  // z-lerp of my coarse column for fine plane k; moves the bracket when needed
+    const int z0 = tz.lo[k], z1 = min(z0 + 1, gc.nz - 1);
+    if (z0 != za || z1 != zb) {  // uniform over the block
+      if (cact) {
+        ca = (z0 == zb) ? cb : coarse(z0);
+        cb = (z1 == z0) ? ca : coarse(z1);
+      }
+      za = z0;
+      zb = z1;
+    }
+    return tz.wh[k] * ca + tz.wl[k] * cb;
+  };
+  // --- my two fine columns
+  const int i0 = ib + 4 * (txi >> 1) + (txi & 1), j = j0 + tyi;
+  const bool fact = i0 < gf.nx && j < gf.ny;
+  const bool v1 = i0 + 2 < gf.nx;  // the second column may fall into the row padding
+  const int i0c = min(i0, gf.nx - 1), i1c = v1 ? i0 + 2 : i0c, jc = min(j, gf.ny - 1);
+  const double why = ty.wh[jc], wly = ty.wl[jc];
+  const double whx0 = tx.wh[i0c], wlx0 = tx.wl[i0c], whx1 = tx.wh[i1c], wlx1 = tx.wl[i1c];
+  const int b0 = (ty.lo[jc] - cy0) * IZ_CXW + (tx.lo[i0c] - cx0);
+  const int b1 = (ty.lo[jc] - cy0) * IZ_CXW + (tx.lo[i1c] - cx0);
+  // the pair lives in colour (i0 + j + k) & 1: two pointers, alternating with k
+  const int ps = (int)gf.ps;
+  const i64 o0 = (i64)(kbeg - gf.k0) * ps + (i64)jc * gf.hp + (i0c >> 1);
+  const i64 ce = ((i0c + jc + kbeg) & 1) ? gf.cs : 0;
+  double* __restrict__ pe = uf + ce + o0;                  // planes kbeg, kbeg+2, ...
+  double* __restrict__ pn = uf + (gf.cs - ce) + o0 + ps;   // planes kbeg+1, kbeg+3, ...
+  auto finish = [&](const double* __restrict__ tile, const double2 uold) {
+    double2 o;
+    double f0 = why * tile[b0] + wly * tile[b0 + IZ_CXW];
+    double f1 = why * tile[b0 + 1] + wly * tile[b0 + IZ_CXW + 1];
+    f0 = whx0 * f0 + wlx0 * f1;
+    o.x = uold.x + f0;  // add_correction, ndsm_multigrid_core.f90:706-710
+    double g0 = why * tile[b1] + wly * tile[b1 + IZ_CXW];
+    double g1 = why * tile[b1 + 1] + wly * tile[b1 + IZ_CXW + 1];
+    g0 = whx1 * g0 + wlx1 * g1;
+    o.y = v1 ? uold.y + g0 : uold.y;
+    return o;
+  };
+  int buf = 0;
+  for (int k = kbeg; k <= kend; k += 2, buf ^= 1) {
+    const bool two = k + 1 <= kend;
+    double2 u0 = make_double2(0.0, 0.0), u1 = u0;
+    if (fact) {
+      u0 = *reinterpret_cast<const double2*>(pe);
+      if (two) u1 = *reinterpret_cast<const double2*>(pn);
+    }
+    const double z0v = zlerp(k);
+    const double z1v = two ? zlerp(k + 1) : 0.0;
+    if (cact) {
+      zt[buf][0][e] = z0v;
+      zt[buf][1][e] = z1v;
+    }
+    __syncthreads();  // tile of this step complete; the other buffer was last read one barrier ago
+    if (fact) {
+      *reinterpret_cast<double2*>(pe) = finish(zt[buf][0], u0);
+      if (two) *reinterpret_cast<double2*>(pn) = finish(zt[buf][1], u1);
+    }
+    pe += 2 * ps;
+    pn += 2 * ps;
+  }
+}
+
+bool interp_zt_fits(const int* lo_x, int nfx, int ncx, const int* lo_y, int nfy, int ncy) {
+  if (ncx < 2 || ncy < 2) return false;
+  for (int i0 = 0; i0 < nfx; i0 += IZ_FX)
+    if (lo_x[std::min(i0 + IZ_FX, nfx) - 1] + 1 - lo_x[i0] + 1 > IZ_CXW) return false;
+  for (int j0 = 0; j0 < nfy; j0 += IZ_BY)
+    if (lo_y[std::min(j0 + IZ_BY, nfy) - 1] + 1 - lo_y[j0] + 1 > IZ_CYW) return false;
+  return true;
+}
+
+void interp_add_zt(const double* uc, const Grid& gc, double* uf, const Grid& gf, const InterpTab& tx,
+                   const InterpTab& ty, const InterpTab& tz, cudaStream_t st) {
+  const int bx = cdiv(gf.nx, IZ_FX), by = cdiv(gf.ny, IZ_BY);
+  const int zc = pick_zchunk(gf.nzl, bx * by, 32);
+  dim3 grid(bx, by, cdiv(gf.nzl, zc));
+  k_interp_add_zt<<<grid, IZ_BX * IZ_BY, 0, st>>>(uc, gc, uf, gf, tx, ty, tz, zc);
+  LAUNCHED();
+}
+
 // host check: every fine tile's coarse footprint fits the fixed shared-memory window
 bool interp_tiled_fits(const int* lo_x, int nfx, int ncx, const int* lo_y, int nfy, int ncy) {
   if (ncx < 2 || ncy < 2) return false;

@@ -73,6 +73,10 @@ void restrict_sep(const double* rf, const Grid& gf, double* rhsc, const Grid& gc
                   const RestrictTab& ty, const RestrictTab& tz, cudaStream_t st);
 // K4 tiled (3D): same arithmetic through a shared-memory window of coarse planes
 bool interp_tiled_fits(const int* lo_x, int nfx, int ncx, const int* lo_y, int nfy, int ncy);
+// K4 z-lerped tile (3D, default): z-lerps shared through a small shared-memory tile, 16-byte u_f accesses.
+bool interp_zt_fits(const int* lo_x, int nfx, int ncx, const int* lo_y, int nfy, int ncy);
+void interp_add_zt(const double* uc, const Grid& gc, double* uf, const Grid& gf, const InterpTab& tx,
+                   const InterpTab& ty, const InterpTab& tz, cudaStream_t st);
 void interp_add_tiled(const double* uc, const Grid& gc, double* uf, const Grid& gf, const InterpTab& tx,
                       const InterpTab& ty, const InterpTab& tz, cudaStream_t st);
 // K5: coarsest-level relaxation solve to ex_tol inside ONE thread block (ndsm_multigrid_core.f90:728-800).

@@ -372,7 +372,12 @@ MG::MG(int ndim, const int* shape, int ngrids, const double* const* mesh, cudaSt
         S.lv[g].it[d] = InterpTab{tab_i_ + o.lo, tab_d_ + o.wl, tab_d_ + o.wh};
         S.lv[g].rt[d] = RestrictTab{tab_i_ + o.first, tab_i_ + o.count, tab_d_ + o.c2, hl[g].w2[d]};
       }
-      if (ndim == 3 && fuse_on && hl[g].n[0] >= 64 && hl[g].n[2] >= 8)
+      // NDSM_B200_INTERP=tiled|simple selects the older prolongation kernels (same bits)
+      const char* ipk = getenv("NDSM_B200_INTERP");
+      S.lv[g].icols = ndim == 3 && !ipk && hl[g].n[0] >= 64 && hl[g].n[2] >= 8 &&
+                      interp_zt_fits(hl[g].lo[0].data(), hl[g].n[0], hl[g + 1].n[0], hl[g].lo[1].data(), hl[g].n[1],
+                                     hl[g + 1].n[1]);
+      if (ndim == 3 && fuse_on && !(ipk && !strcmp(ipk, "simple")) && hl[g].n[0] >= 64 && hl[g].n[2] >= 8)
         S.lv[g].itiled = interp_tiled_fits(hl[g].lo[0].data(), hl[g].n[0], hl[g + 1].n[0], hl[g].lo[1].data(),
                                            hl[g].n[1], hl[g + 1].n[1]);
       if (ndim == 3 && !exact_restrict && hl[g + 1].n[0] >= 16 && hl[g + 1].n[1] >= 8 && hl[g + 1].n[2] >= 8)
@@ -624,7 +629,8 @@ void MG::interp_add_from(int c) {
   for (size_t s = 0; s < ns; ++s) {
     Level& C = slabs_[s].lv[c];
     Level& F = slabs_[s].lv[f];
-    if (F.itiled) interp_add_tiled(C.u, C.g, F.u, F.g, F.it[0], F.it[1], F.it[2], st_);
+    if (F.icols) interp_add_zt(C.u, C.g, F.u, F.g, F.it[0], F.it[1], F.it[2], st_);
+    else if (F.itiled) interp_add_tiled(C.u, C.g, F.u, F.g, F.it[0], F.it[1], F.it[2], st_);
     else interp_add(C.u, C.g, F.u, F.g, F.it[0], F.it[1], F.it[2], st_);
   }
   if (prof) prof_end(PROF_INTERP0, st_);
