@@ -1216,6 +1216,136 @@ k_restrict_sep(const double* __restrict__ rf, const Grid gf, double* __restrict_
   }
 }
 
+// K3 separable, direct (default for regular levels): one thread per coarse column (ic, jc) marching over the
+// fine planes of its z-chunk.  The <= RD_CM x RD_CM window of the fine plane is read straight from the
+// colour-split arrays -- in a window row the even elements sit side by side in one colour and the odd ones in
+// the other, at fixed offsets from two row pointers, and neighbouring threads read neighbouring addresses, so
+// the ~6-fold reuse of every fine value is served by L1 -- and reduced in x then y in registers; the xy-restricted
+// value is accumulated into the (at most three) coarse planes whose z windows are open.  No shared memory, no
+// barriers.  Same weights and summation order as k_restrict_sep (window slots beyond the count add 0 * value).
+#define RD_CM 5  // largest window per dimension handled here (regular ~2:1 coarsening); else k_restrict_sep
+#define RD_BX 32
+#define RD_BY 8
+__global__ void __launch_bounds__(RD_BX * RD_BY, 2)
+k_restrict_direct(const double* __restrict__ rf, const Grid gf, double* __restrict__ rc, const Grid gc,
+                  const RestrictTab tx, const RestrictTab ty, const RestrictTab tz, const int kchunk) {
+  const int ic = blockIdx.x * RD_BX + (threadIdx.x & (RD_BX - 1));
+  const int jc = blockIdx.y * RD_BY + threadIdx.x / RD_BX;
+  const int kc_beg = gc.k0 + blockIdx.z * kchunk;
+  const int kc_end = min(kc_beg + kchunk, gc.k0 + gc.nzl) - 1;
+  if (ic >= gc.nx || jc >= gc.ny || kc_beg > kc_end) return;
+  // 1-D weights of my coarse column: c2*w2 (ndsm_interp.f90:277-282)
+  const int fx = tx.first[ic], cx = tx.count[ic], fy = ty.first[jc], cy = ty.count[jc];
+  double wx[RD_CM], wy[RD_CM];
+#pragma unroll
+  for (int q = 0; q < RD_CM; ++q) {
+    wx[q] = (q < cx) ? tx.c2[(i64)ic * NDSM_RMAX + q] * tx.w2 : 0.0;
+    wy[q] = (q < cy) ? ty.c2[(i64)jc * NDSM_RMAX + q] * ty.w2 : 0.0;
+  }
+  // window row r, element q: fine point (fx+q, fy+r, kf), colour (fx+q + fy+r + kf) & 1, column (fx+q) >> 1.
+  // Even q share the colour of element 0 at columns (fx>>1) + q/2; odd q have the other colour at
+  // ((fx+1)>>1) + q/2.
+  const int hp = gf.hp, ps = (int)gf.ps;
+  const int kf_beg = tz.first[kc_beg], kf_end = tz.first[kc_end] + tz.count[kc_end] - 1;
+  const i64 o0 = (i64)(kf_beg - gf.k0) * ps + (i64)fy * hp;
+  const i64 cse = ((fx + fy + kf_beg) & 1) ? gf.cs : 0;  // colour of element (0,0) in plane kf_beg
+  // in plane kf_beg + t the colour of element (r, q) is that of (0, 0) iff (t + r + q) is even
+  const double* __restrict__ pE = rf + cse + o0 + (fx >> 1);                 // even q, when t + r even
+  const double* __restrict__ pO = rf + (gf.cs - cse) + o0 + ((fx + 1) >> 1);  // odd q, when t + r even
+  const double* __restrict__ qE = rf + (gf.cs - cse) + o0 + (fx >> 1);        // even q, when t + r odd
+  const double* __restrict__ qO = rf + cse + o0 + ((fx + 1) >> 1);            // odd q, when t + r odd
+  const int o3 = (cx > 3) ? 1 : 0, e4 = (cx > 4) ? 2 : 1;                 // column offsets of elements 3 and 4
+  const int r3 = ((cy > 3) ? 3 : 1) * hp, r4 = ((cy > 4) ? 4 : 2) * hp;  // row offsets of rows 3 and 4
+  double acc0 = 0.0, acc1 = 0.0, acc2 = 0.0;  // coarse planes kc_lo, kc_lo+1, kc_lo+2
+  int kc_lo = kc_beg, kc_hi = kc_beg;         // open windows: kc_lo .. kc_hi
+  int last_lo = tz.first[kc_lo] + tz.count[kc_lo] - 1;
+  int first_next = (kc_hi + 1 <= kc_end) ? tz.first[kc_hi + 1] : 0x7fffffff;
+  const int colour_base = (ic + jc) & 1;
+  double* __restrict__ outp = rc + (i64)jc * gc.hp + (ic >> 1);
+  for (int kf = kf_beg, t = 0; kf <= kf_end; ++kf, ++t) {
+    // ---- xy-restricted value of this fine plane
+    const double* __restrict__ rowE = (t & 1) ? qE : pE;
+    const double* __restrict__ rowO = (t & 1) ? qO : pO;
+    const double* __restrict__ altE = (t & 1) ? pE : qE;
+    const double* __restrict__ altO = (t & 1) ? pO : qO;
+    // 5 x 5 loads and multiply-adds without predicates: an element beyond the window (count 3 or 4) re-reads the
+    // window element two places before it (same colour, valid data, an L1 hit) with weight 0
+    double p = 0.0;
+#pragma unroll
+    for (int r = 0; r < RD_CM; ++r) {
+      const int ro = (r == 3) ? r3 : (r == 4 ? r4 : r * hp);
+      const double* __restrict__ e = ((r & 1) ? altE : rowE) + ro;
+      const double* __restrict__ o = ((r & 1) ? altO : rowO) + ro;
+      double sx = wx[0] * e[0];
+      sx += wx[1] * o[0];
+      sx += wx[2] * e[1];
+      sx += wx[3] * o[o3];
+      sx += wx[4] * e[e4];
+      if (r == 0) p = wy[0] * sx;
+      else p += wy[r] * sx;
+    }
+    pE += ps; pO += ps; qE += ps; qO += ps;
+    // ---- z: open the windows that start here, accumulate, emit the one that ends here
+    while (kf >= first_next) {  // uniform
+      ++kc_hi;
+      first_next = (kc_hi + 1 <= kc_end) ? tz.first[kc_hi + 1] : 0x7fffffff;
+    }
+    {
+      const double* __restrict__ w0 = tz.c2 + (i64)kc_lo * NDSM_RMAX;
+      const int q0 = kf - tz.first[kc_lo];
+      acc0 += (w0[q0] * tz.w2) * p;
+      if (kc_hi > kc_lo) {
+        const int q1 = kf - tz.first[kc_lo + 1];
+        acc1 += (w0[NDSM_RMAX + q1] * tz.w2) * p;
+      }
+      if (kc_hi > kc_lo + 1) {
+        const int q2 = kf - tz.first[kc_lo + 2];
+        acc2 += (w0[2 * NDSM_RMAX + q2] * tz.w2) * p;
+      }
+    }
+    while (kf == last_lo) {  // uniform; the one-sided windows at the top face end on the same plane
+      outp[(i64)((colour_base + kc_lo) & 1) * gc.cs + (i64)(kc_lo - gc.k0) * gc.ps] = acc0;
+      acc0 = acc1;
+      acc1 = acc2;
+      acc2 = 0.0;
+      ++kc_lo;
+      if (kc_lo > kc_end) { last_lo = -1; break; }  // kf == kf_end: the march is over
+      if (kc_hi < kc_lo) {  // the next window starts on the following plane
+        kc_hi = kc_lo;
+        first_next = (kc_hi + 1 <= kc_end) ? tz.first[kc_hi + 1] : 0x7fffffff;
+      }
+      last_lo = tz.first[kc_lo] + tz.count[kc_lo] - 1;
+    }
+  }
+}
+
+// host check for k_restrict_direct: windows of at most RD_CM points in every dimension, every z window starts at
+// or before the previous one's end + 1 (contiguous coverage), never more than three z windows open, and windows
+// end in non-decreasing order
+bool restrict_direct_fits(const int* const first[3], const int* const count[3], const int nc[3]) {
+  for (int d = 0; d < 3; ++d)
+    for (int c = 0; c < nc[d]; ++c)
+      if (count[d][c] > RD_CM || count[d][c] < 3) return false;
+  const int* f = first[2];
+  const int* n = count[2];
+  for (int c = 0; c + 1 < nc[2]; ++c) {
+    if (f[c + 1] < f[c] || f[c + 1] + n[c + 1] < f[c] + n[c]) return false;   // starts and ends do not decrease
+    if (f[c + 1] > f[c] + n[c]) return false;                                  // no gap between windows
+    if (c + 3 < nc[2] && f[c + 3] <= f[c] + n[c] - 1) return false;            // at most three windows open
+  }
+  return true;
+}
+
+void restrict_direct(const double* rf, const Grid& gf, double* rhsc, const Grid& gc, const RestrictTab& tx,
+                     const RestrictTab& ty, const RestrictTab& tz, cudaStream_t st) {
+  const int bx = cdiv(gc.nx, RD_BX), by = cdiv(gc.ny, RD_BY);
+  int kchunk = 32;
+  while (kchunk > 2 && (i64)bx * by * cdiv(gc.nzl, kchunk) < 148 * 6) kchunk >>= 1;
+  dim3 grid(bx, by, cdiv(gc.nzl, kchunk));
+  k_restrict_direct<<<grid, RD_BX * RD_BY, 0, st>>>(rf, gf, rhsc, gc, tx, ty, tz, kchunk);
+  LAUNCHED();
+}
+
 bool restrict_sep_fits(const int* first_x, const int* count_x, int ncx, const int* first_y, const int* count_y,
                        int ncy) {
   for (int c0 = 0; c0 < ncx; c0 += RS_CX) {
@@ -1383,42 +1513,36 @@ k_interp_add_tiled(const double* __restrict__ uc, const Grid gc, double* __restr
 #define IZ_FX 64   // fine columns per block
 #define IZ_CXW 36
 #define IZ_CYW 7
+#define IZ_NP 4    // fine planes per step (even)
+#define IZ_ZMAX 32  // longest z-chunk (planes) a block marches: its z table lives in shared memory
 __global__ void __launch_bounds__(IZ_BX * IZ_BY, 4)
 k_interp_add_zt(const double* __restrict__ uc, const Grid gc, double* __restrict__ uf, const Grid gf,
                 const InterpTab tx, const InterpTab ty, const InterpTab tz, const int zchunk) {
-  __shared__ double zt[2][2][IZ_CYW * IZ_CXW];  // [buffer][plane of the step][coarse tile]
+  __shared__ double zt[2][IZ_NP][IZ_CYW * IZ_CXW];  // [buffer][plane of the step][coarse tile]
+  __shared__ double s_wh[IZ_ZMAX], s_wl[IZ_ZMAX];
+  __shared__ int s_lo[IZ_ZMAX];
   const int e = threadIdx.x;
   const int txi = e & (IZ_BX - 1), tyi = e / IZ_BX;
   const int ib = blockIdx.x * IZ_FX, j0 = blockIdx.y * IZ_BY;
   const int kbeg = gf.k0 + blockIdx.z * zchunk;
   const int kend = min(kbeg + zchunk, gf.k0 + gf.nzl) - 1;
   if (kbeg > kend) return;
+  const int n = kend - kbeg + 1;
+  if (e < n) {  // z table of the chunk (the bracket logic below is uniform and must not wait on global loads)
+    s_lo[e] = tz.lo[kbeg + e];
+    s_wh[e] = tz.wh[kbeg + e];
+    s_wl[e] = tz.wl[kbeg + e];
+  }
   const int cx0 = tx.lo[ib], cy0 = ty.lo[j0];
-  // --- my coarse column of the footprint
+  // --- my coarse column of the footprint: colour (xc + yc + zc) & 1 alternates with zc
   const bool cact = e < IZ_CXW * IZ_CYW;
   const int cyo = e / IZ_CXW, cxo = e - cyo * IZ_CXW;
   const int xc = min(cx0 + cxo, gc.nx - 1), yc = min(cy0 + cyo, gc.ny - 1);
-  const int coff = yc * gc.hp + (xc >> 1);
   const bool cpar = ((xc + yc) & 1) != 0;
-  auto coarse = [&](const int zc) {
-    const i64 c0 = (((zc & 1) != 0) != cpar) ? gc.cs : 0;  // colour (xc + yc + zc) & 1
-    return uc[c0 + (i64)(zc - gc.k0) * gc.ps + coff];
-  };
-  int za = tz.lo[kbeg], zb = min(za + 1, gc.nz - 1);
-  double ca = 0.0, cb = 0.0;
-  if (cact) { ca = coarse(za); cb = coarse(zb); }
-  auto zlerp = [&](const int k) {  // z-lerp of my coarse column for fine plane k; moves the bracket when needed
-    const int z0 = tz.lo[k], z1 = min(z0 + 1, gc.nz - 1);
-    if (z0 != za || z1 != zb) {  // uniform over the block
-      if (cact) {
-        ca = (z0 == zb) ? cb : coarse(z0);
-        cb = (z1 == z0) ? ca : coarse(z1);
-      }
-      za = z0;
-      zb = z1;
-    }
-    return tz.wh[k] * ca + tz.wl[k] * cb;
-  };
+  const int cps = (int)gc.ps;
+  const double* __restrict__ cb0 = uc + (cpar ? gc.cs : 0) - (i64)gc.k0 * cps + (yc * gc.hp + (xc >> 1));  // even zc
+  const double* __restrict__ cb1 = uc + (cpar ? 0 : gc.cs) - (i64)gc.k0 * cps + (yc * gc.hp + (xc >> 1));  // odd zc
+  auto coarse = [&](const int zc) { return ((zc & 1) ? cb1 : cb0)[(i64)zc * cps]; };
   // --- my two fine columns
   const int i0 = ib + 4 * (txi >> 1) + (txi & 1), j = j0 + tyi;
   const bool fact = i0 < gf.nx && j < gf.ny;
@@ -1434,6 +1558,10 @@ k_interp_add_zt(const double* __restrict__ uc, const Grid gc, double* __restrict
   const i64 ce = ((i0c + jc + kbeg) & 1) ? gf.cs : 0;
   double* __restrict__ pe = uf + ce + o0;                  // planes kbeg, kbeg+2, ...
   double* __restrict__ pn = uf + (gf.cs - ce) + o0 + ps;   // planes kbeg+1, kbeg+3, ...
+  __syncthreads();
+  int za = s_lo[0], zb = min(za + 1, gc.nz - 1);
+  double ca = 0.0, cb = 0.0;
+  if (cact) { ca = coarse(za); cb = coarse(zb); }
   auto finish = [&](const double* __restrict__ tile, const double2 uold) {
     double2 o;
     double f0 = why * tile[b0] + wly * tile[b0 + IZ_CXW];
@@ -1446,27 +1574,39 @@ k_interp_add_zt(const double* __restrict__ uc, const Grid gc, double* __restrict
     o.y = v1 ? uold.y + g0 : uold.y;
     return o;
   };
+  double* __restrict__ slot = &zt[0][0][e];
+  const double* __restrict__ tile0 = &zt[0][0][0];
   int buf = 0;
-  for (int k = kbeg; k <= kend; k += 2, buf ^= 1) {
-    const bool two = k + 1 <= kend;
-    double2 u0 = make_double2(0.0, 0.0), u1 = u0;
-    if (fact) {
-      u0 = *reinterpret_cast<const double2*>(pe);
-      if (two) u1 = *reinterpret_cast<const double2*>(pn);
-    }
-    const double z0v = zlerp(k);
-    const double z1v = two ? zlerp(k + 1) : 0.0;
-    if (cact) {
-      zt[buf][0][e] = z0v;
-      zt[buf][1][e] = z1v;
+  for (int t = 0; t < n; t += IZ_NP, buf ^= 1) {
+    const int np = min(IZ_NP, n - t);
+    const int bo = buf * (IZ_NP * IZ_CYW * IZ_CXW);
+    double2 uo[IZ_NP];
+#pragma unroll
+    for (int q = 0; q < IZ_NP; ++q)
+      if (fact && q < np) uo[q] = *reinterpret_cast<const double2*>(((q & 1) ? pn : pe) + (q >> 1) * 2 * ps);
+#pragma unroll
+    for (int q = 0; q < IZ_NP; ++q) {
+      if (q < np) {
+        const int z0 = s_lo[t + q], z1 = min(z0 + 1, gc.nz - 1);
+        if (z0 != za || z1 != zb) {  // uniform over the block: move the bracket
+          if (cact) {
+            ca = (z0 == zb) ? cb : coarse(z0);
+            cb = (z1 == z0) ? ca : coarse(z1);
+          }
+          za = z0;
+          zb = z1;
+        }
+        if (cact) slot[bo + q * (IZ_CYW * IZ_CXW)] = s_wh[t + q] * ca + s_wl[t + q] * cb;
+      }
     }
     __syncthreads();  // tile of this step complete; the other buffer was last read one barrier ago
-    if (fact) {
-      *reinterpret_cast<double2*>(pe) = finish(zt[buf][0], u0);
-      if (two) *reinterpret_cast<double2*>(pn) = finish(zt[buf][1], u1);
-    }
-    pe += 2 * ps;
-    pn += 2 * ps;
+#pragma unroll
+    for (int q = 0; q < IZ_NP; ++q)
+      if (fact && q < np)
+        *reinterpret_cast<double2*>(((q & 1) ? pn : pe) + (q >> 1) * 2 * ps) =
+            finish(tile0 + bo + q * (IZ_CYW * IZ_CXW), uo[q]);
+    pe += IZ_NP * ps;
+    pn += IZ_NP * ps;
   }
 }
 
@@ -1482,7 +1622,7 @@ bool interp_zt_fits(const int* lo_x, int nfx, int ncx, const int* lo_y, int nfy,
 void interp_add_zt(const double* uc, const Grid& gc, double* uf, const Grid& gf, const InterpTab& tx,
                    const InterpTab& ty, const InterpTab& tz, cudaStream_t st) {
   const int bx = cdiv(gf.nx, IZ_FX), by = cdiv(gf.ny, IZ_BY);
-  const int zc = pick_zchunk(gf.nzl, bx * by, 32);
+  const int zc = pick_zchunk(gf.nzl, bx * by, IZ_ZMAX);
   dim3 grid(bx, by, cdiv(gf.nzl, zc));
   k_interp_add_zt<<<grid, IZ_BX * IZ_BY, 0, st>>>(uc, gc, uf, gf, tx, ty, tz, zc);
   LAUNCHED();

@@ -67,6 +67,11 @@ void interp_add(const double* uc, const Grid& gc, double* uf, const Grid& gf, co
                 const InterpTab& ty, const InterpTab& tz, cudaStream_t st);
 // K3 separable (3D, default): same 1-D weights applied one dimension at a time (HBM-bound; rounding differs from
 // the reference's triple product at the 1e-16 level)
+// K3 separable, direct: per-thread window reads from the colour-split arrays, no shared memory (same bits as
+// restrict_sep); usable when restrict_direct_fits() holds (windows <= 5 points, <= 3 z windows open).
+bool restrict_direct_fits(const int* const first[3], const int* const count[3], const int nc[3]);
+void restrict_direct(const double* rf, const Grid& gf, double* rhsc, const Grid& gc, const RestrictTab& tx,
+                     const RestrictTab& ty, const RestrictTab& tz, cudaStream_t st);
 bool restrict_sep_fits(const int* first_x, const int* count_x, int ncx, const int* first_y, const int* count_y,
                        int ncy);
 void restrict_sep(const double* rf, const Grid& gf, double* rhsc, const Grid& gc, const RestrictTab& tx,

@@ -383,6 +383,12 @@ MG::MG(int ndim, const int* shape, int ngrids, const double* const* mesh, cudaSt
       if (ndim == 3 && !exact_restrict && hl[g + 1].n[0] >= 16 && hl[g + 1].n[1] >= 8 && hl[g + 1].n[2] >= 8)
         S.lv[g].rsep = restrict_sep_fits(hl[g].first[0].data(), hl[g].count[0].data(), hl[g + 1].n[0],
                                          hl[g].first[1].data(), hl[g].count[1].data(), hl[g + 1].n[1]);
+      if (S.lv[g].rsep && !(getenv("NDSM_B200_RESTRICT") && !strcmp(getenv("NDSM_B200_RESTRICT"), "tile"))) {
+        const int* const fi[3] = {hl[g].first[0].data(), hl[g].first[1].data(), hl[g].first[2].data()};
+        const int* const co[3] = {hl[g].count[0].data(), hl[g].count[1].data(), hl[g].count[2].data()};
+        const int nc[3] = {hl[g + 1].n[0], hl[g + 1].n[1], hl[g + 1].n[2]};
+        S.lv[g].rdirect = restrict_direct_fits(fi, co, nc);
+      }
       if (ndim == 3 && fuse_on && hl[g + 1].n[0] >= 16 && hl[g + 1].n[1] >= 8)
         S.lv[g].fused = restrict_tiled_fits(hl[g].first[0].data(), hl[g].count[0].data(), hl[g + 1].n[0],
                                             hl[g].first[1].data(), hl[g].count[1].data(), hl[g + 1].n[1],
@@ -580,7 +586,9 @@ void MG::restrict_to(int g) {
       out = C.rhs + (i64)gv.k0 * C.g.ps;
     }
     if (gv.nzl <= 0) continue;
-    if (F.rsep)
+    if (F.rdirect)
+      restrict_direct(r_scratch(g, (int)s), F.g, out, gv, F.rt[0], F.rt[1], F.rt[2], st_);
+    else if (F.rsep)
       restrict_sep(r_scratch(g, (int)s), F.g, out, gv, F.rt[0], F.rt[1], F.rt[2], st_);
     else if (F.fused)
       restrict_tiled(r_scratch(g, (int)s), F.g, out, gv, F.rt[0], F.rt[1], F.rt[2], F.rr_hwp, F.rr_fyw, st_);

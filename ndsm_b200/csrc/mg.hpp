@@ -97,6 +97,7 @@ struct Level {
   bool fused = false;
   int rr_hwp = 0, rr_fyw = 0;
   bool itiled = false;  // tiled prolongation from the next level
+  bool rdirect = false;  // direct separable restriction to the next level (default when its windows are regular)
   bool icols = false;   // z-lerped-tile prolongation from the next level (default for large 3D levels)
   bool rsep = false;    // separable restriction towards the next level (default; not bit-identical)
 };
