@@ -443,6 +443,8 @@ static int pick_zchunk(int nplanes, int blocks_per_plane, int zc_max = 16) {
   // every z-chunk re-reads two warm-up planes, so chunks should be long; two to three waves of the resident
   // blocks (148 SMs x 3 blocks of 256 threads) are enough to balance the SMs
   int zc = zc_max;
+  // mid-size levels (257^3: 1.9 waves of 16-plane blocks) balance better with four waves of 8-plane blocks
+  while (zc > 8 && (i64)blocks_per_plane * cdiv(nplanes, zc) < 148 * 4 * 4) zc >>= 1;
   while (zc > 2 && (i64)blocks_per_plane * cdiv(nplanes, zc) < 148 * 3 * 2) zc >>= 1;
   return zc;
 }
@@ -484,7 +486,8 @@ void relax3d_half(double* u, const double* rhs, const Grid& g, const Bounds& b, 
   static const int variant = getenv("NDSM_B200_RELAX_VARIANT") ? atoi(getenv("NDSM_B200_RELAX_VARIANT")) : 0;
   // (a chunk length chosen to fill whole waves of resident blocks -- 29 planes at 513^3, 22 at 257^3 -- was
   // measured slower than 16: 0.196 vs 0.185 ms per pass at 513^3, level 1 0.95 vs 0.77 ms per V-cycle)
-  const int zc = pick_zchunk(khi - klo + 1, bx * by, 16);
+  static const int zc_cap = getenv("NDSM_B200_ZCHUNK") ? std::max(2, atoi(getenv("NDSM_B200_ZCHUNK"))) : 16;
+  const int zc = pick_zchunk(khi - klo + 1, bx * by, zc_cap);
   dim3 grid(bx, by, cdiv(khi - klo + 1, zc));
 #define RELAX_LAUNCH(R, UU, MB) \
   k_relax3d<R, UU, MB><<<grid, RELAX_BX * RELAX_BY, 0, st>>>(u, rhs, g, b, colour, w.wx, w.wy, w.wz, w.w1, klo, khi, zc)
