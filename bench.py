@@ -195,7 +195,7 @@ def kernel_report(lib, npoints, dev_ms):
     cnt, tot = ctypes.c_ulonglong(0), ctypes.c_double(0)
     peak, peak_src = measured_peak()
     kern = {}
-    names = ["k_relax3d<rhs=0> colour pass", "k_residual3d", "k_restrict_sep", "k_interp_add_tiled",
+    names = ["k_relax3d<rhs=0> colour pass", "k_residual3d", "k_restrict_direct", "k_interp_add_zt",
              "update_u (k_diff_partial+final)", "halo exchange (one NCCL group)", "levels >= 2 of one V-cycle",
              "level 1 of one V-cycle (2 brackets per cycle)"]
     bytes_per_pt = [8.0, 16.0, 9.0, 17.0, 24.0, 0.0, 0.0, 0.0]  # SURVEY 8d / DESIGN.md (level 0, rhs == 0)
@@ -215,7 +215,7 @@ def kernel_report(lib, npoints, dev_ms):
 
 # dram__bytes_read.sum + dram__bytes_write.sum per launch of the finest-level colour pass from the committed
 # `ncu --set full` capture (profiles/), keyed by points per launch
-NCU_TRAFFIC_BYTES = {513 ** 3: 560.1e6 + 505.3e6}  # profiles/r01_ncu_full_finest_level_kernels_513.json
+NCU_TRAFFIC_BYTES = {513 ** 3: 562.7e6 + 497.0e6}  # profiles/r01_ncu_full_finest_level_kernels_513.json
 
 
 def run_ours(args, rank, world):

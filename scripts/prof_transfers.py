@@ -1,5 +1,6 @@
 """Profiling target: restriction and prolongation of the finest level pair of an n^3 hierarchy (MG_HANDLE seam)."""
 import os
+os.environ.setdefault("NDSM_B200_HANDLE_RHS0", "0")  # rhs == 0 specialisations, as on the finest level of the solves
 import sys
 
 import numpy as np
@@ -21,4 +22,5 @@ for _ in range(3):
     h.lib.ndsm_b200_mg_interp_add(h.h, 1)
     h.lib.ndsm_b200_mg_residual(h.h, 0)
     h.lib.ndsm_b200_mg_relax(h.h, 0, 1)
+    h.update_u(r, r)
 print("done")
