@@ -95,6 +95,15 @@ int ndsm_b200_poisson_solve(int ndim, const int* nshape, const char* copt, int m
                             int nmaxex, int du_max, double vc_tol, double ex_tol, const double* x,
                             const double* y, const double* z, double* u, const double* rhs,
                             double* du_last, int* ncycles);
+/* The same 3D solve on z-slabs, one process per GPU (after ndsm_b200_dist_init): rank r passes planes [k0,k1) =
+ * ndsm_b200_slab_range(nz, world, r) of u (in: initial guess incl. Dirichlet data, out: solution) and of rhs
+ * (NULL == 0) as dense (k1-k0, ny, nx) DEVICE arrays; nshape3 is the global shape.  Every rank returns the same
+ * ierr / du_last / ncycles.  The finest level must be large enough to be partitioned (NDSM_B200_ERR_ARG otherwise);
+ * pure-Neumann problems (all six copt == 'N') are not supported on partitioned levels yet.  Bit-identical to
+ * ndsm_b200_poisson_solve with the max metric (BASELINE config 5: weak scaling 1025 x 1025 x (128 G + 1)). */
+int ndsm_b200_poisson_solve_rank(const int* nshape3, const char* copt, int ms, int ncycles_max, int nmaxex, int du_max,
+                                 double vc_tol, double ex_tol, const double* x, const double* y, const double* z,
+                                 double* d_u_slab, const double* d_rhs_slab, double* du_last, int* ncycles);
 
 /* ------------------------------------------------------------------------------------------
  * 3. MG_HANDLE operator seam (ndsm_multigrid_core.f90:86-136,165,278,341): the GPU smoother,

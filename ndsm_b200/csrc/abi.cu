@@ -576,9 +576,121 @@ int ndsm_b200_mg_update_u(ndsm_b200_mg* h, const double* u_old_dense, double* u_
   HANDLE_END("ndsm_b200_mg_update_u")
 }
 
+}  // extern "C"
+
+// solve_poisson_bvp (ndsm_poisson.f90:63) for a 3D grid partitioned into z-slabs: du[s] / drhs[s] point at the dense
+// device planes [k0,k1) of local slab s (u in/out; drhs[s] may be nullptr for rhs == 0).  The finest level must
+// be partitioned (grids below the replication threshold belong on the single-GPU entry).
+static int poisson_slabs(const int* nshape, const char* copt, int ms, int ncycles_max, int nmaxex, int du_max,
+                         double vc_tol, double ex_tol, const double* x, const double* y, const double* z, Comm* comm,
+                         const std::vector<double*>& du, const std::vector<const double*>& drhs, double* du_last,
+                         int* ncycles, cudaStream_t st) {
+  const double* mesh[3] = {x, y, z};
+  MG mg(3, nshape, -1, mesh, st, comm);
+  mg.set_options(ms, ex_tol, copt, du_max != 0, nmaxex);
+  const int ns = mg.nslabs();
+  if (mg.plan().ndist == 0 || (int)du.size() != ns || (int)drhs.size() != ns) {
+    error_msg("grid too small to be partitioned over the ranks (see NDSM_SLAB_MIN_POINTS / NDSM_SLAB_MIN_PLANES)",
+              "ndsm_b200_poisson_solve_rank", "NDSM_B200_ERR_ARG");
+    return NDSM_B200_ERR_ARG;
+  }
+  std::vector<std::unique_ptr<DBuf>> ubuf(ns), rbuf(ns);
+  std::vector<double*> up(ns), rp(ns, nullptr);
+  std::vector<const double*> rcp(ns, nullptr);
+  bool has_rhs = false;
+  for (int s = 0; s < ns; ++s) {
+    const Level& L0 = mg.level(0, s);
+    const size_t n = mg.level_doubles(0, s);
+    ubuf[s].reset(new DBuf(n));
+    CUDA_CHECK(cudaMemsetAsync(ubuf[s]->p, 0, n * sizeof(double), st));
+    up[s] = ubuf[s]->p + (i64)L0.H * L0.g.ps;  // local plane 0 behind the lower halo
+    split_from_dense(du[s], up[s], L0.g, 0.0, st);
+    if (drhs[s]) {
+      has_rhs = true;
+      rbuf[s].reset(new DBuf(n));
+      CUDA_CHECK(cudaMemsetAsync(rbuf[s]->p, 0, n * sizeof(double), st));
+      rp[s] = rbuf[s]->p + (i64)L0.H * L0.g.ps;
+      split_from_dense(drhs[s], rp[s], L0.g, 0.0, st);
+      rcp[s] = rp[s];
+    }
+  }
+  if (has_rhs) {  // the extended colour passes read rhs in the halo planes: fetch them once
+    for (int s = 0; s < ns; ++s)
+      if (!rp[s]) throw NdsmError(NDSM_B200_ERR_ARG);  // rhs must be given for every local slab or for none
+    mg.exchange(0, 0, 3, mg.plan().halo, &rp);
+    mg.set_level0_rhs_halo_valid(true);
+  }
+  SolveTrace tr;
+  g_report = Report();
+  const int ierr = mg.solve(up, rcp, vc_tol, ncycles_max, du_last, &tr);
+  g_report.solves[0] = tr;
+  g_report.ndist = mg.plan().ndist;
+  if (ncycles) *ncycles = (int)tr.du.size();
+  for (int s = 0; s < ns; ++s) dense_from_split(up[s], du[s], mg.level(0, s).g, st);
+  CUDA_CHECK(cudaStreamSynchronize(st));
+  return ierr;
+}
+
+static std::unique_ptr<Comm> g_dist;
+static std::unique_ptr<Comm> g_dist_group;  // my group of the hybrid decomposition (>= 3 ranks)
+
+extern "C" {
+
+int ndsm_b200_poisson_solve_rank(const int* nshape3, const char* copt, int ms, int ncycles_max, int nmaxex, int du_max,
+                                 double vc_tol, double ex_tol, const double* x, const double* y, const double* z,
+                                 double* d_u_slab, const double* d_rhs_slab, double* du_last, int* ncycles) {
+  static const char* SUB = "ndsm_b200_poisson_solve_rank";
+  if (!nshape3 || !copt || !x || !y || !z || !d_u_slab) return NDSM_B200_ERR_ARG;
+  if (int e = ensure_device(SUB)) return e;
+  if (!g_dist || g_dist->world() < 2) {
+    error_msg("ndsm_b200_dist_init with >= 2 ranks must come first", SUB, "NDSM_B200_ERR_ARG");
+    return NDSM_B200_ERR_ARG;
+  }
+  try {
+    return poisson_slabs(nshape3, copt, ms, ncycles_max, nmaxex, du_max, vc_tol, ex_tol, x, y, z, g_dist.get(),
+                         std::vector<double*>{d_u_slab}, std::vector<const double*>{d_rhs_slab}, du_last, ncycles,
+                         g_stream);
+  } catch (const NdsmError& e) {
+    return fail(e, SUB);
+  }
+}
+
 int ndsm_b200_poisson_solve(int ndim, const int* nshape, const char* copt, int ms, int ncycles_max, int nmaxex,
                             int du_max, double vc_tol, double ex_tol, const double* x, const double* y,
                             const double* z, double* u, const double* rhs, double* du_last, int* ncycles) {
+  static const char* SUB = "ndsm_b200_poisson_solve";
+  int vworld = 1;
+  if (const char* e = getenv("NDSM_VIRTUAL_SLABS")) vworld = atoi(e);
+  if (ndim == 3 && vworld > 1 && nshape && copt && x && y && z && u) {
+    // the z-slab path with virtual ranks on this one device (tests; same arithmetic as the multi-GPU entry)
+    if (int e = ensure_device(SUB)) return e;
+    try {
+      const int nx = nshape[0], ny = nshape[1], nz = nshape[2];
+      const size_t N = (size_t)nx * ny * nz;
+      cudaStream_t st = g_stream;
+      DBuf dU(N), dR(rhs ? N : 1);
+      CUDA_CHECK(cudaMemcpyAsync(dU.p, u, N * sizeof(double), cudaMemcpyHostToDevice, st));
+      if (rhs) CUDA_CHECK(cudaMemcpyAsync(dR.p, rhs, N * sizeof(double), cudaMemcpyHostToDevice, st));
+      std::unique_ptr<Comm> comm = make_virtual_comm(vworld);
+      std::vector<double*> du(vworld);
+      std::vector<const double*> dr(vworld, nullptr);
+      for (int r = 0; r < vworld; ++r) {
+        int k0 = 0, k1 = 0;
+        output_range(nz, vworld, r, &k0, &k1);
+        du[r] = dU.p + (size_t)k0 * nx * ny;
+        if (rhs) dr[r] = dR.p + (size_t)k0 * nx * ny;
+      }
+      const int ierr = poisson_slabs(nshape, copt, ms, ncycles_max, nmaxex, du_max, vc_tol, ex_tol, x, y, z, comm.get(),
+                                     du, dr, du_last, ncycles, st);
+      if (ierr == 0 || ierr == 1) {
+        CUDA_CHECK(cudaMemcpyAsync(u, dU.p, N * sizeof(double), cudaMemcpyDeviceToHost, st));
+        CUDA_CHECK(cudaStreamSynchronize(st));
+      }
+      return ierr;
+    } catch (const NdsmError& e) {
+      return fail(e, SUB);
+    }
+  }
   ndsm_b200_mg* h = ndsm_b200_new_mg_handle(ndim, nshape, -1, x, y, z, du_max, nmaxex);
   if (!h) return NDSM_B200_ERR_CUDA;
   int rc = ndsm_b200_mg_set_options(h, ms, ex_tol, copt);
@@ -676,8 +788,6 @@ int ndsm_b200_flux_curl(const int* nshape4, int flxcrl, const double* x, const d
 // ------------------------------------------------------------------------------------------
 // multi-GPU: one process per GPU, z-slabs over NCCL
 // ------------------------------------------------------------------------------------------
-static std::unique_ptr<Comm> g_dist;
-static std::unique_ptr<Comm> g_dist_group;  // my group of the hybrid decomposition (>= 3 ranks)
 
 int ndsm_b200_dist_unique_id(void* out128) {
   if (!out128) return NDSM_B200_ERR_ARG;

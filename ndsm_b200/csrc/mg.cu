@@ -522,7 +522,7 @@ void MG::relax(int g) {
         need_halo_colour(g, 1 - colour);
         // extended passes read rhs in the halo planes: exchanged for g > 0, identically zero for the
         // vector-potential solves on g == 0; a caller-supplied level-0 rhs has no trusted halo
-        const bool rhs_halo_ok = (g > 0) || rhs0_[0] == nullptr;
+        const bool rhs_halo_ok = (g > 0) || rhs0_[0] == nullptr || rhs0_halo_ok_;
         ext = rhs_halo_ok ? valid_[g][1 - colour] - 1 : 0;
       }
       // each colour pass is timed separately when profiling (PROF_RELAX0 = one k_relax3d launch on level 0)
@@ -841,6 +841,7 @@ int MG::solve_end(double* du_last) {
   }
   if (ss_.tr) ss_.tr->ierr = ierr;
   bool freed = false;
+  rhs0_halo_ok_ = false;
   for (size_t s = 0; s < slabs_.size(); ++s) {
     rhs0_[s] = nullptr;
     if (ss_.zero_rhs[s]) {

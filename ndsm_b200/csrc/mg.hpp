@@ -151,6 +151,8 @@ class MG {
             double* du_last, SolveTrace* tr);
   int solve(double* u, const double* rhs, double vc_tol, int nmax, double* du_last, SolveTrace* tr);
   void set_level0_rhs(const double* rhs, int s = 0) { rhs0_[s] = rhs; }
+  // the caller filled the halo planes of its level-0 rhs slabs (enables communication-avoiding smoothing there)
+  void set_level0_rhs_halo_valid(bool ok) { rhs0_halo_ok_ = ok; }
   // the same solve as a state machine (one outstanding solve per MG instance)
   void solve_begin(const std::vector<double*>& u, const std::vector<const double*>& rhs, double vc_tol, int nmax,
                    SolveTrace* tr);
@@ -183,6 +185,7 @@ class MG {
   bool all_neumann_ = false;
   int first_colour_ = 0;
   std::vector<const double*> rhs0_;  // level-0 rhs per slab for the current solve (nullptr == 0)
+  bool rhs0_halo_ok_ = false;        // halo planes of a caller-supplied level-0 rhs hold the neighbours' values
   // communication-avoiding smoothing on partitioned levels: valid_[g][c] = number of halo planes (each side)
   // that currently hold up-to-date values of colour c.  A colour pass may also update `e` halo planes if the
   // other colour is valid to depth e+1, so one 4-plane exchange feeds four passes (bit-identical values).

@@ -83,3 +83,37 @@ def vector_potential_rank(x, y, z, faces, niterex_max=10000, ncycles_max=1024, e
         rc = lib.ndsm_b200_vector_solve_rank(_ptr(nshape), _ptr(ioptc), _ptr(ropt), _ptr(x), _ptr(y), _ptr(z), fp,
                                              int(faces_on_device), ctypes.c_void_p(int(A)), ctypes.c_void_p(int(B)), 1)
     return rc, A, B, (k0, k1)
+
+
+def poisson_solve(x, y, z, u, rhs=None, copt="NDDNDD", ms=5, ncycles_max=1024, niterex_max=10000, mean=False,
+                  vc_tol=1e-10, ex_tol=1e-13):
+    """solve_poisson_bvp (ndsm_poisson.f90:63) on full host arrays u, rhs of shape (nz,ny,nx) through
+    ndsm_b200_poisson_solve (single GPU; with NDSM_VIRTUAL_SLABS=G the z-slab path with G virtual ranks).
+    Returns (ierr, u, du_last, ncycles)."""
+    lib = load_library()
+    x, y, z = (np.ascontiguousarray(a, dtype=np.float64) for a in (x, y, z))
+    u = np.array(u, dtype=np.float64, order="C")
+    nshape = np.array([x.size, y.size, z.size], dtype=np.intc)
+    r = None if rhs is None else np.ascontiguousarray(rhs, dtype=np.float64)
+    du, nc = ctypes.c_double(0), ctypes.c_int(0)
+    ierr = lib.ndsm_b200_poisson_solve(3, _ptr(nshape), copt.encode(), ms, ncycles_max, niterex_max, 0 if mean else 1,
+                                       vc_tol, ex_tol, _ptr(x), _ptr(y), _ptr(z), _ptr(u),
+                                       None if r is None else _ptr(r), ctypes.byref(du), ctypes.byref(nc))
+    return ierr, u, du.value, nc.value
+
+
+def poisson_solve_rank(x, y, z, u_slab_ptr, rhs_slab_ptr=None, copt="NDDNDD", ms=5, ncycles_max=1024,
+                       niterex_max=10000, mean=False, vc_tol=1e-10, ex_tol=1e-13):
+    """This rank's z-slab of a 3D scalar Poisson solve (ndsm_b200_poisson_solve_rank).  u_slab_ptr / rhs_slab_ptr
+    are DEVICE pointers to the dense planes [k0,k1) = slab_range(nz, world, rank) (u in/out, rhs may be None).
+    Returns (ierr, du_last, ncycles)."""
+    lib = load_library()
+    x, y, z = (np.ascontiguousarray(a, dtype=np.float64) for a in (x, y, z))
+    nshape = np.array([x.size, y.size, z.size], dtype=np.intc)
+    du, nc = ctypes.c_double(0), ctypes.c_int(0)
+    ierr = lib.ndsm_b200_poisson_solve_rank(_ptr(nshape), copt.encode(), ms, ncycles_max, niterex_max,
+                                            0 if mean else 1, vc_tol, ex_tol, _ptr(x), _ptr(y), _ptr(z),
+                                            ctypes.c_void_p(int(u_slab_ptr)),
+                                            None if rhs_slab_ptr is None else ctypes.c_void_p(int(rhs_slab_ptr)),
+                                            ctypes.byref(du), ctypes.byref(nc))
+    return ierr, du.value, nc.value

@@ -40,6 +40,22 @@ def main():
             else:  # max metric: the slab path is bit-identical to the single-GPU path
                 assert np.array_equal(A, Ar[:, k0:k1]), np.abs(A - Ar[:, k0:k1]).max()
                 assert np.array_equal(B, Br[:, k0:k1]), np.abs(B - Br[:, k0:k1]).max()
+    # scalar Poisson solve (BASELINE config 5) on z-slabs over the world communicator vs the single-GPU entry
+    nx, ny, nz = 48, 40, 24 * world
+    x = np.linspace(0, 1, nx)
+    dx = x[1] - x[0]
+    y, z = np.arange(ny) * dx, np.arange(nz) * dx
+    Z, Y, X = np.meshgrid(z, y, x, indexing="ij")
+    uex = np.cos(np.pi * X) * np.sin(np.pi * Y / y[-1]) * np.sin(np.pi * Z / z[-1])
+    rhs = -(np.pi ** 2) * (1 + 1 / y[-1] ** 2 + 1 / z[-1] ** 2) * uex
+    k0, k1 = ndist.slab_range(nz, world, rank)
+    du_s = torch.zeros((k1 - k0, ny, nx), dtype=torch.float64, device="cuda")
+    dr_s = torch.from_numpy(np.ascontiguousarray(rhs[k0:k1])).cuda()
+    ierr, du, nc = ndist.poisson_solve_rank(x, y, z, du_s.data_ptr(), dr_s.data_ptr())
+    assert lib.ndsm_b200_last_partitioned_levels() > 0
+    rerr, ur, rdu, rnc = ndist.poisson_solve(x, y, z, np.zeros_like(uex), rhs)
+    assert ierr == rerr == 0 and nc == rnc and du == rdu, (ierr, rerr, nc, rnc, du, rdu)
+    assert np.array_equal(du_s.cpu().numpy(), ur[k0:k1])
     dist.barrier()
     print("MULTI_GPU_OK %d of %d" % (rank, world), flush=True)
     from ndsm_b200 import load_library

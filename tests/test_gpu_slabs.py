@@ -89,3 +89,63 @@ def test_virtual_slabs_with_initial_guess(gpu_lib, slab_env):
     from ndsm_b200 import load_library
     assert load_library().ndsm_b200_last_partitioned_levels() > 0
     assert np.array_equal(got[1], ref[1]) and np.array_equal(got[2], ref[2])
+
+
+def poisson_case(shape):
+    nx, ny, nz = shape
+    x = np.linspace(0, 1, nx)
+    dx = x[1] - x[0]
+    y, z = np.arange(ny) * dx, np.arange(nz) * dx
+    Z, Y, X = np.meshgrid(z, y, x, indexing="ij")
+    uex = np.cos(np.pi * X) * np.sin(np.pi * Y / y[-1]) * np.sin(np.pi * Z / z[-1])
+    rhs = -(np.pi ** 2) * (1 + 1 / y[-1] ** 2 + 1 / z[-1] ** 2) * uex
+    return x, y, z, uex, rhs
+
+
+@pytest.mark.parametrize("world,mean", [(2, False), (3, False), (4, True)])
+def test_poisson_virtual_slabs_reproduce_single_slab(gpu_lib, slab_env, world, mean):
+    """BASELINE config 5 (scalar Poisson, copt NDDNDD, u = cos sin sin) through the z-slab path: caller-supplied rhs
+    with exchanged halo planes, communication-avoiding smoothing on level 0."""
+    from ndsm_b200 import dist as ndist
+    x, y, z, uex, rhs = poisson_case((48, 40, 72))
+    os.environ["NDSM_VIRTUAL_SLABS"] = "1"
+    ref = ndist.poisson_solve(x, y, z, np.zeros_like(uex), rhs, mean=mean)
+    os.environ["NDSM_VIRTUAL_SLABS"] = str(world)
+    os.environ["NDSM_SLAB_MIN_PLANES"] = "6"
+    os.environ["NDSM_SLAB_MIN_POINTS"] = "0"
+    got = ndist.poisson_solve(x, y, z, np.zeros_like(uex), rhs, mean=mean)
+    assert gpu_lib.ndsm_b200_last_partitioned_levels() > 0
+    assert got[0] == ref[0] == 0
+    assert np.abs(ref[1] - uex).max() < 2e-2                       # O(h^2)
+    if mean:
+        assert abs(got[3] - ref[3]) <= 1 and rel_err(got[1], ref[1]) <= 1e-12
+    else:
+        assert got[3] == ref[3] and got[2] == ref[2]
+        assert np.array_equal(got[1], ref[1])
+
+
+def test_poisson_virtual_slabs_zero_rhs_and_guess(gpu_lib, slab_env):
+    from ndsm_b200 import dist as ndist
+    x, y, z, uex, _ = poisson_case((40, 36, 60))
+    u0 = np.zeros_like(uex)
+    u0[:, :, 0] = 0.0
+    u0[0], u0[-1], u0[:, 0], u0[:, -1] = 1.0, -0.5, 0.25, 2.0      # Dirichlet data on the D faces (copt NDDNDD)
+    os.environ["NDSM_VIRTUAL_SLABS"] = "1"
+    ref = ndist.poisson_solve(x, y, z, u0, None)
+    os.environ["NDSM_VIRTUAL_SLABS"] = "3"
+    os.environ["NDSM_SLAB_MIN_PLANES"] = "6"
+    os.environ["NDSM_SLAB_MIN_POINTS"] = "0"
+    got = ndist.poisson_solve(x, y, z, u0, None)
+    assert gpu_lib.ndsm_b200_last_partitioned_levels() > 0
+    assert got[0] == ref[0] == 0 and got[3] == ref[3]
+    assert np.array_equal(got[1], ref[1])
+
+
+def test_poisson_slabs_refuse_unpartitionable_grid(gpu_lib, slab_env, capfd):
+    from ndsm_b200 import dist as ndist
+    x, y, z, uex, rhs = poisson_case((24, 24, 24))
+    os.environ["NDSM_VIRTUAL_SLABS"] = "2"
+    os.environ.pop("NDSM_SLAB_MIN_POINTS", None)                   # production threshold: 24^3 stays replicated
+    ierr = ndist.poisson_solve(x, y, z, np.zeros_like(uex), rhs)[0]
+    assert ierr == 5                                               # NDSM_B200_ERR_ARG
+    assert "too small to be partitioned" in capfd.readouterr().err
