@@ -6,14 +6,33 @@ import pytest
 
 from conftest import aniso_mesh
 
+import os
+
 HALO = 6
+
+
+@pytest.fixture(params=[None, 4, 10])
+def halo(request):
+    """Halo depth: the compiled default (6 planes) or the NDSM_HALO_PLANES override (read at planning time)."""
+    saved = os.environ.get("NDSM_HALO_PLANES")
+    if request.param is None:
+        os.environ.pop("NDSM_HALO_PLANES", None)
+    else:
+        os.environ["NDSM_HALO_PLANES"] = str(request.param)
+    yield HALO if request.param is None else request.param
+    if saved is None:
+        os.environ.pop("NDSM_HALO_PLANES", None)
+    else:
+        os.environ["NDSM_HALO_PLANES"] = saved
 
 
 @pytest.mark.parametrize("shape,world,min_planes", [((513, 513, 513), 8, 16), ((513, 513, 513), 2, 16),
                                                     ((1025, 1025, 257), 8, 16), ((129, 129, 129), 4, 16),
                                                     ((44, 44, 44), 3, 4), ((40, 33, 52), 2, 4), ((257, 257, 257), 8, 8)])
-def test_partition_tiles_and_respects_halo(shape, world, min_planes):
+def test_partition_tiles_and_respects_halo(shape, world, min_planes, halo):
     from ndsm_b200.mg import Plan
+    HALO = halo
+    min_planes = max(min_planes, HALO)  # a slab must be able to fill its neighbour's halo
     p = Plan(aniso_mesh(shape))
     ndist, zs = p.slab_partition(world, min_planes)
     assert 0 <= ndist <= p.ngrids - 1  # the coarsest level is never partitioned
