@@ -52,7 +52,6 @@ int vector_solve_core(const int* nshape, const long long* iopt, const double* ro
                       cudaStream_t st, Report& rep, BcCapture* cap, bool stop_after_bc, const CoreHooks* hooks,
                       const Hybrid* hyb) {
   const int nx = nshape[0], ny = nshape[1], nz = nshape[2];
-  const i64 N = (i64)nx * ny * nz;
   const double* mesh[3] = {x, y, z};
   const bool use_du_max = (iopt[IOPT_DUMAX] == IOPT_TRUE);
   double Lq[3], dq[3];
