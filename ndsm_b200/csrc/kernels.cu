@@ -736,6 +736,107 @@ void relax2d_half(double* u, const double* rhs, const Grid& g, const Bounds& b, 
   LAUNCHED();
 }
 
+// ---- 2D pure-Neumann sweeps with the mean subtraction folded into the colour passes (opt-in:
+// NDSM_B200_FUSED_MEAN=1; the chi solves are launch-rate-bound and this halves their launches per sweep).
+// The reference subtracts the mean after every sweep (ndsm_poisson.f90:538-541, mean: ndsm_multigrid_core.f90:1199).
+// Here the red pass of sweep k+1 reads  black_k - mean_k  on the fly (the same subtraction, so the same bits as
+// storing it first), red_k never needs the subtraction because it is overwritten without being read, both passes
+// emit block partial sums of what they wrote, the last block of the black pass (atomic ticket) adds them up in a
+// fixed order, and one k_sub_scalar after the last sweep of the sequence applies the pending mean to both colours.
+// Only the summation order of the mean differs from subtract_mean() (rounding level, as between any two OpenMP runs
+// of the reference).  part: [2][nb] block sums (red pass, black pass), fm: [0] = mean, ticket: zero-initialised.
+template <bool SUB_IN, bool FINAL_REDUCE>
+__global__ void __launch_bounds__(256)
+k_relax2d_fm(double* __restrict__ u, const double* __restrict__ rhs, const Grid g, const Bounds b, const int colour,
+             const double wx, const double wy, const double w0, double* __restrict__ part_mine,
+             const double* __restrict__ part_other, double* __restrict__ fm, unsigned* __restrict__ ticket,
+             const double count) {
+  __shared__ double red[40];
+  __shared__ bool last;
+  const int t = blockIdx.x * 256 + threadIdx.x;
+  const int j = t / g.hp;
+  const int m = t - j * g.hp;
+  double val = 0.0;
+  if (j < g.ny && m < g.mcnt) {
+    const int s = (j + colour) & 1;
+    const int i = 2 * m + s;
+    if (i < g.nx && !dirichlet2d(i, j, g, b)) {
+      double* __restrict__ own = u + (i64)colour * g.cs;
+      const double* __restrict__ opp = u + (i64)(1 - colour) * g.cs;
+      const i64 jo = (i64)j * g.hp + m;
+      const i64 xm = jo - 1 + s, xp = jo + s;
+      const i64 x1 = (i == 0) ? xp : xm, x2 = (i == g.nx - 1) ? xm : xp;
+      const i64 ym = jo - g.hp, yp = jo + g.hp;
+      const i64 y1 = (j == 0) ? yp : ym, y2 = (j == g.ny - 1) ? ym : yp;
+      double a1 = opp[x1], a2 = opp[x2], a3 = opp[y1], a4 = opp[y2];
+      if (SUB_IN) {  // pending mean of the previous sweep
+        const double mp = fm[0];
+        a1 = a1 - mp; a2 = a2 - mp; a3 = a3 - mp; a4 = a4 - mp;
+      }
+      double un = a1 * wx + a2 * wx;  // (:613)
+      un = (un + a3 * wy) + a4 * wy;
+      val = (un - rhs[(i64)colour * g.cs + jo]) * w0;  // (:615)
+      own[jo] = val;
+    }
+  }
+  const double bs = block_sum(val, red);
+  if (threadIdx.x == 0) part_mine[blockIdx.x] = bs;
+  if (FINAL_REDUCE) {
+    __threadfence();
+    if (threadIdx.x == 0) last = (atomicAdd(ticket, 1u) == gridDim.x - 1);
+    __syncthreads();
+    if (last) {  // every block of this pass (and, by stream order, of the other colour's pass) has published its sum
+      double tsum = 0.0;
+      for (int e = threadIdx.x; e < (int)gridDim.x; e += 256) tsum += __ldcg(part_other + e);
+      for (int e = threadIdx.x; e < (int)gridDim.x; e += 256) tsum += __ldcg(part_mine + e);
+      tsum = block_sum(tsum, red);
+      if (threadIdx.x == 0) {
+        fm[0] = tsum / count;
+        *ticket = 0u;
+      }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256)
+k_sub_scalar2d(double* __restrict__ u, const Grid g, const double* __restrict__ fm) {
+  const int t = blockIdx.x * 256 + threadIdx.x;
+  const int j = t / g.hp;
+  const int m = t - j * g.hp;
+  if (j >= g.ny || m >= g.mcnt) return;
+  const int colour = blockIdx.y;
+  const int i = 2 * m + ((j + colour) & 1);
+  if (i >= g.nx) return;
+  const i64 o = (i64)colour * g.cs + (i64)j * g.hp + m;
+  u[o] = u[o] - fm[0];
+}
+
+size_t relax2d_fused_mean_scratch(const Grid& g) { return 2 * (size_t)cdiv((i64)g.hp * g.ny, 256) + 8; }
+
+// nsweeps red+black sweeps of a pure-Neumann 2D level, each followed by the mean subtraction (2 n + 1 launches)
+void relax2d_fused_mean(double* u, const double* rhs, const Grid& g, const Bounds& b, const Weights& w, int nsweeps,
+                        double* scratch, cudaStream_t st) {
+  if (nsweeps <= 0) return;
+  const int nb = cdiv((i64)g.hp * g.ny, 256);
+  double* part_r = scratch;
+  double* part_b = scratch + nb;
+  double* fm = scratch + 2 * (size_t)nb;                       // [0] mean, [1] ticket storage
+  unsigned* ticket = reinterpret_cast<unsigned*>(fm + 1);      // zero from the arena memset, reset by the kernel
+  const double count = (double)((i64)g.nx * g.ny);
+  for (int k = 0; k < nsweeps; ++k) {
+    if (k == 0)
+      k_relax2d_fm<false, false><<<nb, 256, 0, st>>>(u, rhs, g, b, 0, w.wx, w.wy, w.w1, part_r, part_b, fm, ticket, count);
+    else
+      k_relax2d_fm<true, false><<<nb, 256, 0, st>>>(u, rhs, g, b, 0, w.wx, w.wy, w.w1, part_r, part_b, fm, ticket, count);
+    LAUNCHED();
+    k_relax2d_fm<false, true><<<nb, 256, 0, st>>>(u, rhs, g, b, 1, w.wx, w.wy, w.w1, part_b, part_r, fm, ticket, count);
+    LAUNCHED();
+  }
+  dim3 grid(nb, 2);
+  k_sub_scalar2d<<<grid, 256, 0, st>>>(u, g, fm);
+  LAUNCHED();
+}
+
 __global__ void __launch_bounds__(256)
 k_residual2d(const double* __restrict__ u, const double* __restrict__ rhs, double* __restrict__ r, const Grid g,
              const Bounds b, const double wx, const double wy) {

@@ -113,6 +113,11 @@ void vcycle_small(int ndim, const double* rhs_in, double* u_out, const Grid& g0,
 // K6: out[0] = max|a-b|, out[1] = sum|a-b| over owned planes; then a := b  (update_u: a=caller's u, b=V-cycled u;
 // ndsm_multigrid_core.f90:1077-1122).  With copy=false it is du_metrics (:808-853) and leaves a untouched.
 void diff_reduce(double* a, const double* b, const Grid& g, bool copy, double* scratch, double* out, cudaStream_t st);
+// nsweeps pure-Neumann 2D sweeps with the per-sweep mean subtraction folded into the passes (opt-in path of the
+// chi solves, see kernels.cu); scratch: relax2d_fused_mean_scratch(g) doubles, zero-initialised once
+size_t relax2d_fused_mean_scratch(const Grid& g);
+void relax2d_fused_mean(double* u, const double* rhs, const Grid& g, const Bounds& b, const Weights& w, int nsweeps,
+                        double* scratch, cudaStream_t st);
 size_t reduce_scratch_doubles();
 void solve_exact_prepare();  // one-time function attributes (call before stream capture)
 

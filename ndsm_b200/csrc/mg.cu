@@ -291,12 +291,16 @@ MG::MG(int ndim, const int* shape, int ngrids, const double* const* mesh, cudaSt
   }
   const i64 off_sav = take(2 * hl[ngrids - 1].g.cs);
   const i64 off_scr = take((i64)reduce_scratch_doubles());
+  // opt-in: pure-Neumann 2D sweeps with the mean subtraction folded into the passes (read per hierarchy)
+  const bool fused_mean = ndim == 2 && getenv("NDSM_B200_FUSED_MEAN") && atoi(getenv("NDSM_B200_FUSED_MEAN")) != 0;
+  const i64 off_fm = fused_mean ? take((i64)relax2d_fused_mean_scratch(hl[0].g)) : -1;
   const i64 off_all = take(2 * (i64)world + 8);
   const i64 off_info = take(8);
   shared_ = static_cast<double*>(pool_alloc((size_t)total * sizeof(double)));
   CUDA_CHECK(cudaMemsetAsync(shared_, 0, (size_t)total * sizeof(double), st_));
   usav_ = shared_ + off_sav;
   scratch_ = shared_ + off_scr;
+  fm_scratch_ = (off_fm >= 0) ? shared_ + off_fm : nullptr;
   d_all_ = shared_ + off_all;
   d_info_ = reinterpret_cast<int*>(shared_ + off_info);
   h_out_ = static_cast<double*>(pool_alloc_host((2 * (size_t)world + 8) * sizeof(double)));
@@ -546,6 +550,15 @@ void MG::relax(int g) {
   }
 }
 
+void MG::relax_sweeps(int g, int n) {
+  if (fm_scratch_ && ndim_ == 2 && all_neumann_ && n > 0) {
+    Level& L = slabs_[0].lv[g];
+    relax2d_fused_mean(L.u, (g == 0) ? rhs0_[0] : L.rhs, L.g, L.b, L.w, n, fm_scratch_, st_);
+    return;
+  }
+  for (int s = 0; s < n; ++s) relax(g);
+}
+
 // the other colour must be valid at least one plane deep before a pass; refresh both colours when it is not
 void MG::need_halo_colour(int g, int colour) {
   if (valid_[g][colour] >= 1) return;
@@ -680,7 +693,7 @@ void MG::v_cycle() {  // ndsm_multigrid_core.f90:341-377
   for (int g = 0; g < gend; ++g) {  // fine_to_coarse :482-560
     if (pr && g == 1) prof_begin(PROF_LEVEL1, st_);
     if (pr && g == 2) { prof_end(PROF_LEVEL1, st_); prof_begin(PROF_TAIL, st_); }
-    for (int s = 0; s < ms_; ++s) relax(g);
+    relax_sweeps(g, ms_);
     residual(g);
     restrict_to(g);
   }
@@ -695,12 +708,11 @@ void MG::v_cycle() {  // ndsm_multigrid_core.f90:341-377
     solve_exact(ng - 1);
   }
   for (int c = cstart; c >= 1; --c) {  // coarse_to_fine :593-684
-    if (!(ls > 0 && c == ls))
-      for (int s = 0; s < ms_; ++s) relax(c);
+    if (!(ls > 0 && c == ls)) relax_sweeps(c, ms_);
     if (pr && c == 2) { prof_end(PROF_TAIL, st_); prof_begin(PROF_LEVEL1, st_); }
     if (pr && c == 1) prof_end(PROF_LEVEL1, st_);
     interp_add_from(c);
-    for (int s = 0; s < ms_; ++s) relax(c - 1);
+    relax_sweeps(c - 1, ms_);
   }
 }
 

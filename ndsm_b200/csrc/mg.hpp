@@ -137,6 +137,7 @@ class MG {
 
   // operators on a level (enqueue only)
   void relax(int g);            // one full red+black sweep (+ pure-Neumann mean subtraction)
+  void relax_sweeps(int g, int n);  // n sweeps; 2D pure-Neumann levels may fold the mean subtraction into the passes
   void residual(int g);         // r_scratch <- rhs - L u
   void restrict_to(int g);      // rhs[g+1] <- R r_scratch (fine level g); u[g+1] <- 0
   void interp_add_from(int c);  // u[c-1] += P u[c]
@@ -198,6 +199,7 @@ class MG {
   double* shared_ = nullptr;         // replicated levels, usav, reduction scratch, results
   double* usav_ = nullptr;           // coarsest u_sav for the fallback solve_exact
   double* scratch_ = nullptr;        // reduction scratch
+  double* fm_scratch_ = nullptr;     // fused-mean 2D sweeps (NDSM_B200_FUSED_MEAN=1), nullptr when off
   double* d_all_ = nullptr;          // [2*world] gathered (max,sum) pairs
   int* d_info_ = nullptr;            // [2] coarsest-solve iterations / converged
   double* h_out_ = nullptr;          // pinned: [2*world] pairs + 2 ints

@@ -5,6 +5,8 @@ restriction and prolongation kernels keep the reference's evaluation order and a
 -fmad=false, so they are expected to be BIT-IDENTICAL to the oracle; operations whose summation
 order is unspecified in the reference (OpenMP reductions: mean, sum of |du|) are compared at 1e-13.
 """
+import os
+
 import numpy as np
 import pytest
 
@@ -358,3 +360,32 @@ def test_poisson_solve_2d_pure_neumann_matches_oracle(gpu_lib, oracle):
     assert abs(nc - onc) <= 1
     assert rel_err(u, ou) <= 1e-10
     h.close()
+
+
+@pytest.mark.skipif(os.environ.get("NDSM_RUN_EXPERIMENTAL") != "1",
+                    reason="opt-in path, not yet validated on hardware: set NDSM_RUN_EXPERIMENTAL=1")
+def test_fused_mean_2d_sweeps_match_default_path(gpu_lib, tmp_path):
+    """NDSM_B200_FUSED_MEAN=1 folds the pure-Neumann mean subtraction of the chi solves into the colour passes
+    (2 launches per sweep instead of 4).  Same per-sweep semantics; only the summation order of the mean differs."""
+    import subprocess
+    import sys
+    from ndsm_b200 import synthetic, vector_potential
+    shape = (72, 64, 80)
+    x, y, z = synthetic.mesh(*shape)
+    b = synthetic.dipole(x, y, z)
+    ref = vector_potential(x, y, z, b, trace=True)
+    out = tmp_path / "fm.npz"
+    code = ("import numpy as np, json, sys; sys.path.insert(0, %r)\n"
+            "from ndsm_b200 import synthetic, vector_potential\n"
+            "x, y, z = synthetic.mesh(%d, %d, %d); b = synthetic.dipole(x, y, z)\n"
+            "r = vector_potential(x, y, z, b, trace=True)\n"
+            "np.savez(%r, A=r[1], B=r[2], ierr=r[0], nc=[len(r[3][k]['du']) for k in sorted(r[3]) if 'du' in r[3][k]])\n"
+            % (os.path.dirname(os.path.dirname(os.path.abspath(__file__))), shape[0], shape[1], shape[2], str(out)))
+    env = dict(os.environ, NDSM_B200_FUSED_MEAN="1")
+    subprocess.run([sys.executable, "-c", code], check=True, env=env, timeout=600)
+    got = np.load(out)
+    assert int(got["ierr"]) == ref[0] == 0
+    want_nc = [len(ref[3][k]["du"]) for k in sorted(ref[3]) if "du" in ref[3][k]]
+    assert all(abs(int(a) - bb) <= 1 for a, bb in zip(got["nc"], want_nc))
+    assert rel_err(got["A"], ref[1]) <= 1e-10
+    assert rel_err(got["B"], ref[2]) <= 1e-10
