@@ -818,10 +818,11 @@ void relax2d_fused_mean(double* u, const double* rhs, const Grid& g, const Bound
                         double* scratch, cudaStream_t st) {
   if (nsweeps <= 0) return;
   const int nb = cdiv((i64)g.hp * g.ny, 256);
-  double* part_r = scratch;
-  double* part_b = scratch + nb;
-  double* fm = scratch + 2 * (size_t)nb;                       // [0] mean, [1] ticket storage
-  unsigned* ticket = reinterpret_cast<unsigned*>(fm + 1);      // zero from the arena memset, reset by the kernel
+  // fixed slots first (levels of different size share the scratch): [0] mean, [1] ticket, then the partial sums
+  double* fm = scratch;
+  unsigned* ticket = reinterpret_cast<unsigned*>(scratch + 1);  // zero from the arena memset, reset by the kernel
+  double* part_r = scratch + 8;
+  double* part_b = scratch + 8 + nb;
   const double count = (double)((i64)g.nx * g.ny);
   for (int k = 0; k < nsweeps; ++k) {
     if (k == 0)
