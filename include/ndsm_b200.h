@@ -28,7 +28,8 @@ extern "C" {
 #define NDSM_B200_ERR_SHAPE 2         /* min(nshape) < 4: the reference indexes an empty hierarchy here (undefined behaviour) */
 #define NDSM_B200_ERR_CUDA 3          /* no device / CUDA runtime failure / out of memory */
 #define NDSM_B200_ERR_STENCIL 4       /* restriction stencil wider than the compiled capacity */
-#define NDSM_B200_ERR_ARG 5           /* inconsistent arguments (nsize != nx*ny*nz*3, nshape4[3] != 3, NULL pointer) */
+#define NDSM_B200_ERR_ARG 5           /* inconsistent arguments (nsize != nx*ny*nz*3, nshape4[3] != 3, NULL pointer, NDSM_DEVICE out of range) */
+#define NDSM_B200_ERR_INTERNAL 6      /* a consistency check inside the library failed (slab plan, message matching); never a CUDA error */
 
 /* ------------------------------------------------------------------------------------------
  * 1. Reference surface (replaces fortran/ndsm_python_wrapper.f90)
@@ -65,21 +66,28 @@ int get_ropt_ctol(void);        /* :230-234  -> 1 */
 int ndsm_b200_vector_solve_device(const int* nshape4, int* ioptc, double* ropt, const double* x,
                                   const double* y, const double* z, double* dA, double* dB);
 
-/* Multi-GPU (one process per GPU, z-slab domain decomposition with one-plane halo exchange per colour pass over
- * NCCL / NVLink; levels with fewer than NDSM_SLAB_MIN_PLANES (default 16) planes per rank are replicated).
+/* Multi-GPU (one process per GPU, z-slab domain decomposition).  Levels with at least NDSM_SLAB_MIN_PLANES (default
+ * 16) planes per rank and NDSM_SLAB_MIN_POINTS (default 8e6) points are partitioned with NDSM_HALO_PLANES (default 6)
+ * halo planes per side: a colour pass also updates the halo planes it has valid inputs for, so ONE exchange of the
+ * halo feeds up to six colour passes (communication-avoiding smoothing; same arithmetic on the same inputs, hence
+ * the same bits as the single-GPU solve).  Coarser levels are replicated on every rank.
+ * Transport: peer-memory stores over NVLink / NVSwitch (CUDA IPC mappings of a symmetric heap, flag hand-over, two
+ * small kernels per exchange captured in the V-cycle's CUDA graph; csrc/peer.cu).  NCCL only carries the IPC handles;
+ * NDSM_P2P=0 (set before dist_init), or peer mappings being unavailable, moves the data path to NCCL send/recv groups.
+ * Every rank holds a z-slab of all three components and solves them concurrently on three streams; the six 2D chi
+ * solves of the BC setup are distributed (face f on rank f mod world) and their At faces broadcast.
  * Bootstrap: rank 0 calls dist_unique_id, the 128 bytes are distributed by the caller (MPI, torch.distributed,
  * a file ...), every rank calls dist_init on its own device (NDSM_DEVICE or the current device).
  * vector_solve_rank: every rank passes all six boundary faces as dense arrays (face f of shape (n1,n2) with the
  * lower-numbered axis fastest: x-faces (ny,nz), y-faces (nx,nz), z-faces (nx,ny); ndsm_vector_potential.f90:225-246)
  * and receives planes [k0,k1) = slab_range(nz, world, rank) of A and B, laid out (nx,ny,k1-k0,3).  Faces and
  * outputs may be host or device pointers (flags).  The initial guess is zero (what ndsm.py always passes).
- * With 3 or more ranks the three component solves run concurrently on three disjoint groups of ranks (z-slabs
- * inside each group) and A is redistributed for the curl; NDSM_HYBRID=0 (set before dist_init) keeps all ranks
- * on one component at a time.  The V-cycle trace of a rank then only covers the component its group solved. */
+ * The V-cycle trace of a rank covers all three 3D solves, and the chi solves of the faces it owns. */
 int ndsm_b200_dist_unique_id(void* out128);
 int ndsm_b200_dist_init(int rank, int world, const void* id128);
 int ndsm_b200_dist_finalize(void);
 int ndsm_b200_dist_world(void);
+const char* ndsm_b200_dist_transport(void); /* description of the active data path */
 int ndsm_b200_dist_rank(void);
 int ndsm_b200_slab_range(int nz, int world, int rank, int* k0, int* k1);
 int ndsm_b200_vector_solve_rank(const int* nshape4, int* ioptc, double* ropt, const double* x, const double* y,

@@ -2,6 +2,8 @@
 // BIND(C) surface (fortran/ndsm_python_wrapper.f90:56-234) with identical semantics.
 #include <chrono>
 #include <cstring>
+#include <exception>
+#include <map>
 #include <memory>
 #include <thread>
 #include <vector>
@@ -28,8 +30,10 @@ static double now_s() {
 
 static cudaStream_t g_stream = nullptr;
 static int g_device = -1;
+static std::map<int, cudaStream_t> g_streams;  // one library stream per device ever used; never destroyed,
+                                               // so MG handles created on a device keep a valid stream
 
-// Select the device (env NDSM_DEVICE, else the current one) and create the library stream.
+// Select the device (env NDSM_DEVICE, else the current one) and the library stream of that device.
 static int ensure_device(const char* sub) {
   int n = 0;
   if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0) {
@@ -42,33 +46,89 @@ static int ensure_device(const char* sub) {
   if (want < 0) {
     if (cudaGetDevice(&want) != cudaSuccess) want = 0;
   }
-  if (want >= n) want = 0;
+  if (want >= n) {  // two ranks silently sharing GPU 0 would hang the multi-GPU bootstrap
+    error_msg("NDSM_DEVICE is not a visible device ordinal", sub, "NDSM_B200_ERR_ARG");
+    return NDSM_B200_ERR_ARG;
+  }
+  if (cudaSetDevice(want) != cudaSuccess) {
+    error_msg("cudaSetDevice failed", sub, "NDSM_B200_ERR_CUDA");
+    return NDSM_B200_ERR_CUDA;
+  }
   if (g_device != want) {
-    if (cudaSetDevice(want) != cudaSuccess) {
-      error_msg("cudaSetDevice failed", sub, "NDSM_B200_ERR_CUDA");
+    // cached device blocks are keyed by device (pool.cu), so nothing of the old GPU is handed out here;
+    // the old device's cache is dropped because a drop-in caller has no way to reach it again
+    if (g_device >= 0) {
+      cudaSetDevice(g_device);
+      cudaDeviceSynchronize();
+      pool_trim(0);
+      cudaSetDevice(want);
+    }
+    g_device = want;
+    g_stream = g_streams.count(want) ? g_streams[want] : nullptr;
+  }
+  if (!g_stream) {
+    if (cudaStreamCreateWithFlags(&g_stream, cudaStreamNonBlocking) != cudaSuccess) {
+      error_msg("cudaStreamCreate failed", sub, "NDSM_B200_ERR_CUDA");
       return NDSM_B200_ERR_CUDA;
     }
-    if (g_stream) { cudaStreamDestroy(g_stream); g_stream = nullptr; }
-    g_device = want;
-  } else {
-    cudaSetDevice(want);
-  }
-  if (!g_stream && cudaStreamCreateWithFlags(&g_stream, cudaStreamNonBlocking) != cudaSuccess) {
-    error_msg("cudaStreamCreate failed", sub, "NDSM_B200_ERR_CUDA");
-    return NDSM_B200_ERR_CUDA;
+    g_streams[want] = g_stream;
   }
   return 0;
 }
 
 static int fail(const NdsmError& e, const char* sub) {
-  int code = (e.code == 2) ? NDSM_B200_ERR_SHAPE : (e.code == 4) ? NDSM_B200_ERR_STENCIL : NDSM_B200_ERR_CUDA;
-  if (e.code == 2) error_msg("mesh too small for a multigrid hierarchy (min(nshape) < 4)", sub, "NDSM_B200_ERR_SHAPE");
-  else if (e.code == 4) error_msg("restriction stencil exceeds compiled capacity", sub, "NDSM_B200_ERR_STENCIL");
-  else error_msg("CUDA failure", sub, "NDSM_B200_ERR_CUDA");
+  // e.code is always a library kind (common.cuh); a cudaError_t only ever travels in e.cuda_err
+  int code = NDSM_B200_ERR_CUDA;
+  switch (e.code) {
+    case NDSM_ERR_SHAPE:
+      code = NDSM_B200_ERR_SHAPE;
+      error_msg("mesh too small for a multigrid hierarchy (min(nshape) < 4)", sub, "NDSM_B200_ERR_SHAPE");
+      break;
+    case NDSM_ERR_STENCIL:
+      code = NDSM_B200_ERR_STENCIL;
+      error_msg("restriction stencil exceeds compiled capacity", sub, "NDSM_B200_ERR_STENCIL");
+      break;
+    case NDSM_ERR_ARG:
+      code = NDSM_B200_ERR_ARG;
+      error_msg("inconsistent arguments", sub, "NDSM_B200_ERR_ARG");
+      break;
+    case NDSM_ERR_INTERNAL:
+      code = NDSM_B200_ERR_INTERNAL;
+      error_msg("internal consistency check failed (slab plan / message matching)", sub, "NDSM_B200_ERR_INTERNAL");
+      break;
+    default: {
+      char msg[160];
+      if (e.cuda_err)
+        snprintf(msg, sizeof msg, "CUDA failure: %s", cudaGetErrorString((cudaError_t)e.cuda_err));
+      else
+        snprintf(msg, sizeof msg, "CUDA / NCCL failure or out of device memory");
+      error_msg(msg, sub, "NDSM_B200_ERR_CUDA");
+    }
+  }
   cudaDeviceSynchronize();  // buffers released by unwinding may be handed out again by the pool
   cudaGetLastError();
   return code;
 }
+// anything that is not an NdsmError (std::bad_alloc from host staging, std::system_error from std::thread ...)
+// must not unwind across the C ABI into ctypes / Fortran callers
+static int fail_std(const char* what, const char* sub) {
+  char msg[200];
+  snprintf(msg, sizeof msg, "host exception: %s", what ? what : "unknown");
+  error_msg(msg, sub, "NDSM_B200_ERR_CUDA");
+  cudaDeviceSynchronize();
+  cudaGetLastError();
+  return NDSM_B200_ERR_CUDA;
+}
+#define NDSM_CATCH_ALL(sub, wrap)                                      \
+  catch (const NdsmError& e) { return wrap(fail(e, sub)); }            \
+  catch (const std::exception& e) { return wrap(fail_std(e.what(), sub)); } \
+  catch (...) { return wrap(fail_std(nullptr, sub)); }
+#define NDSM_ID(x) (x)
+// declared first in an entry point: after every buffer of the call went back to the pool, cached device memory
+// above the cap is returned to CUDA (pool.hpp; the reference frees everything per call)
+struct WorkspaceTrim {
+  ~WorkspaceTrim() { pool_trim_to_cap(); }
+};
 
 static const int imap_cp[6] = {0, 0, 1, 1, 2, 2};
 static const int imap_nc[6][2] = {{1, 2}, {1, 2}, {0, 2}, {0, 2}, {0, 1}, {0, 1}};
@@ -155,6 +215,7 @@ extern "C" {
 int ndsm_vector_solve(size_t nsize, const int* nshape4, int* ioptc, double* ropt, const double* x, const double* y,
                       const double* z, double* A, double* B) {
   static const char* SUB = "ndsm_vector_solve";
+  WorkspaceTrim trim_on_return;
   const double t0 = now_s();
   if (!nshape4 || !ioptc || !ropt || !x || !y || !z || !A || !B) {
     error_msg("NULL argument", SUB, "NDSM_B200_ERR_ARG");
@@ -186,7 +247,13 @@ int ndsm_vector_solve(size_t nsize, const int* nshape4, int* ioptc, double* ropt
     double t1 = now_s();
     size_t fsz[6], ftot = 0;
     for (int f = 0; f < 6; ++f) { fsz[f] = (size_t)nshape4[imap_nc[f][0]] * nshape4[imap_nc[f][1]]; ftot += fsz[f]; }
-    double* hfaces = static_cast<double*>(pool_alloc_host(ftot * sizeof(double)));
+    struct HostBuf {  // pinned staging, back to the pool on every exit path
+      double* p;
+      explicit HostBuf(size_t n) : p(static_cast<double*>(pool_alloc_host(n * sizeof(double)))) {}
+      ~HostBuf() { release(); }
+      void release() { if (p) pool_free_host(p); p = nullptr; }
+    } hf(ftot);
+    double* hfaces = hf.p;
     DBuf dfaces(ftot);
     double* bn[6];
     {
@@ -202,7 +269,7 @@ int ndsm_vector_solve(size_t nsize, const int* nshape4, int* ioptc, double* ropt
     // 3N doubles on the host (and uploading them when they are not all zero) overlaps the chi solves.
     DBuf dA(3 * N), dB(3 * N);
     CUDA_CHECK(cudaStreamSynchronize(st));
-    pool_free_host(hfaces);
+    hf.release();
     g_report.ms_in = (now_s() - t1) * 1e3;
     bool zero_guess = true;
     std::thread scan([&] { zero_guess = all_zero_host(A, 3 * N); });
@@ -235,9 +302,8 @@ int ndsm_vector_solve(size_t nsize, const int* nshape4, int* ioptc, double* ropt
     CUDA_CHECK(cudaStreamSynchronize(st));
     g_report.ms_out = (now_s() - t1) * 1e3;
     return finish(ierr);
-  } catch (const NdsmError& e) {
-    return finish(fail(e, SUB));
   }
+  NDSM_CATCH_ALL(SUB, finish)
 }
 
 int get_iopt_len(void) { return IOPT_LEN; }
@@ -259,6 +325,7 @@ int get_ropt_ctol(void) { return ROPT_CTOL; }
 int ndsm_b200_vector_solve_device(const int* nshape4, int* ioptc, double* ropt, const double* x, const double* y,
                                   const double* z, double* dA, double* dB) {
   static const char* SUB = "ndsm_b200_vector_solve_device";
+  WorkspaceTrim trim_on_return;
   const double t0 = now_s();
   if (!nshape4 || !ioptc || !ropt || !x || !y || !z || !dA || !dB) return NDSM_B200_ERR_ARG;
   long long iopt[IOPT_LEN];
@@ -293,9 +360,8 @@ int ndsm_b200_vector_solve_device(const int* nshape4, int* ioptc, double* ropt, 
     int ierr = run_core_full(nshape4, iopt, ropt, x, y, z, bn, dA, dA, dB, st);
     CUDA_CHECK(cudaStreamSynchronize(st));
     return finish(ierr);
-  } catch (const NdsmError& e) {
-    return finish(fail(e, SUB));
   }
+  NDSM_CATCH_ALL(SUB, finish)
 }
 
 }  // extern "C"
@@ -319,7 +385,7 @@ ndsm_b200_plan* ndsm_b200_plan_create(int ndim, const int* nshape, int ngrids, c
     p->ndim = ndim;
     p->lv = build_hierarchy(ndim, sh, ngrids, mesh);
     return p;
-  } catch (const NdsmError&) {
+  } catch (...) {
     return nullptr;
   }
 }
@@ -366,7 +432,7 @@ int ndsm_b200_plan_slab_partition(const ndsm_b200_plan* p, int world, int min_pl
     for (size_t l = 0; l < sp.zs.size(); ++l)
       for (int r = 0; r <= world; ++r) zs[l * (world + 1) + r] = sp.zs[l][r];
     return 0;
-  } catch (const NdsmError&) {
+  } catch (...) {
     return NDSM_B200_ERR_ARG;
   }
 }
@@ -377,6 +443,7 @@ int ndsm_b200_plan_slab_partition(const ndsm_b200_plan* p, int world, int min_pl
 // ------------------------------------------------------------------------------------------
 struct ndsm_b200_mg {
   MG* mg = nullptr;
+  int device = -1;         // the handle's arrays and stream live on this device
   double* rhs0 = nullptr;  // level-0 rhs owned by the handle (colour-split)
   SolveTrace tr;
 };
@@ -417,12 +484,14 @@ static double* handle_array(ndsm_b200_mg* h, int which, int level) {
 #define HANDLE_GUARD(sub)                               \
   if (!h || !h->mg) return NDSM_B200_ERR_ARG;           \
   if (int e__ = ensure_device(sub)) return e__;         \
+  if (h->device != g_device) {                          \
+    error_msg("handle belongs to another device", sub, "NDSM_B200_ERR_ARG"); \
+    return NDSM_B200_ERR_ARG;                           \
+  }                                                     \
   try {
 #define HANDLE_END(sub)         \
   }                             \
-  catch (const NdsmError& e) {  \
-    return fail(e, sub);        \
-  }                             \
+  NDSM_CATCH_ALL(sub, NDSM_ID)  \
   return 0;
 
 extern "C" {
@@ -437,6 +506,7 @@ ndsm_b200_mg* ndsm_b200_new_mg_handle(int ndim, const int* nshape, int ngrids, c
     int sh[3] = {nshape[0], nshape[1], ndim == 3 ? nshape[2] : 1};
     ndsm_b200_mg* h = new ndsm_b200_mg();
     h->mg = new MG(ndim, sh, ngrids, mesh, g_stream);
+    h->device = g_device;
     h->mg->set_options(5, 1e-13, "NNNNNN", du_max != 0, nmax_exact);
     // the handle owns a (zero) level-0 rhs so every operator can be called standalone; NDSM_B200_HANDLE_RHS0=0
     // leaves it unset until mg_put(1, 0, ...) so that the rhs == 0 kernel specialisations of the vector-potential
@@ -447,6 +517,12 @@ ndsm_b200_mg* ndsm_b200_new_mg_handle(int ndim, const int* nshape, int ngrids, c
     return h;
   } catch (const NdsmError& e) {
     fail(e, SUB);
+    return nullptr;
+  } catch (const std::exception& e) {
+    fail_std(e.what(), SUB);
+    return nullptr;
+  } catch (...) {
+    fail_std(nullptr, SUB);
     return nullptr;
   }
 }
@@ -538,6 +614,10 @@ int ndsm_b200_mg_solve(ndsm_b200_mg* h, double vc_tol, int nmax, double* u_dense
   static const char* SUB = "ndsm_b200_mg_solve";
   if (!h || !h->mg || !u_dense) return NDSM_B200_ERR_ARG;
   if (int e = ensure_device(SUB)) return e;
+  if (h->device != g_device) {
+    error_msg("handle belongs to another device", SUB, "NDSM_B200_ERR_ARG");
+    return NDSM_B200_ERR_ARG;
+  }
   try {
     MG& mg = *h->mg;
     const Grid& g = mg.level(0).g;
@@ -554,9 +634,8 @@ int ndsm_b200_mg_solve(ndsm_b200_mg* h, double vc_tol, int nmax, double* u_dense
     if (ncycles) *ncycles = (int)h->tr.du.size();
     download_split(mg, us.p, u_dense, g);
     return ierr;
-  } catch (const NdsmError& e) {
-    return fail(e, SUB);
   }
+  NDSM_CATCH_ALL(SUB, NDSM_ID)
 }
 int ndsm_b200_mg_update_u(ndsm_b200_mg* h, const double* u_old_dense, double* u_new_dense, double* du_max,
                           double* du_mean) {
@@ -589,7 +668,7 @@ static int poisson_slabs(const int* nshape, const char* copt, int ms, int ncycle
   MG mg(3, nshape, -1, mesh, st, comm);
   mg.set_options(ms, ex_tol, copt, du_max != 0, nmaxex);
   const int ns = mg.nslabs();
-  if (mg.plan().ndist == 0 || (int)du.size() != ns || (int)drhs.size() != ns) {
+  if ((comm && mg.plan().ndist == 0) || (int)du.size() != ns || (int)drhs.size() != ns) {
     error_msg("grid too small to be partitioned over the ranks (see NDSM_SLAB_MIN_POINTS / NDSM_SLAB_MIN_PLANES)",
               "ndsm_b200_poisson_solve_rank", "NDSM_B200_ERR_ARG");
     return NDSM_B200_ERR_ARG;
@@ -614,9 +693,20 @@ static int poisson_slabs(const int* nshape, const char* copt, int ms, int ncycle
       rcp[s] = rp[s];
     }
   }
-  if (has_rhs) {  // the extended colour passes read rhs in the halo planes: fetch them once
+  if (comm && comm->nlocal() == 1) {
+    // every rank must agree on whether there is a right-hand side: the halo exchange below is collective
+    int mine = has_rhs ? 1 : 0;
+    std::vector<int> all(comm->world(), 0);
+    comm->allgather_host(&mine, all.data(), sizeof(int), st);
+    for (int v : all)
+      if (v != mine) {
+        error_msg("rhs must be given on every rank or on none", "ndsm_b200_poisson_solve_rank", "NDSM_B200_ERR_ARG");
+        return NDSM_B200_ERR_ARG;
+      }
+  }
+  if (has_rhs && comm) {  // the extended colour passes read rhs in the halo planes: fetch them once
     for (int s = 0; s < ns; ++s)
-      if (!rp[s]) throw NdsmError(NDSM_B200_ERR_ARG);  // rhs must be given for every local slab or for none
+      if (!rp[s]) throw NdsmError(NDSM_ERR_ARG);  // rhs must be given for every local slab or for none
     mg.exchange(0, 0, 3, mg.plan().halo, &rp);
     mg.set_level0_rhs_halo_valid(true);
   }
@@ -631,8 +721,9 @@ static int poisson_slabs(const int* nshape, const char* copt, int ms, int ncycle
   return ierr;
 }
 
-static std::unique_ptr<Comm> g_dist;
-static std::unique_ptr<Comm> g_dist_group;  // my group of the hybrid decomposition (>= 3 ranks)
+static std::unique_ptr<Comm> g_dist;       // NCCL communicator: bootstrap, and the data path when peer memory is unavailable
+static std::unique_ptr<Comm> g_dist_peer;  // peer-memory transport over NVLink (peer.cu): the default data path
+static Comm* dist_comm() { return g_dist_peer ? g_dist_peer.get() : g_dist.get(); }
 
 extern "C" {
 
@@ -640,25 +731,25 @@ int ndsm_b200_poisson_solve_rank(const int* nshape3, const char* copt, int ms, i
                                  double vc_tol, double ex_tol, const double* x, const double* y, const double* z,
                                  double* d_u_slab, const double* d_rhs_slab, double* du_last, int* ncycles) {
   static const char* SUB = "ndsm_b200_poisson_solve_rank";
+  WorkspaceTrim trim_on_return;
   if (!nshape3 || !copt || !x || !y || !z || !d_u_slab) return NDSM_B200_ERR_ARG;
   if (int e = ensure_device(SUB)) return e;
-  if (!g_dist || g_dist->world() < 2) {
-    error_msg("ndsm_b200_dist_init with >= 2 ranks must come first", SUB, "NDSM_B200_ERR_ARG");
-    return NDSM_B200_ERR_ARG;
-  }
   try {
-    return poisson_slabs(nshape3, copt, ms, ncycles_max, nmaxex, du_max, vc_tol, ex_tol, x, y, z, g_dist.get(),
+    // without ndsm_b200_dist_init (or with one rank) the "slab" is the whole grid on this GPU: the G = 1 point
+    // of the weak-scaling series
+    Comm* comm = (g_dist && g_dist->world() >= 2) ? dist_comm() : nullptr;
+    return poisson_slabs(nshape3, copt, ms, ncycles_max, nmaxex, du_max, vc_tol, ex_tol, x, y, z, comm,
                          std::vector<double*>{d_u_slab}, std::vector<const double*>{d_rhs_slab}, du_last, ncycles,
                          g_stream);
-  } catch (const NdsmError& e) {
-    return fail(e, SUB);
   }
+  NDSM_CATCH_ALL(SUB, NDSM_ID)
 }
 
 int ndsm_b200_poisson_solve(int ndim, const int* nshape, const char* copt, int ms, int ncycles_max, int nmaxex,
                             int du_max, double vc_tol, double ex_tol, const double* x, const double* y,
                             const double* z, double* u, const double* rhs, double* du_last, int* ncycles) {
   static const char* SUB = "ndsm_b200_poisson_solve";
+  WorkspaceTrim trim_on_return;
   int vworld = 1;
   if (const char* e = getenv("NDSM_VIRTUAL_SLABS")) vworld = atoi(e);
   if (ndim == 3 && vworld > 1 && nshape && copt && x && y && z && u) {
@@ -687,9 +778,8 @@ int ndsm_b200_poisson_solve(int ndim, const int* nshape, const char* copt, int m
         CUDA_CHECK(cudaStreamSynchronize(st));
       }
       return ierr;
-    } catch (const NdsmError& e) {
-      return fail(e, SUB);
     }
+    NDSM_CATCH_ALL(SUB, NDSM_ID)
   }
   ndsm_b200_mg* h = ndsm_b200_new_mg_handle(ndim, nshape, -1, x, y, z, du_max, nmaxex);
   if (!h) return NDSM_B200_ERR_CUDA;
@@ -737,9 +827,8 @@ int ndsm_b200_bc_setup(const int* nshape4, const int* ioptc, const double* ropt,
                                  g_report, &cap, true);
     if (phi6) for (int f = 0; f < 6; ++f) phi6[f] = g_report.phi[f];
     return ierr;
-  } catch (const NdsmError& e) {
-    return fail(e, SUB);
   }
+  NDSM_CATCH_ALL(SUB, NDSM_ID)
 }
 
 int ndsm_b200_flux_curl(const int* nshape4, int flxcrl, const double* x, const double* y, const double* z,
@@ -780,9 +869,8 @@ int ndsm_b200_flux_curl(const int* nshape4, int flxcrl, const double* x, const d
     CUDA_CHECK(cudaMemcpyAsync(B, dB.p, 3 * N * sizeof(double), cudaMemcpyDeviceToHost, st));
     CUDA_CHECK(cudaStreamSynchronize(st));
     return 0;
-  } catch (const NdsmError& e) {
-    return fail(e, SUB);
   }
+  NDSM_CATCH_ALL(SUB, NDSM_ID)
 }
 
 // ------------------------------------------------------------------------------------------
@@ -798,27 +886,25 @@ int ndsm_b200_dist_init(int rank, int world, const void* id128) {
   if (!id128 || world < 1 || rank < 0 || rank >= world) return NDSM_B200_ERR_ARG;
   if (int e = ensure_device(SUB)) return e;
   try {
-    g_dist_group.reset();
+    g_dist_peer.reset();
+    peer_fabric_shutdown();
     g_dist.reset();
     g_dist = make_nccl_comm(rank, world, id128);
-    const bool hybrid_on = !(getenv("NDSM_HYBRID") && atoi(getenv("NDSM_HYBRID")) == 0);
-    if (world >= 3 && hybrid_on) {
-      int gf[3], gs[3];
-      hybrid_groups(world, gf, gs);
-      const int colour = (rank >= gf[2]) ? 2 : (rank >= gf[1]) ? 1 : 0;
-      g_dist_group = g_dist->split(colour);
-    }
+    // NDSM_P2P=0 keeps every exchange on NCCL send/recv groups (the round-1 data path)
+    const bool p2p_on = !(getenv("NDSM_P2P") && atoi(getenv("NDSM_P2P")) == 0);
+    if (world >= 2 && p2p_on) g_dist_peer = make_peer_comm(g_dist.get(), g_stream);
     return 0;
-  } catch (const NdsmError& e) {
-    return fail(e, SUB);
   }
+  NDSM_CATCH_ALL(SUB, NDSM_ID)
 }
 int ndsm_b200_dist_finalize(void) {
   cudaDeviceSynchronize();
-  g_dist_group.reset();
+  g_dist_peer.reset();
+  peer_fabric_shutdown();
   g_dist.reset();
   return 0;
 }
+const char* ndsm_b200_dist_transport(void) { return dist_comm() ? dist_comm()->transport() : "none"; }
 int ndsm_b200_dist_world(void) { return g_dist ? g_dist->world() : 1; }
 int ndsm_b200_dist_rank(void) { return g_dist ? g_dist->first_rank() : 0; }
 int ndsm_b200_slab_range(int nz, int world, int rank, int* k0, int* k1) {
@@ -831,6 +917,7 @@ int ndsm_b200_vector_solve_rank(const int* nshape4, int* ioptc, double* ropt, co
                                 const double* z, const double* const* faces6, int faces_on_device, double* A_slab,
                                 double* B_slab, int out_on_device) {
   static const char* SUB = "ndsm_b200_vector_solve_rank";
+  WorkspaceTrim trim_on_return;
   const double t0 = now_s();
   if (!nshape4 || !ioptc || !ropt || !x || !y || !z || !faces6 || !A_slab || !B_slab) return NDSM_B200_ERR_ARG;
   long long iopt[IOPT_LEN];
@@ -878,16 +965,8 @@ int ndsm_b200_vector_solve_rank(const int* nshape4, int* ioptc, double* ropt, co
     }
     CUDA_CHECK(cudaStreamSynchronize(st));
     g_report.ms_in = (now_s() - t1) * 1e3;
-    Hybrid hyb;
-    const bool use_hybrid = g_dist && g_dist_group && world >= 3;
-    if (use_hybrid) {
-      hyb.world = g_dist.get();
-      hyb.group = g_dist_group.get();
-      hybrid_groups(world, hyb.gfirst, hyb.gsize);
-      hyb.comp = (rank >= hyb.gfirst[2]) ? 2 : (rank >= hyb.gfirst[1]) ? 1 : 0;
-    }
-    int ierr = vector_solve_core(nshape4, iopt, ropt, x, y, z, bn, DenseIn(), g_dist.get(), std::vector<SlabOut>{so}, st,
-                                 g_report, nullptr, false, nullptr, use_hybrid ? &hyb : nullptr);
+    int ierr = vector_solve_core(nshape4, iopt, ropt, x, y, z, bn, DenseIn(), dist_comm(), std::vector<SlabOut>{so}, st,
+                                 g_report, nullptr, false, nullptr);
     t1 = now_s();
     if (!out_on_device) {
       CUDA_CHECK(cudaMemcpyAsync(A_slab, so.A, 3 * nslab * sizeof(double), cudaMemcpyDeviceToHost, st));
@@ -896,9 +975,8 @@ int ndsm_b200_vector_solve_rank(const int* nshape4, int* ioptc, double* ropt, co
     CUDA_CHECK(cudaStreamSynchronize(st));
     g_report.ms_out = (now_s() - t1) * 1e3;
     return finish(ierr);
-  } catch (const NdsmError& e) {
-    return finish(fail(e, SUB));
   }
+  NDSM_CATCH_ALL(SUB, finish)
 }
 
 // ------------------------------------------------------------------------------------------

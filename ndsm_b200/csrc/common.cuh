@@ -41,13 +41,18 @@ struct Bounds {    // inclusive 0-based index range of non-Dirichlet points (nds
     cudaError_t e__ = (call);                                                                 \
     if (e__ != cudaSuccess) {                                                                 \
       fprintf(stderr, "ERROR(%s):%s:%s:%d\n", __func__, cudaGetErrorString(e__), __FILE__, __LINE__); \
-      throw NdsmError(e__);                                                                   \
+      throw NdsmError(NDSM_ERR_CUDA, (int)e__);                                               \
     }                                                                                         \
   } while (0)
 
+// Library error kinds carried by NdsmError.  The first five are the public NDSM_B200_ERR_* codes of
+// include/ndsm_b200.h; NDSM_ERR_INTERNAL is a broken invariant of this library (reported as its own message).
+// A CUDA runtime error never travels as a library code: it is NDSM_ERR_CUDA with the cudaError_t beside it.
+enum { NDSM_ERR_SHAPE = 2, NDSM_ERR_CUDA = 3, NDSM_ERR_STENCIL = 4, NDSM_ERR_ARG = 5, NDSM_ERR_INTERNAL = 6 };
 struct NdsmError {
-  int code;
-  explicit NdsmError(int c) : code(c) {}
+  int code;      // one of the NDSM_ERR_* kinds
+  int cuda_err;  // cudaError_t when code == NDSM_ERR_CUDA and the CUDA runtime reported it, else 0
+  explicit NdsmError(int c, int ce = 0) : code(c), cuda_err(ce) {}
 };
 
 __host__ __device__ inline i64 gidx(const Grid& g, int i, int j, int k) {

@@ -984,6 +984,51 @@ k_sub_mean(double* __restrict__ u, const Grid g, const double* __restrict__ part
   u[o] = u[o] - mean;
 }
 
+// Pure-Neumann gauge on a z-partitioned level (ndsm_optimized.f90:173-189 with the sum taken over all slabs):
+// slab_sum leaves this slab's sum over its owned planes in out[0] (out[1] = 0), the pairs of all ranks are
+// gathered in rank order, and subtract_gathered_mean adds them up in that fixed order on every rank -- the
+// same mean bits everywhere, so halo planes stay consistent with the neighbour's owned planes.
+__global__ void __launch_bounds__(REDUCE_THREADS) k_sum_final(const double* __restrict__ part, int nparts,
+                                                              double* __restrict__ out) {
+  __shared__ double red[40];
+  double s = 0.0;
+  for (int e = threadIdx.x; e < nparts; e += REDUCE_THREADS) s += part[e];
+  s = block_sum(s, red);
+  if (threadIdx.x == 0) { out[0] = s; out[1] = 0.0; }
+}
+void slab_sum(const double* u, const Grid& g, double* scratch, double* out2, cudaStream_t st) {
+  const i64 n = (i64)g.nzl * g.ps;
+  const int nb = (int)std::min<i64>(REDUCE_BLOCKS, std::max<i64>(1, cdiv(n, REDUCE_THREADS)));
+  k_sum_partial<<<nb, REDUCE_THREADS, 0, st>>>(u, n, g.cs, scratch);
+  LAUNCHED();
+  k_sum_final<<<1, REDUCE_THREADS, 0, st>>>(scratch, nb, out2);
+  LAUNCHED();
+}
+__global__ void __launch_bounds__(256)
+k_sub_gathered_mean(double* __restrict__ u, const Grid g, const double* __restrict__ pairs, const int world,
+                    const double count, const int kl0) {
+  double s = 0.0;
+  for (int r = 0; r < world; ++r) s += pairs[2 * r];  // rank order
+  const double mean = s / count;
+  const int t = blockIdx.x * 256 + threadIdx.x;
+  const int j = t / g.hp;
+  const int m = t - j * g.hp;
+  if (j >= g.ny || m >= g.mcnt) return;
+  const int kl = kl0 + (int)blockIdx.y;  // local plane, halo planes included
+  const int k = g.k0 + kl;
+  if (k < 0 || k >= g.nz) return;
+  const int colour = blockIdx.z;
+  const int i = 2 * m + ((j + k + colour) & 1);
+  if (i >= g.nx) return;
+  const i64 o = (i64)colour * g.cs + (i64)kl * g.ps + (i64)j * g.hp + m;
+  u[o] = u[o] - mean;
+}
+void subtract_gathered_mean(double* u, const Grid& g, const double* pairs, int world, int halo, cudaStream_t st) {
+  dim3 grid(cdiv((i64)g.hp * g.ny, 256), g.nzl + 2 * halo, 2);
+  k_sub_gathered_mean<<<grid, 256, 0, st>>>(u, g, pairs, world, (double)((i64)g.nx * g.ny * g.nz), -halo);
+  LAUNCHED();
+}
+
 void subtract_mean(double* u, const Grid& g, double* scratch, cudaStream_t st) {
   const i64 n = (i64)g.nzl * g.ps;
   const int nb = (int)std::min<i64>(REDUCE_BLOCKS, std::max<i64>(1, cdiv(n, REDUCE_THREADS)));

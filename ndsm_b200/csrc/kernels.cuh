@@ -52,6 +52,10 @@ void residual2d(const double* u, const double* rhs, double* r, const Grid& g, co
 // u -= sum(u)/N over all points (pure-Neumann gauge; ndsm_poisson.f90:529-547, ndsm_optimized.f90:173-189).
 // scratch: >= reduce_scratch_doubles() doubles.
 void subtract_mean(double* u, const Grid& g, double* scratch, cudaStream_t st);
+// the same on a z-partitioned level: out2[0] = sum over this slab's owned planes; after the pairs of all ranks
+// have been gathered (rank order), the mean is subtracted from the owned and the halo planes
+void slab_sum(const double* u, const Grid& g, double* scratch, double* out2, cudaStream_t st);
+void subtract_gathered_mean(double* u, const Grid& g, const double* pairs, int world, int halo, cudaStream_t st);
 // K3: rhs_c = R r_f (ndsm_multigrid_core.f90:1010-1065 + ndsm_interp.f90:186-292), exact reference summation order.
 void restrict_level(const double* rf, const Grid& gf, double* rhsc, const Grid& gc, const RestrictTab& tx,
                     const RestrictTab& ty, const RestrictTab& tz, cudaStream_t st);

@@ -202,6 +202,9 @@ SlabPlan plan_slabs(const std::vector<HostLevel>& hl, int ndim, int world, int m
   return p;
 }
 
+void* Comm::sym_alloc(size_t bytes) { return pool_alloc(bytes); }
+void Comm::sym_free(void* p) { pool_free(p); }
+
 // ---------------------------------------------------------------------------------------------
 // virtual communication: every rank lives in this process on one device; messages are device copies
 // ---------------------------------------------------------------------------------------------
@@ -241,6 +244,7 @@ struct VirtualComm : Comm {
   void bcast(int, double*, size_t, cudaStream_t) override {}
   std::unique_ptr<Comm> clone(cudaStream_t) override { return std::unique_ptr<Comm>(new VirtualComm(w)); }
   std::unique_ptr<Comm> split(int) override { return nullptr; }
+  const char* transport() const override { return "virtual ranks on one device (device copies)"; }
 };
 }  // namespace
 std::unique_ptr<Comm> make_virtual_comm(int world) { return std::unique_ptr<Comm>(new VirtualComm(world)); }
@@ -295,13 +299,20 @@ MG::MG(int ndim, const int* shape, int ngrids, const double* const* mesh, cudaSt
   const bool fused_mean = ndim == 2 && getenv("NDSM_B200_FUSED_MEAN") && atoi(getenv("NDSM_B200_FUSED_MEAN")) != 0;
   const i64 off_fm = fused_mean ? take((i64)relax2d_fused_mean_scratch(hl[0].g)) : -1;
   const i64 off_all = take(2 * (i64)world + 8);
+  const i64 off_allm = take(2 * (2 * (i64)world + 8));  // two alternating buffers of gathered slab sums (pure Neumann)
   const i64 off_info = take(8);
-  shared_ = static_cast<double*>(pool_alloc((size_t)total * sizeof(double)));
+  // bcast() / gather2() write into this arena on the other ranks (replicated levels, gathered (max,sum) pairs):
+  // it comes from the communicator's symmetric heap (collective; its size does not depend on the rank)
+  shared_ = static_cast<double*>(comm_ ? comm_->sym_alloc((size_t)total * sizeof(double))
+                                       : pool_alloc((size_t)total * sizeof(double)));
+  if (comm_ && nd > 0) comm_->reserve((size_t)2 * H * (size_t)hl[0].g.ps);  // both colours of a full halo
   CUDA_CHECK(cudaMemsetAsync(shared_, 0, (size_t)total * sizeof(double), st_));
   usav_ = shared_ + off_sav;
   scratch_ = shared_ + off_scr;
   fm_scratch_ = (off_fm >= 0) ? shared_ + off_fm : nullptr;
   d_all_ = shared_ + off_all;
+  d_allm_[0] = shared_ + off_allm;
+  d_allm_[1] = shared_ + off_allm + 2 * (i64)world + 8;
   d_info_ = reinterpret_cast<int*>(shared_ + off_info);
   h_out_ = static_cast<double*>(pool_alloc_host((2 * (size_t)world + 8) * sizeof(double)));
 
@@ -445,7 +456,8 @@ MG::~MG() {
   pool_free(tab_i_);
   pool_free(tab_d_);
   for (auto& S : slabs_) pool_free(S.arena);
-  pool_free(shared_);
+  if (comm_) comm_->sym_free(shared_);
+  else pool_free(shared_);
   pool_free_host(h_out_);
 }
 
@@ -544,9 +556,19 @@ void MG::relax(int g) {
     relax2d_half(L.u, rhs, L.g, L.b, 0, L.w, st_);
     relax2d_half(L.u, rhs, L.g, L.b, 1, L.w, st_);
   }
-  if (all_neumann_) {
-    if (dist) throw NdsmError(6);  // pure-Neumann gauge on partitioned levels is not needed by this path
-    subtract_mean(slabs_[0].lv[g].u, slabs_[0].lv[g].g, scratch_, st_);
+  if (all_neumann_) {  // u -= sum(u)/N after every sweep (ndsm_optimized.f90:173-189, ndsm_poisson.f90:538-541)
+    if (dist) {
+      // partitioned level: slab sums over the owned planes, gathered in rank order, subtracted from owned and
+      // halo planes alike (the neighbour subtracts the same value from the planes my halo mirrors).  Two
+      // gathered buffers alternate: a peer may already deliver the next sweep's sum while this one is applied.
+      double* pairs = d_allm_[mean_parity_];
+      mean_parity_ ^= 1;
+      for (auto& S : slabs_) slab_sum(S.lv[g].u, S.lv[g].g, scratch_, S.d_out + 2, st_);
+      for (auto& S : slabs_) comm_->gather2(S.rank, S.d_out + 2, pairs, st_);
+      for (auto& S : slabs_) subtract_gathered_mean(S.lv[g].u, S.lv[g].g, pairs, plan_.world, S.lv[g].H, st_);
+    } else {
+      subtract_mean(slabs_[0].lv[g].u, slabs_[0].lv[g].g, scratch_, st_);
+    }
   }
 }
 
@@ -772,6 +794,9 @@ void MG::solve_begin(const std::vector<double*>& u, const std::vector<const doub
                                cudaMemcpyDeviceToDevice, st_));  // :100
   }
   for (auto& v : valid_) v = {{0, 0}};  // the caller's halo planes are not trusted; refreshed on first use
+  // no rank may write into another rank's arena (replicated levels, gathered pairs) before that rank has
+  // cleared / filled it: everything enqueued above is ordered before any peer's first message of this solve
+  if (comm_ && plan_.ndist > 0) comm_->barrier(st_);
 
   // The loop body is a static launch sequence (the coarsest solve iterates inside one kernel), so it is
   // captured once into a CUDA graph and replayed every V-cycle: ~250-500 launches per cycle otherwise.
@@ -821,6 +846,10 @@ bool MG::solve_poll() {
   const double N = (double)((i64)g0.nx * g0.ny * g0.nz);
   CUDA_CHECK(cudaStreamSynchronize(st_));
   prof_collect();
+  if (comm_ && comm_->failed()) {
+    fprintf(stderr, "ERROR(solve_poisson_bvp):a peer did not answer within the time-out (NDSM_P2P_TIMEOUT_MS):NDSM_B200_ERR_INTERNAL\n");
+    throw NdsmError(NDSM_ERR_INTERNAL);
+  }
   const int npairs = (plan_.ndist > 0 && comm_) ? plan_.world : 1;
   double dmax = 0.0, dsum = 0.0;
   for (int q = 0; q < npairs; ++q) {  // fixed rank order: every rank takes the same decision

@@ -69,12 +69,35 @@ struct Comm {
   // lets independent solves overlap their exchanges on different streams
   virtual std::unique_ptr<Comm> clone(cudaStream_t st) = 0;
   // sub-communicator of the ranks that pass the same colour (collective); ranks keep their relative order.
-  // Not available for virtual ranks (returns nullptr).
+  // Not available for virtual ranks or the peer-memory transport (returns nullptr).
   virtual std::unique_ptr<Comm> split(int colour) = 0;
+  // Memory that bcast() / gather2() may target.  The peer-memory transport writes straight into the other
+  // ranks' copies of such a buffer, so it must sit at the same offset of a symmetric heap on every rank:
+  // sym_alloc is COLLECTIVE (every rank calls it in the same order with the same size).  Other transports
+  // hand out ordinary pool memory.
+  virtual void* sym_alloc(size_t bytes);
+  virtual void sym_free(void* p);
+  // largest message (doubles) one send() of this communicator will carry to a neighbour (collective)
+  virtual void reserve(size_t) {}
+  // all ranks have enqueued everything that precedes this call (collective, stream ordered)
+  virtual void barrier(cudaStream_t) {}
+  // host bootstrap: every rank contributes `bytes` bytes, result ordered by rank (synchronises the stream)
+  virtual void allgather_host(const void*, void*, size_t, cudaStream_t) { throw NdsmError(NDSM_ERR_INTERNAL); }
+  // true once a device-side wait of this transport has timed out (results are then invalid)
+  virtual bool failed() { return false; }
+  virtual const char* transport() const = 0;
+  // one-sided transport (peer-memory stores): independent solves may use clones of it concurrently
+  virtual bool one_sided() const { return false; }
 };
 std::unique_ptr<Comm> make_virtual_comm(int world);  // all ranks in this process, on the current device
 bool nccl_unique_id(void* out128);                    // ncclGetUniqueId (rank 0)
 std::unique_ptr<Comm> make_nccl_comm(int rank, int world, const void* id128);  // one rank per process / GPU
+// Peer-memory transport (peer.cu): one process per GPU, halo planes and replicated levels are written straight
+// into the neighbours' HBM over NVLink (CUDA IPC mappings of a symmetric heap) and handed over with flags in
+// peer memory; `boot` is only used to exchange the IPC handles.  Returns nullptr (after one stderr line) when
+// peer mappings cannot be set up, in which case the caller stays on `boot`.
+std::unique_ptr<Comm> make_peer_comm(Comm* boot, cudaStream_t st);
+void peer_fabric_shutdown();  // unmap / free the symmetric heap (before the boot communicator goes away)
 
 struct SolveTrace {
   std::vector<double> du;      // du after each V-cycle
@@ -201,6 +224,8 @@ class MG {
   double* scratch_ = nullptr;        // reduction scratch
   double* fm_scratch_ = nullptr;     // fused-mean 2D sweeps (NDSM_B200_FUSED_MEAN=1), nullptr when off
   double* d_all_ = nullptr;          // [2*world] gathered (max,sum) pairs
+  double* d_allm_[2] = {nullptr, nullptr};  // gathered slab sums of the pure-Neumann mean, alternating
+  int mean_parity_ = 0;
   int* d_info_ = nullptr;            // [2] coarsest-solve iterations / converged
   double* h_out_ = nullptr;          // pinned: [2*world] pairs + 2 ints
   // levels >= small_from_ (each <= SMALL_MAX_POINTS points) run as one single-block kernel; 0 = disabled

@@ -84,7 +84,11 @@ struct NcclComm : Comm {
     NCCL_CHECK(g_nccl.CommSplit(comm, colour, rank_, &nc, nullptr));
     return std::unique_ptr<Comm>(new NcclComm(nc));
   }
-  ~NcclComm() override { if (comm) g_nccl.CommDestroy(comm); }
+  ~NcclComm() override {
+    if (bar_) cudaFree(bar_);
+    if (comm) g_nccl.CommDestroy(comm);
+  }
+  double* bar_ = nullptr;
   int world() const override { return world_; }
   int first_rank() const override { return rank_; }
   int nlocal() const override { return 1; }
@@ -101,6 +105,20 @@ struct NcclComm : Comm {
   }
   void bcast(int root_rank, double* buf, size_t n, cudaStream_t st) override {
     NCCL_CHECK(g_nccl.Broadcast(buf, buf, n, ncclDouble, root_rank, comm, st));
+  }
+  const char* transport() const override { return "NCCL send/recv groups"; }
+  void barrier(cudaStream_t st) override {  // a 2-double all-gather orders the ranks on the stream
+    if (!bar_) CUDA_CHECK(cudaMalloc(&bar_, (2 * (size_t)world_ + 2) * sizeof(double)));
+    NCCL_CHECK(g_nccl.AllGather(bar_ + 2 * world_, bar_, 2, ncclDouble, comm, st));
+  }
+  void allgather_host(const void* send, void* recv_all, size_t bytes, cudaStream_t st) override {
+    char* d = nullptr;
+    CUDA_CHECK(cudaMalloc(&d, bytes * ((size_t)world_ + 1)));
+    CUDA_CHECK(cudaMemcpyAsync(d + bytes * world_, send, bytes, cudaMemcpyHostToDevice, st));
+    NCCL_CHECK(g_nccl.AllGather(d + bytes * world_, d, bytes, ncclChar, comm, st));
+    CUDA_CHECK(cudaMemcpyAsync(recv_all, d, bytes * world_, cudaMemcpyDeviceToHost, st));
+    CUDA_CHECK(cudaStreamSynchronize(st));
+    cudaFree(d);
   }
   std::unique_ptr<Comm> clone(cudaStream_t st) override {
     // rank 0 draws a fresh unique id and hands it to the others through this communicator

@@ -32,6 +32,24 @@ struct DevBuf {  // RAII device allocation
   DevBuf& operator=(const DevBuf&) = delete;
 };
 
+// NDSM_B200_TRACE=1: wall-clock checkpoints of the host orchestration on stderr (where does a stage's time go:
+// hierarchy construction, graph capture/instantiation, the V-cycle loop)
+struct HostTrace {
+  bool on;
+  std::chrono::steady_clock::time_point t0, last;
+  HostTrace() : on(getenv("NDSM_B200_TRACE") && atoi(getenv("NDSM_B200_TRACE")) != 0) {
+    t0 = last = std::chrono::steady_clock::now();
+  }
+  void mark(const char* what) {
+    if (!on) return;
+    const auto now = std::chrono::steady_clock::now();
+    fprintf(stderr, "TRACE %-28s +%8.3f ms  (total %8.3f ms)\n", what,
+            std::chrono::duration<double, std::milli>(now - last).count(),
+            std::chrono::duration<double, std::milli>(now - t0).count());
+    last = now;
+  }
+};
+
 struct EvTimer {
   cudaEvent_t a, b;
   cudaStream_t st;
@@ -49,8 +67,7 @@ struct EvTimer {
 
 int vector_solve_core(const int* nshape, const long long* iopt, const double* ropt, const double* x, const double* y,
                       const double* z, double* const* bn, const DenseIn& A0_in, Comm* comm, const std::vector<SlabOut>& outs_in,
-                      cudaStream_t st, Report& rep, BcCapture* cap, bool stop_after_bc, const CoreHooks* hooks,
-                      const Hybrid* hyb) {
+                      cudaStream_t st, Report& rep, BcCapture* cap, bool stop_after_bc, const CoreHooks* hooks) {
   const int nx = nshape[0], ny = nshape[1], nz = nshape[2];
   const double* mesh[3] = {x, y, z};
   const bool use_du_max = (iopt[IOPT_DUMAX] == IOPT_TRUE);
@@ -64,6 +81,7 @@ int vector_solve_core(const int* nshape, const long long* iopt, const double* ro
   const unsigned long long launches0 = g_launches;
   EvTimer tm(st), tall(st);
   tall.start();
+  HostTrace trace;
 
   // mesh vectors on the device (flux-balance fields)
   DevBuf dmesh((size_t)nx + ny + nz);
@@ -86,16 +104,42 @@ int vector_solve_core(const int* nshape, const long long* iopt, const double* ro
   CUDA_CHECK(cudaMemcpyAsync(phi, d_phi, sizeof phi, cudaMemcpyDeviceToHost, st));
   CUDA_CHECK(cudaStreamSynchronize(st));
   for (int f = 0; f < 6; ++f) rep.phi[f] = phi[f];
+  trace.mark("face fluxes (trapz)");
   const double Aq[6] = {Lq[1] * Lq[2], Lq[1] * Lq[2], Lq[0] * Lq[2], Lq[0] * Lq[2], Lq[0] * Lq[1], Lq[0] * Lq[1]};
 
-  DevBuf At[6][2];
+  // Multi-GPU: the six chi problems are independent (ndsm_vector_potential.f90:338-365), so face f is solved by
+  // rank f mod world only and the resulting Dirichlet data At (two arrays per face) are broadcast to every rank
+  // (peer-memory transport: written straight into the other ranks' copies).  One rank holding all slabs (virtual
+  // ranks) and the BC-capture hook of the tests keep all six faces local.
+  static const bool bc_dist_env = !(getenv("NDSM_BC_DISTRIBUTE") && atoi(getenv("NDSM_BC_DISTRIBUTE")) == 0);
+  const bool dist_bc = comm && comm->world() > 1 && comm->nlocal() == 1 && !cap && bc_dist_env;
+  const int bcW = dist_bc ? comm->world() : 1, bcme = dist_bc ? comm->first_rank() : 0;
+  auto mine = [&](int f) { return !dist_bc || f % bcW == bcme; };
+  // nothing of this call may reach a rank that is still working on the previous one
+  if (comm && comm->nlocal() == 1) comm->barrier(st);
+  struct BcBuf {  // dense face array that a broadcast may target
+    Comm* c = nullptr;
+    double* p = nullptr;
+    void alloc(Comm* comm_, size_t n) {
+      c = comm_;
+      p = static_cast<double*>(c ? c->sym_alloc(n * sizeof(double)) : pool_alloc(n * sizeof(double)));
+    }
+    ~BcBuf() {
+      if (!p) return;
+      if (c) c->sym_free(p);
+      else pool_free(p);
+    }
+  };
+  BcBuf At[6][2], binfo;
+  for (int f = 0; f < 6; ++f)
+    for (int t = 0; t < 2; ++t) At[f][t].alloc(dist_bc ? comm : nullptr, (size_t)n1[f] * n2[f]);
+  binfo.alloc(dist_bc ? comm : nullptr, 8);
   int ierr_last = 0;
   if (g_debug) debug_msg("compute_vector_potential", "Solve BVP on each boundary...");
   {
-    // The six chi problems are independent (ndsm_vector_potential.f90:338-365) and each is a chain of tiny,
-    // latency-bound kernels, so they run concurrently: one hierarchy and one stream per face, V-cycles
-    // interleaved by this host thread.  (With the debug flag they run one after the other so that the
-    // reference's message order is kept.)
+    // The chi problems are chains of tiny, latency-bound kernels, so the ones this rank owns run concurrently: one
+    // hierarchy and one stream per face, V-cycles interleaved by this host thread.  (With the debug flag they
+    // run one after the other so that the reference's message order is kept.)
     struct FaceSolve {
       std::unique_ptr<MG> mg;
       DevBuf chi, rhs;
@@ -108,6 +152,7 @@ int vector_solve_core(const int* nshape, const long long* iopt, const double* ro
     } guard{fs};
     CUDA_CHECK(cudaStreamSynchronize(st));
     for (int f = 0; f < 6; ++f) {
+      if (!mine(f)) continue;
       CUDA_CHECK(cudaStreamCreateWithFlags(&fs[f].st, cudaStreamNonBlocking));
       const int sh2[3] = {n1[f], n2[f], 1};
       const double* m2[2] = {mesh[imap_nc[f][0]], mesh[imap_nc[f][1]]};
@@ -119,30 +164,38 @@ int vector_solve_core(const int* nshape, const long long* iopt, const double* ro
       CUDA_CHECK(cudaMemsetAsync(fs[f].rhs.p, 0, 2 * (size_t)g2.cs * sizeof(double), fs[f].st));
       CUDA_CHECK(cudaMemsetAsync(fs[f].chi.p, 0, 2 * (size_t)g2.cs * sizeof(double), fs[f].st));  // :345
       split_from_dense(bn[f], fs[f].rhs.p, g2, phi[f] / Aq[f], fs[f].st);                         // :348
-      At[f][0].alloc((size_t)n1[f] * n2[f]);
-      At[f][1].alloc((size_t)n1[f] * n2[f]);
     }
+    trace.mark("2D hierarchy construction");
     auto run_face_to_end = [&](int f) {
       double du_last;
       fs[f].ierr = fs[f].mg->solve(fs[f].chi.p, fs[f].rhs.p, ropt[ROPT_VTOL], (int)iopt[IOPT_NCYCLES], &du_last, &rep.solves[f]);
     };
     if (g_debug) {
-      for (int f = 0; f < 6; ++f) run_face_to_end(f);
+      for (int f = 0; f < 6; ++f)
+        if (mine(f)) run_face_to_end(f);
     } else {
       for (int f = 0; f < 6; ++f)
-        fs[f].mg->solve_begin(fs[f].chi.p, fs[f].rhs.p, ropt[ROPT_VTOL], (int)iopt[IOPT_NCYCLES], &rep.solves[f]);
+        if (mine(f))
+          fs[f].mg->solve_begin(fs[f].chi.p, fs[f].rhs.p, ropt[ROPT_VTOL], (int)iopt[IOPT_NCYCLES], &rep.solves[f]);
+      trace.mark("chi solve_begin (graph capture)");
+      for (int f = 0; f < 6; ++f)
+        if (mine(f)) fs[f].mg->solve_enqueue();
       bool any = true;
-      while (any) {
+      while (any) {  // a face is re-enqueued right after its own poll, so its stream never waits for the others
         any = false;
-        for (int f = 0; f < 6; ++f)
-          if (!fs[f].mg->solve_done()) fs[f].mg->solve_enqueue();
-        for (int f = 0; f < 6; ++f)
-          if (!fs[f].mg->solve_done()) { fs[f].mg->solve_poll(); any = true; }
+        for (int f = 0; f < 6; ++f) {
+          if (!mine(f) || fs[f].mg->solve_done()) continue;
+          if (!fs[f].mg->solve_poll()) fs[f].mg->solve_enqueue();
+          any = true;
+        }
       }
-      for (int f = 0; f < 6; ++f) { double du_last; fs[f].ierr = fs[f].mg->solve_end(&du_last); }
+      trace.mark("chi V-cycle loop");
+      for (int f = 0; f < 6; ++f)
+        if (mine(f)) { double du_last; fs[f].ierr = fs[f].mg->solve_end(&du_last); }
     }
     ierr_last = fs[5].ierr;  // :360,480 -- only the last chi solve's ierr survives (reference quirk)
     for (int f = 0; f < 6; ++f) {
+      if (!mine(f)) continue;
       const Grid g2 = fs[f].mg->level(0).g;
       compute_At(fs[f].chi.p, g2, 1.0 / (2.0 * dq[imap_cp[f]]), f, At[f][0].p, At[f][1].p, fs[f].st);  // :394-398 (dq of normal dir)
       if (cap) {
@@ -157,94 +210,30 @@ int vector_solve_core(const int* nshape, const long long* iopt, const double* ro
       }
       CUDA_CHECK(cudaStreamSynchronize(fs[f].st));
     }
+    if (dist_bc) {  // all-gather of the At faces and of the chi solves' ierr
+      double hinfo[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+      for (int f = 0; f < 6; ++f)
+        if (mine(f)) {
+          hinfo[f] = (double)fs[f].ierr;
+          CUDA_CHECK(cudaMemcpyAsync(binfo.p + f, &hinfo[f], sizeof(double), cudaMemcpyHostToDevice, st));
+        }
+      comm->begin(st);
+      for (int f = 0; f < 6; ++f) {
+        comm->bcast(f % bcW, At[f][0].p, (size_t)n1[f] * n2[f], st);
+        comm->bcast(f % bcW, At[f][1].p, (size_t)n1[f] * n2[f], st);
+        comm->bcast(f % bcW, binfo.p + f, 1, st);
+      }
+      comm->end(st);
+      double hall[8];
+      CUDA_CHECK(cudaMemcpyAsync(hall, binfo.p, 6 * sizeof(double), cudaMemcpyDeviceToHost, st));
+      CUDA_CHECK(cudaStreamSynchronize(st));
+      if (comm->failed()) throw NdsmError(NDSM_ERR_INTERNAL);
+      ierr_last = (int)hall[5];
+    }
   }
   rep.ms_bc = tm.stop();
+  trace.mark("At faces, BC setup done");
   if (stop_after_bc) {
-    rep.launches = g_launches - launches0;
-    return ierr_last;
-  }
-
-  // ---------------- hybrid: my group solves ONE component, then all-to-all of dense A planes ------------
-  if (hyb) {
-    tm.start();
-    const int c = hyb->comp, me = hyb->world->first_rank(), W = hyb->world->world();
-    const int sh3h[3] = {nx, ny, nz};
-    const i64 plh = (i64)nx * ny;
-    static const int wf[3][4] = {{2, 3, 4, 5}, {0, 1, 4, 5}, {0, 1, 2, 3}};
-    static const int wa[3][4] = {{0, 0, 0, 0}, {0, 0, 1, 1}, {1, 1, 1, 1}};
-    static const char* cop[3] = {"NDDNDD", "DNDDND", "DDNDDN"};
-    const bool flux_first = (iopt[IOPT_FLXCRL] != 1);
-    if (!flux_first && me == 0) printf(" FLAG SET: FLXCRL\n");
-    int a0, a1;  // planes of component c this rank converts and sends out
-    output_range(nz, hyb->gsize[c], me - hyb->gfirst[c], &a0, &a1);
-    DevBuf mine((size_t)std::max(a1 - a0, 1) * plh);
-    {
-      MG mg(3, sh3h, -1, mesh, st, hyb->gsize[c] > 1 ? hyb->group : nullptr);
-      rep.ndist = mg.plan().ndist;
-      const Level& L0 = mg.level(0, 0);
-      rep.slab_points = (unsigned long long)nx * ny * L0.g.nzl;
-      const size_t lv0 = mg.level_doubles(0, 0);
-      DevBuf As1(lv0);
-      CUDA_CHECK(cudaMemsetAsync(As1.p, 0, lv0 * sizeof(double), st));
-      double* p0 = As1.p + (i64)L0.H * L0.g.ps;
-      for (int w = 0; w < 4; ++w) {
-        const int f = wf[c][w];
-        write_face(p0, L0.g, imap_cp[f], (f % 2 == 0) ? 0 : nshape[imap_cp[f]] - 1, At[f][wa[c][w]].p, st);
-      }
-      mg.set_options(c == 2 ? 5 : (int)iopt[IOPT_MS], ropt[ROPT_CTOL], cop[c], use_du_max, (int)iopt[IOPT_NMAXEX]);
-      double du_last;
-      mg.solve(p0, nullptr, ropt[ROPT_VTOL], (int)iopt[IOPT_NCYCLES], &du_last, &rep.solves[6 + c]);
-      if (L0.g.k0 > a0 || L0.g.k0 + L0.g.nzl < a1) throw NdsmError(6);
-      unsplit_A(p0, L0.g, c, dx_, dy_, dz_, phi, Lq, flux_first, a0, a1, mine.p, st);
-      CUDA_CHECK(cudaStreamSynchronize(st));
-    }
-    rep.ms_solve3d = tm.stop();
-    tm.start();
-    // planes every rank needs: its output range plus the planes the curl stencil touches
-    auto need = [&](int d, int* ka, int* kb, int* k0, int* k1) {
-      output_range(nz, W, d, k0, k1);
-      *ka = (*k0 == 0) ? 0 : *k0 - 1;
-      *kb = (*k1 == nz) ? nz : *k1 + 1;
-      if (*k0 == 0 && *kb < 3) *kb = 3 < nz ? 3 : nz;
-      if (*k1 == nz && *ka > nz - 3) *ka = nz - 3 > 0 ? nz - 3 : 0;
-    };
-    if (outs_in.size() != 1) throw NdsmError(6);
-    const SlabOut& o = outs_in[0];
-    int ka, kb, k0, k1;
-    need(me, &ka, &kb, &k0, &k1);
-    if (o.k0 != k0 || o.k1 != k1) throw NdsmError(6);
-    const i64 csA = (i64)(kb - ka) * plh;
-    DevBuf tmp((size_t)3 * csA);
-    hyb->world->begin(st);
-    for (int cc = 0; cc < 3; ++cc)
-      for (int q = hyb->gfirst[cc]; q < hyb->gfirst[cc] + hyb->gsize[cc]; ++q) {
-        int qa0, qa1;
-        output_range(nz, hyb->gsize[cc], q - hyb->gfirst[cc], &qa0, &qa1);
-        for (int d = 0; d < W; ++d) {
-          int dka, dkb, dk0, dk1;
-          need(d, &dka, &dkb, &dk0, &dk1);
-          const int v0 = std::max(qa0, dka), v1 = std::min(qa1, dkb);
-          if (v1 <= v0) continue;
-          const size_t n = (size_t)(v1 - v0) * plh;
-          if (q == me && d == me) {
-            CUDA_CHECK(cudaMemcpyAsync(tmp.p + cc * csA + (i64)(v0 - ka) * plh, mine.p + (i64)(v0 - a0) * plh,
-                                       n * sizeof(double), cudaMemcpyDeviceToDevice, st));
-          } else if (q == me) {
-            hyb->world->send(me, d, mine.p + (i64)(v0 - a0) * plh, n, st);
-          } else if (d == me) {
-            hyb->world->recv(me, q, tmp.p + cc * csA + (i64)(v0 - ka) * plh, n, st);
-          }
-        }
-      }
-    hyb->world->end(st);
-    curl_dense(tmp.p, ka, csA, nx, ny, nz, dq[0], dq[1], dq[2], k0, k1, o.B, o.cstride, st);
-    for (int cc = 0; cc < 3; ++cc)
-      CUDA_CHECK(cudaMemcpyAsync(o.A + cc * o.cstride, tmp.p + cc * csA + (i64)(k0 - ka) * plh,
-                                 (size_t)(k1 - k0) * plh * sizeof(double), cudaMemcpyDeviceToDevice, st));
-    if (!flux_first) add_flux_dense(o.A, o.cstride, o.B, o.cstride, nx, ny, k0, k1, dx_, dy_, dz_, phi, Lq, st);
-    CUDA_CHECK(cudaStreamSynchronize(st));
-    rep.ms_post = tm.stop();
-    rep.ms_device = tall.stop();
     rep.launches = g_launches - launches0;
     return ierr_last;
   }
@@ -254,14 +243,16 @@ int vector_solve_core(const int* nshape, const long long* iopt, const double* ro
   tm.start();
   if (g_debug) debug_msg("compute_vector_potential", "Solve BVP 3D...");
   const int sh3[3] = {nx, ny, nz};
-  // Multi-GPU: the three component solves are independent (ndsm_vector_potential.f90:647-689), so they run
-  // concurrently on three streams with three communicators: the halo-exchange latency of one solve is hidden
-  // behind the kernels of the other two.  On one GPU the solves are bandwidth-bound and run one after another
-  // on one hierarchy (a third of the memory).
-  // opt-in: fine with virtual ranks, but NCCL serialises kernels of concurrently used communicators badly
-  // (measured 10x slower on 2 GPUs), so the default is one solve at a time
-  static const bool conc_env = getenv("NDSM_CONCURRENT_COMPONENTS") && atoi(getenv("NDSM_CONCURRENT_COMPONENTS")) != 0;
-  const bool concurrent = comm && comm->world() > 1 && conc_env && !prof_enabled() && !g_debug;
+  // Multi-GPU: the three component solves are independent (ndsm_vector_potential.f90:647-689), so every rank holds
+  // a z-slab of all three and runs them concurrently on three streams, each with its own channel of the
+  // peer-memory transport: while one component sits in its latency-bound tail (replicated coarse levels, halo
+  // hand-shakes) the other two keep the HBM busy.  On one GPU the solves are bandwidth-bound and run one after
+  // another on one hierarchy (a third of the memory, and the finished components overlap their D2H copies).
+  // Over NCCL concurrently used communicators serialise badly (measured 10x slower), so there it is opt-in.
+  const char* conc_env = getenv("NDSM_CONCURRENT_COMPONENTS");
+  const bool conc_default = comm && comm->world() > 1 && comm->nlocal() == 1 && comm->one_sided();
+  const bool conc_want = conc_env ? atoi(conc_env) != 0 : conc_default;
+  const bool concurrent = conc_want && !prof_enabled() && !g_debug && (!comm || comm->nlocal() == 1);
   struct Ctx {
     std::unique_ptr<MG> mg;
     std::unique_ptr<Comm> own_comm;
@@ -280,11 +271,14 @@ int vector_solve_core(const int* nshape, const long long* iopt, const double* ro
     if (q > 0) {
       CUDA_CHECK(cudaStreamCreateWithFlags(&ctx[q].st, cudaStreamNonBlocking));
       ctx[q].own_stream = true;
-      ctx[q].own_comm = comm->clone(st);
-      cq = ctx[q].own_comm.get();
+      if (comm) {
+        ctx[q].own_comm = comm->clone(ctx[q].st);
+        cq = ctx[q].own_comm.get();
+      }
     }
     ctx[q].mg.reset(new MG(3, sh3, -1, mesh, ctx[q].st, cq));
   }
+  trace.mark("3D hierarchy construction");
   MG* mg3 = ctx[0].mg.get();
   auto mgc = [&](int c) { return ctx[concurrent ? c : 0].mg.get(); };
   const int ns = mg3->nslabs();
@@ -349,13 +343,16 @@ int vector_solve_core(const int* nshape, const long long* iopt, const double* ro
       set_opts(c);
       mgc(c)->solve_begin(Ap[c], norhs, ropt[ROPT_VTOL], (int)iopt[IOPT_NCYCLES], &rep.solves[6 + c]);
     }
+    // every stream always has its next V-cycle queued: a component is re-enqueued right after its own poll
+    for (int c = 0; c < 3; ++c) mgc(c)->solve_enqueue();
     bool any = true;
     while (any) {
       any = false;
-      for (int c = 0; c < 3; ++c)
-        if (!mgc(c)->solve_done()) mgc(c)->solve_enqueue();
-      for (int c = 0; c < 3; ++c)
-        if (!mgc(c)->solve_done()) { mgc(c)->solve_poll(); any = true; }
+      for (int c = 0; c < 3; ++c) {
+        if (mgc(c)->solve_done()) continue;
+        if (!mgc(c)->solve_poll()) mgc(c)->solve_enqueue();
+        any = true;
+      }
     }
     for (int c = 0; c < 3; ++c) {
       double du_last;
@@ -365,6 +362,7 @@ int vector_solve_core(const int* nshape, const long long* iopt, const double* ro
     }
   }
   rep.ms_solve3d = tm.stop();
+  trace.mark("three 3D solves");
 
   // ---------------- flux-balance fields + curl (K8) ----------------
   tm.start();
@@ -404,19 +402,10 @@ int vector_solve_core(const int* nshape, const long long* iopt, const double* ro
     CUDA_CHECK(cudaStreamSynchronize(st));  // tmp goes out of scope
   }
   rep.ms_post = tm.stop();
+  trace.mark("flux fields + curl");
   rep.ms_device = tall.stop();
   rep.launches = g_launches - launches0;
   return ierr_last;  // :480 -- ierr of the LAST chi solve (reference quirk)
-}
-
-// contiguous groups of ranks, sizes as equal as possible (larger groups first)
-void hybrid_groups(int world, int* gfirst3, int* gsize3) {
-  int at = 0;
-  for (int c = 0; c < 3; ++c) {
-    gsize3[c] = world / 3 + (c < world % 3 ? 1 : 0);
-    gfirst3[c] = at;
-    at += gsize3[c];
-  }
 }
 
 void output_range(int nz, int world, int rank, int* k0, int* k1) {

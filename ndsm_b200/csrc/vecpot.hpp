@@ -54,24 +54,12 @@ struct CoreHooks {
   std::function<void(int)> component_ready;
 };
 
-// Hybrid decomposition for >= 3 ranks (one process per GPU): the three component solves are independent
-// (ndsm_vector_potential.f90:647-689), so the ranks are split into three contiguous groups, group c solves
-// component c (z-slabs inside the group, its own communicator) and the results are redistributed over the
-// world communicator so that every rank can compute the curl on its own output planes.
-struct Hybrid {
-  Comm* world = nullptr;
-  Comm* group = nullptr;  // communicator of my group
-  int comp = 0;           // the component my group solves
-  int gfirst[3] = {0, 0, 0}, gsize[3] = {1, 1, 1};
-};
-void hybrid_groups(int world, int* gfirst3, int* gsize3);
-
 // bn[f]: dense device faces (face f has shape (n1,n2) per ndsm_vector_potential.f90:225-246), all six on every
 // rank.  comm == nullptr: single slab.  outs: one entry per slab held by this process.
 // stop_after_bc: only run the BC setup (tests).  Returns iopt(IOPT_IERR).
 int vector_solve_core(const int* nshape, const long long* iopt, const double* ropt, const double* x, const double* y,
                       const double* z, double* const* bn, const DenseIn& A0, Comm* comm, const std::vector<SlabOut>& outs,
                       cudaStream_t st, Report& rep, BcCapture* cap, bool stop_after_bc,
-                      const CoreHooks* hooks = nullptr, const Hybrid* hyb = nullptr);
+                      const CoreHooks* hooks = nullptr);
 
 }  // namespace ndsm

@@ -75,6 +75,7 @@ def _declare(lib):
     lib.ndsm_b200_last_slab_points.restype = c.c_ulonglong
     lib.ndsm_b200_dist_unique_id.argtypes = [vp]
     lib.ndsm_b200_dist_init.argtypes = [c.c_int, c.c_int, vp]
+    lib.ndsm_b200_dist_transport.restype = c.c_char_p
     lib.ndsm_b200_slab_range.argtypes = [c.c_int, c.c_int, c.c_int, vp, vp]
     lib.ndsm_b200_vector_solve_rank.argtypes = [vp, vp, vp, vp, vp, vp, vp, c.c_int, vp, vp, c.c_int]
     lib.ndsm_b200_release_workspace.restype = None

@@ -87,6 +87,15 @@ int orc_num_threads(void) {
   return 1;
 #endif
 }
+/* bench.py pins the thread count of the CPU arm here: OMP_NUM_THREADS of a launcher (torch.distributed.run sets 1)
+ * is read by libgomp once, when it is loaded, and must not decide the baseline */
+void orc_set_num_threads(int n) {
+#ifdef _OPENMP
+  if (n > 0) omp_set_num_threads(n);
+#else
+  (void)n;
+#endif
+}
 
 /* ------------------------------------------------------------------ */
 /* Small parallel helpers: ndsm_multigrid_core.f90:1134-1223            */

@@ -73,6 +73,8 @@ def lib():
         L.orc_interp_table.argtypes = [i64, vp, i64, vp, vp, vp, vp]
         L.orc_restrict_table.argtypes = [i64, vp, i64, vp, vp, vp, vp, vp]
         L.orc_bracket.argtypes = [vp, i64, c.c_double, vp, vp, vp]
+        L.orc_set_num_threads.argtypes = [c.c_int]
+        L.orc_set_num_threads.restype = None
         L.ndsm_vector_solve.argtypes = [c.c_size_t] + [vp] * 8
         L.orc_poisson_solve.argtypes = [c.c_int, vp, c.c_char_p, i64, i64, i64, c.c_int, c.c_double, c.c_double,
                                         vp, vp, vp, vp, vp, vp, vp]
@@ -314,3 +316,23 @@ def flux_curl(x, y, z, phi, A, flxcrl=0):
 
 def num_threads():
     return lib().orc_num_threads()
+
+
+def set_num_threads(n):
+    lib().orc_set_num_threads(int(n))
+
+
+def poisson_solve(mesh, copt, u, rhs=None, ms=5, ncycles_max=1024, niterex_max=10000, mean=False, vc_tol=1e-10,
+                  ex_tol=1e-13):
+    """solve_poisson_bvp (ndsm_poisson.f90:63) on a caller-defined 2D/3D problem; u, rhs in numpy order
+    (nz,ny,nx).  Returns (ierr, u, du_last, ncycles)."""
+    mesh = [_f(m) for m in mesh]
+    nshape = np.array([m.size for m in mesh], dtype=np.intc)
+    u = np.array(u, dtype=np.float64, order="C")
+    r = np.zeros_like(u) if rhs is None else _f(rhs)
+    du, nc = c.c_double(0), c.c_int(0)
+    z = mesh[2] if len(mesh) > 2 else None
+    ierr = lib().orc_poisson_solve(len(mesh), _p(nshape), copt.encode(), ms, ncycles_max, niterex_max,
+                                   0 if mean else 1, vc_tol, ex_tol, _p(mesh[0]), _p(mesh[1]), _p(z), _p(u), _p(r),
+                                   c.byref(du), c.byref(nc))
+    return ierr, u, du.value, nc.value

@@ -123,3 +123,43 @@ def test_257_matches_oracle(gpu_lib, oracle):
         assert len(gpu[3][name]["du"]) == len(ora[3][name]["du"])
     assert rel_err(gpu[1], ora[1]) <= 1e-10
     assert rel_err(gpu[2], ora[2]) <= 1e-10
+
+
+def test_257_mean_metric_matches_oracle(gpu_lib, oracle):
+    """BASELINE config 2: the dipole at 257^3 with the MEAN convergence metric (ndsm.py mean=True ->
+    iopt[IOPT_DUMAX]=0; du_metrics / update_u sum branch, ndsm_multigrid_core.f90:848,1116), point by point
+    against the oracle and against the analytic dipole field."""
+    from ndsm_b200 import synthetic, vector_potential
+    x, y, z = synthetic.mesh(257)
+    b = synthetic.dipole(x, y, z)
+    gpu = vector_potential(x, y, z, b, mean=True, trace=True)
+    ora = oracle.vector_potential(x, y, z, b, mean=True, trace=True)
+    assert gpu[0] == ora[0] == 0
+    for name in ["chi%d" % f for f in range(1, 7)] + ["Ax", "Ay", "Az"]:
+        assert abs(len(gpu[3][name]["du"]) - len(ora[3][name]["du"])) <= 1, name
+    assert rel_err(gpu[1], ora[1]) <= 1e-10
+    assert rel_err(gpu[2], ora[2]) <= 1e-10
+    # analytic check on B (A is gauge dependent): second-order truncation error, far below the field scale
+    err = np.linalg.norm(gpu[2] - b, axis=0)
+    assert err.mean() < 0.01 * np.linalg.norm(b, axis=0).mean()
+    # the mean metric stops earlier than the max metric (fewer or equal V-cycles)
+    mx = vector_potential(x, y, z, b, mean=False, trace=True)
+    for name in ("Ax", "Ay", "Az"):
+        assert len(gpu[3][name]["du"]) <= len(mx[3][name]["du"]), name
+
+
+def test_full_size_513_matches_oracle_point_by_point(full, oracle):
+    """The headline configuration itself (513^3 dipole, max metric) against the CPU oracle: same V-cycle counts,
+    same coarsest-solve iteration counts, A and B within 1e-10 relative at every one of the 4.05e8 output values.
+    One oracle solve is ~44 V-cycles x 1-2 s on the GPU box's host cores."""
+    ora = oracle.vector_potential(full["x"], full["y"], full["z"], full["b"], trace=True)
+    assert ora[0] == 0
+    tr_g, tr_o = full["tr"], ora[3]
+    for name in ["chi%d" % f for f in range(1, 7)]:
+        assert abs(len(tr_g[name]["du"]) - len(tr_o[name]["du"])) <= 1, name
+    for name in ("Ax", "Ay", "Az"):
+        assert len(tr_g[name]["du"]) == len(tr_o[name]["du"]), name
+        assert tr_g[name]["nexact"] == tr_o[name]["nexact"], name
+        np.testing.assert_allclose(tr_g[name]["du"], tr_o[name]["du"], rtol=1e-6)
+    assert rel_err(full["A"], ora[1]) <= 1e-10
+    assert rel_err(full["B"], ora[2]) <= 1e-10

@@ -149,3 +149,33 @@ def test_poisson_slabs_refuse_unpartitionable_grid(gpu_lib, slab_env, capfd):
     ierr = ndist.poisson_solve(x, y, z, np.zeros_like(uex), rhs)[0]
     assert ierr == 5                                               # NDSM_B200_ERR_ARG
     assert "too small to be partitioned" in capfd.readouterr().err
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_poisson_pure_neumann_3d_on_partitioned_levels(gpu_lib, slab_env, oracle, world):
+    """All six faces Neumann (copt NNNNNN): the gauge is fixed by subtracting the global mean after every sweep
+    (ndsm_optimized.f90:173-189).  On z-partitioned levels the mean is the rank-ordered sum of the slab sums; it
+    differs from the single-slab summation order only in rounding, like two OpenMP runs of the reference."""
+    from ndsm_b200 import dist as ndist
+    nx, ny, nz = 40, 36, 56
+    x = np.linspace(0, 1, nx)
+    dx = x[1] - x[0]
+    y, z = np.arange(ny) * dx, np.arange(nz) * dx
+    Z, Y, X = np.meshgrid(z, y, x, indexing="ij")
+    uex = np.cos(np.pi * X) * np.cos(2 * np.pi * Y / y[-1]) * np.cos(np.pi * Z / z[-1])   # zero mean, du/dn = 0
+    rhs = -(np.pi ** 2) * (1 + 4 / y[-1] ** 2 + 1 / z[-1] ** 2) * uex
+    os.environ["NDSM_VIRTUAL_SLABS"] = "1"
+    ref = ndist.poisson_solve(x, y, z, np.zeros_like(uex), rhs, copt="NNNNNN")
+    os.environ["NDSM_VIRTUAL_SLABS"] = str(world)
+    os.environ["NDSM_SLAB_MIN_PLANES"] = "6"
+    os.environ["NDSM_SLAB_MIN_POINTS"] = "0"
+    got = ndist.poisson_solve(x, y, z, np.zeros_like(uex), rhs, copt="NNNNNN")
+    assert gpu_lib.ndsm_b200_last_partitioned_levels() > 0
+    assert got[0] == ref[0] == 0
+    assert abs(got[3] - ref[3]) <= 1
+    assert rel_err(got[1], ref[1]) <= 1e-10
+    ora = oracle.poisson_solve([x, y, z], "NNNNNN", np.zeros_like(uex), rhs)
+    assert ora[0] == 0 and abs(got[3] - ora[3]) <= 1
+    assert rel_err(got[1], ora[1]) <= 1e-10
+    assert abs(got[1].mean()) <= 1e-12 * np.abs(got[1]).max() + 1e-15          # the gauge: zero mean
+    assert np.abs(got[1] - uex).max() < 5e-2                                    # O(h^2)

@@ -4,6 +4,7 @@ against (a) the reference's golden tables and (b) the CPU oracle on the same inp
 Tolerances (north_star): same V-cycle count +-1, final A and B within 1e-10 relative.
 """
 import ctypes
+import os
 
 import numpy as np
 import pytest
@@ -241,3 +242,33 @@ def test_launch_counter_moves(gpu_lib):
     _, b = synthetic.test_case1(x, y, z)
     vector_potential(x, y, z, b)
     assert gpu_lib.ndsm_b200_launch_count() > n0 + 100
+
+
+REF_DIR = os.environ.get("NDSM_REFERENCE_DIR", "/root/reference")
+
+
+@pytest.mark.skipif(not os.path.exists(os.path.join(REF_DIR, "ndsm.py")),
+                    reason="reference tree not present (set NDSM_REFERENCE_DIR to a directory holding the "
+                           "reference's unmodified ndsm.py)")
+def test_unmodified_reference_wrapper_drives_the_cuda_library(gpu_lib):
+    """The drop-in claim itself: the reference's own, unmodified ndsm.py loads ndsm_b200/lib/ndsmf.so through its
+    ctypes path (ndsm.py:136-210: LoadLibrary(libpath), the index getters, ndsm_vector_solve) and reproduces the
+    reference's golden rows for 22^3 and 44^3 (results_test1.txt:6-7, results_test2.txt:6)."""
+    import sys
+    from ndsm_b200 import synthetic
+    from ndsm_b200.lib_loader import LIB_PATH
+    sys.path.insert(0, REF_DIR)
+    try:
+        sys.modules.pop("ndsm", None)
+        import ndsm as ref_ndsm
+    finally:
+        sys.path.remove(REF_DIR)
+    assert os.path.dirname(os.path.abspath(ref_ndsm.__file__)) == os.path.abspath(REF_DIR)
+    gold = load_golden()
+    for n, mean in ((22, False), (44, False), (22, True)):
+        x, y, z = synthetic.mesh(n)
+        A1, b1 = synthetic.test_case1(x, y, z)
+        ierr, A2, b2 = ref_ndsm.vector_potential(x, y, z, b1.copy(), mean=mean, libpath=LIB_PATH)
+        assert ierr == 0
+        want = gold["mean" if mean else "max"][gold["n"].index(n)]
+        assert rows_match(error_row(x, A1, b1, A2, b2), want, last_digit_slack=0), (n, mean)
