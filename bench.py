@@ -138,7 +138,9 @@ class Config:
     def describe(self):
         nx, ny, nz = self.shape
         return {"workload": self.workload, "shape": [nx, ny, nz],
-                "l2": "inputs larger than L2 (each %dx%dx%d fp64 array = %.2f GB)" % (nx, ny, nz, 8 * self.npoints / 1e9)}
+                "l2": ("inputs larger than L2 (each %dx%dx%d fp64 array = %.2f GB)" if 8 * self.npoints > 126e6 else
+                       "arrays of %dx%dx%d fp64 = %.3f GB fit the 126 MB L2: not a bandwidth measurement")
+                      % (nx, ny, nz, 8 * self.npoints / 1e9)}
 
     def mesh(self):
         from ndsm_b200 import synthetic

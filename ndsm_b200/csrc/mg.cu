@@ -295,8 +295,9 @@ MG::MG(int ndim, const int* shape, int ngrids, const double* const* mesh, cudaSt
   }
   const i64 off_sav = take(2 * hl[ngrids - 1].g.cs);
   const i64 off_scr = take((i64)reduce_scratch_doubles());
-  // opt-in: pure-Neumann 2D sweeps with the mean subtraction folded into the passes (read per hierarchy)
-  const bool fused_mean = ndim == 2 && getenv("NDSM_B200_FUSED_MEAN") && atoi(getenv("NDSM_B200_FUSED_MEAN")) != 0;
+  // pure-Neumann 2D sweeps with the mean subtraction folded into the passes (measured: chi V-cycle loop 16.4 ->
+  // 13.5 ms at 513^2); NDSM_B200_FUSED_MEAN=0 selects the separate reduction kernels (read per hierarchy)
+  const bool fused_mean = ndim == 2 && !(getenv("NDSM_B200_FUSED_MEAN") && atoi(getenv("NDSM_B200_FUSED_MEAN")) == 0);
   const i64 off_fm = fused_mean ? take((i64)relax2d_fused_mean_scratch(hl[0].g)) : -1;
   const i64 off_all = take(2 * (i64)world + 8);
   const i64 off_allm = take(2 * (2 * (i64)world + 8));  // two alternating buffers of gathered slab sums (pure Neumann)

@@ -160,6 +160,8 @@ def test_full_size_513_matches_oracle_point_by_point(full, oracle):
     for name in ("Ax", "Ay", "Az"):
         assert len(tr_g[name]["du"]) == len(tr_o[name]["du"]), name
         assert tr_g[name]["nexact"] == tr_o[name]["nexact"], name
-        np.testing.assert_allclose(tr_g[name]["du"], tr_o[name]["du"], rtol=1e-6)
+        # the Dirichlet data come from the chi solves, whose mean has no defined summation order: the du history
+        # agrees to rounding of |A| ~ 1 (absolute 1e-14), which is 1e-4 relative once du reaches vc_tol = 1e-10
+        np.testing.assert_allclose(tr_g[name]["du"], tr_o[name]["du"], rtol=1e-6, atol=1e-14)
     assert rel_err(full["A"], ora[1]) <= 1e-10
     assert rel_err(full["B"], ora[2]) <= 1e-10

@@ -362,11 +362,10 @@ def test_poisson_solve_2d_pure_neumann_matches_oracle(gpu_lib, oracle):
     h.close()
 
 
-@pytest.mark.skipif(os.environ.get("NDSM_RUN_EXPERIMENTAL") != "1",
-                    reason="opt-in path, not yet validated on hardware: set NDSM_RUN_EXPERIMENTAL=1")
-def test_fused_mean_2d_sweeps_match_default_path(gpu_lib, tmp_path):
-    """NDSM_B200_FUSED_MEAN=1 folds the pure-Neumann mean subtraction of the chi solves into the colour passes
-    (2 launches per sweep instead of 4).  Same per-sweep semantics; only the summation order of the mean differs."""
+def test_fused_mean_2d_sweeps_match_unfused_path(gpu_lib, tmp_path):
+    """The chi solves fold the pure-Neumann mean subtraction into the colour passes (2 launches per sweep instead
+    of 4; NDSM_B200_FUSED_MEAN=0 selects the separate k_sum_partial / k_sub_mean path).  Same per-sweep semantics;
+    only the summation order of the mean differs."""
     import subprocess
     import sys
     from ndsm_b200 import synthetic, vector_potential
@@ -379,13 +378,14 @@ def test_fused_mean_2d_sweeps_match_default_path(gpu_lib, tmp_path):
             "from ndsm_b200 import synthetic, vector_potential\n"
             "x, y, z = synthetic.mesh(%d, %d, %d); b = synthetic.dipole(x, y, z)\n"
             "r = vector_potential(x, y, z, b, trace=True)\n"
-            "np.savez(%r, A=r[1], B=r[2], ierr=r[0], nc=[len(r[3][k]['du']) for k in sorted(r[3]) if 'du' in r[3][k]])\n"
+            "names = ['chi%%d' %% f for f in range(1, 7)] + ['Ax', 'Ay', 'Az']\n"
+            "np.savez(%r, A=r[1], B=r[2], ierr=r[0], nc=[len(r[3][k]['du']) for k in names])\n"
             % (os.path.dirname(os.path.dirname(os.path.abspath(__file__))), shape[0], shape[1], shape[2], str(out)))
-    env = dict(os.environ, NDSM_B200_FUSED_MEAN="1")
+    env = dict(os.environ, NDSM_B200_FUSED_MEAN="0")
     subprocess.run([sys.executable, "-c", code], check=True, env=env, timeout=600)
     got = np.load(out)
     assert int(got["ierr"]) == ref[0] == 0
-    want_nc = [len(ref[3][k]["du"]) for k in sorted(ref[3]) if "du" in ref[3][k]]
+    want_nc = [len(ref[3][k]["du"]) for k in ["chi%d" % f for f in range(1, 7)] + ["Ax", "Ay", "Az"]]
     assert all(abs(int(a) - bb) <= 1 for a, bb in zip(got["nc"], want_nc))
     assert rel_err(got["A"], ref[1]) <= 1e-10
     assert rel_err(got["B"], ref[2]) <= 1e-10
