@@ -1,5 +1,6 @@
 // abi.cu -- the C ABI of ndsmf.so (include/ndsm_b200.h).  Section 1 re-exports the reference's
 // BIND(C) surface (fortran/ndsm_python_wrapper.f90:56-234) with identical semantics.
+#include <atomic>
 #include <chrono>
 #include <cstring>
 #include <exception>
@@ -271,33 +272,43 @@ int ndsm_vector_solve(size_t nsize, const int* nshape4, int* ioptc, double* ropt
     CUDA_CHECK(cudaStreamSynchronize(st));
     hf.release();
     g_report.ms_in = (now_s() - t1) * 1e3;
-    bool zero_guess = true;
-    std::thread scan([&] { zero_guess = all_zero_host(A, 3 * N); });
+    // The three components are scanned one after the other by a helper thread: Ax is known before the BC setup
+    // ends, Ay and Az long before their solves start, so the solves never wait for the scan.
+    std::atomic<int> scanned[3];
+    for (auto& v : scanned) v.store(-1);  // -1: not yet known, 0: holds a non-zero value, 1: all zeros
+    std::thread scan([&] {
+      for (int c = 0; c < 3; ++c) scanned[c].store(all_zero_host(A + (size_t)c * N, N) ? 1 : 0);
+    });
     struct Joiner { std::thread& t; ~Joiner() { if (t.joinable()) t.join(); } } joiner{scan};
     // result delivery: page-locked destinations are copied directly, pageable ones (what numpy hands us)
     // through the sink's own pinned staging so that the main thread keeps launching the next solve
     HostSink sink(g_device);
-    bool copied[3] = {false, false, false};
+    bool copiedA[3] = {false, false, false}, copiedB[3] = {false, false, false};
     CoreHooks hooks;
-    hooks.guess = [&]() {
-      scan.join();
+    hooks.guess = [&](int c) {
+      while (scanned[c].load() < 0) std::this_thread::yield();
       DenseIn g;
-      if (!zero_guess) {
-        CUDA_CHECK(cudaMemcpyAsync(dA.p, A, 3 * N * sizeof(double), cudaMemcpyHostToDevice, st));
-        g.p = dA.p; g.kfirst = 0; g.cstride = (long long)N;
+      if (scanned[c].load() == 0) {
+        CUDA_CHECK(cudaMemcpyAsync(dA.p + (size_t)c * N, A + (size_t)c * N, N * sizeof(double), cudaMemcpyHostToDevice, st));
+        g.p = dA.p + (size_t)c * N; g.kfirst = 0; g.cstride = (long long)N;
       }
       return g;
     };
     hooks.component_ready = [&](int c) {
       sink.push(A + (size_t)c * N, dA.p + (size_t)c * N, N, st);
-      copied[c] = true;
+      copiedA[c] = true;
+    };
+    hooks.b_ready = [&](int c) {
+      sink.push(B + (size_t)c * N, dB.p + (size_t)c * N, N, st);
+      copiedB[c] = true;
     };
     if (g_debug) debug_msg(SUB, "Calling compute_vector_potential...");
     int ierr = run_core_full(nshape4, iopt, ropt, x, y, z, bn, nullptr, dA.p, dB.p, st, &hooks);
     t1 = now_s();
     for (int c = 0; c < 3; ++c)
-      if (!copied[c]) sink.push(A + (size_t)c * N, dA.p + (size_t)c * N, N, st);
-    sink.push(B, dB.p, 3 * N, st);
+      if (!copiedA[c]) sink.push(A + (size_t)c * N, dA.p + (size_t)c * N, N, st);
+    for (int c = 0; c < 3; ++c)
+      if (!copiedB[c]) sink.push(B + (size_t)c * N, dB.p + (size_t)c * N, N, st);
     sink.wait();
     CUDA_CHECK(cudaStreamSynchronize(st));
     g_report.ms_out = (now_s() - t1) * 1e3;

@@ -487,7 +487,9 @@ void relax3d_half(double* u, const double* rhs, const Grid& g, const Bounds& b, 
   // (a chunk length chosen to fill whole waves of resident blocks -- 29 planes at 513^3, 22 at 257^3 -- was
   // measured slower than 16: 0.196 vs 0.185 ms per pass at 513^3, level 1 0.95 vs 0.77 ms per V-cycle)
   static const int zc_cap = getenv("NDSM_B200_ZCHUNK") ? std::max(2, atoi(getenv("NDSM_B200_ZCHUNK"))) : 16;
-  const int zc = pick_zchunk(khi - klo + 1, bx * by, zc_cap);
+  const char* zf = getenv("NDSM_B200_ZCHUNK_FORCE");  // tuning sweeps (read per launch: scripts/sweep_zchunk.py)
+  const int zc_force = zf ? atoi(zf) : 0;
+  const int zc = zc_force > 0 ? zc_force : pick_zchunk(khi - klo + 1, bx * by, zc_cap);
   dim3 grid(bx, by, cdiv(khi - klo + 1, zc));
 #define RELAX_LAUNCH(R, UU, MB) \
   k_relax3d<R, UU, MB><<<grid, RELAX_BX * RELAX_BY, 0, st>>>(u, rhs, g, b, colour, w.wx, w.wy, w.wz, w.w1, klo, khi, zc)
@@ -1933,6 +1935,12 @@ bool solve_exact_smem(int ndim, double* u, const double* rhs, const Grid& g, con
 // The 3D arithmetic is bit-identical to the per-level kernels (restriction in the reference's summation order);
 // in 2D only the pure-Neumann mean uses a different (block-strided) summation order.
 // ---------------------------------------------------------------------------------------
+// Thread teams: a level of Q compressed (one-colour) points is worked on by the first T = min(blockDim,
+// round32(Q)) threads only; they synchronise among themselves (named barrier 1, or __syncwarp when the team is one
+// warp: the 4^3 / 4^2 coarsest solve runs 30-50 dependent iterations with three synchronisations each), the rest
+// of the block waits at the next block-wide barrier.  A thread's points (m, j, k) -- compressed column, row,
+// plane; i = 2m + ((colour + j + k) & 1) -- are decoded once per visit of a level, not once per point and pass.
+#define SM_PMAX 3  // points per thread and colour: Q <= 0.6 * SMALL_MAX_POINTS, blockDim = min(1024, round32(Q))
 __device__ __forceinline__ void sm_decode(const SmallLevel& L, int p, int& i, int& j, int& k) {
   const int sxy = L.nx * L.ny;
   k = p / sxy;
@@ -1940,88 +1948,167 @@ __device__ __forceinline__ void sm_decode(const SmallLevel& L, int p, int& i, in
   j = rem / L.nx;
   i = rem - j * L.nx;
 }
+__device__ __forceinline__ int sm_team(const SmallLevel& L) {
+  const int Q = ((L.nx + 1) >> 1) * L.ny * L.nz;
+  return min((int)blockDim.x, (Q + 31) & ~31);
+}
+__device__ __forceinline__ void team_sync(const int T) {
+  if (T <= 32) __syncwarp();
+  else asm volatile("bar.sync 1, %0;" ::"r"(T) : "memory");
+}
+// reductions over the team; consecutive reductions must be separated by a team_sync (red[] is reused)
+__device__ __forceinline__ double team_sum(double v, double* red, const int T) {
+  v = warp_sum(v);
+  if (T <= 32) return __shfl_sync(0xffffffffu, v, 0);
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = T >> 5;
+  if (lane == 0) red[wid] = v;
+  team_sync(T);
+  double t = (lane < nw) ? red[lane] : 0.0;  // every warp adds the partial sums itself, in the same order
+  t = warp_sum(t);
+  return __shfl_sync(0xffffffffu, t, 0);
+}
+__device__ __forceinline__ double team_max(double v, double* red, const int T) {
+  v = warp_max(v);
+  if (T <= 32) return __shfl_sync(0xffffffffu, v, 0);
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = T >> 5;
+  if (lane == 0) red[wid] = v;
+  team_sync(T);
+  double t = (lane < nw) ? red[lane] : 0.0;
+  t = warp_max(t);
+  return __shfl_sync(0xffffffffu, t, 0);
+}
 
-template <int NDIM>
-__device__ void sm_relax(double* __restrict__ u, const double* __restrict__ rhs, const SmallLevel& L,
-                         const int first_colour, const int all_neumann, double* red) {
-  const int N = L.nx * L.ny * L.nz, sxy = L.nx * L.ny;
-  for (int pass = 0; pass < 2; ++pass) {
-    const int colour = first_colour ^ pass;
-    for (int p = threadIdx.x; p < N; p += blockDim.x) {
-      int i, j, k;
-      sm_decode(L, p, i, j, k);
-      if (((i + j + k) & 1) != colour) continue;
-      if (i < L.b.lb[0] || i > L.b.ub[0] || j < L.b.lb[1] || j > L.b.ub[1]) continue;
-      if (NDIM == 3) {
-        if (k < L.b.lb[2] || k > L.b.ub[2]) continue;
-        const int xl = (i - 1 < 0) ? 1 : i - 1, xh = (i + 1 > L.nx - 1) ? L.nx - 2 : i + 1;
-        const int yl = (j - 1 < 0) ? 1 : j - 1, yh = (j + 1 > L.ny - 1) ? L.ny - 2 : j + 1;
-        const int zl = (k - 1 < 0) ? 1 : k - 1, zh = (k + 1 > L.nz - 1) ? L.nz - 2 : k + 1;
-        double unew = ((u[xh + j * L.nx + k * sxy] + u[xl + j * L.nx + k * sxy]) * L.w.wx +
-                       (u[i + yh * L.nx + k * sxy] + u[i + yl * L.nx + k * sxy]) * L.w.wy) +
-                      (u[i + j * L.nx + zh * sxy] + u[i + j * L.nx + zl * sxy]) * L.w.wz;
-        unew = unew - rhs[p];
-        u[p] = L.w.w1 * unew;
-      } else {
-        const int x1 = (i == 0) ? i + 1 : i - 1, x2 = (i == L.nx - 1) ? i - 1 : i + 1;
-        const int y1 = (j == 0) ? j + 1 : j - 1, y2 = (j == L.ny - 1) ? j - 1 : j + 1;
-        double un = u[x1 + j * L.nx] * L.w.wx + u[x2 + j * L.nx] * L.w.wx;
-        un = (un + u[i + y1 * L.nx] * L.w.wy) + u[i + y2 * L.nx] * L.w.wy;
-        u[p] = (un - rhs[p]) * L.w.w1;
-      }
+struct SmPts {  // this thread's compressed points on the current level
+  int n, m[SM_PMAX], j[SM_PMAX], k[SM_PMAX];
+};
+__device__ __forceinline__ void sm_points(const SmallLevel& L, const int T, SmPts& P) {
+  const int mcnt = (L.nx + 1) >> 1, Q = mcnt * L.ny * L.nz, rowq = mcnt * L.ny;
+  P.n = 0;
+#pragma unroll
+  for (int s = 0; s < SM_PMAX; ++s) {
+    const int q = threadIdx.x + s * T;
+    P.m[s] = P.j[s] = P.k[s] = 0;
+    if (q < Q) {
+      const int k = q / rowq, rem = q - k * rowq, j = rem / mcnt;
+      P.k[s] = k; P.j[s] = j; P.m[s] = rem - j * mcnt;
+      P.n = s + 1;
     }
-    __syncthreads();
   }
-  if (all_neumann) {
-    double s = 0.0;
-    for (int p = threadIdx.x; p < N; p += blockDim.x) s += u[p];
-    s = block_sum(s, red);
-    const double mean = s / (double)N;
-    for (int p = threadIdx.x; p < N; p += blockDim.x) u[p] = u[p] - mean;
-    __syncthreads();
+}
+
+// nsweeps red/black sweeps by the team (callers are inside `if (threadIdx.x < T)`).  Pure-Neumann levels subtract
+// the mean after every sweep (ndsm_poisson.f90:538-541): like k_relax2d_fm the subtraction stays pending -- the
+// next red pass reads black - mean on the fly (same bits as storing it first), red is overwritten unread -- and
+// is applied to both colours after the last sweep.  Ends with a team_sync.
+template <int NDIM>
+__device__ void sm_relax_sweeps(double* __restrict__ u, const double* __restrict__ rhs, const SmallLevel& L,
+                                const int first_colour, const int all_neumann, const int nsweeps, const SmPts& P,
+                                const int T, double* red) {
+  const int sxy = L.nx * L.ny;
+  const double count = (double)(L.nx * L.ny * L.nz);
+  double pend = 0.0;  // mean of the previous sweep, not yet subtracted in shared memory
+  for (int sw = 0; sw < nsweeps; ++sw) {
+    double wsum = 0.0;
+    for (int pass = 0; pass < 2; ++pass) {
+      const int colour = first_colour ^ pass;
+      const bool sub = (all_neumann && pass == 0 && sw > 0);  // the red pass reads black values of the last sweep
+#pragma unroll
+      for (int s = 0; s < SM_PMAX; ++s) {
+        if (s >= P.n) break;
+        const int j = P.j[s], k = P.k[s], i = 2 * P.m[s] + ((colour + j + k) & 1);
+        if (i >= L.nx) continue;
+        if (i < L.b.lb[0] || i > L.b.ub[0] || j < L.b.lb[1] || j > L.b.ub[1]) continue;
+        const int p = i + j * L.nx + k * sxy;
+        if (NDIM == 3) {
+          if (k < L.b.lb[2] || k > L.b.ub[2]) continue;
+          const int xl = (i - 1 < 0) ? 1 : i - 1, xh = (i + 1 > L.nx - 1) ? L.nx - 2 : i + 1;
+          const int yl = (j - 1 < 0) ? 1 : j - 1, yh = (j + 1 > L.ny - 1) ? L.ny - 2 : j + 1;
+          const int zl = (k - 1 < 0) ? 1 : k - 1, zh = (k + 1 > L.nz - 1) ? L.nz - 2 : k + 1;
+          double a0 = u[xh + j * L.nx + k * sxy], a1 = u[xl + j * L.nx + k * sxy];
+          double a2 = u[i + yh * L.nx + k * sxy], a3 = u[i + yl * L.nx + k * sxy];
+          double a4 = u[i + j * L.nx + zh * sxy], a5 = u[i + j * L.nx + zl * sxy];
+          if (sub) { a0 = a0 - pend; a1 = a1 - pend; a2 = a2 - pend; a3 = a3 - pend; a4 = a4 - pend; a5 = a5 - pend; }
+          double unew = ((a0 + a1) * L.w.wx + (a2 + a3) * L.w.wy) + (a4 + a5) * L.w.wz;  // ndsm_optimized.f90:123-125
+          unew = unew - rhs[p];
+          const double v = L.w.w1 * unew;
+          u[p] = v;
+          wsum += v;
+        } else {
+          const int x1 = (i == 0) ? i + 1 : i - 1, x2 = (i == L.nx - 1) ? i - 1 : i + 1;
+          const int y1 = (j == 0) ? j + 1 : j - 1, y2 = (j == L.ny - 1) ? j - 1 : j + 1;
+          double a0 = u[x1 + j * L.nx], a1 = u[x2 + j * L.nx], a2 = u[i + y1 * L.nx], a3 = u[i + y2 * L.nx];
+          if (sub) { a0 = a0 - pend; a1 = a1 - pend; a2 = a2 - pend; a3 = a3 - pend; }
+          double un = a0 * L.w.wx + a1 * L.w.wx;  // ndsm_poisson.f90:613
+          un = (un + a2 * L.w.wy) + a3 * L.w.wy;
+          const double v = (un - rhs[p]) * L.w.w1;
+          u[p] = v;
+          wsum += v;
+        }
+      }
+      team_sync(T);
+    }
+    if (all_neumann) pend = team_sum(wsum, red, T) / count;
+  }
+  if (all_neumann && nsweeps > 0) {  // apply the pending mean to both colours
+#pragma unroll
+    for (int s = 0; s < SM_PMAX; ++s) {
+      if (s >= P.n) break;
+      const int j = P.j[s], k = P.k[s], i0 = 2 * P.m[s];
+      const int base = j * L.nx + k * sxy;
+      if (i0 < L.nx) u[base + i0] = u[base + i0] - pend;
+      if (i0 + 1 < L.nx) u[base + i0 + 1] = u[base + i0 + 1] - pend;
+    }
+    team_sync(T);
   }
 }
 
 template <int NDIM>
 __device__ void sm_residual(const double* __restrict__ u, const double* __restrict__ rhs, double* __restrict__ r,
-                            const SmallLevel& L) {
-  const int N = L.nx * L.ny * L.nz, sxy = L.nx * L.ny;
-  for (int p = threadIdx.x; p < N; p += blockDim.x) {
-    int i, j, k;
-    sm_decode(L, p, i, j, k);
-    double res = 0.0;
-    const bool in = !(i < L.b.lb[0] || i > L.b.ub[0] || j < L.b.lb[1] || j > L.b.ub[1] ||
-                      (NDIM == 3 && (k < L.b.lb[2] || k > L.b.ub[2])));
-    if (in) {
-      if (NDIM == 3) {
-        const int xl = (i - 1 < 0) ? 1 : i - 1, xh = (i + 1 > L.nx - 1) ? L.nx - 2 : i + 1;
-        const int yl = (j - 1 < 0) ? 1 : j - 1, yh = (j + 1 > L.ny - 1) ? L.ny - 2 : j + 1;
-        const int zl = (k - 1 < 0) ? 1 : k - 1, zh = (k + 1 > L.nz - 1) ? L.nz - 2 : k + 1;
-        double tt = ((u[xl + j * L.nx + k * sxy] + u[xh + j * L.nx + k * sxy]) * L.w.wx +
-                     (u[i + yl * L.nx + k * sxy] + u[i + yh * L.nx + k * sxy]) * L.w.wy) +
-                    (u[i + j * L.nx + zl * sxy] + u[i + j * L.nx + zh * sxy]) * L.w.wz;
-        tt = tt - rhs[p];
-        tt = tt - u[p] * L.w.wc;
-        res = -tt;
-      } else {
-        const int x1 = (i == 0) ? i + 1 : i - 1, x2 = (i == L.nx - 1) ? i - 1 : i + 1;
-        const int y1 = (j == 0) ? j + 1 : j - 1, y2 = (j == L.ny - 1) ? j - 1 : j + 1;
-        const double uc = u[p];
-        double lap = ((u[x1 + j * L.nx] - 2 * uc) + u[x2 + j * L.nx]) * L.w.wx;
-        lap = lap + ((u[i + y1 * L.nx] - 2 * uc) + u[i + y2 * L.nx]) * L.w.wy;
-        res = rhs[p] - lap;
+                            const SmallLevel& L, const SmPts& P, const int T) {
+  const int sxy = L.nx * L.ny;
+#pragma unroll
+  for (int s = 0; s < SM_PMAX; ++s) {
+    if (s >= P.n) break;
+    const int j = P.j[s], k = P.k[s];
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      const int i = 2 * P.m[s] + e;
+      if (i >= L.nx) continue;
+      const int p = i + j * L.nx + k * sxy;
+      double res = 0.0;
+      const bool in = !(i < L.b.lb[0] || i > L.b.ub[0] || j < L.b.lb[1] || j > L.b.ub[1] ||
+                        (NDIM == 3 && (k < L.b.lb[2] || k > L.b.ub[2])));
+      if (in) {
+        if (NDIM == 3) {
+          const int xl = (i - 1 < 0) ? 1 : i - 1, xh = (i + 1 > L.nx - 1) ? L.nx - 2 : i + 1;
+          const int yl = (j - 1 < 0) ? 1 : j - 1, yh = (j + 1 > L.ny - 1) ? L.ny - 2 : j + 1;
+          const int zl = (k - 1 < 0) ? 1 : k - 1, zh = (k + 1 > L.nz - 1) ? L.nz - 2 : k + 1;
+          double tt = ((u[xl + j * L.nx + k * sxy] + u[xh + j * L.nx + k * sxy]) * L.w.wx +
+                       (u[i + yl * L.nx + k * sxy] + u[i + yh * L.nx + k * sxy]) * L.w.wy) +
+                      (u[i + j * L.nx + zl * sxy] + u[i + j * L.nx + zh * sxy]) * L.w.wz;
+          tt = tt - rhs[p];
+          tt = tt - u[p] * L.w.wc;
+          res = -tt;
+        } else {
+          const int x1 = (i == 0) ? i + 1 : i - 1, x2 = (i == L.nx - 1) ? i - 1 : i + 1;
+          const int y1 = (j == 0) ? j + 1 : j - 1, y2 = (j == L.ny - 1) ? j - 1 : j + 1;
+          const double uc = u[p];
+          double lap = ((u[x1 + j * L.nx] - 2 * uc) + u[x2 + j * L.nx]) * L.w.wx;
+          lap = lap + ((u[i + y1 * L.nx] - 2 * uc) + u[i + y2 * L.nx]) * L.w.wy;
+          res = rhs[p] - lap;
+        }
       }
+      r[p] = res;
     }
-    r[p] = res;
   }
-  __syncthreads();
+  team_sync(T);
 }
 
-// rhs_c = R r_f in the reference's order (same as k_restrict); also u_c = 0
+// rhs_c = R r_f in the reference's order (same as k_restrict); also u_c = 0.  Worked on by the FINE level's team.
 __device__ void sm_restrict(const double* __restrict__ rf, const SmallLevel& F, double* __restrict__ rc,
-                            double* __restrict__ uc, const SmallLevel& C) {
+                            double* __restrict__ uc, const SmallLevel& C, const int T) {
   const int NC = C.nx * C.ny * C.nz, fxy = F.nx * F.ny;
-  for (int p = threadIdx.x; p < NC; p += blockDim.x) {
+  for (int p = threadIdx.x; p < NC; p += T) {
     int ic, jc, kc;
     sm_decode(C, p, ic, jc, kc);
     const int ax = F.rt[0].first[ic], cx = F.rt[0].count[ic];
@@ -2044,14 +2131,13 @@ __device__ void sm_restrict(const double* __restrict__ rf, const SmallLevel& F, 
     rc[p] = fc;
     uc[p] = 0.0;
   }
-  __syncthreads();
 }
 
-// u_f += P u_c (same lerp order as k_interp_add)
+// u_f += P u_c (same lerp order as k_interp_add), by the FINE level's team
 __device__ void sm_interp_add(const double* __restrict__ ucv, const SmallLevel& C, double* __restrict__ uf,
-                              const SmallLevel& F) {
+                              const SmallLevel& F, const int T) {
   const int NF = F.nx * F.ny * F.nz, cxy = C.nx * C.ny;
-  for (int p = threadIdx.x; p < NF; p += blockDim.x) {
+  for (int p = threadIdx.x; p < NF; p += T) {
     int i, j, k;
     sm_decode(F, p, i, j, k);
     const int x0 = F.it[0].lo[i], y0 = F.it[1].lo[j], z0 = F.it[2].lo[k];
@@ -2072,7 +2158,6 @@ __device__ void sm_interp_add(const double* __restrict__ ucv, const SmallLevel& 
     f0 = whx * f0 + wlx * f1;
     uf[p] = uf[p] + f0;
   }
-  __syncthreads();
 }
 
 template <int NDIM>
@@ -2094,54 +2179,96 @@ k_vcycle_small(const double* __restrict__ rhs_in, double* __restrict__ u_out, co
     }
     __syncthreads();
   }
+  SmPts P;
   // ---- fine_to_coarse
   for (int l = 0; l + 1 < nl; ++l) {
     const SmallLevel& F = a.lv[l];
     const SmallLevel& C = a.lv[l + 1];
-    for (int s = 0; s < a.ms; ++s) sm_relax<NDIM>(sm + F.off_u, sm + F.off_rhs, F, a.first_colour, a.all_neumann, red);
-    sm_residual<NDIM>(sm + F.off_u, sm + F.off_rhs, sm + a.off_r, F);
-    sm_restrict(sm + a.off_r, F, sm + C.off_rhs, sm + C.off_u, C);
+    const int T = sm_team(F);
+    if ((int)threadIdx.x < T) {
+      sm_points(F, T, P);
+      sm_relax_sweeps<NDIM>(sm + F.off_u, sm + F.off_rhs, F, a.first_colour, a.all_neumann, a.ms, P, T, red);
+      sm_residual<NDIM>(sm + F.off_u, sm + F.off_rhs, sm + a.off_r, F, P, T);
+      sm_restrict(sm + a.off_r, F, sm + C.off_rhs, sm + C.off_u, C, T);
+    }
+    __syncthreads();
   }
   // ---- solve_exact on the coarsest level (ndsm_multigrid_core.f90:728-800)
   {
     const SmallLevel& L = a.lv[nl - 1];
-    const int N = L.nx * L.ny * L.nz;
-    double* su = sm + L.off_u;
-    double* ss = sm + a.off_sav;
-    for (int p = threadIdx.x; p < N; p += blockDim.x) ss[p] = 0.0;
-    __syncthreads();
-    double du = 1.7976931348623157e308;
-    int iters = 0, converged = 0;
-    for (int it = 0; it < a.nmax_exact; ++it) {
-      if (du <= a.ex_tol) { converged = 1; break; }
-      sm_relax<NDIM>(su, sm + L.off_rhs, L, a.first_colour, a.all_neumann, red);
-      double dmax = 0.0, dsum = 0.0;
-      for (int p = threadIdx.x; p < N; p += blockDim.x) {
-        const double v = su[p];
-        const double d = fabs(ss[p] - v);
-        dmax = fmax(dmax, d);
-        dsum += d;
-        ss[p] = v;
+    const int T = sm_team(L);
+    if ((int)threadIdx.x < T) {
+      sm_points(L, T, P);
+      const int sxy = L.nx * L.ny;
+      const double count = (double)(L.nx * L.ny * L.nz);
+      double* su = sm + L.off_u;
+      double* ss = sm + a.off_sav;
+#pragma unroll
+      for (int s = 0; s < SM_PMAX; ++s) {
+        if (s >= P.n) break;
+        const int base = P.j[s] * L.nx + P.k[s] * sxy, i0 = 2 * P.m[s];
+        if (i0 < L.nx) ss[base + i0] = 0.0;
+        if (i0 + 1 < L.nx) ss[base + i0 + 1] = 0.0;
       }
-      if (a.du_max) du = block_max(dmax, red);
-      else du = block_sum(dsum, red) / (double)N;
-      ++iters;
+      double du = 1.7976931348623157e308;
+      int iters = 0, converged = 0;
+      for (int it = 0; it < a.nmax_exact; ++it) {
+        if (du <= a.ex_tol) { converged = 1; break; }
+        sm_relax_sweeps<NDIM>(su, sm + L.off_rhs, L, a.first_colour, a.all_neumann, 1, P, T, red);
+        double dmax = 0.0, dsum = 0.0;
+#pragma unroll
+        for (int s = 0; s < SM_PMAX; ++s) {  // du_metrics + copy (:808-853, :1161-1184); u_sav is private to the owner
+          if (s >= P.n) break;
+          const int base = P.j[s] * L.nx + P.k[s] * sxy;
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            const int i = 2 * P.m[s] + e;
+            if (i >= L.nx) continue;
+            const double v = su[base + i];
+            const double d = fabs(ss[base + i] - v);
+            dmax = fmax(dmax, d);
+            dsum += d;
+            ss[base + i] = v;
+          }
+        }
+        if (a.du_max) du = team_max(dmax, red, T);
+        else du = team_sum(dsum, red, T) / count;
+        team_sync(T);  // red[] is reused by the next iteration's reductions
+        ++iters;
+      }
+      if (threadIdx.x == 0) { info[0] = iters; info[1] = converged; }
     }
     __syncthreads();
-    if (threadIdx.x == 0) { info[0] = iters; info[1] = converged; }
   }
   // ---- coarse_to_fine
   for (int l = nl - 1; l >= 1; --l) {
     const SmallLevel& C = a.lv[l];
     const SmallLevel& F = a.lv[l - 1];
-    for (int s = 0; s < a.ms; ++s) sm_relax<NDIM>(sm + C.off_u, sm + C.off_rhs, C, a.first_colour, a.all_neumann, red);
-    sm_interp_add(sm + C.off_u, C, sm + F.off_u, F);
-    for (int s = 0; s < a.ms; ++s) sm_relax<NDIM>(sm + F.off_u, sm + F.off_rhs, F, a.first_colour, a.all_neumann, red);
+    const int TC = sm_team(C), TF = sm_team(F);
+    if ((int)threadIdx.x < TC) {
+      sm_points(C, TC, P);
+      sm_relax_sweeps<NDIM>(sm + C.off_u, sm + C.off_rhs, C, a.first_colour, a.all_neumann, a.ms, P, TC, red);
+    }
+    __syncthreads();
+    if ((int)threadIdx.x < TF) {
+      sm_interp_add(sm + C.off_u, C, sm + F.off_u, F, TF);
+      team_sync(TF);
+      sm_points(F, TF, P);
+      if (l - 1 > 0)  // level ls itself is smoothed below, together with the pre-smooth that follows
+        sm_relax_sweeps<NDIM>(sm + F.off_u, sm + F.off_rhs, F, a.first_colour, a.all_neumann, a.ms, P, TF, red);
+    }
+    __syncthreads();
   }
-  // ---- the pre-smooth that opens coarse_to_fine(ls), then write u[ls] back
+  // ---- post-smooth of level ls and the pre-smooth that opens coarse_to_fine(ls): two separate calls of relax with
+  // ms sweeps each (the mean is applied between them exactly as between any two sweeps), then write u[ls] back
   {
     const SmallLevel& L = a.lv[0];
-    for (int s = 0; s < a.ms; ++s) sm_relax<NDIM>(sm + L.off_u, sm + L.off_rhs, L, a.first_colour, a.all_neumann, red);
+    const int T = sm_team(L);
+    if ((int)threadIdx.x < T) {
+      sm_points(L, T, P);
+      sm_relax_sweeps<NDIM>(sm + L.off_u, sm + L.off_rhs, L, a.first_colour, a.all_neumann, (nl > 1 ? 2 : 1) * a.ms, P, T, red);
+    }
+    __syncthreads();
     const int N = L.nx * L.ny * L.nz;
     for (int p = threadIdx.x; p < N; p += blockDim.x) {
       int i, j, k;
@@ -2163,8 +2290,8 @@ void vcycle_small(int ndim, const double* rhs_in, double* u_out, const Grid& g0,
                   cudaStream_t st) {
   vcycle_small_prepare();
   const size_t bytes = (size_t)a.smem_doubles * sizeof(double);
-  const int n0 = a.lv[0].nx * a.lv[0].ny * a.lv[0].nz;
-  const int threads = std::min(1024, std::max(64, ((n0 / 2 + 31) / 32) * 32));
+  const int q0 = ((a.lv[0].nx + 1) / 2) * a.lv[0].ny * a.lv[0].nz;  // compressed points of the largest level
+  const int threads = std::min(1024, std::max(32, ((q0 + 31) / 32) * 32));
   if (ndim == 3) k_vcycle_small<3><<<1, threads, bytes, st>>>(rhs_in, u_out, g0, a, info);
   else k_vcycle_small<2><<<1, threads, bytes, st>>>(rhs_in, u_out, g0, a, info);
   LAUNCHED();
@@ -2312,9 +2439,11 @@ __global__ void __launch_bounds__(256)
 k_unsplit_A(const double* __restrict__ As, const Grid g, const int comp, const double* __restrict__ x,
             const double* __restrict__ y, const double* __restrict__ z, const FluxPar f, const int add_flux,
             const int ka, double* __restrict__ Ad) {
-  const int i = blockIdx.x * 256 + threadIdx.x;
-  if (i >= g.nx) return;
-  const int j = blockIdx.y, kl = blockIdx.z, k = ka + kl;
+  // one thread per point of a dense plane, flattened (i + nx*j): consecutive threads write consecutive doubles
+  const int n = blockIdx.x * 256 + threadIdx.x;
+  if (n >= g.nx * g.ny) return;
+  const int j = n / g.nx, i = n - j * g.nx;
+  const int kl = blockIdx.y, k = ka + kl;
   double a = As[gidx(g, i, j, k)];  // k may address a halo plane of the slab
   if (add_flux) {
     const double X = x[i], Y = y[j], Z = z[k];
@@ -2327,7 +2456,7 @@ k_unsplit_A(const double* __restrict__ As, const Grid g, const int comp, const d
     else                { A1 = +((g1 * X) * Y); A2 = 0.0;             A3 = -((g2 * X) * Y); Ac = -((f.phi[2] * f.Lq[1]) * X) / Vq; }
     a = (a + Ac) + inv3 * ((A1 + A2) + A3);  // (:932-947)
   }
-  Ad[i + (i64)g.nx * (j + (i64)g.ny * kl)] = a;
+  Ad[n + (i64)g.nx * g.ny * kl] = a;
 }
 
 void unsplit_A(const double* As, const Grid& g, int comp, const double* x, const double* y, const double* z,
@@ -2336,7 +2465,7 @@ void unsplit_A(const double* As, const Grid& g, int comp, const double* x, const
   for (int q = 0; q < 6; ++q) f.phi[q] = phi[q];
   for (int q = 0; q < 3; ++q) f.Lq[q] = Lq[q];
   if (kb <= ka) return;
-  dim3 grid(cdiv(g.nx, 256), g.ny, kb - ka);
+  dim3 grid(cdiv((i64)g.nx * g.ny, 256), kb - ka);
   k_unsplit_A<<<grid, 256, 0, st>>>(As, g, comp, x, y, z, f, add_flux ? 1 : 0, ka, A_dense);
   LAUNCHED();
 }
@@ -2358,34 +2487,47 @@ __device__ __forceinline__ double derivq(const double* __restrict__ u, i64 n, in
   }
   return d;
 }
-// A: dense planes starting at global plane ka, components csA apart; B: planes starting at k0, components csB apart
+// A: dense planes starting at global plane ka, components csA apart; B: planes starting at k0, components csB apart.
+// One thread per point of a plane, flattened (i + nx*j).  COMP < 0: all three components of B; COMP = c: only
+// B_c (so that a component of B can leave for the host as soon as the two components of A it needs are final).
+template <int COMP>
 __global__ void __launch_bounds__(256)
 k_curl(const double* __restrict__ A, const int ka, const i64 csA, const int nx, const int ny, const int nz,
        const double dqx, const double dqy, const double dqz, const int k0, double* __restrict__ B, const i64 csB) {
-  const int i = blockIdx.x * 256 + threadIdx.x;
-  if (i >= nx) return;
-  const int j = blockIdx.y, k = k0 + blockIdx.z;
+  const int p = blockIdx.x * 256 + threadIdx.x;
+  if (p >= nx * ny) return;
+  const int j = p / nx, i = p - j * nx;
+  const int k = k0 + blockIdx.y;
   const i64 sy = nx, sz = (i64)nx * ny;
-  const i64 n = i + sy * j + sz * (k - ka);
+  const i64 n = p + sz * (k - ka);
   const double* __restrict__ Ax = A;
   const double* __restrict__ Ay = A + csA;
   const double* __restrict__ Az = A + 2 * csA;
-  const double dAx_dy = derivq(Ax, n, j, ny, sy, dqy);
-  const double dAx_dz = derivq(Ax, n, k, nz, sz, dqz);
-  const double dAy_dx = derivq(Ay, n, i, nx, 1, dqx);
-  const double dAy_dz = derivq(Ay, n, k, nz, sz, dqz);
-  const double dAz_dx = derivq(Az, n, i, nx, 1, dqx);
-  const double dAz_dy = derivq(Az, n, j, ny, sy, dqy);
-  const i64 o = i + sy * j + sz * (k - k0);
-  B[o] = dAz_dy - dAy_dz;          // (:802-804)
-  B[o + csB] = dAx_dz - dAz_dx;
-  B[o + 2 * csB] = dAy_dx - dAx_dy;
+  const i64 o = p + sz * (k - k0);
+  if (COMP < 0 || COMP == 0) {
+    const double dAz_dy = derivq(Az, n, j, ny, sy, dqy);
+    const double dAy_dz = derivq(Ay, n, k, nz, sz, dqz);
+    B[o] = dAz_dy - dAy_dz;          // (:802-804)
+  }
+  if (COMP < 0 || COMP == 1) {
+    const double dAx_dz = derivq(Ax, n, k, nz, sz, dqz);
+    const double dAz_dx = derivq(Az, n, i, nx, 1, dqx);
+    B[o + csB] = dAx_dz - dAz_dx;
+  }
+  if (COMP < 0 || COMP == 2) {
+    const double dAy_dx = derivq(Ay, n, i, nx, 1, dqx);
+    const double dAx_dy = derivq(Ax, n, j, ny, sy, dqy);
+    B[o + 2 * csB] = dAy_dx - dAx_dy;
+  }
 }
 void curl_dense(const double* A, int ka, i64 csA, int nx, int ny, int nz, double dqx, double dqy, double dqz, int k0,
-                int k1, double* B, i64 csB, cudaStream_t st) {
+                int k1, double* B, i64 csB, cudaStream_t st, int comp) {
   if (k1 <= k0) return;
-  dim3 grid(cdiv(nx, 256), ny, k1 - k0);
-  k_curl<<<grid, 256, 0, st>>>(A, ka, csA, nx, ny, nz, dqx, dqy, dqz, k0, B, csB);
+  dim3 grid(cdiv((i64)nx * ny, 256), k1 - k0);
+  if (comp == 0) k_curl<0><<<grid, 256, 0, st>>>(A, ka, csA, nx, ny, nz, dqx, dqy, dqz, k0, B, csB);
+  else if (comp == 1) k_curl<1><<<grid, 256, 0, st>>>(A, ka, csA, nx, ny, nz, dqx, dqy, dqz, k0, B, csB);
+  else if (comp == 2) k_curl<2><<<grid, 256, 0, st>>>(A, ka, csA, nx, ny, nz, dqx, dqy, dqz, k0, B, csB);
+  else k_curl<-1><<<grid, 256, 0, st>>>(A, ka, csA, nx, ny, nz, dqx, dqy, dqz, k0, B, csB);
   LAUNCHED();
 }
 

@@ -144,8 +144,9 @@ void unsplit_A(const double* As, const Grid& g, int comp, const double* x, const
                const double* phi /*6*/, const double* Lq /*3*/, bool add_flux, int ka, int kb, double* A_dense,
                cudaStream_t st);
 // B[planes k0..k1) = curl A; A holds planes from ka on (needs k-1,k+1 or the one-sided stencil planes)
+// comp < 0: all three components of B; comp = c: only B_c (reads the two components of A it depends on)
 void curl_dense(const double* A, int ka, i64 csA, int nx, int ny, int nz, double dqx, double dqy, double dqz, int k0,
-                int k1, double* B, i64 csB, cudaStream_t st);
+                int k1, double* B, i64 csB, cudaStream_t st, int comp = -1);
 void add_flux_dense(double* A, i64 csA, double* B, i64 csB, int nx, int ny, int k0, int k1, const double* x,
                     const double* y, const double* z, const double* phi, const double* Lq, cudaStream_t st);
 

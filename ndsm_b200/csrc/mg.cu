@@ -281,6 +281,30 @@ MG::MG(int ndim, const int* shape, int ngrids, const double* const* mesh, cudaSt
   valid_.assign(ngrids, std::array<int, 2>{{0, 0}});
   const int nd = plan_.ndist;
   const int H = plan_.halo;
+  // halo planes the transfers really read (the same number on every rank, so that both sides of an exchange agree):
+  // restriction reads r of the fine level over the z windows of the coarse planes a rank produces, prolongation
+  // reads the two coarse planes that bracket each owned fine plane
+  rneed_.assign(ngrids, H);
+  ineed_.assign(ngrids, H);
+  for (int g = 0; g < nd; ++g) {
+    int rn = 0, in = 0;
+    for (int r = 0; r < world; ++r) {
+      const int f0 = plan_.zs[g][r], f1 = plan_.zs[g][r + 1];
+      for (int c = plan_.zs[g + 1][r]; c < plan_.zs[g + 1][r + 1]; ++c) {
+        const int a = hl[g].first[2][c], b = a + hl[g].count[2][c];
+        rn = std::max(rn, std::max(f0 - a, b - f1));
+      }
+      if (g + 1 < nd) {
+        const int c0 = plan_.zs[g + 1][r], c1 = plan_.zs[g + 1][r + 1], ncz = hl[g + 1].n[2];
+        for (int k = f0; k < f1; ++k) {
+          const int lo = hl[g].lo[2][k], hi = (lo + 1 < ncz) ? lo + 1 : ncz - 1;
+          in = std::max(in, std::max(c0 - lo, hi + 1 - c1));
+        }
+      }
+    }
+    rneed_[g] = std::min(H, std::max(rn, 1));
+    if (g + 1 < nd) ineed_[g + 1] = std::min(H, std::max(in, 1));
+  }
   const int nlocal = (nd > 0 && comm_) ? comm_->nlocal() : 1;
   slabs_.resize(nlocal);
   rhs0_.assign(nlocal, nullptr);
@@ -582,11 +606,19 @@ void MG::relax_sweeps(int g, int n) {
   for (int s = 0; s < n; ++s) relax(g);
 }
 
-// the other colour must be valid at least one plane deep before a pass; refresh both colours when it is not
+// A pass needs the OTHER colour at least one plane deep; when it is not, only that colour is exchanged: the pass
+// that follows recomputes its own colour in the halo planes (extended pass) from exactly these values, so the own
+// colour's halo would be overwritten before anything reads it.  Half the bytes of a two-colour exchange.
 void MG::need_halo_colour(int g, int colour) {
   if (valid_[g][colour] >= 1) return;
-  exchange(g, 0, 3, plan_.halo);
-  valid_[g][0] = valid_[g][1] = plan_.halo;
+  static const bool one_colour = !(getenv("NDSM_HALO_ONE_COLOUR") && atoi(getenv("NDSM_HALO_ONE_COLOUR")) == 0);
+  if (!one_colour) {
+    exchange(g, 0, 3, plan_.halo);
+    valid_[g][0] = valid_[g][1] = plan_.halo;
+    return;
+  }
+  exchange(g, 0, 1 << colour, plan_.halo);
+  valid_[g][colour] = plan_.halo;
 }
 
 void MG::residual(int g) {
@@ -607,7 +639,7 @@ void MG::restrict_to(int g) {
   const int c = g + 1;
   const bool fdist = g < plan_.ndist, cdist = c < plan_.ndist;
   const size_t ns = fdist ? slabs_.size() : 1;
-  if (fdist) exchange(g, 2, 3, plan_.halo);
+  if (fdist) exchange(g, 2, 3, rneed_[g]);
   const bool prof = (g == 0 && ndim_ == 3 && ns == 1);
   if (prof) prof_begin(PROF_RESTRICT0, st_);
   for (size_t s = 0; s < ns; ++s) {
@@ -667,7 +699,11 @@ void MG::interp_add_from(int c) {
   const int f = c - 1;
   const bool fdist = f < plan_.ndist, cdist = c < plan_.ndist;
   const size_t ns = fdist ? slabs_.size() : 1;
-  if (cdist) { exchange(c, 0, 3, plan_.halo); valid_[c][0] = valid_[c][1] = plan_.halo; }
+  if (cdist && (valid_[c][0] < ineed_[c] || valid_[c][1] < ineed_[c])) {
+    exchange(c, 0, 3, ineed_[c]);
+    valid_[c][0] = std::max(valid_[c][0], ineed_[c]);
+    valid_[c][1] = std::max(valid_[c][1], ineed_[c]);
+  }
   const bool prof = (c == 1 && ndim_ == 3 && ns == 1);
   if (prof) prof_begin(PROF_INTERP0, st_);
   for (size_t s = 0; s < ns; ++s) {

@@ -239,7 +239,14 @@ int vector_solve_core(const int* nshape, const long long* iopt, const double* ro
   }
 
   // ---------------- three 3D solves (solve, :598-691) ----------------
-  const DenseIn A0 = (hooks && hooks->guess) ? hooks->guess() : A0_in;
+  // initial guess of component c as received (the reference never zeroes A): the caller's dense array, or the
+  // host entry's per-component hook
+  auto guess_of = [&](int c) {
+    if (hooks && hooks->guess) return hooks->guess(c);
+    DenseIn g = A0_in;
+    if (g.p) g.p += (i64)c * g.cstride;
+    return g;
+  };
   tm.start();
   if (g_debug) debug_msg("compute_vector_potential", "Solve BVP 3D...");
   const int sh3[3] = {nx, ny, nz};
@@ -300,25 +307,26 @@ int vector_solve_core(const int* nshape, const long long* iopt, const double* ro
     lvl[s] = mg3->level_doubles(0, s);
     As[s].alloc(3 * lvl[s]);
     CUDA_CHECK(cudaMemsetAsync(As[s].p, 0, 3 * lvl[s] * sizeof(double), st));
-    for (int c = 0; c < 3; ++c) {
-      double* p0 = As[s].p + c * lvl[s] + (i64)L0.H * L0.g.ps;
-      Ap[c].push_back(p0);
-      if (A0.p)  // initial guess as received (reference never zeroes A)
-        split_from_dense(A0.p + c * A0.cstride + (i64)(L0.g.k0 - A0.kfirst) * nx * ny, p0, L0.g, 0.0, st);
-    }
+    for (int c = 0; c < 3; ++c) Ap[c].push_back(As[s].p + c * lvl[s] + (i64)L0.H * L0.g.ps);
   }
   static const int wf[3][4] = {{2, 3, 4, 5}, {0, 1, 4, 5}, {0, 1, 2, 3}};  // face write order :647-650,663-666,679-682
   static const int wa[3][4] = {{0, 0, 0, 0}, {0, 0, 1, 1}, {1, 1, 1, 1}};  // At(1,.) or At(2,.)
   static const char* cop[3] = {"NDDNDD", "DNDDND", "DDNDDN"};              // :655,671,687
   const std::vector<const double*> norhs(ns, nullptr);                     // rhs = 0 (:640-641)
-  for (int c = 0; c < 3; ++c)
-    for (int s = 0; s < ns; ++s)
+  // component c's starting iterate: the guess, then the Dirichlet faces on top of it (:647-650,663-666,679-682)
+  auto prepare = [&](int c, cudaStream_t sc) {
+    const DenseIn A0 = guess_of(c);
+    for (int s = 0; s < ns; ++s) {
+      const Grid& g0 = mg3->level(0, s).g;
+      if (A0.p) split_from_dense(A0.p + (i64)(g0.k0 - A0.kfirst) * nx * ny, Ap[c][s], g0, 0.0, sc);
       for (int w = 0; w < 4; ++w) {
         const int f = wf[c][w];
         const int layer = (f % 2 == 0) ? 0 : nshape[imap_cp[f]] - 1;
-        write_face(Ap[c][s], mg3->level(0, s).g, imap_cp[f], layer, At[f][wa[c][w]].p, st);
+        write_face(Ap[c][s], g0, imap_cp[f], layer, At[f][wa[c][w]].p, sc);
       }
-  CUDA_CHECK(cudaStreamSynchronize(st));
+    }
+  };
+  CUDA_CHECK(cudaStreamSynchronize(st));  // the memsets above precede the component streams' work
   auto set_opts = [&](int c) {
     mgc(c)->set_options(c == 2 ? 5 : (int)iopt[IOPT_MS], ropt[ROPT_CTOL], cop[c], use_du_max, (int)iopt[IOPT_NMAXEX]);  // :685
   };
@@ -327,20 +335,28 @@ int vector_solve_core(const int* nshape, const long long* iopt, const double* ro
   const bool flux_first = (iopt[IOPT_FLXCRL] != 1);  // :453-477
   const bool early_out = !concurrent && ns == 1 && flux_first && outs[0].k0 == 0 && outs[0].k1 == nz &&
                          mg3->plan().ndist == 0;
+  // ... and a component of B = curl A as soon as the two components of A it depends on are (Bz after Ay)
+  const bool early_b = early_out && hooks && hooks->b_ready;
   if (!concurrent) {
     for (int c = 0; c < 3; ++c) {
       set_opts(c);
+      prepare(c, st);
       double du_last;
       mg3->solve(Ap[c], norhs, ropt[ROPT_VTOL], (int)iopt[IOPT_NCYCLES], &du_last, &rep.solves[6 + c]);
       mg3->exchange(0, 0, 3, 1, &Ap[c]);  // halo planes of the converged component (curl needs k-1, k+1)
       if (early_out) {
         unsplit_A(Ap[c][0], mg3->level(0, 0).g, c, dx_, dy_, dz_, phi, Lq, true, 0, nz, outs[0].A + c * outs[0].cstride, st);
         if (hooks && hooks->component_ready) hooks->component_ready(c);
+        if (early_b && c == 1) {  // Bz = dAy/dx - dAx/dy (:804)
+          curl_dense(outs[0].A, 0, outs[0].cstride, nx, ny, nz, dq[0], dq[1], dq[2], 0, nz, outs[0].B, outs[0].cstride, st, 2);
+          hooks->b_ready(2);
+        }
       }
     }
   } else {
     for (int c = 0; c < 3; ++c) {
       set_opts(c);
+      prepare(c, ctx[c].st);
       mgc(c)->solve_begin(Ap[c], norhs, ropt[ROPT_VTOL], (int)iopt[IOPT_NCYCLES], &rep.solves[6 + c]);
     }
     // every stream always has its next V-cycle queued: a component is re-enqueued right after its own poll
@@ -393,7 +409,14 @@ int vector_solve_core(const int* nshape, const long long* iopt, const double* ro
     if (!early_out)
       for (int c = 0; c < 3; ++c)
         unsplit_A(Ap[c][s], g3, c, dx_, dy_, dz_, phi, Lq, flux_first, ka, kb, Ad + c * csA, st);
-    curl_dense(Ad, ka, csA, nx, ny, nz, dq[0], dq[1], dq[2], k0, k1, o.B, o.cstride, st);
+    if (early_b) {  // Bz left after the Ay solve; Bx and By need Az
+      for (int c = 0; c < 2; ++c) {
+        curl_dense(Ad, ka, csA, nx, ny, nz, dq[0], dq[1], dq[2], k0, k1, o.B, o.cstride, st, c);
+        hooks->b_ready(c);
+      }
+    } else {
+      curl_dense(Ad, ka, csA, nx, ny, nz, dq[0], dq[1], dq[2], k0, k1, o.B, o.cstride, st);
+    }
     if (!in_place)
       for (int c = 0; c < 3; ++c)
         CUDA_CHECK(cudaMemcpyAsync(o.A + c * o.cstride, Ad + c * csA + (i64)(k0 - ka) * pl, (size_t)(k1 - k0) * pl * sizeof(double),

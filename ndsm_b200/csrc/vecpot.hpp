@@ -45,13 +45,16 @@ struct SlabOut {   // where one slab delivers A and B: planes [k0,k1), component
 // balanced z-range of rank `rank` (identical to the finest-level slab partition)
 void output_range(int nz, int world, int rank, int* k0, int* k1);
 
-// Optional hooks of the core (single-slab host entry): `guess` is called after the BC setup and returns the
-// initial guess (lets the host check / upload of A overlap the chi solves); `component_ready(c)` is called
-// as soon as component c of A is final in the output array (flux-balance field included), on stream st,
-// so that its device-to-host copy can overlap the remaining solves.
+// Optional hooks of the core (single-slab host entry).  `guess(c)` is called right before component c is solved and
+// returns that component's initial guess (p == nullptr: zeros; kfirst/cstride describe the dense array p points
+// into) -- the host scans / uploads A component by component, overlapped with the BC setup and the earlier solves.
+// `component_ready(c)` is called as soon as component c of A is final in the output array (flux-balance field
+// included) and `b_ready(c)` as soon as component c of B = curl A is (Bz once Ax and Ay are solved, Bx and By after
+// Az), on stream st, so that their device-to-host copies overlap the remaining solves.
 struct CoreHooks {
-  std::function<DenseIn()> guess;
+  std::function<DenseIn(int)> guess;
   std::function<void(int)> component_ready;
+  std::function<void(int)> b_ready;
 };
 
 // bn[f]: dense device faces (face f has shape (n1,n2) per ndsm_vector_potential.f90:225-246), all six on every
