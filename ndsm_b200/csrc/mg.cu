@@ -279,6 +279,7 @@ MG::MG(int ndim, const int* shape, int ngrids, const double* const* mesh, cudaSt
   if (const char* e = getenv("NDSM_SLAB_MIN_POINTS")) min_points = atoll(e);
   plan_ = plan_slabs(hl, ndim, world, min_planes, min_points);
   valid_.assign(ngrids, std::array<int, 2>{{0, 0}});
+  static_ok_.assign(ngrids, std::array<bool, 2>{{false, false}});
   const int nd = plan_.ndist;
   const int H = plan_.halo;
   // halo planes the transfers really read (the same number on every rank, so that both sides of an exchange agree):
@@ -304,6 +305,10 @@ MG::MG(int ndim, const int* shape, int ngrids, const double* const* mesh, cudaSt
     }
     rneed_[g] = std::min(H, std::max(rn, 1));
     if (g + 1 < nd) ineed_[g + 1] = std::min(H, std::max(in, 1));
+  }
+  if (getenv("NDSM_HALO_EXACT_DEPTH") && atoi(getenv("NDSM_HALO_EXACT_DEPTH")) == 0) {  // full-depth transfers exchanges
+    rneed_.assign(ngrids, H);
+    ineed_.assign(ngrids, H);
   }
   const int nlocal = (nd > 0 && comm_) ? comm_->nlocal() : 1;
   slabs_.resize(nlocal);
@@ -550,6 +555,7 @@ void MG::need_halo(int g, int depth) {
   if (valid_[g][0] >= depth && valid_[g][1] >= depth) return;
   exchange(g, 0, 3, plan_.halo);
   valid_[g][0] = valid_[g][1] = plan_.halo;
+  static_ok_[g][0] = static_ok_[g][1] = true;
 }
 
 void MG::relax(int g) {
@@ -606,19 +612,24 @@ void MG::relax_sweeps(int g, int n) {
   for (int s = 0; s < n; ++s) relax(g);
 }
 
-// A pass needs the OTHER colour at least one plane deep; when it is not, only that colour is exchanged: the pass
-// that follows recomputes its own colour in the halo planes (extended pass) from exactly these values, so the own
-// colour's halo would be overwritten before anything reads it.  Half the bytes of a two-colour exchange.
+// A pass needs the OTHER colour at least one plane deep.  When it is not, only that colour has to be exchanged:
+// the pass that follows recomputes its own colour in the halo planes (extended pass) from exactly these values,
+// so the own colour's halo is overwritten before anything reads it -- except its Dirichlet points, which no pass
+// updates.  Those are current in the halo once the colour has been exchanged at full depth since the level was
+// last changed from outside the smoother (start of a solve, prolongation: the correction is added on Dirichlet
+// faces too, ndsm_multigrid_core.f90:706-710); until then both colours travel.  Half the bytes otherwise.
 void MG::need_halo_colour(int g, int colour) {
   if (valid_[g][colour] >= 1) return;
-  static const bool one_colour = !(getenv("NDSM_HALO_ONE_COLOUR") && atoi(getenv("NDSM_HALO_ONE_COLOUR")) == 0);
-  if (!one_colour) {
+  const bool one_colour = !(getenv("NDSM_HALO_ONE_COLOUR") && atoi(getenv("NDSM_HALO_ONE_COLOUR")) == 0);
+  if (!one_colour || !static_ok_[g][1 - colour]) {
     exchange(g, 0, 3, plan_.halo);
     valid_[g][0] = valid_[g][1] = plan_.halo;
+    static_ok_[g][0] = static_ok_[g][1] = true;
     return;
   }
   exchange(g, 0, 1 << colour, plan_.halo);
   valid_[g][colour] = plan_.halo;
+  static_ok_[g][colour] = true;
 }
 
 void MG::residual(int g) {
@@ -687,6 +698,7 @@ void MG::finish_restrict(int g) {
     for (auto& S : slabs_) rp.push_back(S.lv[c].rhs);
     exchange(c, 0, 3, plan_.halo, &rp);
     valid_[c][0] = valid_[c][1] = plan_.halo;  // u[c] = 0 everywhere, halos included
+    static_ok_[c][0] = static_ok_[c][1] = true;
   }
   const size_t nc = cdist ? slabs_.size() : 1;
   for (size_t s = 0; s < nc; ++s) {  // ndsm_multigrid_core.f90:557-558
@@ -714,7 +726,10 @@ void MG::interp_add_from(int c) {
     else interp_add(C.u, C.g, F.u, F.g, F.it[0], F.it[1], F.it[2], st_);
   }
   if (prof) prof_end(PROF_INTERP0, st_);
-  if (fdist) valid_[f][0] = valid_[f][1] = 0;  // owned planes changed; halos are refreshed by the next consumer
+  if (fdist) {  // owned planes changed (Dirichlet faces included); halos are refreshed by the next consumer
+    valid_[f][0] = valid_[f][1] = 0;
+    static_ok_[f][0] = static_ok_[f][1] = false;
+  }
 }
 
 // solve_exact (ndsm_multigrid_core.f90:728-800) -- always on a replicated level
@@ -831,6 +846,7 @@ void MG::solve_begin(const std::vector<double*>& u, const std::vector<const doub
                                cudaMemcpyDeviceToDevice, st_));  // :100
   }
   for (auto& v : valid_) v = {{0, 0}};  // the caller's halo planes are not trusted; refreshed on first use
+  for (auto& v : static_ok_) v = {{false, false}};
   // no rank may write into another rank's arena (replicated levels, gathered pairs) before that rank has
   // cleared / filled it: everything enqueued above is ordered before any peer's first message of this solve
   if (comm_ && plan_.ndist > 0) comm_->barrier(st_);

@@ -214,6 +214,8 @@ class MG {
   // that currently hold up-to-date values of colour c.  A colour pass may also update `e` halo planes if the
   // other colour is valid to depth e+1, so one 4-plane exchange feeds four passes (bit-identical values).
   std::vector<std::array<int, 2>> valid_;
+  // static_ok_[g][c]: the Dirichlet points of colour c (never updated by a pass) are current in the halo planes
+  std::vector<std::array<bool, 2>> static_ok_;
   std::vector<int> rneed_, ineed_;   // halo planes the restriction (of r, per fine level) / prolongation (of u, per
                                      // coarse level) read; the same on every rank
   void finish_restrict(int g);
