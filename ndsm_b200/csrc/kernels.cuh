@@ -117,6 +117,8 @@ void vcycle_small(int ndim, const double* rhs_in, double* u_out, const Grid& g0,
 // K6: out[0] = max|a-b|, out[1] = sum|a-b| over owned planes; then a := b  (update_u: a=caller's u, b=V-cycled u;
 // ndsm_multigrid_core.f90:1077-1122).  With copy=false it is du_metrics (:808-853) and leaves a untouched.
 void diff_reduce(double* a, const double* b, const Grid& g, bool copy, double* scratch, double* out, cudaStream_t st);
+// npairs (max,sum) pairs and info[2] -> mapped pinned host memory (device-accessible pointer), npairs <= 24
+void publish_results(const double* pairs, int npairs, const int* info, double* host_mapped, cudaStream_t st);
 // nsweeps pure-Neumann 2D sweeps with the per-sweep mean subtraction folded into the passes (opt-in path of the
 // chi solves, see kernels.cu); scratch: relax2d_fused_mean_scratch(g) doubles, zero-initialised once
 size_t relax2d_fused_mean_scratch(const Grid& g);

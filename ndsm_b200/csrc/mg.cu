@@ -345,6 +345,12 @@ MG::MG(int ndim, const int* shape, int ngrids, const double* const* mesh, cudaSt
   d_allm_[1] = shared_ + off_allm + 2 * (i64)world + 8;
   d_info_ = reinterpret_cast<int*>(shared_ + off_info);
   h_out_ = static_cast<double*>(pool_alloc_host((2 * (size_t)world + 8) * sizeof(double)));
+  {  // pinned memory is mapped under unified addressing; kernels write the per-cycle results there directly
+    void* dp = nullptr;
+    if (world <= 24 && cudaHostGetDevicePointer(&dp, h_out_, 0) == cudaSuccess) h_out_dev_ = static_cast<double*>(dp);
+    else cudaGetLastError();
+    if (getenv("NDSM_B200_MAPPED_RESULTS") && atoi(getenv("NDSM_B200_MAPPED_RESULTS")) == 0) h_out_dev_ = nullptr;
+  }
 
   // --- per-slab arenas: partitioned levels (with halos), residual scratch, local reduction result
   for (int s = 0; s < nlocal; ++s) {
@@ -815,13 +821,15 @@ void MG::enqueue_cycle() {
   }
   if (prof) prof_end(PROF_DIFF0, st_);
   const int npairs = dist ? plan_.world : 1;
-  if (dist) {
+  if (dist)
     for (auto& S : slabs_) comm_->gather2(S.rank, S.d_out, d_all_, st_);
-    CUDA_CHECK(cudaMemcpyAsync(h_out_, d_all_, 2 * npairs * sizeof(double), cudaMemcpyDeviceToHost, st_));
+  const double* pairs = dist ? d_all_ : slabs_[0].d_out;
+  if (h_out_dev_) {  // results straight into mapped pinned memory (no copy-engine node, see k_publish)
+    publish_results(pairs, npairs, d_info_, h_out_dev_, st_);
   } else {
-    CUDA_CHECK(cudaMemcpyAsync(h_out_, slabs_[0].d_out, 2 * sizeof(double), cudaMemcpyDeviceToHost, st_));
+    CUDA_CHECK(cudaMemcpyAsync(h_out_, pairs, 2 * npairs * sizeof(double), cudaMemcpyDeviceToHost, st_));
+    CUDA_CHECK(cudaMemcpyAsync(h_out_ + 2 * npairs, d_info_, 2 * sizeof(int), cudaMemcpyDeviceToHost, st_));
   }
-  CUDA_CHECK(cudaMemcpyAsync(h_out_ + 2 * npairs, d_info_, 2 * sizeof(int), cudaMemcpyDeviceToHost, st_));
 }
 
 // solve_poisson_bvp (ndsm_poisson.f90:63-155), split into begin / enqueue / poll / end so that several

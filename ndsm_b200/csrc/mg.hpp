@@ -232,6 +232,7 @@ class MG {
   int mean_parity_ = 0;
   int* d_info_ = nullptr;            // [2] coarsest-solve iterations / converged
   double* h_out_ = nullptr;          // pinned: [2*world] pairs + 2 ints
+  double* h_out_dev_ = nullptr;      // device view of h_out_ (mapped), nullptr: copy nodes instead
   // levels >= small_from_ (each <= SMALL_MAX_POINTS points) run as one single-block kernel; 0 = disabled
   int small_from_ = 0;
   SmallArgs small_args_;
