@@ -183,8 +183,8 @@ SlabPlan plan_slabs(const std::vector<HostLevel>& hl, int ndim, int world, int m
   for (int lv = 0; lv < p.ndist; ++lv) {
     const int nzf = hl[lv].n[2], ncz = hl[lv + 1].n[2];
     for (int r = 0; r < world; ++r) {
-      // one plane less than the halo: the fused residual+restriction evaluates the residual on every fine
-      // plane of the stencil, which reads u one plane further out
+      // one plane less than the halo is allowed for the stencil (head-room kept from an earlier fused
+      // residual+restriction, which read u one plane further out; the exchange depth actually used is rneed_)
       const int f0 = p.zs[lv][r] - (p.halo - 1), f1 = p.zs[lv][r + 1] + (p.halo - 1);
       for (int c = p.zs[lv + 1][r]; c < p.zs[lv + 1][r + 1]; ++c) {
         const int a = hl[lv].first[2][c], b = a + hl[lv].count[2][c];
@@ -699,7 +699,7 @@ void MG::finish_restrict(int g) {
     }
     comm_->end(st_);
   }
-  if (cdist) {  // extended colour passes and the fused residual read rhs in the halo planes
+  if (cdist) {  // extended colour passes read rhs in the halo planes
     std::vector<double*> rp;
     for (auto& S : slabs_) rp.push_back(S.lv[c].rhs);
     exchange(c, 0, 3, plan_.halo, &rp);
