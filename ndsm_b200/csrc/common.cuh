@@ -18,6 +18,7 @@
 #include <cstdint>
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
 
 typedef long long i64;
 
@@ -55,6 +56,36 @@ struct NdsmError {
   explicit NdsmError(int c, int ce = 0) : code(c), cuda_err(ce) {}
 };
 
+// Programmatic dependent launch (PDL): every kernel of this library starts with pdl_enter() and is launched with
+// the programmatic-stream-serialization attribute (launch_k), in streams and in captured graphs alike.  The
+// dependent grid's blocks are scheduled and run up to griddepcontrol.wait while the previous kernel is still
+// draining; wait returns when that kernel has completed and its writes are visible.  Nothing above pdl_enter()
+// touches global memory.  The trigger comes AFTER the wait, so at most one dependent grid is ever parked behind
+// the running one.  The V-cycle's small levels are chains of 2-5 us kernels: the launch gap is a large share.
+__device__ __forceinline__ void pdl_enter() {
+#if defined(__CUDA_ARCH__)
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+#endif
+}
+
 __host__ __device__ inline i64 gidx(const Grid& g, int i, int j, int k) {
   return (i64)((i + j + k) & 1) * g.cs + (i64)(k - g.k0) * g.ps + (i64)j * g.hp + (i >> 1);
+}
+
+// host side: launch with the PDL attribute (NDSM_B200_PDL=0 launches plainly); throws on a launch error
+bool pdl_enabled();
+template <typename... KArgs, typename... Args>
+inline void launch_k(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg = cudaLaunchConfig_t();
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  CUDA_CHECK(cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...));
 }

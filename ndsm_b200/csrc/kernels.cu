@@ -16,6 +16,11 @@ namespace ndsm {
 unsigned long long g_launches = 0;
 #define LAUNCHED() (++g_launches)
 
+bool pdl_enabled() {  // read per launch: tests and benches toggle it between solves
+  const char* e = getenv("NDSM_B200_PDL");
+  return !(e && atoi(e) == 0);
+}
+
 static inline int cdiv(i64 a, i64 b) { return (int)((a + b - 1) / b); }
 
 // ---------------------------------------------------------------------------------------
@@ -281,6 +286,7 @@ __global__ void __launch_bounds__(RELAX_BX * RELAX_BY, MINB)
 k_relax3d(double* __restrict__ u, const double* __restrict__ rhs, const Grid g, const Bounds b, const int colour,
           const double wx, const double wy, const double wz, const double w1, const int klo, const int khi,
           const int zchunk) {
+  pdl_enter();
   const int kbeg = klo + blockIdx.z * zchunk;
   const int kend = min(kbeg + zchunk - 1, khi);
   if (kbeg > kend) return;
@@ -341,6 +347,7 @@ __global__ void __launch_bounds__(RELAX_BX * RELAX_BY, HAS_RHS ? 2 : 3)
 k_relax3d_staged(double* __restrict__ u, const double* __restrict__ rhs, const Grid g, const Bounds b,
                  const int colour, const double wx, const double wy, const double wz, const double w1,
                  const int klo, const int khi, const int zchunk) {
+  pdl_enter();
   constexpr int NST = HAS_RHS ? 8 : 12;
   extern __shared__ __align__(16) double smem[];
   const int kbeg = klo + blockIdx.z * zchunk;
@@ -475,10 +482,10 @@ void relax3d_half(double* u, const double* rhs, const Grid& g, const Bounds& b, 
     const size_t sm_norhs = (size_t)12 * RS3_ROWS * RS3_PITCH * sizeof(double);
     const size_t sm_rhs = (size_t)8 * (RS3_ROWS * RS3_PITCH + RELAX_BY * 2 * RELAX_BX) * sizeof(double);
     if (rhs)
-      k_relax3d_staged<true><<<grid, RELAX_BX * RELAX_BY, sm_rhs, st>>>(u, rhs, g, b, colour, w.wx, w.wy, w.wz, w.w1,
+      launch_k(k_relax3d_staged<true>, grid, RELAX_BX * RELAX_BY, sm_rhs, st, u, rhs, g, b, colour, w.wx, w.wy, w.wz, w.w1,
                                                                         klo, khi, zc);
     else
-      k_relax3d_staged<false><<<grid, RELAX_BX * RELAX_BY, sm_norhs, st>>>(u, rhs, g, b, colour, w.wx, w.wy, w.wz,
+      launch_k(k_relax3d_staged<false>, grid, RELAX_BX * RELAX_BY, sm_norhs, st, u, rhs, g, b, colour, w.wx, w.wy, w.wz,
                                                                           w.w1, klo, khi, zc);
     LAUNCHED();
     return;
@@ -492,7 +499,7 @@ void relax3d_half(double* u, const double* rhs, const Grid& g, const Bounds& b, 
   const int zc = zc_force > 0 ? zc_force : pick_zchunk(khi - klo + 1, bx * by, zc_cap);
   dim3 grid(bx, by, cdiv(khi - klo + 1, zc));
 #define RELAX_LAUNCH(R, UU, MB) \
-  k_relax3d<R, UU, MB><<<grid, RELAX_BX * RELAX_BY, 0, st>>>(u, rhs, g, b, colour, w.wx, w.wy, w.wz, w.w1, klo, khi, zc)
+  launch_k(k_relax3d<R, UU, MB>, grid, RELAX_BX * RELAX_BY, 0, st, u, rhs, g, b, colour, w.wx, w.wy, w.wz, w.w1, klo, khi, zc)
   // measured at 513^3 (B200): rhs == 0: U=4 at 4 blocks/SM 186 us per colour pass (U=2: 188, U=4 at 3 blocks: 190);
   // with rhs: U=2 at 4 blocks/SM 254 us (U=4 at 3 blocks: 260)
   if (rhs) {
@@ -642,6 +649,7 @@ template <bool HAS_RHS>
 __global__ void __launch_bounds__(RELAX_BX * RELAX_BY, 3)
 k_residual3d(const double* __restrict__ u, const double* __restrict__ rhs, double* __restrict__ r, const Grid g,
              const Bounds b, const double wx, const double wy, const double wz, const double wc, const int zchunk) {
+  pdl_enter();
   const int colour = blockIdx.z & 1;
   const int kbeg = g.k0 + (blockIdx.z >> 1) * zchunk;
   const int kend = min(kbeg + zchunk - 1, g.k0 + g.nzl - 1);
@@ -695,9 +703,9 @@ void residual3d(const double* u, const double* rhs, double* r, const Grid& g, co
   const int zc = pick_zchunk(g.nzl, bx * by * 2);
   dim3 grid(bx, by, cdiv(g.nzl, zc) * 2);
   if (rhs)
-    k_residual3d<true><<<grid, RELAX_BX * RELAX_BY, 0, st>>>(u, rhs, r, g, b, w.wx, w.wy, w.wz, w.wc, zc);
+    launch_k(k_residual3d<true>, grid, RELAX_BX * RELAX_BY, 0, st, u, rhs, r, g, b, w.wx, w.wy, w.wz, w.wc, zc);
   else
-    k_residual3d<false><<<grid, RELAX_BX * RELAX_BY, 0, st>>>(u, rhs, r, g, b, w.wx, w.wy, w.wz, w.wc, zc);
+    launch_k(k_residual3d<false>, grid, RELAX_BX * RELAX_BY, 0, st, u, rhs, r, g, b, w.wx, w.wy, w.wz, w.wc, zc);
   LAUNCHED();
 }
 
@@ -712,6 +720,7 @@ __device__ __forceinline__ bool dirichlet2d(int i, int j, const Grid& g, const B
 __global__ void __launch_bounds__(256)
 k_relax2d(double* __restrict__ u, const double* __restrict__ rhs, const Grid g, const Bounds b, const int colour,
           const double wx, const double wy, const double w0) {
+  pdl_enter();
   const int t = blockIdx.x * 256 + threadIdx.x;
   const int j = t / g.hp;
   const int m = t - j * g.hp;
@@ -734,7 +743,7 @@ k_relax2d(double* __restrict__ u, const double* __restrict__ rhs, const Grid g, 
 
 void relax2d_half(double* u, const double* rhs, const Grid& g, const Bounds& b, int colour, const Weights& w,
                   cudaStream_t st) {
-  k_relax2d<<<cdiv((i64)g.hp * g.ny, 256), 256, 0, st>>>(u, rhs, g, b, colour, w.wx, w.wy, w.w1);
+  launch_k(k_relax2d, cdiv((i64)g.hp * g.ny, 256), 256, 0, st, u, rhs, g, b, colour, w.wx, w.wy, w.w1);
   LAUNCHED();
 }
 
@@ -753,6 +762,7 @@ k_relax2d_fm(double* __restrict__ u, const double* __restrict__ rhs, const Grid 
              const double wx, const double wy, const double w0, double* __restrict__ part_mine,
              const double* __restrict__ part_other, double* __restrict__ fm, unsigned* __restrict__ ticket,
              const double count) {
+  pdl_enter();
   __shared__ double red[40];
   __shared__ bool last;
   const int t = blockIdx.x * 256 + threadIdx.x;
@@ -802,6 +812,7 @@ k_relax2d_fm(double* __restrict__ u, const double* __restrict__ rhs, const Grid 
 
 __global__ void __launch_bounds__(256)
 k_sub_scalar2d(double* __restrict__ u, const Grid g, const double* __restrict__ fm) {
+  pdl_enter();
   const int t = blockIdx.x * 256 + threadIdx.x;
   const int j = t / g.hp;
   const int m = t - j * g.hp;
@@ -828,21 +839,22 @@ void relax2d_fused_mean(double* u, const double* rhs, const Grid& g, const Bound
   const double count = (double)((i64)g.nx * g.ny);
   for (int k = 0; k < nsweeps; ++k) {
     if (k == 0)
-      k_relax2d_fm<false, false><<<nb, 256, 0, st>>>(u, rhs, g, b, 0, w.wx, w.wy, w.w1, part_r, part_b, fm, ticket, count);
+      launch_k(k_relax2d_fm<false, false>, nb, 256, 0, st, u, rhs, g, b, 0, w.wx, w.wy, w.w1, part_r, part_b, fm, ticket, count);
     else
-      k_relax2d_fm<true, false><<<nb, 256, 0, st>>>(u, rhs, g, b, 0, w.wx, w.wy, w.w1, part_r, part_b, fm, ticket, count);
+      launch_k(k_relax2d_fm<true, false>, nb, 256, 0, st, u, rhs, g, b, 0, w.wx, w.wy, w.w1, part_r, part_b, fm, ticket, count);
     LAUNCHED();
-    k_relax2d_fm<false, true><<<nb, 256, 0, st>>>(u, rhs, g, b, 1, w.wx, w.wy, w.w1, part_b, part_r, fm, ticket, count);
+    launch_k(k_relax2d_fm<false, true>, nb, 256, 0, st, u, rhs, g, b, 1, w.wx, w.wy, w.w1, part_b, part_r, fm, ticket, count);
     LAUNCHED();
   }
   dim3 grid(nb, 2);
-  k_sub_scalar2d<<<grid, 256, 0, st>>>(u, g, fm);
+  launch_k(k_sub_scalar2d, grid, 256, 0, st, u, g, fm);
   LAUNCHED();
 }
 
 __global__ void __launch_bounds__(256)
 k_residual2d(const double* __restrict__ u, const double* __restrict__ rhs, double* __restrict__ r, const Grid g,
              const Bounds b, const double wx, const double wy) {
+  pdl_enter();
   const int t = blockIdx.x * 256 + threadIdx.x;
   const int j = t / g.hp;
   const int m = t - j * g.hp;
@@ -871,7 +883,7 @@ k_residual2d(const double* __restrict__ u, const double* __restrict__ rhs, doubl
 void residual2d(const double* u, const double* rhs, double* r, const Grid& g, const Bounds& b, const Weights& w,
                 cudaStream_t st) {
   dim3 grid(cdiv((i64)g.hp * g.ny, 256), 2);
-  k_residual2d<<<grid, 256, 0, st>>>(u, rhs, r, g, b, w.wx, w.wy);
+  launch_k(k_residual2d, grid, 256, 0, st, u, rhs, r, g, b, w.wx, w.wy);
   LAUNCHED();
 }
 
@@ -887,6 +899,7 @@ template <bool COPY>
 __global__ void __launch_bounds__(REDUCE_THREADS)
 k_diff_partial(double* __restrict__ a, const double* __restrict__ b, const i64 n_per_colour, const i64 cs,
                double* __restrict__ part) {
+  pdl_enter();
   // 16-byte accesses, four independent load pairs in flight per thread (planes are 256-byte multiples)
   __shared__ double red[40];
   double dmax = 0.0, dsum = 0.0;
@@ -927,6 +940,7 @@ k_diff_partial(double* __restrict__ a, const double* __restrict__ b, const i64 n
 }
 __global__ void __launch_bounds__(REDUCE_THREADS) k_diff_final(const double* __restrict__ part, int nparts,
                                                                double* __restrict__ out) {
+  pdl_enter();
   __shared__ double red[40];
   double dmax = 0.0, dsum = 0.0;
   for (int e = threadIdx.x; e < nparts; e += REDUCE_THREADS) {
@@ -947,12 +961,13 @@ __global__ void __launch_bounds__(REDUCE_THREADS) k_diff_final(const double* __r
 // per overlapped GB); a 40-byte store over PCIe does not.
 __global__ void k_publish(const double* __restrict__ pairs, const int npairs, const int* __restrict__ info,
                           double* __restrict__ host) {
+  pdl_enter();
   const int t = threadIdx.x;
   if (t < 2 * npairs) host[t] = pairs[t];
   if (t < 2) reinterpret_cast<int*>(host + 2 * npairs)[t] = info[t];
 }
 void publish_results(const double* pairs, int npairs, const int* info, double* host_mapped, cudaStream_t st) {
-  k_publish<<<1, 64, 0, st>>>(pairs, npairs, info, host_mapped);
+  launch_k(k_publish, 1, 64, 0, st, pairs, npairs, info, host_mapped);
   LAUNCHED();
 }
 
@@ -961,16 +976,17 @@ void diff_reduce(double* a, const double* b, const Grid& g, bool copy, double* s
   const i64 n = (i64)g.nzl * g.ps;
   const int nb = (int)std::min<i64>(REDUCE_BLOCKS, std::max<i64>(1, cdiv(n / 8, REDUCE_THREADS)));
   if (copy)
-    k_diff_partial<true><<<nb, REDUCE_THREADS, 0, st>>>(a, b, n, g.cs, scratch);
+    launch_k(k_diff_partial<true>, nb, REDUCE_THREADS, 0, st, a, b, n, g.cs, scratch);
   else
-    k_diff_partial<false><<<nb, REDUCE_THREADS, 0, st>>>(a, b, n, g.cs, scratch);
+    launch_k(k_diff_partial<false>, nb, REDUCE_THREADS, 0, st, a, b, n, g.cs, scratch);
   LAUNCHED();
-  k_diff_final<<<1, REDUCE_THREADS, 0, st>>>(scratch, nb, out);
+  launch_k(k_diff_final, 1, REDUCE_THREADS, 0, st, scratch, nb, out);
   LAUNCHED();
 }
 
 __global__ void __launch_bounds__(REDUCE_THREADS)
 k_sum_partial(const double* __restrict__ u, const i64 n_per_colour, const i64 cs, double* __restrict__ part) {
+  pdl_enter();
   __shared__ double red[40];
   double s = 0.0;
   for (int c = 0; c < 2; ++c)
@@ -984,6 +1000,7 @@ k_sum_partial(const double* __restrict__ u, const i64 n_per_colour, const i64 cs
 __global__ void __launch_bounds__(256)
 k_sub_mean(double* __restrict__ u, const Grid g, const double* __restrict__ part, const int nparts,
            const double inv_count_num /* N as double */) {
+  pdl_enter();
   __shared__ double red[40];
   double s = 0.0;
   for (int e = threadIdx.x; e < nparts; e += 256) s += part[e];
@@ -1007,6 +1024,7 @@ k_sub_mean(double* __restrict__ u, const Grid g, const double* __restrict__ part
 // same mean bits everywhere, so halo planes stay consistent with the neighbour's owned planes.
 __global__ void __launch_bounds__(REDUCE_THREADS) k_sum_final(const double* __restrict__ part, int nparts,
                                                               double* __restrict__ out) {
+  pdl_enter();
   __shared__ double red[40];
   double s = 0.0;
   for (int e = threadIdx.x; e < nparts; e += REDUCE_THREADS) s += part[e];
@@ -1016,14 +1034,15 @@ __global__ void __launch_bounds__(REDUCE_THREADS) k_sum_final(const double* __re
 void slab_sum(const double* u, const Grid& g, double* scratch, double* out2, cudaStream_t st) {
   const i64 n = (i64)g.nzl * g.ps;
   const int nb = (int)std::min<i64>(REDUCE_BLOCKS, std::max<i64>(1, cdiv(n, REDUCE_THREADS)));
-  k_sum_partial<<<nb, REDUCE_THREADS, 0, st>>>(u, n, g.cs, scratch);
+  launch_k(k_sum_partial, nb, REDUCE_THREADS, 0, st, u, n, g.cs, scratch);
   LAUNCHED();
-  k_sum_final<<<1, REDUCE_THREADS, 0, st>>>(scratch, nb, out2);
+  launch_k(k_sum_final, 1, REDUCE_THREADS, 0, st, scratch, nb, out2);
   LAUNCHED();
 }
 __global__ void __launch_bounds__(256)
 k_sub_gathered_mean(double* __restrict__ u, const Grid g, const double* __restrict__ pairs, const int world,
                     const double count, const int kl0) {
+  pdl_enter();
   double s = 0.0;
   for (int r = 0; r < world; ++r) s += pairs[2 * r];  // rank order
   const double mean = s / count;
@@ -1042,17 +1061,17 @@ k_sub_gathered_mean(double* __restrict__ u, const Grid g, const double* __restri
 }
 void subtract_gathered_mean(double* u, const Grid& g, const double* pairs, int world, int halo, cudaStream_t st) {
   dim3 grid(cdiv((i64)g.hp * g.ny, 256), g.nzl + 2 * halo, 2);
-  k_sub_gathered_mean<<<grid, 256, 0, st>>>(u, g, pairs, world, (double)((i64)g.nx * g.ny * g.nz), -halo);
+  launch_k(k_sub_gathered_mean, grid, 256, 0, st, u, g, pairs, world, (double)((i64)g.nx * g.ny * g.nz), -halo);
   LAUNCHED();
 }
 
 void subtract_mean(double* u, const Grid& g, double* scratch, cudaStream_t st) {
   const i64 n = (i64)g.nzl * g.ps;
   const int nb = (int)std::min<i64>(REDUCE_BLOCKS, std::max<i64>(1, cdiv(n, REDUCE_THREADS)));
-  k_sum_partial<<<nb, REDUCE_THREADS, 0, st>>>(u, n, g.cs, scratch);
+  launch_k(k_sum_partial, nb, REDUCE_THREADS, 0, st, u, n, g.cs, scratch);
   LAUNCHED();
   dim3 grid(cdiv((i64)g.hp * g.ny, 256), g.nzl, 2);
-  k_sub_mean<<<grid, 256, 0, st>>>(u, g, scratch, nb, (double)((i64)g.nx * g.ny * g.nz));
+  launch_k(k_sub_mean, grid, 256, 0, st, u, g, scratch, nb, (double)((i64)g.nx * g.ny * g.nz));
   LAUNCHED();
 }
 
@@ -1065,6 +1084,7 @@ void subtract_mean(double* u, const Grid& g, double* scratch, cudaStream_t st) {
 __global__ void __launch_bounds__(128)
 k_restrict(const double* __restrict__ rf, const Grid gf, double* __restrict__ rc, const Grid gc,
            const RestrictTab tx, const RestrictTab ty, const RestrictTab tz) {
+  pdl_enter();
   const int t = blockIdx.x * 128 + threadIdx.x;
   const int jc = t / gc.hp;
   const int mc = t - jc * gc.hp;
@@ -1108,7 +1128,7 @@ k_restrict(const double* __restrict__ rf, const Grid gf, double* __restrict__ rc
 void restrict_level(const double* rf, const Grid& gf, double* rhsc, const Grid& gc, const RestrictTab& tx,
                     const RestrictTab& ty, const RestrictTab& tz, cudaStream_t st) {
   dim3 grid(cdiv((i64)gc.hp * gc.ny, 128), gc.nzl, 2);
-  k_restrict<<<grid, 128, 0, st>>>(rf, gf, rhsc, gc, tx, ty, tz);
+  launch_k(k_restrict, grid, 128, 0, st, rf, gf, rhsc, gc, tx, ty, tz);
   LAUNCHED();
 }
 
@@ -1130,6 +1150,7 @@ __global__ void __launch_bounds__(RR_CX * RR_CY, 2)
 k_restrict_tiled(const double* __restrict__ rf, const Grid gf, double* __restrict__ rc, const Grid gc,
                  const RestrictTab tx, const RestrictTab ty, const RestrictTab tz, const int hwp, const int fyw,
                  const int kchunk) {
+  pdl_enter();
   extern __shared__ double sr[];  // [RR_WZ][fyw][2*hwp]
   const int txi = threadIdx.x & (RR_CX - 1), tyi = threadIdx.x / RR_CX;
   const int ic0 = blockIdx.x * RR_CX, jc0 = blockIdx.y * RR_CY;
@@ -1256,7 +1277,7 @@ void restrict_tiled(const double* rf, const Grid& gf, double* rhsc, const Grid& 
   int kchunk = 16;
   while (kchunk > 2 && (i64)bx * by * cdiv(gc.nzl, kchunk) < 148 * 4) kchunk >>= 1;
   dim3 grid(bx, by, cdiv(gc.nzl, kchunk));
-  k_restrict_tiled<<<grid, RR_CX * RR_CY, smem, st>>>(rf, gf, rhsc, gc, tx, ty, tz, hwp, fyw, kchunk);
+  launch_k(k_restrict_tiled, grid, RR_CX * RR_CY, smem, st, rf, gf, rhsc, gc, tx, ty, tz, hwp, fyw, kchunk);
   LAUNCHED();
 }
 
@@ -1277,6 +1298,7 @@ void restrict_tiled(const double* rf, const Grid& gf, double* rhsc, const Grid& 
 __global__ void __launch_bounds__(RS_CX * RS_CY, 2)
 k_restrict_sep(const double* __restrict__ rf, const Grid gf, double* __restrict__ rc, const Grid gc,
                const RestrictTab tx, const RestrictTab ty, const RestrictTab tz, const int kchunk) {
+  pdl_enter();
   __shared__ double sA[RS_FYW][RS_FXW + 1];  // fine plane tile, natural order
   __shared__ double sB[RS_FYW][RS_CX + 1];   // x-restricted rows
   const int txi = threadIdx.x & (RS_CX - 1), tyi = threadIdx.x / RS_CX;
@@ -1397,6 +1419,7 @@ k_restrict_sep(const double* __restrict__ rf, const Grid gf, double* __restrict_
 __global__ void __launch_bounds__(RD_BX * RD_BY, 2)
 k_restrict_direct(const double* __restrict__ rf, const Grid gf, double* __restrict__ rc, const Grid gc,
                   const RestrictTab tx, const RestrictTab ty, const RestrictTab tz, const int kchunk) {
+  pdl_enter();
   const int ic = blockIdx.x * RD_BX + (threadIdx.x & (RD_BX - 1));
   const int jc = blockIdx.y * RD_BY + threadIdx.x / RD_BX;
   const int kc_beg = gc.k0 + blockIdx.z * kchunk;
@@ -1510,7 +1533,7 @@ void restrict_direct(const double* rf, const Grid& gf, double* rhsc, const Grid&
   int kchunk = 32;
   while (kchunk > 2 && (i64)bx * by * cdiv(gc.nzl, kchunk) < 148 * 6) kchunk >>= 1;
   dim3 grid(bx, by, cdiv(gc.nzl, kchunk));
-  k_restrict_direct<<<grid, RD_BX * RD_BY, 0, st>>>(rf, gf, rhsc, gc, tx, ty, tz, kchunk);
+  launch_k(k_restrict_direct, grid, RD_BX * RD_BY, 0, st, rf, gf, rhsc, gc, tx, ty, tz, kchunk);
   LAUNCHED();
 }
 
@@ -1533,7 +1556,7 @@ void restrict_sep(const double* rf, const Grid& gf, double* rhsc, const Grid& gc
   int kchunk = 32;
   while (kchunk > 2 && (i64)bx * by * cdiv(gc.nzl, kchunk) < 148 * 8) kchunk >>= 1;
   dim3 grid(bx, by, cdiv(gc.nzl, kchunk));
-  k_restrict_sep<<<grid, RS_CX * RS_CY, 0, st>>>(rf, gf, rhsc, gc, tx, ty, tz, kchunk);
+  launch_k(k_restrict_sep, grid, RS_CX * RS_CY, 0, st, rf, gf, rhsc, gc, tx, ty, tz, kchunk);
   LAUNCHED();
 }
 
@@ -1546,6 +1569,7 @@ void restrict_sep(const double* rf, const Grid& gf, double* rhsc, const Grid& gc
 __global__ void __launch_bounds__(256)
 k_interp_add(const double* __restrict__ uc, const Grid gc, double* __restrict__ uf, const Grid gf,
              const InterpTab tx, const InterpTab ty, const InterpTab tz) {
+  pdl_enter();
   const int t = blockIdx.x * 256 + threadIdx.x;
   const int j = t / gf.hp;
   const int m = t - j * gf.hp;
@@ -1586,6 +1610,7 @@ k_interp_add(const double* __restrict__ uc, const Grid gc, double* __restrict__ 
 __global__ void __launch_bounds__(IP_FX * IP_TY)
 k_interp_add_tiled(const double* __restrict__ uc, const Grid gc, double* __restrict__ uf, const Grid gf,
                    const InterpTab tx, const InterpTab ty, const InterpTab tz, const int zchunk) {
+  pdl_enter();
   __shared__ double sc[IP_CZW * IP_CYW * IP_CXW];
   const int txi = threadIdx.x & (IP_FX - 1), tyi = threadIdx.x / IP_FX;
   const int i0 = blockIdx.x * IP_FX, j0 = blockIdx.y * (2 * IP_TY);
@@ -1686,6 +1711,7 @@ k_interp_add_tiled(const double* __restrict__ uc, const Grid gc, double* __restr
 __global__ void __launch_bounds__(IZ_BX * IZ_BY, 4)
 k_interp_add_zt(const double* __restrict__ uc, const Grid gc, double* __restrict__ uf, const Grid gf,
                 const InterpTab tx, const InterpTab ty, const InterpTab tz, const int zchunk) {
+  pdl_enter();
   __shared__ double zt[2][IZ_NP][IZ_CYW * IZ_CXW];  // [buffer][plane of the step][coarse tile]
   __shared__ double s_wh[IZ_ZMAX], s_wl[IZ_ZMAX];
   __shared__ int s_lo[IZ_ZMAX];
@@ -1792,7 +1818,7 @@ void interp_add_zt(const double* uc, const Grid& gc, double* uf, const Grid& gf,
   const int bx = cdiv(gf.nx, IZ_FX), by = cdiv(gf.ny, IZ_BY);
   const int zc = pick_zchunk(gf.nzl, bx * by, IZ_ZMAX);
   dim3 grid(bx, by, cdiv(gf.nzl, zc));
-  k_interp_add_zt<<<grid, IZ_BX * IZ_BY, 0, st>>>(uc, gc, uf, gf, tx, ty, tz, zc);
+  launch_k(k_interp_add_zt, grid, IZ_BX * IZ_BY, 0, st, uc, gc, uf, gf, tx, ty, tz, zc);
   LAUNCHED();
 }
 
@@ -1811,14 +1837,14 @@ void interp_add_tiled(const double* uc, const Grid& gc, double* uf, const Grid& 
   const int bx = cdiv(gf.nx, IP_FX), by = cdiv(gf.ny, 2 * IP_TY);
   const int zc = pick_zchunk(gf.nzl, bx * by);
   dim3 grid(bx, by, cdiv(gf.nzl, zc));
-  k_interp_add_tiled<<<grid, IP_FX * IP_TY, 0, st>>>(uc, gc, uf, gf, tx, ty, tz, zc);
+  launch_k(k_interp_add_tiled, grid, IP_FX * IP_TY, 0, st, uc, gc, uf, gf, tx, ty, tz, zc);
   LAUNCHED();
 }
 
 void interp_add(const double* uc, const Grid& gc, double* uf, const Grid& gf, const InterpTab& tx,
                 const InterpTab& ty, const InterpTab& tz, cudaStream_t st) {
   dim3 grid(cdiv((i64)gf.hp * gf.ny, 256), gf.nzl, 2);
-  k_interp_add<<<grid, 256, 0, st>>>(uc, gc, uf, gf, tx, ty, tz);
+  launch_k(k_interp_add, grid, 256, 0, st, uc, gc, uf, gf, tx, ty, tz);
   LAUNCHED();
 }
 
@@ -1835,6 +1861,7 @@ k_solve_exact(double* __restrict__ u, const double* __restrict__ rhs, const Grid
               const int first_colour, const double wx, const double wy, const double wz, const double w1,
               const int all_neumann, const int du_max, const double ex_tol, const int nmax,
               int* __restrict__ info) {
+  pdl_enter();
   extern __shared__ double sm[];
   __shared__ double red[40];
   const int N = g.nx * g.ny * g.nz;
@@ -1928,10 +1955,10 @@ bool solve_exact_smem(int ndim, double* u, const double* rhs, const Grid& g, con
   int threads = (int)std::min<i64>(1024, std::max<i64>(64, ((N / 2 + 31) / 32) * 32));
   solve_exact_prepare();
   if (ndim == 3)
-    k_solve_exact<3><<<1, threads, bytes, st>>>(u, rhs, g, b, first_colour, w.wx, w.wy, w.wz, w.w1,
+    launch_k(k_solve_exact<3>, 1, threads, bytes, st, u, rhs, g, b, first_colour, w.wx, w.wy, w.wz, w.w1,
                                                 all_neumann ? 1 : 0, du_max ? 1 : 0, ex_tol, nmax, info);
   else
-    k_solve_exact<2><<<1, threads, bytes, st>>>(u, rhs, g, b, first_colour, w.wx, w.wy, w.wz, w.w1,
+    launch_k(k_solve_exact<2>, 1, threads, bytes, st, u, rhs, g, b, first_colour, w.wx, w.wy, w.wz, w.w1,
                                                 all_neumann ? 1 : 0, du_max ? 1 : 0, ex_tol, nmax, info);
   LAUNCHED();
   return true;
@@ -2179,6 +2206,7 @@ template <int NDIM>
 __global__ void __launch_bounds__(1024)
 k_vcycle_small(const double* __restrict__ rhs_in, double* __restrict__ u_out, const Grid g0, const SmallArgs a,
                int* __restrict__ info) {
+  pdl_enter();
   extern __shared__ double sm[];
   __shared__ double red[40];
   const int nl = a.nlev;
@@ -2307,8 +2335,8 @@ void vcycle_small(int ndim, const double* rhs_in, double* u_out, const Grid& g0,
   const size_t bytes = (size_t)a.smem_doubles * sizeof(double);
   const int q0 = ((a.lv[0].nx + 1) / 2) * a.lv[0].ny * a.lv[0].nz;  // compressed points of the largest level
   const int threads = std::min(1024, std::max(32, ((q0 + 31) / 32) * 32));
-  if (ndim == 3) k_vcycle_small<3><<<1, threads, bytes, st>>>(rhs_in, u_out, g0, a, info);
-  else k_vcycle_small<2><<<1, threads, bytes, st>>>(rhs_in, u_out, g0, a, info);
+  if (ndim == 3) launch_k(k_vcycle_small<3>, 1, threads, bytes, st, rhs_in, u_out, g0, a, info);
+  else launch_k(k_vcycle_small<2>, 1, threads, bytes, st, rhs_in, u_out, g0, a, info);
   LAUNCHED();
 }
 
@@ -2317,6 +2345,7 @@ void vcycle_small(int ndim, const double* rhs_in, double* u_out, const Grid& g0,
 // ---------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 k_split_from_dense(const double* __restrict__ dense, double* __restrict__ split, const Grid g, const double shift) {
+  pdl_enter();
   const int i = blockIdx.x * 256 + threadIdx.x;
   if (i >= g.nx) return;
   const int j = blockIdx.y, kl = blockIdx.z;
@@ -2324,11 +2353,12 @@ k_split_from_dense(const double* __restrict__ dense, double* __restrict__ split,
 }
 void split_from_dense(const double* dense, double* split, const Grid& g, double shift, cudaStream_t st) {
   dim3 grid(cdiv(g.nx, 256), g.ny, g.nzl);
-  k_split_from_dense<<<grid, 256, 0, st>>>(dense, split, g, shift);
+  launch_k(k_split_from_dense, grid, 256, 0, st, dense, split, g, shift);
   LAUNCHED();
 }
 __global__ void __launch_bounds__(256)
 k_dense_from_split(const double* __restrict__ split, double* __restrict__ dense, const Grid g) {
+  pdl_enter();
   const int i = blockIdx.x * 256 + threadIdx.x;
   if (i >= g.nx) return;
   const int j = blockIdx.y, kl = blockIdx.z;
@@ -2336,7 +2366,7 @@ k_dense_from_split(const double* __restrict__ split, double* __restrict__ dense,
 }
 void dense_from_split(const double* split, double* dense, const Grid& g, cudaStream_t st) {
   dim3 grid(cdiv(g.nx, 256), g.ny, g.nzl);
-  k_dense_from_split<<<grid, 256, 0, st>>>(split, dense, g);
+  launch_k(k_dense_from_split, grid, 256, 0, st, split, dense, g);
   LAUNCHED();
 }
 
@@ -2347,6 +2377,7 @@ void dense_from_split(const double* split, double* dense, const Grid& g, cudaStr
 __global__ void __launch_bounds__(256)
 k_extract_face(const double* __restrict__ Bc, const int nx, const int ny, const int nz, const int dim,
                const int layer, double* __restrict__ face) {
+  pdl_enter();
   const int n1 = (dim == 0) ? ny : nx;
   const int n2 = (dim == 2) ? ny : nz;
   const int a = blockIdx.x * 256 + threadIdx.x;
@@ -2362,13 +2393,14 @@ void extract_face(const double* Bc, int nx, int ny, int nz, int dim, int layer, 
   const int n1 = (dim == 0) ? ny : nx;
   const int n2 = (dim == 2) ? ny : nz;
   dim3 grid(cdiv(n1, 256), n2);
-  k_extract_face<<<grid, 256, 0, st>>>(Bc, nx, ny, nz, dim, layer, face);
+  launch_k(k_extract_face, grid, 256, 0, st, Bc, nx, ny, nz, dim, layer, face);
   LAUNCHED();
 }
 
 // trapz_2D (ndsm_vector_potential.f90:1070-1106): SUM(w*f) with w = 1, 1/2 (edges), 1/4 (corners)
 __global__ void __launch_bounds__(REDUCE_THREADS)
 k_trapz_partial(const double* __restrict__ f, const int n1, const int n2, double* __restrict__ part) {
+  pdl_enter();
   __shared__ double red[40];
   const i64 n = (i64)n1 * n2;
   double s = 0.0;
@@ -2384,6 +2416,7 @@ k_trapz_partial(const double* __restrict__ f, const int n1, const int n2, double
 __global__ void __launch_bounds__(REDUCE_THREADS)
 k_trapz_final(const double* __restrict__ part, const int nparts, const double dq1, const double dq2,
               double* __restrict__ out) {
+  pdl_enter();
   __shared__ double red[40];
   double s = 0.0;
   for (int e = threadIdx.x; e < nparts; e += REDUCE_THREADS) s += part[e];
@@ -2394,9 +2427,9 @@ void trapz_face(const double* face, int n1, int n2, double dq1, double dq2, doub
                 cudaStream_t st) {
   const i64 n = (i64)n1 * n2;
   const int nb = (int)std::min<i64>(REDUCE_BLOCKS, std::max<i64>(1, cdiv(n, REDUCE_THREADS)));
-  k_trapz_partial<<<nb, REDUCE_THREADS, 0, st>>>(face, n1, n2, scratch);
+  launch_k(k_trapz_partial, nb, REDUCE_THREADS, 0, st, face, n1, n2, scratch);
   LAUNCHED();
-  k_trapz_final<<<1, REDUCE_THREADS, 0, st>>>(scratch, nb, dq1, dq2, out);
+  launch_k(k_trapz_final, 1, REDUCE_THREADS, 0, st, scratch, nb, dq1, dq2, out);
   LAUNCHED();
 }
 
@@ -2405,6 +2438,7 @@ void trapz_face(const double* face, int n1, int n2, double dq1, double dq2, doub
 __global__ void __launch_bounds__(256)
 k_compute_At(const double* __restrict__ chi, const Grid g, const double fac, const int yface,
              double* __restrict__ At1, double* __restrict__ At2) {
+  pdl_enter();
   const int i = blockIdx.x * 256 + threadIdx.x;
   const int j = blockIdx.y;
   if (i >= g.nx || j >= g.ny) return;
@@ -2418,13 +2452,14 @@ k_compute_At(const double* __restrict__ chi, const Grid g, const double fac, con
 void compute_At(const double* chi_split, const Grid& g2, double fac, int face_id, double* At1, double* At2,
                 cudaStream_t st) {
   dim3 grid(cdiv(g2.nx, 256), g2.ny);
-  k_compute_At<<<grid, 256, 0, st>>>(chi_split, g2, fac, (face_id == 2 || face_id == 3) ? 1 : 0, At1, At2);
+  launch_k(k_compute_At, grid, 256, 0, st, chi_split, g2, fac, (face_id == 2 || face_id == 3) ? 1 : 0, At1, At2);
   LAUNCHED();
 }
 
 // extract_bn with dir=-1 (ndsm_vector_potential.f90:647-682,739): Dirichlet data -> face of A (colour-split)
 __global__ void __launch_bounds__(256)
 k_write_face(double* __restrict__ A, const Grid g, const int dim, const int layer, const double* __restrict__ face) {
+  pdl_enter();
   const int n1 = (dim == 0) ? g.ny : g.nx;
   const int n2 = (dim == 2) ? g.ny : g.nz;
   const int a = blockIdx.x * 256 + threadIdx.x;
@@ -2441,7 +2476,7 @@ void write_face(double* A_split, const Grid& g, int dim, int layer, const double
   const int n1 = (dim == 0) ? g.ny : g.nx;
   const int n2 = (dim == 2) ? g.ny : g.nz;
   dim3 grid(cdiv(n1, 256), n2);
-  k_write_face<<<grid, 256, 0, st>>>(A_split, g, dim, layer, face);
+  launch_k(k_write_face, grid, 256, 0, st, A_split, g, dim, layer, face);
   LAUNCHED();
 }
 
@@ -2454,6 +2489,7 @@ __global__ void __launch_bounds__(256)
 k_unsplit_A(const double* __restrict__ As, const Grid g, const int comp, const double* __restrict__ x,
             const double* __restrict__ y, const double* __restrict__ z, const FluxPar f, const int add_flux,
             const int ka, double* __restrict__ Ad) {
+  pdl_enter();
   // one thread per point of a dense plane, flattened (i + nx*j): consecutive threads write consecutive doubles
   const int n = blockIdx.x * 256 + threadIdx.x;
   if (n >= g.nx * g.ny) return;
@@ -2481,7 +2517,7 @@ void unsplit_A(const double* As, const Grid& g, int comp, const double* x, const
   for (int q = 0; q < 3; ++q) f.Lq[q] = Lq[q];
   if (kb <= ka) return;
   dim3 grid(cdiv((i64)g.nx * g.ny, 256), kb - ka);
-  k_unsplit_A<<<grid, 256, 0, st>>>(As, g, comp, x, y, z, f, add_flux ? 1 : 0, ka, A_dense);
+  launch_k(k_unsplit_A, grid, 256, 0, st, As, g, comp, x, y, z, f, add_flux ? 1 : 0, ka, A_dense);
   LAUNCHED();
 }
 
@@ -2509,6 +2545,7 @@ template <int COMP>
 __global__ void __launch_bounds__(256)
 k_curl(const double* __restrict__ A, const int ka, const i64 csA, const int nx, const int ny, const int nz,
        const double dqx, const double dqy, const double dqz, const int k0, double* __restrict__ B, const i64 csB) {
+  pdl_enter();
   const int p = blockIdx.x * 256 + threadIdx.x;
   if (p >= nx * ny) return;
   const int j = p / nx, i = p - j * nx;
@@ -2539,10 +2576,10 @@ void curl_dense(const double* A, int ka, i64 csA, int nx, int ny, int nz, double
                 int k1, double* B, i64 csB, cudaStream_t st, int comp) {
   if (k1 <= k0) return;
   dim3 grid(cdiv((i64)nx * ny, 256), k1 - k0);
-  if (comp == 0) k_curl<0><<<grid, 256, 0, st>>>(A, ka, csA, nx, ny, nz, dqx, dqy, dqz, k0, B, csB);
-  else if (comp == 1) k_curl<1><<<grid, 256, 0, st>>>(A, ka, csA, nx, ny, nz, dqx, dqy, dqz, k0, B, csB);
-  else if (comp == 2) k_curl<2><<<grid, 256, 0, st>>>(A, ka, csA, nx, ny, nz, dqx, dqy, dqz, k0, B, csB);
-  else k_curl<-1><<<grid, 256, 0, st>>>(A, ka, csA, nx, ny, nz, dqx, dqy, dqz, k0, B, csB);
+  if (comp == 0) launch_k(k_curl<0>, grid, 256, 0, st, A, ka, csA, nx, ny, nz, dqx, dqy, dqz, k0, B, csB);
+  else if (comp == 1) launch_k(k_curl<1>, grid, 256, 0, st, A, ka, csA, nx, ny, nz, dqx, dqy, dqz, k0, B, csB);
+  else if (comp == 2) launch_k(k_curl<2>, grid, 256, 0, st, A, ka, csA, nx, ny, nz, dqx, dqy, dqz, k0, B, csB);
+  else launch_k(k_curl<-1>, grid, 256, 0, st, A, ka, csA, nx, ny, nz, dqx, dqy, dqz, k0, B, csB);
   LAUNCHED();
 }
 
@@ -2551,6 +2588,7 @@ __global__ void __launch_bounds__(256)
 k_add_flux_dense(double* __restrict__ A, const i64 csA, double* __restrict__ B, const i64 csB, const int nx,
                  const int ny, const int k0, const double* __restrict__ x, const double* __restrict__ y,
                  const double* __restrict__ z, const FluxPar f) {
+  pdl_enter();
   const int i = blockIdx.x * 256 + threadIdx.x;
   if (i >= nx) return;
   const int j = blockIdx.y, kl = blockIdx.z, k = k0 + kl;
@@ -2579,7 +2617,7 @@ void add_flux_dense(double* A, i64 csA, double* B, i64 csB, int nx, int ny, int 
   for (int q = 0; q < 3; ++q) f.Lq[q] = Lq[q];
   if (k1 <= k0) return;
   dim3 grid(cdiv(nx, 256), ny, k1 - k0);
-  k_add_flux_dense<<<grid, 256, 0, st>>>(A, csA, B, csB, nx, ny, k0, x, y, z, f);
+  launch_k(k_add_flux_dense, grid, 256, 0, st, A, csA, B, csB, nx, ny, k0, x, y, z, f);
   LAUNCHED();
 }
 

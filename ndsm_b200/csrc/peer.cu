@@ -270,6 +270,7 @@ __device__ __forceinline__ void copy_segment(const double* __restrict__ src, dou
 }
 
 __global__ void __launch_bounds__(256) k_push(const PushArgs a) {
+  pdl_enter();
   __shared__ u64 par[MAX_WORLD];
   __shared__ bool last;
   if (threadIdx.x < a.npeer)  // parity of the staged message this launch carries to each peer
@@ -297,6 +298,7 @@ __global__ void __launch_bounds__(256) k_push(const PushArgs a) {
 }
 
 __global__ void __launch_bounds__(256) k_wait_unpack(const WaitArgs a) {
+  pdl_enter();
   __shared__ u64 par[MAX_WORLD];
   __shared__ bool last;
   if (threadIdx.x < a.npeer) {
@@ -419,7 +421,7 @@ struct PeerComm : Comm {
       a.sent_st[p] = g_fab.word(CW_SENT_ST, ch, r);
     }
     a.ticket = g_fab.ticket(ch, 0);
-    k_push<<<blocks_for(a.seg, a.nseg), 256, 0, st>>>(a);
+    launch_k(k_push, blocks_for(a.seg, a.nseg), 256, 0, st, a);
     CUDA_CHECK(cudaGetLastError());
     ++g_launches;
   }
@@ -445,7 +447,7 @@ struct PeerComm : Comm {
     a.d_err = g_fab.d_err();
     a.h_err_map = g_fab.d_err_map;
     a.timeout_ns = g_fab.timeout_ns;
-    k_wait_unpack<<<blocks_for(a.seg, a.nseg), 256, 0, st>>>(a);
+    launch_k(k_wait_unpack, blocks_for(a.seg, a.nseg), 256, 0, st, a);
     CUDA_CHECK(cudaGetLastError());
     ++g_launches;
   }
