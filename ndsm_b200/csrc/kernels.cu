@@ -11,15 +11,16 @@
 #include <cstdlib>
 #include <vector>
 
+bool pdl_enabled() {  // declared in common.cuh; read per launch: tests and benches toggle it between solves
+  const char* e = getenv("NDSM_B200_PDL");
+  return !(e && atoi(e) == 0);
+}
+
 namespace ndsm {
 
 unsigned long long g_launches = 0;
 #define LAUNCHED() (++g_launches)
 
-bool pdl_enabled() {  // read per launch: tests and benches toggle it between solves
-  const char* e = getenv("NDSM_B200_PDL");
-  return !(e && atoi(e) == 0);
-}
 
 static inline int cdiv(i64 a, i64 b) { return (int)((a + b - 1) / b); }
 
