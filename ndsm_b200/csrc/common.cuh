@@ -68,6 +68,14 @@ __device__ __forceinline__ void pdl_enter() {
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 #endif
 }
+// For kernels that may SPIN on something another GPU produces (peer.cu, k_wait_unpack): no early trigger, so that
+// no dependent grid is parked on the SMs while this one waits -- a parked full wave would keep the kernels of the
+// other component streams (whose messages the peer is waiting for) off this GPU: a cross-GPU deadlock.
+__device__ __forceinline__ void pdl_enter_no_trigger() {
+#if defined(__CUDA_ARCH__)
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+#endif
+}
 
 __host__ __device__ inline i64 gidx(const Grid& g, int i, int j, int k) {
   return (i64)((i + j + k) & 1) * g.cs + (i64)(k - g.k0) * g.ps + (i64)j * g.hp + (i >> 1);

@@ -298,7 +298,7 @@ __global__ void __launch_bounds__(256) k_push(const PushArgs a) {
 }
 
 __global__ void __launch_bounds__(256) k_wait_unpack(const WaitArgs a) {
-  pdl_enter();
+  pdl_enter_no_trigger();
   __shared__ u64 par[MAX_WORLD];
   __shared__ bool last;
   if (threadIdx.x < a.npeer) {
