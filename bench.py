@@ -353,13 +353,14 @@ def load_ncu_traffic():
     return out
 
 
-def kernel_report(lib, npoints, dev_ms, rhs_zero=True):
+def kernel_report(lib, npoints, dev_ms, rhs_zero=True, single_gpu=True):
     """Per-kernel-class CUDA-event timings gathered by the library (finest level of this rank's slab)."""
     cnt, tot = ctypes.c_ulonglong(0), ctypes.c_double(0)
     peak, peak_src = measured_peak()
     kern = {}
     b0 = 8.0 if rhs_zero else 12.0
-    bytes_per_pt = [b0, 16.0 if rhs_zero else 24.0, 9.0, 17.0, 24.0, 0.0, 0.0, 0.0]  # SURVEY 8d / DESIGN.md (level 0)
+    # SURVEY 8d / DESIGN.md (level 0); update_u on one GPU only measures the difference (ping-pong cycles, no copy): 16 B/pt
+    bytes_per_pt = [b0, 16.0 if rhs_zero else 24.0, 9.0, 17.0, 16.0 if single_gpu else 24.0, 0.0, 0.0, 0.0]
     for cls in range(8):
         lib.ndsm_b200_profile_get(cls, ctypes.byref(cnt), ctypes.byref(tot))
         if cnt.value:
@@ -516,7 +517,7 @@ def run_ours(args, rank, world):
         device_step()
         lib.ndsm_b200_last_timing(p(tim))
         prof_ms += tim[6]
-    roofline = kernel_report(lib, int(lib.ndsm_b200_last_slab_points()) or npts_local, prof_ms)
+    roofline = kernel_report(lib, int(lib.ndsm_b200_last_slab_points()) or npts_local, prof_ms, single_gpu=(world == 1))
     lib.ndsm_b200_profile_enable(0)
 
     # ---------------- end-to-end arm: host buffers, H2D and D2H inside the timed region -------------
@@ -668,7 +669,7 @@ def run_poisson(args, cfg, lib, rank, world, local, dist):
         device_step()
     torch.cuda.synchronize()
     prof_ms = (time.perf_counter() - t1) * 1e3
-    roofline = kernel_report(lib, npts_local, prof_ms, rhs_zero=False)
+    roofline = kernel_report(lib, npts_local, prof_ms, rhs_zero=False, single_gpu=(world == 1))
     lib.ndsm_b200_profile_enable(0)
 
     # end to end: host slabs of u and rhs (pinned) -> device -> solve -> host

@@ -61,6 +61,7 @@ static int ensure_device(const char* sub) {
     if (g_device >= 0) {
       cudaSetDevice(g_device);
       cudaDeviceSynchronize();
+      solver_cache_clear();
       pool_trim(0);
       cudaSetDevice(want);
     }
@@ -108,6 +109,7 @@ static int fail(const NdsmError& e, const char* sub) {
   }
   cudaDeviceSynchronize();  // buffers released by unwinding may be handed out again by the pool
   cudaGetLastError();
+  solver_cache_clear();     // a solve that was cut short leaves its hierarchy in an undefined state
   return code;
 }
 // anything that is not an NdsmError (std::bad_alloc from host staging, std::system_error from std::thread ...)
@@ -118,6 +120,7 @@ static int fail_std(const char* what, const char* sub) {
   error_msg(msg, sub, "NDSM_B200_ERR_CUDA");
   cudaDeviceSynchronize();
   cudaGetLastError();
+  solver_cache_clear();
   return NDSM_B200_ERR_CUDA;
 }
 #define NDSM_CATCH_ALL(sub, wrap)                                      \
@@ -897,6 +900,7 @@ int ndsm_b200_dist_init(int rank, int world, const void* id128) {
   if (!id128 || world < 1 || rank < 0 || rank >= world) return NDSM_B200_ERR_ARG;
   if (int e = ensure_device(SUB)) return e;
   try {
+    solver_cache_clear();
     g_dist_peer.reset();
     peer_fabric_shutdown();
     g_dist.reset();
@@ -910,6 +914,7 @@ int ndsm_b200_dist_init(int rank, int world, const void* id128) {
 }
 int ndsm_b200_dist_finalize(void) {
   cudaDeviceSynchronize();
+  solver_cache_clear();
   g_dist_peer.reset();
   peer_fabric_shutdown();
   g_dist.reset();
@@ -1024,6 +1029,7 @@ int ndsm_b200_profile_get(int cls, unsigned long long* count, double* total_ms) 
 }
 void ndsm_b200_release_workspace(void) {
   cudaDeviceSynchronize();
+  solver_cache_clear();
   pool_release();
 }
 unsigned long long ndsm_b200_workspace_bytes(void) { return (unsigned long long)pool_cached_bytes(); }

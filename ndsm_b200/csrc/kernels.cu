@@ -284,15 +284,17 @@ __device__ __forceinline__ void relax_pair_march(const double* __restrict__ po, 
 
 template <bool HAS_RHS, int U = 2, int MINB = 4>
 __global__ void __launch_bounds__(RELAX_BX * RELAX_BY, MINB)
-k_relax3d(double* __restrict__ u, const double* __restrict__ rhs, const Grid g, const Bounds b, const int colour,
-          const double wx, const double wy, const double wz, const double w1, const int klo, const int khi,
-          const int zchunk) {
+k_relax3d(double* __restrict__ u, const double* __restrict__ uread, const double* __restrict__ rhs, const Grid g,
+          const Bounds b, const int colour, const double wx, const double wy, const double wz, const double w1,
+          const int klo, const int khi, const int zchunk) {
   pdl_enter();
   const int kbeg = klo + blockIdx.z * zchunk;
   const int kend = min(kbeg + zchunk - 1, khi);
   if (kbeg > kend) return;
+  // uread == u except in the first pass of a ping-pong V-cycle, which reads the other colour of the previous
+  // iterate's array and writes its own colour into the new one (MG::relax)
   double* __restrict__ own = u + (i64)colour * g.cs;
-  const double* __restrict__ opp = u + (i64)(1 - colour) * g.cs;
+  const double* __restrict__ opp = uread + (i64)(1 - colour) * g.cs;
   const double* __restrict__ rh = HAS_RHS ? rhs + (i64)colour * g.cs : nullptr;
 
   if (blockIdx.x == gridDim.x - 1) {  // edge blocks: 4 edge columns x RELAX_EDGE_ROWS rows, scalar path
@@ -458,7 +460,7 @@ static int pick_zchunk(int nplanes, int blocks_per_plane, int zc_max = 16) {
 }
 
 void relax3d_half(double* u, const double* rhs, const Grid& g, const Bounds& b, int colour, const Weights& w,
-                  int ext, cudaStream_t st) {
+                  int ext, cudaStream_t st, const double* uread) {
   // ext > 0: also update `ext` halo planes on each side of the slab (communication-avoiding smoothing)
   const int klo = max(b.lb[2], g.k0 - ext), khi = min(b.ub[2], g.k0 + g.nzl - 1 + ext);
   const int nrows = b.ub[1] - b.lb[1] + 1;
@@ -469,7 +471,7 @@ void relax3d_half(double* u, const double* rhs, const Grid& g, const Bounds& b, 
   // pass): every staged value is read ~3.5 times from shared memory (own column, two y neighbours, x neighbour)
   // on top of the cp.async writes, which makes the kernel shared-memory-bandwidth-bound before HBM saturates
   static const bool staged_on = getenv("NDSM_B200_STAGED") && atoi(getenv("NDSM_B200_STAGED")) != 0;
-  if (staged_on && npairs >= RELAX_BX && khi - klo + 1 >= 16 && nrows >= RELAX_BY) {
+  if (staged_on && !uread && npairs >= RELAX_BX && khi - klo + 1 >= 16 && nrows >= RELAX_BY) {
     // shared-memory staged path: long z-chunks amortise the pipeline fill
     static bool attr = false;
     if (!attr) {
@@ -500,7 +502,7 @@ void relax3d_half(double* u, const double* rhs, const Grid& g, const Bounds& b, 
   const int zc = zc_force > 0 ? zc_force : pick_zchunk(khi - klo + 1, bx * by, zc_cap);
   dim3 grid(bx, by, cdiv(khi - klo + 1, zc));
 #define RELAX_LAUNCH(R, UU, MB) \
-  launch_k(k_relax3d<R, UU, MB>, grid, RELAX_BX * RELAX_BY, 0, st, u, rhs, g, b, colour, w.wx, w.wy, w.wz, w.w1, klo, khi, zc)
+  launch_k(k_relax3d<R, UU, MB>, grid, RELAX_BX * RELAX_BY, 0, st, u, uread ? uread : u, rhs, g, b, colour, w.wx, w.wy, w.wz, w.w1, klo, khi, zc)
   // measured at 513^3 (B200): rhs == 0: U=4 at 4 blocks/SM 186 us per colour pass (U=2: 188, U=4 at 3 blocks: 190);
   // with rhs: U=2 at 4 blocks/SM 254 us (U=4 at 3 blocks: 260)
   if (rhs) {
@@ -954,6 +956,36 @@ __global__ void __launch_bounds__(REDUCE_THREADS) k_diff_final(const double* __r
     out[0] = dmax;
     out[1] = dsum;
   }
+}
+
+// Ping-pong V-cycles (MG::enqueue_cycle): the points that no colour pass updates -- Dirichlet faces, edges and
+// corners included -- are carried from the previous iterate's array into the new one (the prolongation adds its
+// correction on Dirichlet faces too, ndsm_multigrid_core.f90:706-710, so they are not constant).
+// blockIdx.z = face (x0,x1,y0,y1,z0,z1); a face takes part when its side of the box is outside the update bounds.
+__global__ void __launch_bounds__(256)
+k_copy_fixed(const double* __restrict__ src, double* __restrict__ dst, const Grid g, const Bounds b) {
+  pdl_enter();
+  const int f = blockIdx.z, d = f >> 1, hi = f & 1;
+  const int n[3] = {g.nx, g.ny, g.nz};
+  const bool fixed = hi ? (b.ub[d] < n[d] - 1) : (b.lb[d] > 0);
+  if (!fixed) return;
+  const int layer = hi ? n[d] - 1 : 0;
+  const int n1 = (d == 0) ? g.ny : g.nx, n2 = (d == 2) ? g.ny : g.nz;
+  const int a = blockIdx.x * 256 + threadIdx.x, bb = blockIdx.y;
+  if (a >= n1 || bb >= n2) return;
+  int i, j, k;
+  if (d == 0) { i = layer; j = a; k = bb; }
+  else if (d == 1) { i = a; j = layer; k = bb; }
+  else { i = a; j = bb; k = layer; }
+  if (k < g.k0 || k >= g.k0 + g.nzl) return;
+  const i64 o = gidx(g, i, j, k);
+  dst[o] = src[o];
+}
+void copy_fixed_points(const double* src, double* dst, const Grid& g, const Bounds& b, cudaStream_t st) {
+  const int n1 = std::max(g.nx, g.ny), n2 = std::max(g.ny, g.nz);
+  dim3 grid(cdiv(n1, 256), n2, 6);
+  launch_k(k_copy_fixed, grid, 256, 0, st, src, dst, g, b);
+  LAUNCHED();
 }
 
 // Hands the results of one V-cycle to the host through MAPPED pinned memory: npairs (max,sum) pairs and the two

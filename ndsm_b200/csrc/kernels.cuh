@@ -39,8 +39,11 @@ struct RestrictTab {  // restriction table of one dimension (ndsm_interp.f90:218
 
 // K1: one colour pass of the 3D red/black Gauss-Seidel sweep (ndsm_optimized.f90:103-167).
 // rhs may be nullptr (rhs == 0 on the finest level of the vector-potential solves).
+// uread (optional): array whose OTHER colour is read instead of u's (first pass of a ping-pong V-cycle).
 void relax3d_half(double* u, const double* rhs, const Grid& g, const Bounds& b, int colour, const Weights& w,
-                  int ext, cudaStream_t st);
+                  int ext, cudaStream_t st, const double* uread = nullptr);
+// dst := src on the points no colour pass updates (Dirichlet faces incl. edges), both colours
+void copy_fixed_points(const double* src, double* dst, const Grid& g, const Bounds& b, cudaStream_t st);
 // K2: residual r = rhs - L u on non-Dirichlet points, 0 elsewhere (ndsm_optimized.f90:346-447).
 void residual3d(const double* u, const double* rhs, double* r, const Grid& g, const Bounds& b, const Weights& w,
                 cudaStream_t st);

@@ -395,6 +395,7 @@ MG::MG(int ndim, const int* shape, int ngrids, const double* const* mesh, cudaSt
     }
   }
 
+  u0_home_ = slabs_[0].lv[0].u;
   // --- pack every transfer table into one int and one double buffer: two uploads per hierarchy
   std::vector<int> hi;
   std::vector<double> hd;
@@ -489,6 +490,7 @@ void MG::build_small_args() {
 }
 
 MG::~MG() {
+  drop_graphs();
   pool_free(tab_i_);
   pool_free(tab_d_);
   for (auto& S : slabs_) pool_free(S.arena);
@@ -582,8 +584,9 @@ void MG::relax(int g) {
       if (g == 0 && ns == 1) prof_begin(PROF_RELAX0, st_);
       for (size_t s = 0; s < ns; ++s) {
         Level& L = slabs_[s].lv[g];
-        relax3d_half(L.u, (g == 0) ? rhs0_[s] : L.rhs, L.g, L.b, colour, L.w, ext, st_);
+        relax3d_half(L.u, (g == 0) ? rhs0_[s] : L.rhs, L.g, L.b, colour, L.w, ext, st_, (g == 0) ? pp_read_ : nullptr);
       }
+      if (g == 0) pp_read_ = nullptr;  // only the first pass of the cycle reads the previous iterate's array
       if (g == 0 && ns == 1) prof_end(PROF_RELAX0, st_);
       if (dist) valid_[g][colour] = ext;
     }
@@ -810,14 +813,31 @@ bool MG::coarsest_in_smem(const double* rhs_coarsest) const {
 }
 
 // one iteration of solve_poisson_bvp's loop body, enqueue only: V-cycle, update_u, results to pinned memory
+//
+// Ping-pong (single slab, 3D): update_u (:1077-1122) copies the new iterate over the old one after measuring their
+// difference -- 8 of its 24 B/point.  Instead, cycle n works in array B[n%2] (B0 = the hierarchy's level-0 array,
+// B1 = the caller's) and reads the previous iterate from the other one: the first colour pass reads the other
+// colour there and writes its own colour here, which touches exactly the data an in-place pass touches; the
+// points no pass updates are carried over first (copy_fixed_points); update_u only measures the difference.
 void MG::enqueue_cycle() {
+  const bool pp = ss_.pingpong;
+  double* cur = nullptr;
+  if (pp) {
+    Level& L0 = slabs_[0].lv[0];
+    double* other = (ss_.it & 1) ? ss_.u[0] : u0_home_;
+    cur = (ss_.it & 1) ? u0_home_ : ss_.u[0];
+    L0.u = other;
+    copy_fixed_points(cur, other, L0.g, L0.b, st_);
+    pp_read_ = cur;
+  }
   v_cycle();
   const bool dist = plan_.ndist > 0 && comm_;
   const bool prof = (ndim_ == 3 && slabs_.size() == 1);
   if (prof) prof_begin(PROF_DIFF0, st_);
   for (size_t s = 0; s < slabs_.size(); ++s) {
     Level& L0 = slabs_[s].lv[0];
-    diff_reduce(ss_.u[s], L0.u, L0.g, true, scratch_, slabs_[s].d_out, st_);  // update_u :122
+    if (pp) diff_reduce(cur, L0.u, L0.g, false, scratch_, slabs_[s].d_out, st_);
+    else diff_reduce(ss_.u[s], L0.u, L0.g, true, scratch_, slabs_[s].d_out, st_);  // update_u :122
   }
   if (prof) prof_end(PROF_DIFF0, st_);
   const int npairs = dist ? plan_.world : 1;
@@ -839,6 +859,8 @@ void MG::solve_begin(const std::vector<double*>& u, const std::vector<const doub
   if (u.size() != slabs_.size() || rhs.size() != slabs_.size()) throw NdsmError(6);
   ss_ = SolveState();
   ss_.u = u; ss_.vc_tol = vc_tol; ss_.nmax = nmax; ss_.tr = tr;
+  if (slabs_.size() == 1) slabs_[0].lv[0].u = u0_home_;  // a ping-pong solve that was cut short may have left it redirected
+  pp_read_ = nullptr;
   ss_.zero_rhs.assign(slabs_.size(), nullptr);
   for (size_t s = 0; s < slabs_.size(); ++s) {
     Level& L0 = slabs_[s].lv[0];
@@ -860,29 +882,13 @@ void MG::solve_begin(const std::vector<double*>& u, const std::vector<const doub
   if (comm_ && plan_.ndist > 0) comm_->barrier(st_);
 
   // The loop body is a static launch sequence (the coarsest solve iterates inside one kernel), so it is
-  // captured once into a CUDA graph and replayed every V-cycle: ~250-500 launches per cycle otherwise.
+  // captured into a CUDA graph and replayed every V-cycle: ~250-500 launches per cycle otherwise.
   static const bool graphs_on = !(getenv("NDSM_B200_GRAPH") && atoi(getenv("NDSM_B200_GRAPH")) == 0);
   const double* rhs_coarsest = (ngrids() == 1) ? rhs0_[0] : slabs_[0].lv.back().rhs;
-  if (graphs_on && !prof_enabled() && nmax > 1 && (small_from_ > 0 || coarsest_in_smem(rhs_coarsest))) {
-    solve_exact_prepare();
-    vcycle_small_prepare();
-    const unsigned long long l0 = g_launches;
-    cudaGraph_t graph = nullptr;
-    CUDA_CHECK(cudaStreamBeginCapture(st_, cudaStreamCaptureModeThreadLocal));
-    try {
-      enqueue_cycle();
-    } catch (...) {
-      cudaStreamEndCapture(st_, &graph);
-      if (graph) cudaGraphDestroy(graph);
-      throw;
-    }
-    CUDA_CHECK(cudaStreamEndCapture(st_, &graph));
-    ss_.graph_launches = g_launches - l0;
-    g_launches = l0;  // nothing ran during capture
-    cudaError_t e = cudaGraphInstantiate(&ss_.gexec, graph, 0);
-    cudaGraphDestroy(graph);
-    if (e != cudaSuccess) { ss_.gexec = nullptr; cudaGetLastError(); }
-  }
+  ss_.use_graph = graphs_on && !prof_enabled() && nmax > 1 && (small_from_ > 0 || coarsest_in_smem(rhs_coarsest));
+  const bool pp_env = !(getenv("NDSM_B200_PINGPONG") && atoi(getenv("NDSM_B200_PINGPONG")) == 0);
+  ss_.pingpong = pp_env && ndim_ == 3 && slabs_.size() == 1 && !(plan_.ndist > 0 && comm_) && ngrids() >= 2 &&
+                 ms_ >= 1 && nmax > 1;
   if (g_debug) debug_msg("solve_poisson_bvp", "Performing V cycles...");
   if (nmax <= 0) ss_.done = true;
 }
@@ -891,14 +897,73 @@ void MG::solve_begin(double* u, const double* rhs, double vc_tol, int nmax, Solv
   solve_begin(std::vector<double*>{u}, std::vector<const double*>{rhs}, vc_tol, nmax, tr);
 }
 
+std::vector<unsigned long long> MG::graph_key(int parity) const {
+  std::vector<unsigned long long> k;
+  auto add = [&](const void* p) { k.push_back((unsigned long long)(size_t)p); };
+  k.push_back((unsigned long long)parity | ((unsigned long long)ss_.pingpong << 1) | ((unsigned long long)ms_ << 8) |
+              ((unsigned long long)nmax_exact_ << 24));
+  unsigned long long bits;
+  memcpy(&bits, &ex_tol_, sizeof bits);
+  k.push_back(bits);
+  unsigned long long c = 0;
+  for (int d = 0; d < 2 * ndim_; ++d) c = c * 3 + (copt_[d] == 'D' ? 1 : 2);
+  k.push_back(c | ((unsigned long long)du_max_ << 40) | ((unsigned long long)pdl_enabled() << 41));
+  for (size_t s = 0; s < slabs_.size(); ++s) { add(ss_.u[s]); add(rhs0_[s]); add(slabs_[s].lv[0].u); }
+  add(u0_home_);
+  k.push_back(comm_ ? comm_->epoch() : 0ull);
+  return k;
+}
+
+void MG::drop_graphs() {
+  for (auto& g : gslot_) {
+    if (g.exec) cudaGraphExecDestroy(g.exec);
+    g.exec = nullptr;
+    g.key.clear();
+  }
+}
+
+void MG::capture_cycle(int parity) {
+  GraphSlot& gs = gslot_[parity];
+  if (gs.exec) { cudaGraphExecDestroy(gs.exec); gs.exec = nullptr; }
+  solve_exact_prepare();
+  vcycle_small_prepare();
+  // the halo state is whatever the previous cycle left when the graph is replayed; capture the pessimistic pattern
+  for (auto& v : valid_) v = {{0, 0}};
+  for (auto& v : static_ok_) v = {{false, false}};
+  const unsigned long long l0 = g_launches;
+  cudaGraph_t graph = nullptr;
+  CUDA_CHECK(cudaStreamBeginCapture(st_, cudaStreamCaptureModeThreadLocal));
+  try {
+    enqueue_cycle();
+  } catch (...) {
+    cudaStreamEndCapture(st_, &graph);
+    if (graph) cudaGraphDestroy(graph);
+    throw;
+  }
+  CUDA_CHECK(cudaStreamEndCapture(st_, &graph));
+  gs.launches = g_launches - l0;
+  g_launches = l0;  // nothing ran during capture
+  cudaError_t e = cudaGraphInstantiate(&gs.exec, graph, 0);
+  cudaGraphDestroy(graph);
+  if (e != cudaSuccess) { gs.exec = nullptr; cudaGetLastError(); }
+  gs.key = graph_key(parity);
+}
+
 void MG::solve_enqueue() {
   if (ss_.done) return;
-  if (ss_.gexec) {
-    CUDA_CHECK(cudaGraphLaunch(ss_.gexec, st_));
-    g_launches += ss_.graph_launches;
-  } else {
-    enqueue_cycle();
+  if (ss_.use_graph) {
+    const int parity = ss_.pingpong ? (ss_.it & 1) : 0;
+    GraphSlot& gs = gslot_[parity];
+    if (ss_.pingpong) slabs_[0].lv[0].u = (ss_.it & 1) ? ss_.u[0] : u0_home_;  // the array this cycle works in (part of the key)
+    if (!gs.exec || gs.key != graph_key(parity)) capture_cycle(parity);
+    if (gs.exec) {
+      CUDA_CHECK(cudaGraphLaunch(gs.exec, st_));
+      g_launches += gs.launches;
+      return;
+    }
+    ss_.use_graph = false;  // instantiation failed: launch directly from here on
   }
+  enqueue_cycle();
 }
 
 bool MG::solve_poll() {
@@ -933,8 +998,14 @@ bool MG::solve_poll() {
 }
 
 int MG::solve_end(double* du_last) {
-  if (ss_.gexec) cudaGraphExecDestroy(ss_.gexec);
-  ss_.gexec = nullptr;
+  if (ss_.pingpong) {
+    Level& L0 = slabs_[0].lv[0];
+    L0.u = u0_home_;
+    // after an odd number of cycles the last iterate sits in the hierarchy's array: hand it to the caller
+    if (ss_.it & 1)
+      CUDA_CHECK(cudaMemcpyAsync(ss_.u[0], u0_home_, (size_t)2 * L0.g.cs * sizeof(double), cudaMemcpyDeviceToDevice, st_));
+    pp_read_ = nullptr;
+  }
   if (du_last) *du_last = ss_.du;
   int ierr = 0;
   if (!ss_.converged) {

@@ -88,6 +88,10 @@ struct Comm {
   virtual const char* transport() const = 0;
   // one-sided transport (peer-memory stores): independent solves may use clones of it concurrently
   virtual bool one_sided() const { return false; }
+  // the communicator outlives a call (hierarchies built on it may be kept between calls)
+  virtual bool persistent() const { return false; }
+  // changes whenever something a captured graph may have baked in (the inbox) is reallocated
+  virtual unsigned long long epoch() const { return 0; }
 };
 std::unique_ptr<Comm> make_virtual_comm(int world);  // all ranks in this process, on the current device
 bool nccl_unique_id(void* out128);                    // ncclGetUniqueId (rank 0)
@@ -242,11 +246,24 @@ class MG {
     double vc_tol = 0, du = 1.7976931348623157e308;
     int nmax = 0, it = 0;
     bool converged = false, done = false;
-    cudaGraphExec_t gexec = nullptr;
-    unsigned long long graph_launches = 0;
+    bool use_graph = false;
+    bool pingpong = false;  // V-cycles alternate between the hierarchy's level-0 array and the caller's (see enqueue_cycle)
     SolveTrace* tr = nullptr;
     std::vector<double*> zero_rhs;
   } ss_;
+  // The V-cycle graph outlives the solve: a hierarchy that is kept across calls (vecpot.cu's solver cache) replays
+  // it as long as every pointer and option baked into its kernel nodes is unchanged (the key).  Two slots: the
+  // even and the odd cycle of a ping-pong solve address different arrays.
+  struct GraphSlot {
+    cudaGraphExec_t exec = nullptr;
+    std::vector<unsigned long long> key;
+    unsigned long long launches = 0;
+  } gslot_[2];
+  std::vector<unsigned long long> graph_key(int parity) const;
+  void capture_cycle(int parity);
+  void drop_graphs();
+  double* u0_home_ = nullptr;       // the hierarchy's own level-0 array (single slab), where even cycles work
+  const double* pp_read_ = nullptr;  // ping-pong: array the first colour pass of the cycle reads (previous iterate)
 };
 
 }  // namespace ndsm

@@ -107,6 +107,7 @@ struct NcclComm : Comm {
     NCCL_CHECK(g_nccl.Broadcast(buf, buf, n, ncclDouble, root_rank, comm, st));
   }
   const char* transport() const override { return "NCCL send/recv groups"; }
+  bool persistent() const override { return true; }
   void barrier(cudaStream_t st) override {  // a 2-double all-gather orders the ranks on the stream
     if (!bar_) CUDA_CHECK(cudaMalloc(&bar_, (2 * (size_t)world_ + 2) * sizeof(double)));
     NCCL_CHECK(g_nccl.AllGather(bar_ + 2 * world_, bar_, 2, ncclDouble, comm, st));

@@ -370,6 +370,7 @@ struct PeerComm : Comm {
   const char* transport() const override { return "peer-memory stores over NVLink (CUDA IPC symmetric heap) + flags"; }
   bool failed() override { return g_fab.h_err && *g_fab.h_err != 0; }
   bool one_sided() const override { return true; }
+  bool persistent() const override { return true; }
   void* sym_alloc(size_t bytes) override { return g_fab.alloc(bytes, alloc_stream); }
   void sym_free(void* p) override { g_fab.free(p); }
   void allgather_host(const void* s, void* r, size_t b, cudaStream_t st) override { g_fab.boot->allgather_host(s, r, b, st); }
@@ -386,7 +387,10 @@ struct PeerComm : Comm {
     if (inbox) g_fab.free(inbox);
     cap = doubles;
     inbox = static_cast<double*>(g_fab.alloc(4 * cap * sizeof(double), alloc_stream));
+    ++epoch_;
   }
+  unsigned long long epoch_ = 0;
+  unsigned long long epoch() const override { return epoch_ ^ ((unsigned long long)(size_t)inbox << 8); }
 
   void begin(cudaStream_t) override { sends.clear(); recvs.clear(); bcs.clear(); }
   void send(int, int to, const double* src, size_t n, cudaStream_t) override { sends.push_back(Send{to, src, n}); }

@@ -7,6 +7,8 @@
 
 #include <chrono>
 #include <algorithm>
+#include <cstring>
+#include <string>
 #include <cmath>
 #include <memory>
 
@@ -65,6 +67,107 @@ struct EvTimer {
   }
 };
 
+// ---------------------------------------------------------------------------------------------------------------
+// Solver cache.  A drop-in caller solves the same mesh again and again (a time series of magnetograms): the
+// hierarchies (host tables, device arenas, symmetric-heap blocks, channels), their streams and their captured
+// V-cycle graphs are kept between calls instead of being rebuilt -- 6 + 3 hierarchy constructions and up to 12
+// graph captures per call otherwise (measured: 3.5 ms of a 16 ms BC setup, 2.5 ms of an 80 ms 8-GPU solve).
+// Slots 0-5: chi faces, 6-8: the three components (6 alone when they are solved one after the other).
+// A slot is rebuilt when anything it was built from differs: shape, mesh values, communicator, stream, device,
+// or any NDSM_* environment variable.  NDSM_B200_CACHE=0, a workspace cap of 0 (the reference's per-call
+// ownership) and ndsm_b200_release_workspace() drop it.
+// ---------------------------------------------------------------------------------------------------------------
+extern "C" char** environ;
+namespace {
+std::string env_signature() {
+  std::vector<std::string> v;
+  for (char** e = environ; e && *e; ++e)
+    if (!strncmp(*e, "NDSM_", 5) && strncmp(*e, "NDSM_B200_TRACE", 15) && strncmp(*e, "NDSM_DEVICE", 11)) v.push_back(*e);
+  std::sort(v.begin(), v.end());
+  std::string s;
+  for (auto& x : v) { s += x; s += ';'; }
+  return s;
+}
+struct SolverSlot {
+  int ndim = 0, shape[3] = {0, 0, 0}, device = -1;
+  std::vector<double> mesh[3];
+  Comm* base_comm = nullptr;
+  bool cloned = false;
+  cudaStream_t given_st = nullptr;
+  std::string env;
+  // resources
+  cudaStream_t st = nullptr;
+  bool own_stream = false;
+  std::unique_ptr<Comm> own_comm;
+  std::unique_ptr<MG> mg;
+  bool used = false;
+  void clear() {
+    mg.reset();
+    own_comm.reset();
+    if (own_stream && st) cudaStreamDestroy(st);
+    st = nullptr;
+    own_stream = false;
+    base_comm = nullptr;
+    ndim = 0;
+    used = false;
+  }
+};
+// heap-allocated and never destroyed: at process exit the pool, the CUDA context and the communicators may already be
+// gone when static destructors run (the cache is emptied explicitly by solver_cache_clear())
+SolverSlot* const g_slots = new SolverSlot[9];
+
+// hierarchy of slot `id` for this problem: the cached one when everything matches, a fresh one otherwise.
+// given_st == nullptr: the slot owns its stream.  clone: the slot works on its own clone of base_comm.
+SolverSlot& acquire_slot(int id, int ndim, const int* shape3, const double* const* mesh, Comm* base_comm, bool clone,
+                         cudaStream_t given_st, cudaStream_t clone_st_hint) {
+  SolverSlot& S = g_slots[id];
+  int dev = 0;
+  cudaGetDevice(&dev);
+  const std::string env = env_signature();
+  bool same = S.mg && S.ndim == ndim && S.device == dev && S.base_comm == base_comm && S.cloned == clone &&
+              S.given_st == given_st && S.env == env;
+  for (int d = 0; d < 3 && same; ++d) same = (S.shape[d] == shape3[d]);
+  for (int d = 0; d < ndim && same; ++d)
+    same = (S.mesh[d].size() == (size_t)shape3[d]) && !memcmp(S.mesh[d].data(), mesh[d], sizeof(double) * shape3[d]);
+  if (!same) {
+    S.clear();
+    S.ndim = ndim;
+    S.device = dev;
+    S.base_comm = base_comm;
+    S.cloned = clone;
+    S.given_st = given_st;
+    S.env = env;
+    for (int d = 0; d < 3; ++d) S.shape[d] = shape3[d];
+    for (int d = 0; d < ndim; ++d) S.mesh[d].assign(mesh[d], mesh[d] + shape3[d]);
+    if (given_st) {
+      S.st = given_st;
+    } else {
+      CUDA_CHECK(cudaStreamCreateWithFlags(&S.st, cudaStreamNonBlocking));
+      S.own_stream = true;
+    }
+    Comm* c = base_comm;
+    if (clone && base_comm) {
+      S.own_comm = base_comm->clone(clone_st_hint ? clone_st_hint : S.st);
+      c = S.own_comm.get();
+    }
+    S.mg.reset(new MG(ndim, shape3, -1, mesh, S.st, c));
+  }
+  S.used = true;
+  return S;
+}
+bool cache_enabled(Comm* comm) {
+  if (getenv("NDSM_B200_CACHE") && atoi(getenv("NDSM_B200_CACHE")) == 0) return false;
+  if (getenv("NDSM_B200_WORKSPACE_CAP_MB") && strtoull(getenv("NDSM_B200_WORKSPACE_CAP_MB"), nullptr, 10) == 0 &&
+      !(getenv("NDSM_B200_KEEP_WORKSPACE") && atoi(getenv("NDSM_B200_KEEP_WORKSPACE")) != 0))
+    return false;
+  return !comm || comm->persistent();
+}
+}  // namespace
+
+void solver_cache_clear() {
+  for (int i = 8; i >= 0; --i) g_slots[i].clear();
+}
+
 int vector_solve_core(const int* nshape, const long long* iopt, const double* ropt, const double* x, const double* y,
                       const double* z, double* const* bn, const DenseIn& A0_in, Comm* comm, const std::vector<SlabOut>& outs_in,
                       cudaStream_t st, Report& rep, BcCapture* cap, bool stop_after_bc, const CoreHooks* hooks) {
@@ -82,6 +185,14 @@ int vector_solve_core(const int* nshape, const long long* iopt, const double* ro
   EvTimer tm(st), tall(st);
   tall.start();
   HostTrace trace;
+  // hierarchies not worth (or not safe) keeping are dropped when this call returns
+  struct CacheScope {
+    bool keep;
+    ~CacheScope() {
+      if (!keep) solver_cache_clear();
+      else for (int i = 0; i < 9; ++i) g_slots[i].used = false;
+    }
+  } cache_scope{cache_enabled(comm) && !cap && !g_debug};
 
   // mesh vectors on the device (flux-balance fields)
   DevBuf dmesh((size_t)nx + ny + nz);
@@ -141,22 +252,19 @@ int vector_solve_core(const int* nshape, const long long* iopt, const double* ro
     // hierarchy and one stream per face, V-cycles interleaved by this host thread.  (With the debug flag they
     // run one after the other so that the reference's message order is kept.)
     struct FaceSolve {
-      std::unique_ptr<MG> mg;
+      MG* mg = nullptr;  // owned by the solver cache (slot f)
       DevBuf chi, rhs;
       cudaStream_t st = nullptr;
       int ierr = 0;
     } fs[6];
-    struct StreamGuard {
-      FaceSolve* f;
-      ~StreamGuard() { for (int i = 0; i < 6; ++i) if (f[i].st) cudaStreamDestroy(f[i].st); }
-    } guard{fs};
     CUDA_CHECK(cudaStreamSynchronize(st));
     for (int f = 0; f < 6; ++f) {
       if (!mine(f)) continue;
-      CUDA_CHECK(cudaStreamCreateWithFlags(&fs[f].st, cudaStreamNonBlocking));
       const int sh2[3] = {n1[f], n2[f], 1};
-      const double* m2[2] = {mesh[imap_nc[f][0]], mesh[imap_nc[f][1]]};
-      fs[f].mg.reset(new MG(2, sh2, -1, m2, fs[f].st));
+      const double* m2[3] = {mesh[imap_nc[f][0]], mesh[imap_nc[f][1]], nullptr};
+      SolverSlot& slot = acquire_slot(f, 2, sh2, m2, nullptr, false, nullptr, nullptr);
+      fs[f].mg = slot.mg.get();
+      fs[f].st = slot.st;
       fs[f].mg->set_options((int)iopt[IOPT_MS], ropt[ROPT_CTOL], "NNNN", use_du_max, (int)iopt[IOPT_NMAXEX]);  // :355-357
       const Grid g2 = fs[f].mg->level(0).g;
       fs[f].chi.alloc(2 * (size_t)g2.cs);
@@ -261,33 +369,20 @@ int vector_solve_core(const int* nshape, const long long* iopt, const double* ro
   const bool conc_want = conc_env ? atoi(conc_env) != 0 : conc_default;
   const bool concurrent = conc_want && !prof_enabled() && !g_debug && (!comm || comm->nlocal() == 1);
   struct Ctx {
-    std::unique_ptr<MG> mg;
-    std::unique_ptr<Comm> own_comm;
+    MG* mg = nullptr;  // owned by the solver cache (slots 6-8)
     cudaStream_t st = nullptr;
-    bool own_stream = false;
-    ~Ctx() {
-      mg.reset();
-      own_comm.reset();
-      if (own_stream && st) cudaStreamDestroy(st);
-    }
   } ctx[3];
   const int nctx = concurrent ? 3 : 1;
   for (int q = 0; q < nctx; ++q) {
-    Comm* cq = comm;
-    ctx[q].st = st;
-    if (q > 0) {
-      CUDA_CHECK(cudaStreamCreateWithFlags(&ctx[q].st, cudaStreamNonBlocking));
-      ctx[q].own_stream = true;
-      if (comm) {
-        ctx[q].own_comm = comm->clone(ctx[q].st);
-        cq = ctx[q].own_comm.get();
-      }
-    }
-    ctx[q].mg.reset(new MG(3, sh3, -1, mesh, ctx[q].st, cq));
+    // component 0 (and the sequential solves) work on the call's stream and communicator; concurrent
+    // components 1 and 2 get a stream and a channel of their own
+    SolverSlot& slot = acquire_slot(6 + q, 3, sh3, mesh, comm, q > 0 && comm != nullptr, q == 0 ? st : nullptr, nullptr);
+    ctx[q].mg = slot.mg.get();
+    ctx[q].st = slot.st;
   }
   trace.mark("3D hierarchy construction");
-  MG* mg3 = ctx[0].mg.get();
-  auto mgc = [&](int c) { return ctx[concurrent ? c : 0].mg.get(); };
+  MG* mg3 = ctx[0].mg;
+  auto mgc = [&](int c) { return ctx[concurrent ? c : 0].mg; };
   const int ns = mg3->nslabs();
   std::vector<SlabOut> outs = outs_in;
   if (ns == 1 && outs.size() > 1) {  // every virtual rank shares one undivided solve: one contiguous output

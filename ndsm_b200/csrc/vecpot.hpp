@@ -57,6 +57,9 @@ struct CoreHooks {
   std::function<void(int)> b_ready;
 };
 
+// drops the hierarchies, streams and graphs kept between calls (vecpot.cu, "Solver cache")
+void solver_cache_clear();
+
 // bn[f]: dense device faces (face f has shape (n1,n2) per ndsm_vector_potential.f90:225-246), all six on every
 // rank.  comm == nullptr: single slab.  outs: one entry per slab held by this process.
 // stop_after_bc: only run the BC setup (tests).  Returns iopt(IOPT_IERR).

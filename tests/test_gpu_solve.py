@@ -272,3 +272,42 @@ def test_unmodified_reference_wrapper_drives_the_cuda_library(gpu_lib):
         assert ierr == 0
         want = gold["mean" if mean else "max"][gold["n"].index(n)]
         assert rows_match(error_row(x, A1, b1, A2, b2), want, last_digit_slack=0), (n, mean)
+
+
+def test_solver_cache_and_pingpong_are_transparent(gpu_lib):
+    """Hierarchies, streams and captured V-cycle graphs are kept between calls (vecpot.cu "Solver cache"), and on
+    one GPU the V-cycles alternate between two arrays instead of copying the iterate (MG::enqueue_cycle).  Neither
+    may change a single bit: interleaved calls with different inputs, options and shapes reproduce what a
+    cache-less, copy-based run of each gives."""
+    from ndsm_b200 import synthetic, vector_potential
+    x, y, z = synthetic.mesh(48, 40, 44)
+    cases = [dict(b=synthetic.dipole(x, y, z)), dict(b=synthetic.charges(x, y, z)), dict(b=synthetic.dipole(x, y, z), mean=True),
+             dict(b=synthetic.dipole(x, y, z), ms=3), dict(b=synthetic.dipole(x, y, z))]
+    x2, y2, z2 = synthetic.mesh(40, 48, 36)
+    saved = {k: os.environ.get(k) for k in ("NDSM_B200_CACHE", "NDSM_B200_PINGPONG")}
+
+    def run_all():
+        out = []
+        for c in cases:
+            kw = {k: v for k, v in c.items() if k != "b"}
+            out.append(vector_potential(x, y, z, c["b"], trace=True, **kw))
+            out.append(vector_potential(x2, y2, z2, synthetic.dipole(x2, y2, z2), trace=True))   # another shape in between
+        return out
+    try:
+        os.environ.pop("NDSM_B200_CACHE", None)
+        os.environ.pop("NDSM_B200_PINGPONG", None)
+        got = run_all()
+        os.environ["NDSM_B200_CACHE"] = "0"
+        os.environ["NDSM_B200_PINGPONG"] = "0"
+        want = run_all()
+    finally:
+        for k, v in saved.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
+    for g, w in zip(got, want):
+        assert g[0] == w[0] == 0
+        for name in NAMES:
+            assert g[3][name]["du"] == w[3][name]["du"], name
+        assert np.array_equal(g[1], w[1]) and np.array_equal(g[2], w[2])
