@@ -282,7 +282,7 @@ __device__ __forceinline__ void relax_pair_march(const double* __restrict__ po, 
   }
 }
 
-template <bool HAS_RHS, int U = 2, int MINB = 4>
+template <bool HAS_RHS, int U = 2, int MINB = 4, bool SPLIT = false>
 __global__ void __launch_bounds__(RELAX_BX * RELAX_BY, MINB)
 k_relax3d(double* __restrict__ u, const double* __restrict__ uread, const double* __restrict__ rhs, const Grid g,
           const Bounds b, const int colour, const double wx, const double wy, const double wz, const double w1,
@@ -291,10 +291,11 @@ k_relax3d(double* __restrict__ u, const double* __restrict__ uread, const double
   const int kbeg = klo + blockIdx.z * zchunk;
   const int kend = min(kbeg + zchunk - 1, khi);
   if (kbeg > kend) return;
-  // uread == u except in the first pass of a ping-pong V-cycle, which reads the other colour of the previous
-  // iterate's array and writes its own colour into the new one (MG::relax)
+  // SPLIT: the first pass of a ping-pong V-cycle reads the other colour of the previous iterate's array (uread)
+  // and writes its own colour into the new one (MG::relax); every other pass works inside u (uread is unused, so
+  // the common instantiations keep their register allocation)
   double* __restrict__ own = u + (i64)colour * g.cs;
-  const double* __restrict__ opp = uread + (i64)(1 - colour) * g.cs;
+  const double* __restrict__ opp = (SPLIT ? uread : u) + (i64)(1 - colour) * g.cs;
   const double* __restrict__ rh = HAS_RHS ? rhs + (i64)colour * g.cs : nullptr;
 
   if (blockIdx.x == gridDim.x - 1) {  // edge blocks: 4 edge columns x RELAX_EDGE_ROWS rows, scalar path
@@ -501,8 +502,15 @@ void relax3d_half(double* u, const double* rhs, const Grid& g, const Bounds& b, 
   const int zc_force = zf ? atoi(zf) : 0;
   const int zc = zc_force > 0 ? zc_force : pick_zchunk(khi - klo + 1, bx * by, zc_cap);
   dim3 grid(bx, by, cdiv(khi - klo + 1, zc));
-#define RELAX_LAUNCH(R, UU, MB) \
-  launch_k(k_relax3d<R, UU, MB>, grid, RELAX_BX * RELAX_BY, 0, st, u, uread ? uread : u, rhs, g, b, colour, w.wx, w.wy, w.wz, w.w1, klo, khi, zc)
+#define RELAX_LAUNCH(R, UU, MB)                                                                                        \
+  do {                                                                                                                  \
+    if (uread)                                                                                                          \
+      launch_k(k_relax3d<R, UU, MB, true>, grid, RELAX_BX * RELAX_BY, 0, st, u, uread, rhs, g, b, colour, w.wx, w.wy,   \
+               w.wz, w.w1, klo, khi, zc);                                                                               \
+    else                                                                                                                \
+      launch_k(k_relax3d<R, UU, MB, false>, grid, RELAX_BX * RELAX_BY, 0, st, u, u, rhs, g, b, colour, w.wx, w.wy,      \
+               w.wz, w.w1, klo, khi, zc);                                                                               \
+  } while (0)
   // measured at 513^3 (B200): rhs == 0: U=4 at 4 blocks/SM 186 us per colour pass (U=2: 188, U=4 at 3 blocks: 190);
   // with rhs: U=2 at 4 blocks/SM 254 us (U=4 at 3 blocks: 260)
   if (rhs) {
@@ -1449,7 +1457,8 @@ k_restrict_sep(const double* __restrict__ rf, const Grid gf, double* __restrict_
 #define RD_CM 5  // largest window per dimension handled here (regular ~2:1 coarsening); else k_restrict_sep
 #define RD_BX 32
 #define RD_BY 8
-__global__ void __launch_bounds__(RD_BX * RD_BY, 2)
+template <int MINB>
+__global__ void __launch_bounds__(RD_BX * RD_BY, MINB)
 k_restrict_direct(const double* __restrict__ rf, const Grid gf, double* __restrict__ rc, const Grid gc,
                   const RestrictTab tx, const RestrictTab ty, const RestrictTab tz, const int kchunk) {
   pdl_enter();
@@ -1566,7 +1575,11 @@ void restrict_direct(const double* rf, const Grid& gf, double* rhsc, const Grid&
   int kchunk = 32;
   while (kchunk > 2 && (i64)bx * by * cdiv(gc.nzl, kchunk) < 148 * 6) kchunk >>= 1;
   dim3 grid(bx, by, cdiv(gc.nzl, kchunk));
-  launch_k(k_restrict_direct, grid, RD_BX * RD_BY, 0, st, rf, gf, rhsc, gc, tx, ty, tz, kchunk);
+  const char* mb = getenv("NDSM_B200_RD_MINB");  // tuning: resident blocks per SM the register allocation aims at
+  const int minb = mb ? atoi(mb) : 2;
+  if (minb == 4) launch_k(k_restrict_direct<4>, grid, RD_BX * RD_BY, 0, st, rf, gf, rhsc, gc, tx, ty, tz, kchunk);
+  else if (minb == 3) launch_k(k_restrict_direct<3>, grid, RD_BX * RD_BY, 0, st, rf, gf, rhsc, gc, tx, ty, tz, kchunk);
+  else launch_k(k_restrict_direct<2>, grid, RD_BX * RD_BY, 0, st, rf, gf, rhsc, gc, tx, ty, tz, kchunk);
   LAUNCHED();
 }
 
@@ -1739,9 +1752,10 @@ k_interp_add_tiled(const double* __restrict__ uc, const Grid gc, double* __restr
 #define IZ_FX 64   // fine columns per block
 #define IZ_CXW 36
 #define IZ_CYW 7
-#define IZ_NP 4    // fine planes per step (even)
+// IZ_NP (template): fine planes per step (even), 4 by default
 #define IZ_ZMAX 32  // longest z-chunk (planes) a block marches: its z table lives in shared memory
-__global__ void __launch_bounds__(IZ_BX * IZ_BY, 4)
+template <int IZ_NP, int MINB>
+__global__ void __launch_bounds__(IZ_BX * IZ_BY, MINB)
 k_interp_add_zt(const double* __restrict__ uc, const Grid gc, double* __restrict__ uf, const Grid gf,
                 const InterpTab tx, const InterpTab ty, const InterpTab tz, const int zchunk) {
   pdl_enter();
@@ -1851,7 +1865,12 @@ void interp_add_zt(const double* uc, const Grid& gc, double* uf, const Grid& gf,
   const int bx = cdiv(gf.nx, IZ_FX), by = cdiv(gf.ny, IZ_BY);
   const int zc = pick_zchunk(gf.nzl, bx * by, IZ_ZMAX);
   dim3 grid(bx, by, cdiv(gf.nzl, zc));
-  launch_k(k_interp_add_zt, grid, IZ_BX * IZ_BY, 0, st, uc, gc, uf, gf, tx, ty, tz, zc);
+  const char* npv = getenv("NDSM_B200_IZ_NP");  // tuning: fine planes per barrier / resident blocks
+  const int npi = npv ? atoi(npv) : 4;
+  if (npi == 8) launch_k(k_interp_add_zt<8, 3>, grid, IZ_BX * IZ_BY, 0, st, uc, gc, uf, gf, tx, ty, tz, zc);
+  else if (npi == 6) launch_k(k_interp_add_zt<6, 4>, grid, IZ_BX * IZ_BY, 0, st, uc, gc, uf, gf, tx, ty, tz, zc);
+  else if (npi == 2) launch_k(k_interp_add_zt<2, 4>, grid, IZ_BX * IZ_BY, 0, st, uc, gc, uf, gf, tx, ty, tz, zc);
+  else launch_k(k_interp_add_zt<4, 4>, grid, IZ_BX * IZ_BY, 0, st, uc, gc, uf, gf, tx, ty, tz, zc);
   LAUNCHED();
 }
 
