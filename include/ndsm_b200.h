@@ -133,6 +133,7 @@ int ndsm_b200_mg_get(ndsm_b200_mg* h, int which, int level, double* dense);
 int ndsm_b200_mg_relax(ndsm_b200_mg* h, int level, int nsweeps);             /* MG_RELAX :115-121 */
 int ndsm_b200_mg_residual(ndsm_b200_mg* h, int level);                        /* MG_RESIDUAL :126-132 -> r */
 int ndsm_b200_mg_restrict(ndsm_b200_mg* h, int level);                        /* mg_restrict :1010: r(level) -> rhs(level+1), u(level+1)=0 */
+int ndsm_b200_mg_residual_restrict(ndsm_b200_mg* h, int level, int* fused);    /* fine_to_coarse's transfer :539-558 in one step: rhs(level+1) = R (rhs - L u), u(level+1) = 0; *fused = 1 when r was never written (K2+K3 fused kernels) */
 int ndsm_b200_mg_interp_add(ndsm_b200_mg* h, int level);                      /* mg_interp+add_correction :865,692: u(level-1) += P u(level) */
 int ndsm_b200_mg_solve_exact(ndsm_b200_mg* h, int level, int* iters);         /* solve_exact :728 */
 int ndsm_b200_mg_v_cycle(ndsm_b200_mg* h);                                    /* v_cycle :341 */

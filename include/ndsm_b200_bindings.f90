@@ -244,6 +244,13 @@ MODULE NDSM_B200_BINDINGS
       INTEGER(C_INT), VALUE :: level
       INTEGER(C_INT)        :: ierr
     END FUNCTION
+    FUNCTION ndsm_b200_mg_residual_restrict(h,level,fused) BIND(C,NAME="ndsm_b200_mg_residual_restrict") RESULT(ierr)
+      IMPORT :: C_INT, C_PTR
+      TYPE(C_PTR), VALUE          :: h
+      INTEGER(C_INT), VALUE       :: level
+      INTEGER(C_INT), INTENT(OUT) :: fused
+      INTEGER(C_INT)              :: ierr
+    END FUNCTION
     FUNCTION ndsm_b200_mg_interp_add(h,level) BIND(C,NAME="ndsm_b200_mg_interp_add") RESULT(ierr)      ! mg_interp + add_correction (:865,:692)
       IMPORT :: C_INT, C_PTR
       TYPE(C_PTR), VALUE    :: h

@@ -602,6 +602,20 @@ int ndsm_b200_mg_restrict(ndsm_b200_mg* h, int level) {
   CUDA_CHECK(cudaStreamSynchronize(h->mg->stream()));
   HANDLE_END("ndsm_b200_mg_restrict")
 }
+int ndsm_b200_mg_residual_restrict(ndsm_b200_mg* h, int level, int* fused) {
+  HANDLE_GUARD("ndsm_b200_mg_residual_restrict")
+  if (level < 0 || level + 1 >= h->mg->ngrids()) return NDSM_B200_ERR_ARG;
+  const bool f = h->mg->fused_restrict_ok(level);
+  if (fused) *fused = f ? 1 : 0;
+  if (f) {
+    h->mg->residual_restrict_to(level);
+  } else {
+    h->mg->residual(level);
+    h->mg->restrict_to(level);
+  }
+  CUDA_CHECK(cudaStreamSynchronize(h->mg->stream()));
+  HANDLE_END("ndsm_b200_mg_residual_restrict")
+}
 int ndsm_b200_mg_interp_add(ndsm_b200_mg* h, int level) {
   HANDLE_GUARD("ndsm_b200_mg_interp_add")
   if (level < 1 || level >= h->mg->ngrids()) return NDSM_B200_ERR_ARG;

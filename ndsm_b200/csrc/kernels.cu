@@ -1583,6 +1583,219 @@ void restrict_direct(const double* rf, const Grid& gf, double* rhsc, const Grid&
   LAUNCHED();
 }
 
+// ---------------------------------------------------------------------------------------
+// K2+K3 fused (default where k_restrict_direct applies): the residual is evaluated in registers and restricted in z
+// on the fly, so r is never written: fine_to_coarse moves 16 B (u) + 4 B (rz out) + 4 B (rz in) + 1 B per fine point
+// instead of 16 + 8 + 8 + 1.
+//   k_residual_rz : a thread owns FOUR consecutive fine points (i0 .. i0+3, i0 = 4t) of one row -- the compressed
+//                   columns (m0, m0+1) of BOTH colours, one 16-byte load per colour and plane -- and marches in z.
+//                   The values of the two colours at planes k-1, k, k+1 live in a register ring (a plane's centre
+//                   values are its neighbours' z values), x neighbours are the other colour's values of the same
+//                   thread plus one scalar on each side, y neighbours two 16-byte loads per colour.  Each r(k)
+//                   (same expression order as poisson_residual_3D, ndsm_optimized.f90:424-430) is accumulated with
+//                   the weight (c2*w2) of every coarse plane whose z window is open (<= 3) and the z-restricted
+//                   value rz(i, j, kc) is written to a dense array when its window closes.
+//   k_restrict_xy : one thread per coarse point: the 5 x 5 window of rz in the reference's x-then-y order
+//                   (the same weights and re-read trick as k_restrict_direct).
+// The three 1-D weight sets are the reference's (ndsm_interp.f90:277-282); applying z first instead of last changes
+// the rounding (1e-16 level; tests: <= 1e-14 against the literal triple product, like k_restrict_direct).
+// ---------------------------------------------------------------------------------------
+#define RZ_BX 32
+#define RZ_BY 8
+template <bool HAS_RHS>
+__global__ void __launch_bounds__(RZ_BX * RZ_BY, 2)
+k_residual_rz(const double* __restrict__ u, const double* __restrict__ rhs, double* __restrict__ rz, const Grid g,
+              const Bounds b, const double wx, const double wy, const double wz, const double wc,
+              const RestrictTab tz, const int kc0, const int kc1, const int kchunk, const int rzp, const i64 rzps) {
+  pdl_enter();
+  const int i0 = 4 * (blockIdx.x * RZ_BX + (threadIdx.x & (RZ_BX - 1)));
+  const int j = blockIdx.y * RZ_BY + threadIdx.x / RZ_BX;
+  const int kc_beg = kc0 + blockIdx.z * kchunk;
+  const int kc_end = min(kc_beg + kchunk, kc1) - 1;
+  if (i0 >= g.nx || j >= g.ny || kc_beg > kc_end) return;
+  const int m0 = i0 >> 1;
+  const int ps = (int)g.ps;
+  const int kf_beg = tz.first[kc_beg], kf_end = tz.first[kc_end] + tz.count[kc_end] - 1;
+  // rows of the y neighbours (mirrored Neumann ghosts, ndsm_optimized.f90:116-117)
+  const int jl = (j - 1 < 0) ? 1 : j - 1, jh = (j + 1 > g.ny - 1) ? g.ny - 2 : j + 1;
+  const int dl = (jl - j) * g.hp, dh = (jh - j) * g.hp;
+  // x: which of my points is the first / last of the row (mirrored ghosts :113-114), which exist, which are Dirichlet
+  const int last = g.nx - 1 - i0;  // index of the row's last point in my group (>= 4: not mine)
+  const bool has_xl = (i0 > 0), has_xr = (i0 + 4 <= g.nx - 1);
+  const bool jin = (j >= b.lb[1] && j <= b.ub[1]);
+  bool in[4];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) in[q] = jin && (i0 + q >= b.lb[0]) && (i0 + q <= b.ub[0]);
+  // arrays of plane kf_beg: E holds my points (i0, i2), O holds (i1, i3); they swap roles on every plane
+  const i64 row = (i64)(kf_beg - g.k0) * ps + (i64)j * g.hp + m0;
+  const int s0 = (j + kf_beg) & 1;
+  const double* __restrict__ pe = u + (s0 ? g.cs : 0) + row;
+  const double* __restrict__ po = u + (s0 ? 0 : g.cs) + row;
+  const double* __restrict__ re = HAS_RHS ? rhs + (s0 ? g.cs : 0) + row : nullptr;
+  const double* __restrict__ ro = HAS_RHS ? rhs + (s0 ? 0 : g.cs) + row : nullptr;
+  // ring: values at (i0, i2) and (i1, i3) in planes kf-1 (m) and kf (c); plane kf-1 of the first plane is mirrored at k = 0
+  double2 Am, Bm, Ac, Bc;
+  {
+    // in plane kf_beg-1 (or its mirror image, plane 1) the roles of the two arrays are swapped
+    const int dm = (kf_beg - 1 < 0) ? ps : -ps;
+    Am = *reinterpret_cast<const double2*>(po + dm);
+    Bm = *reinterpret_cast<const double2*>(pe + dm);
+    Ac = *reinterpret_cast<const double2*>(pe);
+    Bc = *reinterpret_cast<const double2*>(po);
+  }
+  double acc[3][4];
+#pragma unroll
+  for (int w = 0; w < 3; ++w)
+#pragma unroll
+    for (int q = 0; q < 4; ++q) acc[w][q] = 0.0;
+  int kc_lo = kc_beg, kc_hi = kc_beg;
+  int last_lo = tz.first[kc_lo] + tz.count[kc_lo] - 1;
+  int first_next = (kc_hi + 1 <= kc_end) ? tz.first[kc_hi + 1] : 0x7fffffff;
+  double* __restrict__ outp = rz + (i64)j * rzp + i0;
+  for (int kf = kf_beg; kf <= kf_end; ++kf) {
+    // ---- loads of this plane: next plane's values (z neighbours), y neighbours, the two outer x neighbours, rhs
+    double2 An, Bn;
+    if (kf + 1 > g.nz - 1) { An = Am; Bn = Bm; }  // mirrored top plane (:119-120)
+    else {
+      An = *reinterpret_cast<const double2*>(po + ps);
+      Bn = *reinterpret_cast<const double2*>(pe + ps);
+    }
+    const double2 AyL = *reinterpret_cast<const double2*>(po + dl), AyH = *reinterpret_cast<const double2*>(po + dh);
+    const double2 ByL = *reinterpret_cast<const double2*>(pe + dl), ByH = *reinterpret_cast<const double2*>(pe + dh);
+    const double XL = has_xl ? po[-1] : 0.0;
+    const double XR = has_xr ? pe[2] : 0.0;
+    double2 RA = make_double2(0.0, 0.0), RB = make_double2(0.0, 0.0);
+    if (HAS_RHS) {
+      RA = *reinterpret_cast<const double2*>(re);
+      RB = *reinterpret_cast<const double2*>(ro);
+    }
+    // ---- residual of my four points (ndsm_optimized.f90:424-430); W = [XL, u0, u1, u2, u3, XR]
+    const double W[6] = {XL, Ac.x, Bc.x, Ac.y, Bc.y, XR};
+    const double yl[4] = {AyL.x, ByL.x, AyL.y, ByL.y}, yh[4] = {AyH.x, ByH.x, AyH.y, ByH.y};
+    const double zm[4] = {Am.x, Bm.x, Am.y, Bm.y}, zn[4] = {An.x, Bn.x, An.y, Bn.y};
+    const double rh[4] = {RA.x, RB.x, RA.y, RB.y};
+    const bool kin = (kf >= b.lb[2] && kf <= b.ub[2]);
+    double r[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      double xl = W[q], xh = W[q + 2];
+      if (q == 0 && !has_xl) xl = xh;  // i = 0: ghost i-1 mirrors i+1
+      if (q == last) xh = xl;          // i = nx-1: ghost i+1 mirrors i-1
+      double tt = ((xl + xh) * wx + (yl[q] + yh[q]) * wy) + (zm[q] + zn[q]) * wz;
+      if (HAS_RHS) tt = tt - rh[q];
+      tt = tt - W[q + 1] * wc;
+      r[q] = (kin && in[q]) ? -tt : 0.0;
+    }
+    // ---- z restriction: open the windows that start here, accumulate, emit the ones that end here
+    while (kf >= first_next) {  // uniform
+      ++kc_hi;
+      first_next = (kc_hi + 1 <= kc_end) ? tz.first[kc_hi + 1] : 0x7fffffff;
+    }
+    {
+      const double* __restrict__ w0 = tz.c2 + (i64)kc_lo * NDSM_RMAX;
+      const double z0 = w0[kf - tz.first[kc_lo]] * tz.w2;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) acc[0][q] += z0 * r[q];
+      if (kc_hi > kc_lo) {
+        const double z1 = w0[NDSM_RMAX + kf - tz.first[kc_lo + 1]] * tz.w2;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) acc[1][q] += z1 * r[q];
+      }
+      if (kc_hi > kc_lo + 1) {
+        const double z2 = w0[2 * NDSM_RMAX + kf - tz.first[kc_lo + 2]] * tz.w2;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) acc[2][q] += z2 * r[q];
+      }
+    }
+    while (kf == last_lo) {  // uniform; the one-sided windows at the top face end on the same plane
+      double* __restrict__ o = outp + (i64)(kc_lo - kc0) * rzps;
+      *reinterpret_cast<double2*>(o) = make_double2(acc[0][0], acc[0][1]);
+      *reinterpret_cast<double2*>(o + 2) = make_double2(acc[0][2], acc[0][3]);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) { acc[0][q] = acc[1][q]; acc[1][q] = acc[2][q]; acc[2][q] = 0.0; }
+      ++kc_lo;
+      if (kc_lo > kc_end) { last_lo = -1; break; }
+      if (kc_hi < kc_lo) {
+        kc_hi = kc_lo;
+        first_next = (kc_hi + 1 <= kc_end) ? tz.first[kc_hi + 1] : 0x7fffffff;
+      }
+      last_lo = tz.first[kc_lo] + tz.count[kc_lo] - 1;
+    }
+    // ---- next plane: the arrays swap roles
+    Am = Ac; Bm = Bc; Ac = An; Bc = Bn;
+    const double* __restrict__ t = pe;
+    pe = po + ps;
+    po = t + ps;
+    if (HAS_RHS) {
+      const double* __restrict__ tr = re;
+      re = ro + ps;
+      ro = tr + ps;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256)
+k_restrict_xy(const double* __restrict__ rz, const int rzp, const i64 rzps, const int kc0, double* __restrict__ rc,
+              const Grid gc, const RestrictTab tx, const RestrictTab ty) {
+  pdl_enter();
+  const int ic = blockIdx.x * 32 + (threadIdx.x & 31);
+  const int jc = blockIdx.y * 8 + (threadIdx.x >> 5);
+  const int kc = gc.k0 + blockIdx.z;
+  if (ic >= gc.nx || jc >= gc.ny) return;
+  const int fx = tx.first[ic], cx = tx.count[ic], fy = ty.first[jc], cy = ty.count[jc];
+  double wxv[RD_CM], wyv[RD_CM];
+#pragma unroll
+  for (int q = 0; q < RD_CM; ++q) {
+    wxv[q] = (q < cx) ? tx.c2[(i64)ic * NDSM_RMAX + q] * tx.w2 : 0.0;
+    wyv[q] = (q < cy) ? ty.c2[(i64)jc * NDSM_RMAX + q] * ty.w2 : 0.0;
+  }
+  // window slots beyond the count re-read a valid element (weight 0)
+  const int o3 = (cx > 3) ? 3 : 1, o4 = (cx > 4) ? 4 : 2;
+  const int r3 = ((cy > 3) ? 3 : 1) * rzp, r4 = ((cy > 4) ? 4 : 2) * rzp;
+  const double* __restrict__ base = rz + (i64)(kc - kc0) * rzps + (i64)fy * rzp + fx;
+  double p = 0.0;
+#pragma unroll
+  for (int r = 0; r < RD_CM; ++r) {
+    const double* __restrict__ e = base + ((r == 3) ? r3 : (r == 4 ? r4 : r * rzp));
+    double sx = wxv[0] * e[0];
+    sx += wxv[1] * e[1];
+    sx += wxv[2] * e[2];
+    sx += wxv[3] * e[o3];
+    sx += wxv[4] * e[o4];
+    if (r == 0) p = wyv[0] * sx;
+    else p += wyv[r] * sx;
+  }
+  rc[(i64)((ic + jc + kc) & 1) * gc.cs + (i64)(kc - gc.k0) * gc.ps + (i64)jc * gc.hp + (ic >> 1)] = p;
+}
+
+size_t residual_restrict_scratch(const Grid& gf, int ncz_local) {
+  return (size_t)ncz_local * gf.ny * (2 * (size_t)gf.hp);
+}
+
+// rhsc[planes gc.k0 .. gc.k0+gc.nzl) = R (rhs - L u); rz: scratch of residual_restrict_scratch(gf, gc.nzl) doubles.
+// u must be valid one plane beyond the fine planes the z windows of those coarse planes cover.
+void residual_restrict(const double* u, const double* rhs, const Grid& gf, const Bounds& b, const Weights& w,
+                       double* rz, double* rhsc, const Grid& gc, const RestrictTab& tx, const RestrictTab& ty,
+                       const RestrictTab& tz, cudaStream_t st) {
+  if (gc.nzl <= 0) return;
+  const int rzp = 2 * gf.hp;
+  const i64 rzps = (i64)rzp * gf.ny;
+  const int bx = cdiv(cdiv(gf.nx, 4), RZ_BX), by = cdiv(gf.ny, RZ_BY);
+  int kchunk = 16;  // coarse planes per block: a chunk re-reads ~3 fine planes of its neighbours
+  while (kchunk > 2 && (i64)bx * by * cdiv(gc.nzl, kchunk) < 148 * 2 * 3) kchunk >>= 1;
+  dim3 grid(bx, by, cdiv(gc.nzl, kchunk));
+  if (rhs)
+    launch_k(k_residual_rz<true>, grid, RZ_BX * RZ_BY, 0, st, u, rhs, rz, gf, b, w.wx, w.wy, w.wz, w.wc, tz, gc.k0,
+             gc.k0 + gc.nzl, kchunk, rzp, rzps);
+  else
+    launch_k(k_residual_rz<false>, grid, RZ_BX * RZ_BY, 0, st, u, rhs, rz, gf, b, w.wx, w.wy, w.wz, w.wc, tz, gc.k0,
+             gc.k0 + gc.nzl, kchunk, rzp, rzps);
+  LAUNCHED();
+  dim3 grid2(cdiv(gc.nx, 32), cdiv(gc.ny, 8), gc.nzl);
+  launch_k(k_restrict_xy, grid2, 256, 0, st, (const double*)rz, rzp, rzps, gc.k0, rhsc, gc, tx, ty);
+  LAUNCHED();
+}
+
 bool restrict_sep_fits(const int* first_x, const int* count_x, int ncx, const int* first_y, const int* count_y,
                        int ncy) {
   for (int c0 = 0; c0 < ncx; c0 += RS_CX) {

@@ -79,6 +79,12 @@ void interp_add(const double* uc, const Grid& gc, double* uf, const Grid& gf, co
 bool restrict_direct_fits(const int* const first[3], const int* const count[3], const int nc[3]);
 void restrict_direct(const double* rf, const Grid& gf, double* rhsc, const Grid& gc, const RestrictTab& tx,
                      const RestrictTab& ty, const RestrictTab& tz, cudaStream_t st);
+// K2+K3 fused (levels where restrict_direct_fits holds): rhsc[planes gc.k0..) = R (rhs - L u) without ever writing r;
+// rz: scratch of residual_restrict_scratch(gf, gc.nzl) doubles; u valid one plane beyond the z windows it covers
+size_t residual_restrict_scratch(const Grid& gf, int ncz_local);
+void residual_restrict(const double* u, const double* rhs, const Grid& gf, const Bounds& b, const Weights& w,
+                       double* rz, double* rhsc, const Grid& gc, const RestrictTab& tx, const RestrictTab& ty,
+                       const RestrictTab& tz, cudaStream_t st);
 bool restrict_sep_fits(const int* first_x, const int* count_x, int ncx, const int* first_y, const int* count_y,
                        int ncy);
 void restrict_sep(const double* rf, const Grid& gf, double* rhsc, const Grid& gc, const RestrictTab& tx,

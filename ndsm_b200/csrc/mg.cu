@@ -687,6 +687,44 @@ void MG::restrict_to(int g) {
   finish_restrict(g);
 }
 
+// fine_to_coarse without the residual array (K2+K3 fused, kernels.cu): usable where the direct restriction is, and
+// where rhs is valid in the halo planes the z windows reach into
+bool MG::fused_restrict_ok(int g) const {
+  if (ndim_ != 3 || g + 1 >= ngrids()) return false;
+  if (getenv("NDSM_B200_FUSED_RESTRICT") && atoi(getenv("NDSM_B200_FUSED_RESTRICT")) == 0) return false;
+  if (!slabs_[0].lv[g].rdirect) return false;
+  const bool fdist = g < plan_.ndist && comm_;
+  if (fdist && g == 0 && rhs0_[0] != nullptr && !rhs0_halo_ok_) return false;
+  return true;
+}
+
+void MG::residual_restrict_to(int g) {
+  const int c = g + 1;
+  const bool fdist = g < plan_.ndist && comm_, cdist = c < plan_.ndist;
+  const size_t ns = (g < plan_.ndist) ? slabs_.size() : 1;
+  // the residual is evaluated on every fine plane of the z windows (rneed_ planes into the halo), which reads u
+  // one plane further out
+  if (fdist) need_halo(g, rneed_[g] + 1);
+  const bool prof = (g == 0 && ndim_ == 3 && ns == 1);
+  if (prof) prof_begin(PROF_RESTRICT0, st_);
+  for (size_t s = 0; s < ns; ++s) {
+    Level& F = slabs_[s].lv[g];
+    Level& C = slabs_[s].lv[c];
+    Grid gv = C.g;
+    double* out = C.rhs;
+    if ((g < plan_.ndist) && !cdist) {  // partitioned -> replicated: this rank produces planes [zs[c][r], zs[c][r+1])
+      const int r = slabs_[s].rank;
+      gv.k0 = plan_.zs[c][r];
+      gv.nzl = plan_.zs[c][r + 1] - gv.k0;
+      out = C.rhs + (i64)gv.k0 * C.g.ps;
+    }
+    if (gv.nzl <= 0) continue;
+    residual_restrict(F.u, (g == 0) ? rhs0_[s] : F.rhs, F.g, F.b, F.w, slabs_[s].r, out, gv, F.rt[0], F.rt[1], F.rt[2], st_);
+  }
+  if (prof) prof_end(PROF_RESTRICT0, st_);
+  finish_restrict(g);
+}
+
 // all-gather of a replicated coarse rhs, halo planes of a partitioned one, u[c] = 0
 void MG::finish_restrict(int g) {
   const int c = g + 1;
@@ -777,8 +815,12 @@ void MG::v_cycle() {  // ndsm_multigrid_core.f90:341-377
     if (pr && g == 1) prof_begin(PROF_LEVEL1, st_);
     if (pr && g == 2) { prof_end(PROF_LEVEL1, st_); prof_begin(PROF_TAIL, st_); }
     relax_sweeps(g, ms_);
-    residual(g);
-    restrict_to(g);
+    if (fused_restrict_ok(g)) {
+      residual_restrict_to(g);
+    } else {
+      residual(g);
+      restrict_to(g);
+    }
   }
   const int ls = small_from_;
   int cstart = ng - 1;

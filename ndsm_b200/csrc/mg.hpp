@@ -167,6 +167,8 @@ class MG {
   void relax_sweeps(int g, int n);  // n sweeps; 2D pure-Neumann levels may fold the mean subtraction into the passes
   void residual(int g);         // r_scratch <- rhs - L u
   void restrict_to(int g);      // rhs[g+1] <- R r_scratch (fine level g); u[g+1] <- 0
+  bool fused_restrict_ok(int g) const;
+  void residual_restrict_to(int g);  // rhs[g+1] <- R (rhs - L u) without writing r (K2+K3 fused); u[g+1] <- 0
   void interp_add_from(int c);  // u[c-1] += P u[c]
   int solve_exact(int g);       // coarsest level (synchronises only in the fallback path)
   void v_cycle();               // from the finest grid; leaves coarsest info in d_info_

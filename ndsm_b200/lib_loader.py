@@ -48,6 +48,7 @@ def _declare(lib):
     lib.ndsm_b200_mg_residual.argtypes = [vp, c.c_int]
     lib.ndsm_b200_mg_restrict.argtypes = [vp, c.c_int]
     lib.ndsm_b200_mg_interp_add.argtypes = [vp, c.c_int]
+    lib.ndsm_b200_mg_residual_restrict.argtypes = [vp, c.c_int, vp]
     lib.ndsm_b200_mg_solve_exact.argtypes = [vp, c.c_int, vp]
     lib.ndsm_b200_mg_v_cycle.argtypes = [vp]
     lib.ndsm_b200_mg_solve.argtypes = [vp, c.c_double, c.c_int, vp, vp, vp, vp]

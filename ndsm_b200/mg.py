@@ -84,6 +84,12 @@ class MGHandle:
         self._chk(self.lib.ndsm_b200_mg_restrict(self.h, level), "restrict")
         return self.get(self.RHS, level + 1)
 
+    def residual_restrict(self, level):
+        """rhs(level+1) = R (rhs - L u) in one step; returns (rhs_coarse, fused?)."""
+        f = ctypes.c_int(0)
+        self._chk(self.lib.ndsm_b200_mg_residual_restrict(self.h, level, ctypes.byref(f)), "residual_restrict")
+        return self.get(self.RHS, level + 1), bool(f.value)
+
     def interp_add(self, level):
         self._chk(self.lib.ndsm_b200_mg_interp_add(self.h, level), "interp_add")
         return self.get(self.U, level - 1)

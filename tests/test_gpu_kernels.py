@@ -389,3 +389,33 @@ def test_fused_mean_2d_sweeps_match_unfused_path(gpu_lib, tmp_path):
     assert all(abs(int(a) - bb) <= 1 for a, bb in zip(got["nc"], want_nc))
     assert rel_err(got["A"], ref[1]) <= 1e-10
     assert rel_err(got["B"], ref[2]) <= 1e-10
+
+
+@pytest.mark.parametrize("copt", ["NDDNDD", "DNDDND", "DDNDDN", "NNNNNN", "DDDDDD"])
+@pytest.mark.parametrize("shape", [(65, 65, 65), (72, 40, 96), (129, 97, 33), (45, 27, 13)])
+def test_fused_residual_restrict_matches_oracle(gpu_lib, oracle, shape, copt):
+    """K2+K3 fused (k_residual_rz + k_restrict_xy): rhs_c = R (rhs - L u) without the residual array, against the
+    oracle's residual followed by its literal restriction, and against the unfused kernels.  Same tolerance as the
+    separable restriction (<= 1e-14: the three 1-D weight sets are applied z first instead of as a triple product)."""
+    mesh = aniso_mesh(shape)
+    h = mg(gpu_lib, mesh, copt)
+    nfused = 0
+    for g in range(h.ngrids - 1):
+        shp = h.shape(g)
+        u, rhs = rand(shp, 70 + g), rand(shp, 80 + g)
+        h.put(h.U, g, u)
+        h.put(h.RHS, g, rhs)
+        got, fused = h.residual_restrict(g)
+        nfused += fused
+        r = oracle.residual3d(copt, h.level_mesh(g), rhs, u)
+        want = oracle.mg_restrict(h.level_mesh(g), h.level_mesh(g + 1), r, mode=0)
+        assert rel_err(got, want) <= 1e-14, (g, fused)
+        assert not h.get(h.U, g + 1).any()
+        # the unfused pair on the same data
+        h.put(h.U, g, u)
+        assert np.array_equal(h.residual(g), r)
+        unf = h.restrict(g)
+        assert rel_err(got, unf) <= 1e-14
+    if min(shape) >= 33:
+        assert nfused >= 1          # the regular finest levels really take the fused path
+    h.close()
