@@ -335,8 +335,7 @@ def run_reference(args, rank, world):
 # ------------------------------------------------------------------------------------------------
 # GPU arm
 # ------------------------------------------------------------------------------------------------
-PROF_NAMES = ["k_relax3d colour pass (finest level)", "k_residual3d (unfused path only)",
-              "residual + restriction, finest -> level 1 (k_residual_rz + k_restrict_xy; r is never written)",
+PROF_NAMES = ["k_relax3d colour pass (finest level)", "k_residual3d", "restriction (finest -> level 1, k_restrict_direct)",
               "k_interp_add_zt", "update_u (k_diff_partial+final)", "halo exchange", "levels >= 2 of one V-cycle",
               "level 1 of one V-cycle (2 brackets per cycle)"]
 
@@ -361,8 +360,7 @@ def kernel_report(lib, npoints, dev_ms, rhs_zero=True, single_gpu=True):
     kern = {}
     b0 = 8.0 if rhs_zero else 12.0
     # SURVEY 8d / DESIGN.md (level 0); update_u on one GPU only measures the difference (ping-pong cycles, no copy): 16 B/pt
-    # class 2 is the fused residual+restriction: 16 B (u; 24 with rhs) + 8 B per coarse point = 17 (25) B per fine point
-    bytes_per_pt = [b0, 16.0 if rhs_zero else 24.0, 17.0 if rhs_zero else 25.0, 17.0, 16.0 if single_gpu else 24.0, 0.0, 0.0, 0.0]
+    bytes_per_pt = [b0, 16.0 if rhs_zero else 24.0, 9.0, 17.0, 16.0 if single_gpu else 24.0, 0.0, 0.0, 0.0]
     for cls in range(8):
         lib.ndsm_b200_profile_get(cls, ctypes.byref(cnt), ctypes.byref(tot))
         if cnt.value:

@@ -691,7 +691,10 @@ void MG::restrict_to(int g) {
 // where rhs is valid in the halo planes the z windows reach into
 bool MG::fused_restrict_ok(int g) const {
   if (ndim_ != 3 || g + 1 >= ngrids()) return false;
-  if (getenv("NDSM_B200_FUSED_RESTRICT") && atoi(getenv("NDSM_B200_FUSED_RESTRICT")) == 0) return false;
+  // opt-in: measured on B200 at 513^3 the fused pair takes 0.655 + 0.370 ms against 0.419 + 0.508 ms for
+  // k_residual3d + k_restrict_direct -- k_residual_rz is instruction-bound (310 instructions per warp and plane, a
+  // third of them register moves and selects of the 4-point bookkeeping), so saving 8 B/point does not pay yet
+  if (!(getenv("NDSM_B200_FUSED_RESTRICT") && atoi(getenv("NDSM_B200_FUSED_RESTRICT")) != 0)) return false;
   if (!slabs_[0].lv[g].rdirect) return false;
   const bool fdist = g < plan_.ndist && comm_;
   if (fdist && g == 0 && rhs0_[0] != nullptr && !rhs0_halo_ok_) return false;

@@ -398,6 +398,18 @@ def test_fused_residual_restrict_matches_oracle(gpu_lib, oracle, shape, copt):
     oracle's residual followed by its literal restriction, and against the unfused kernels.  Same tolerance as the
     separable restriction (<= 1e-14: the three 1-D weight sets are applied z first instead of as a triple product)."""
     mesh = aniso_mesh(shape)
+    saved = os.environ.get("NDSM_B200_FUSED_RESTRICT")
+    os.environ["NDSM_B200_FUSED_RESTRICT"] = "1"     # opt-in path (slower than the unfused pair today, see mg.cu)
+    try:
+        _fused_residual_restrict_case(gpu_lib, oracle, mesh, shape, copt)
+    finally:
+        if saved is None:
+            os.environ.pop("NDSM_B200_FUSED_RESTRICT", None)
+        else:
+            os.environ["NDSM_B200_FUSED_RESTRICT"] = saved
+
+
+def _fused_residual_restrict_case(gpu_lib, oracle, mesh, shape, copt):
     h = mg(gpu_lib, mesh, copt)
     nfused = 0
     for g in range(h.ngrids - 1):
