@@ -144,8 +144,19 @@ static void gather_face_host(const double* B, int nx, int ny, int nz, int f, dou
   const double* Bc = B + c * N;
   const int layer = (f % 2 == 0) ? 0 : (c == 0 ? nx : c == 1 ? ny : nz) - 1;
   if (c == 0) {
-    for (int k = 0; k < nz; ++k)
-      for (int j = 0; j < ny; ++j) face[j + (size_t)ny * k] = Bc[layer + (size_t)nx * (j + (size_t)ny * k)];
+    // one value per row of the array: a stride-nx walk over the whole component, split over a few threads
+    unsigned nt = std::thread::hardware_concurrency();
+    nt = (nt == 0) ? 1 : (nt > 8 ? 8 : nt);
+    if ((size_t)ny * nz < (1u << 16)) nt = 1;
+    auto work = [&](unsigned t) {
+      const int k0 = (int)((long long)nz * t / nt), k1 = (int)((long long)nz * (t + 1) / nt);
+      for (int k = k0; k < k1; ++k)
+        for (int j = 0; j < ny; ++j) face[j + (size_t)ny * k] = Bc[layer + (size_t)nx * (j + (size_t)ny * k)];
+    };
+    std::vector<std::thread> th;
+    for (unsigned t = 1; t < nt; ++t) th.emplace_back(work, t);
+    work(0);
+    for (auto& x : th) x.join();
   } else if (c == 1) {
     for (int k = 0; k < nz; ++k)
       memcpy(face + (size_t)nx * k, Bc + (size_t)nx * (layer + (size_t)ny * k), sizeof(double) * nx);
