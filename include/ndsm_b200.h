@@ -163,6 +163,10 @@ int ndsm_b200_ngrids_for(int nmin); /* FLOOR(LOG(nmin/2.0)/LOG(2.0)), ndsm_vecto
  * (ndist+1) rows of world+1 plane boundaries (row ndist = producers of the first replicated level).
  * zs must have room for ngrids*(world+1) ints. */
 int ndsm_b200_plan_slab_partition(const ndsm_b200_plan* p, int world, int min_planes, int* ndist, int* zs);
+/* Host-only replay of the offset allocator of the multi-GPU symmetric heap (csrc/sym_alloc.hpp): ops[i] > 0 allocates
+ * that many bytes and stores the offset in out[i] (-1: no room); ops[i] < 0 frees the block of operation -ops[i]-1.
+ * Every rank runs the same sequence and must arrive at the same offsets (CPU tests, world_size 2 over gloo). */
+int ndsm_b200_plan_sym_heap(long long segment_bytes, const long long* ops, int nops, long long* out);
 
 /* Stage hooks of the driver (host dense arrays) */
 int ndsm_b200_bc_setup(const int* nshape4, const int* ioptc, const double* ropt, const double* x, const double* y,

@@ -12,7 +12,7 @@ CSRC = os.path.join(PKG_DIR, "csrc")
 LIB_DIR = os.path.join(PKG_DIR, "lib")
 LIB_PATH = os.path.join(LIB_DIR, "ndsmf.so")
 SOURCES = ["kernels.cu", "pool.cu", "hostsink.cu", "mg.cu", "nccl_comm.cu", "peer.cu", "vecpot.cu", "abi.cu"]
-HEADERS = ["common.cuh", "kernels.cuh", "pool.hpp", "hostsink.hpp", "mg.hpp", "vecpot.hpp", os.path.join(REPO_DIR, "include", "ndsm_b200.h")]
+HEADERS = ["common.cuh", "kernels.cuh", "pool.hpp", "hostsink.hpp", "mg.hpp", "vecpot.hpp", "sym_alloc.hpp", os.path.join(REPO_DIR, "include", "ndsm_b200.h")]
 
 NVCC_FLAGS = [
     "-O3", "-std=c++17",

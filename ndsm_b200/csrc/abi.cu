@@ -13,6 +13,7 @@
 #include "pool.hpp"
 #include "vecpot.hpp"
 #include "hostsink.hpp"
+#include "sym_alloc.hpp"
 
 using namespace ndsm;
 
@@ -449,6 +450,26 @@ int ndsm_b200_plan_restrict(const ndsm_b200_plan* p, int level, int dim, int* fi
   return 0;
 }
 int ndsm_b200_ngrids_for(int nmin) { return ngrids_for(nmin); }
+// Host-only replay of the symmetric-heap allocator (sym_alloc.hpp): ops[i] > 0 allocates ops[i] bytes (rounded up to
+// 512 like the heap does) and stores its offset in out[i] (-1: does not fit); ops[i] < 0 frees the block allocated
+// by operation -ops[i]-1 (out[i] = its offset).  Lets the CPU tests check that every rank derives the same layout.
+int ndsm_b200_plan_sym_heap(long long segment_bytes, const long long* ops, int nops, long long* out) {
+  if (!ops || !out || nops < 0 || segment_bytes <= 0) return NDSM_B200_ERR_ARG;
+  SegmentAllocator a;
+  a.reset((size_t)segment_bytes);
+  for (int i = 0; i < nops; ++i) {
+    if (ops[i] > 0) {
+      const size_t off = a.take(((size_t)ops[i] + 511) / 512 * 512);
+      out[i] = (off == (size_t)-1) ? -1 : (long long)off;
+    } else {
+      const long long j = -ops[i] - 1;
+      if (j < 0 || j >= i || ops[j] <= 0 || out[j] < 0) return NDSM_B200_ERR_ARG;
+      a.give((size_t)out[j]);
+      out[i] = out[j];
+    }
+  }
+  return 0;
+}
 int ndsm_b200_plan_slab_partition(const ndsm_b200_plan* p, int world, int min_planes, int* ndist, int* zs) {
   if (!p || !ndist || !zs || world < 1) return NDSM_B200_ERR_ARG;
   try {

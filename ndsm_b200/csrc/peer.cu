@@ -25,6 +25,7 @@
 
 #include "mg.hpp"
 #include "pool.hpp"
+#include "sym_alloc.hpp"
 
 namespace ndsm {
 
@@ -41,43 +42,11 @@ constexpr size_t SEG_MIN = (size_t)256 << 20;
 // ---------------------------------------------------------------------------------------------
 // symmetric heap: segments of cudaMalloc memory, every rank maps every other rank's copy (CUDA IPC)
 // ---------------------------------------------------------------------------------------------
-// Allocation inside a segment is first-fit over an offset-ordered free list with coalescing: every rank performs
-// the same sequence of sym_alloc / sym_free calls with the same sizes, so every rank gets the same offsets.
-struct Segment {
+// Allocation inside a segment: sym_alloc.hpp (first fit, coalescing; the same call sequence on every rank gives the
+// same offsets on every rank).
+struct Segment : SegmentAllocator {
   char* base[MAX_WORLD];
   size_t bytes = 0;
-  std::map<size_t, size_t> free_list;  // offset -> size
-  std::map<size_t, size_t> live;       // offset -> size
-  size_t take(size_t b) {              // returns the offset or (size_t)-1
-    for (auto it = free_list.begin(); it != free_list.end(); ++it)
-      if (it->second >= b) {
-        const size_t off = it->first, rest = it->second - b;
-        free_list.erase(it);
-        if (rest) free_list[off + b] = rest;
-        live[off] = b;
-        return off;
-      }
-    return (size_t)-1;
-  }
-  void give(size_t off) {
-    auto lv = live.find(off);
-    if (lv == live.end()) return;
-    size_t sz = lv->second;
-    live.erase(lv);
-    auto nx = free_list.lower_bound(off);
-    if (nx != free_list.end() && off + sz == nx->first) {  // merge with the following block
-      sz += nx->second;
-      nx = free_list.erase(nx);
-    }
-    if (nx != free_list.begin()) {
-      auto pv = std::prev(nx);
-      if (pv->first + pv->second == off) {  // merge with the preceding block
-        pv->second += sz;
-        return;
-      }
-    }
-    free_list[off] = sz;
-  }
 };
 
 // control block at the start of segment 0 (u64 words, zero-initialised)
@@ -150,7 +119,7 @@ struct Fabric {
       fprintf(stderr, "ERROR(peer):cudaIpcOpenMemHandle failed on some rank:NDSM_B200_ERR_CUDA\n");
       throw NdsmError(NDSM_ERR_CUDA);
     }
-    s.free_list[0] = bytes;
+    s.reset(bytes);
     segs.push_back(s);
   }
 

@@ -64,6 +64,7 @@ def _declare(lib):
     lib.ndsm_b200_plan_restrict.argtypes = [vp, c.c_int, c.c_int, vp, vp, vp, vp]
     lib.ndsm_b200_ngrids_for.argtypes = [c.c_int]
     lib.ndsm_b200_plan_slab_partition.argtypes = [vp, c.c_int, c.c_int, vp, vp]
+    lib.ndsm_b200_plan_sym_heap.argtypes = [c.c_longlong, vp, c.c_int, vp]
     lib.ndsm_b200_bc_setup.argtypes = [vp] * 11
     lib.ndsm_b200_flux_curl.argtypes = [vp, c.c_int, vp, vp, vp, vp, vp, vp]
     lib.ndsm_b200_launch_count.restype = c.c_ulonglong
