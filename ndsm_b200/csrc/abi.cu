@@ -273,14 +273,25 @@ int ndsm_vector_solve(size_t nsize, const int* nshape4, int* ioptc, double* ropt
     DBuf dfaces(ftot);
     double* bn[6];
     {
-      size_t o = 0;
+      // the six faces are gathered concurrently (strided walks over a multi-GB host array: latency-bound), and a
+      // face goes up as soon as it is complete
+      size_t off[6], o = 0;
       for (int f = 0; f < 6; ++f) {
-        gather_face_host(B, nx, ny, nz, f, hfaces + o);
+        off[f] = o;
         bn[f] = dfaces.p + o;
         o += fsz[f];
       }
+      const bool par = ftot >= (1u << 18);
+      std::vector<std::thread> th;
+      struct JoinAll { std::vector<std::thread>& t; ~JoinAll() { for (auto& x : t) if (x.joinable()) x.join(); } } join_all{th};
+      if (par)
+        for (int f = 0; f < 6; ++f) th.emplace_back([&, f] { gather_face_host(B, nx, ny, nz, f, hfaces + off[f]); });
+      for (int f = 0; f < 6; ++f) {
+        if (par) th[f].join();
+        else gather_face_host(B, nx, ny, nz, f, hfaces + off[f]);
+        CUDA_CHECK(cudaMemcpyAsync(dfaces.p + off[f], hfaces + off[f], fsz[f] * sizeof(double), cudaMemcpyHostToDevice, st));
+      }
     }
-    CUDA_CHECK(cudaMemcpyAsync(dfaces.p, hfaces, ftot * sizeof(double), cudaMemcpyHostToDevice, st));
     // --- A is the initial guess as received (reference never zeroes it); ndsm.py passes zeros.  Scanning
     // 3N doubles on the host (and uploading them when they are not all zero) overlaps the chi solves.
     DBuf dA(3 * N), dB(3 * N);
