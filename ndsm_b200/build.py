@@ -11,7 +11,7 @@ REPO_DIR = os.path.dirname(PKG_DIR)
 CSRC = os.path.join(PKG_DIR, "csrc")
 LIB_DIR = os.path.join(PKG_DIR, "lib")
 LIB_PATH = os.path.join(LIB_DIR, "ndsmf.so")
-SOURCES = ["kernels.cu", "pool.cu", "hostsink.cu", "mg.cu", "nccl_comm.cu", "peer.cu", "vecpot.cu", "abi.cu"]
+SOURCES = ["kernels.cu", "pool.cu", "hostsink.cu", "mg.cu", "mg_batch.cu", "nccl_comm.cu", "peer.cu", "vecpot.cu", "abi.cu"]
 HEADERS = ["common.cuh", "kernels.cuh", "pool.hpp", "hostsink.hpp", "mg.hpp", "vecpot.hpp", "sym_alloc.hpp", os.path.join(REPO_DIR, "include", "ndsm_b200.h")]
 
 NVCC_FLAGS = [
@@ -48,14 +48,20 @@ def build_library(force=False, verbose=False):
     if not force and not _stale(LIB_PATH, deps):
         return LIB_PATH
     os.makedirs(LIB_DIR, exist_ok=True)
-    cmd = [_nvcc()] + NVCC_FLAGS + ["-o", LIB_PATH] + srcs
+    tmp = LIB_PATH + ".tmp.%d" % os.getpid()   # link elsewhere, then rename: a snapshot never sees half a library
+    cmd = [_nvcc()] + NVCC_FLAGS + ["-o", tmp] + srcs
     if verbose:
         cmd.insert(1, "-Xptxas=-v")
     env = dict(os.environ)
     # nvcc must use the system g++ (the CC/CXX wrappers exported in this image lack libgomp specs etc.)
     env.pop("CC", None)
     env.pop("CXX", None)
-    subprocess.run(cmd, check=True, cwd=CSRC, env=env)
+    try:
+        subprocess.run(cmd, check=True, cwd=CSRC, env=env)
+        os.replace(tmp, LIB_PATH)
+    finally:
+        if os.path.exists(tmp):
+            os.remove(tmp)
     return LIB_PATH
 
 

@@ -1092,6 +1092,7 @@ void ndsm_b200_release_workspace(void) {
 unsigned long long ndsm_b200_workspace_bytes(void) { return (unsigned long long)pool_cached_bytes(); }
 unsigned long long ndsm_b200_last_slab_points(void) { return g_report.slab_points; }
 int ndsm_b200_last_partitioned_levels(void) { return g_report.ndist; }
+int ndsm_b200_last_components_mode(void) { return g_report.components_mode; }
 const char* ndsm_b200_version(void) { return "ndsm-b200 0.1 (sm_100a, fp64, -fmad=false)"; }
 
 }  // extern "C"

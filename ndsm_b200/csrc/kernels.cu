@@ -282,22 +282,12 @@ __device__ __forceinline__ void relax_pair_march(const double* __restrict__ po, 
   }
 }
 
-template <bool HAS_RHS, int U = 2, int MINB = 4, bool SPLIT = false>
-__global__ void __launch_bounds__(RELAX_BX * RELAX_BY, MINB)
-k_relax3d(double* __restrict__ u, const double* __restrict__ uread, const double* __restrict__ rhs, const Grid g,
-          const Bounds b, const int colour, const double wx, const double wy, const double wz, const double w1,
-          const int klo, const int khi, const int zchunk) {
-  pdl_enter();
-  const int kbeg = klo + blockIdx.z * zchunk;
-  const int kend = min(kbeg + zchunk - 1, khi);
-  if (kbeg > kend) return;
-  // SPLIT: the first pass of a ping-pong V-cycle reads the other colour of the previous iterate's array (uread)
-  // and writes its own colour into the new one (MG::relax); every other pass works inside u (uread is unused, so
-  // the common instantiations keep their register allocation)
-  double* __restrict__ own = u + (i64)colour * g.cs;
-  const double* __restrict__ opp = (SPLIT ? uread : u) + (i64)(1 - colour) * g.cs;
-  const double* __restrict__ rh = HAS_RHS ? rhs + (i64)colour * g.cs : nullptr;
-
+// the work of one thread block of a colour pass on planes kbeg..kend (own / opp / rh: the colour sub-arrays)
+template <bool HAS_RHS, int U>
+__device__ __forceinline__ void relax3d_block(double* __restrict__ own, const double* __restrict__ opp,
+                                              const double* __restrict__ rh, const Grid& g, const Bounds& b,
+                                              const int colour, const double wx, const double wy, const double wz,
+                                              const double w1, const int kbeg, const int kend) {
   if (blockIdx.x == gridDim.x - 1) {  // edge blocks: 4 edge columns x RELAX_EDGE_ROWS rows, scalar path
     const int m = edge_column(threadIdx.x & 3, g.mcnt);
     const int j = b.lb[1] + blockIdx.y * RELAX_EDGE_ROWS + (threadIdx.x >> 2);
@@ -325,6 +315,44 @@ k_relax3d(double* __restrict__ u, const double* __restrict__ uread, const double
     relax_pair_march<HAS_RHS, U, 1>(po, own + o0, pr, ps, dl, dh, n_main, mirror_top, Zm, Zc, wx, wy, wz, w1);
   else
     relax_pair_march<HAS_RHS, U, 0>(po, own + o0, pr, ps, dl, dh, n_main, mirror_top, Zm, Zc, wx, wy, wz, w1);
+}
+
+template <bool HAS_RHS, int U = 2, int MINB = 4, bool SPLIT = false>
+__global__ void __launch_bounds__(RELAX_BX * RELAX_BY, MINB)
+k_relax3d(double* __restrict__ u, const double* __restrict__ uread, const double* __restrict__ rhs, const Grid g,
+          const Bounds b, const int colour, const double wx, const double wy, const double wz, const double w1,
+          const int klo, const int khi, const int zchunk) {
+  pdl_enter();
+  const int kbeg = klo + blockIdx.z * zchunk;
+  const int kend = min(kbeg + zchunk - 1, khi);
+  if (kbeg > kend) return;
+  // SPLIT: the first pass of a ping-pong V-cycle reads the other colour of the previous iterate's array (uread)
+  // and writes its own colour into the new one (MG::relax); every other pass works inside u (uread is unused, so
+  // the common instantiations keep their register allocation)
+  double* __restrict__ own = u + (i64)colour * g.cs;
+  const double* __restrict__ opp = (SPLIT ? uread : u) + (i64)(1 - colour) * g.cs;
+  const double* __restrict__ rh = HAS_RHS ? rhs + (i64)colour * g.cs : nullptr;
+  relax3d_block<HAS_RHS, U>(own, opp, rh, g, b, colour, wx, wy, wz, w1, kbeg, kend);
+}
+
+// Batched colour pass: up to three independent problems on the SAME grid (the components Ax, Ay, Az of the
+// vector-potential solve on a multi-GPU slab: thin slabs make one component's launch too small for the machine).
+// blockIdx.z = member * nchunks + z-chunk; each member brings its own array, Dirichlet pattern and pass colour.
+template <bool HAS_RHS, int U, int MINB>
+__global__ void __launch_bounds__(RELAX_BX * RELAX_BY, MINB)
+k_relax3d_batch(const RelaxBatch bt, const Grid g, const double wx, const double wy, const double wz, const double w1,
+                const int zchunk, const int nchunks) {
+  pdl_enter();
+  const int bi = blockIdx.z / nchunks, ch = blockIdx.z - bi * nchunks;
+  const int kbeg = bt.klo[bi] + ch * zchunk;
+  const int kend = min(kbeg + zchunk - 1, bt.khi[bi]);
+  if (kbeg > kend) return;
+  const int colour = bt.colour[bi];
+  const Bounds b = bt.b[bi];
+  double* __restrict__ own = bt.u[bi] + (i64)colour * g.cs;
+  const double* __restrict__ opp = bt.u[bi] + (i64)(1 - colour) * g.cs;
+  const double* __restrict__ rh = HAS_RHS ? bt.rhs[bi] + (i64)colour * g.cs : nullptr;
+  relax3d_block<HAS_RHS, U>(own, opp, rh, g, b, colour, wx, wy, wz, w1, kbeg, kend);
 }
 
 // ---- shared-memory z-plane staging (cp.async ring): the interior path for levels large enough to fill it.
@@ -524,6 +552,27 @@ void relax3d_half(double* u, const double* rhs, const Grid& g, const Bounds& b, 
   LAUNCHED();
 }
 
+void relax3d_half_batch(const RelaxBatch& in, const Grid& g, const Weights& w, int ext, cudaStream_t st) {
+  RelaxBatch bt = in;
+  int nplanes = 0, nrows = 0;
+  for (int q = 0; q < bt.n; ++q) {
+    bt.klo[q] = max(bt.b[q].lb[2], g.k0 - ext);
+    bt.khi[q] = min(bt.b[q].ub[2], g.k0 + g.nzl - 1 + ext);
+    nplanes = max(nplanes, bt.khi[q] - bt.klo[q] + 1);
+    nrows = max(nrows, bt.b[q].ub[1] - bt.b[q].lb[1] + 1);
+  }
+  if (nplanes <= 0 || nrows <= 0) return;
+  const int npairs = (g.mcnt > 4) ? (((g.mcnt - 1) & ~1) - 2) / 2 : 0;
+  const int bx = cdiv(npairs, RELAX_BX) + 1, by = cdiv(nrows, RELAX_BY);
+  // the members' launches merge into one: the z-chunks can be as long as on a slab of n times the planes
+  const int zc = pick_zchunk(nplanes * bt.n, bx * by, 16);
+  const int nch = cdiv(nplanes, zc);
+  dim3 grid(bx, by, nch * bt.n);
+  if (bt.rhs[0]) launch_k(k_relax3d_batch<true, 2, 4>, grid, RELAX_BX * RELAX_BY, 0, st, bt, g, w.wx, w.wy, w.wz, w.w1, zc, nch);
+  else launch_k(k_relax3d_batch<false, 4, 4>, grid, RELAX_BX * RELAX_BY, 0, st, bt, g, w.wx, w.wy, w.wz, w.w1, zc, nch);
+  LAUNCHED();
+}
+
 // ---------------------------------------------------------------------------------------
 // K2  3D residual                                     (ndsm_optimized.f90:346-447)
 // Same z-march as K1, both colours (blockIdx.z), writes r = 0 on Dirichlet faces.
@@ -656,15 +705,12 @@ __device__ __forceinline__ void residual_pair_march(const double* __restrict__ p
   }
 }
 
+// the work of one thread block of the residual kernel: colour `colour`, planes kbeg..kend
 template <bool HAS_RHS>
-__global__ void __launch_bounds__(RELAX_BX * RELAX_BY, 3)
-k_residual3d(const double* __restrict__ u, const double* __restrict__ rhs, double* __restrict__ r, const Grid g,
-             const Bounds b, const double wx, const double wy, const double wz, const double wc, const int zchunk) {
-  pdl_enter();
-  const int colour = blockIdx.z & 1;
-  const int kbeg = g.k0 + (blockIdx.z >> 1) * zchunk;
-  const int kend = min(kbeg + zchunk - 1, g.k0 + g.nzl - 1);
-  if (kbeg > kend) return;
+__device__ __forceinline__ void residual3d_block(const double* __restrict__ u, const double* __restrict__ rhs,
+                                                 double* __restrict__ r, const Grid& g, const Bounds& b,
+                                                 const int colour, const int kbeg, const int kend, const double wx,
+                                                 const double wy, const double wz, const double wc) {
   const double* __restrict__ own = u + (i64)colour * g.cs;
   const double* __restrict__ opp = u + (i64)(1 - colour) * g.cs;
   const double* __restrict__ rh = HAS_RHS ? rhs + (i64)colour * g.cs : nullptr;
@@ -707,6 +753,34 @@ k_residual3d(const double* __restrict__ u, const double* __restrict__ rhs, doubl
     residual_pair_march<HAS_RHS, 2, 0>(po, own + o0, pr, ro + o0, ps, dl, dh, n_main, mirror_top, Zm, Zc, wx, wy, wz, wc);
 }
 
+
+template <bool HAS_RHS>
+__global__ void __launch_bounds__(RELAX_BX * RELAX_BY, 3)
+k_residual3d(const double* __restrict__ u, const double* __restrict__ rhs, double* __restrict__ r, const Grid g,
+             const Bounds b, const double wx, const double wy, const double wz, const double wc, const int zchunk) {
+  pdl_enter();
+  const int colour = blockIdx.z & 1;
+  const int kbeg = g.k0 + (blockIdx.z >> 1) * zchunk;
+  const int kend = min(kbeg + zchunk - 1, g.k0 + g.nzl - 1);
+  if (kbeg > kend) return;
+  residual3d_block<HAS_RHS>(u, rhs, r, g, b, colour, kbeg, kend, wx, wy, wz, wc);
+}
+
+// batched residual (see k_relax3d_batch): blockIdx.z = member * nz2 + (z-chunk * 2 + colour)
+template <bool HAS_RHS>
+__global__ void __launch_bounds__(RELAX_BX * RELAX_BY, 3)
+k_residual3d_batch(const ResidualBatch bt, const Grid g, const double wx, const double wy, const double wz,
+                   const double wc, const int zchunk, const int nz2) {
+  pdl_enter();
+  const int bi = blockIdx.z / nz2, z2 = blockIdx.z - bi * nz2;
+  const int colour = z2 & 1;
+  const int kbeg = g.k0 + (z2 >> 1) * zchunk;
+  const int kend = min(kbeg + zchunk - 1, g.k0 + g.nzl - 1);
+  if (kbeg > kend) return;
+  const Bounds b = bt.b[bi];
+  residual3d_block<HAS_RHS>(bt.u[bi], HAS_RHS ? bt.rhs[bi] : nullptr, bt.r[bi], g, b, colour, kbeg, kend, wx, wy, wz, wc);
+}
+
 void residual3d(const double* u, const double* rhs, double* r, const Grid& g, const Bounds& b, const Weights& w,
                 cudaStream_t st) {
   const int npairs = (g.mcnt > 4) ? (((g.mcnt - 1) & ~1) - 2) / 2 : 0;
@@ -717,6 +791,17 @@ void residual3d(const double* u, const double* rhs, double* r, const Grid& g, co
     launch_k(k_residual3d<true>, grid, RELAX_BX * RELAX_BY, 0, st, u, rhs, r, g, b, w.wx, w.wy, w.wz, w.wc, zc);
   else
     launch_k(k_residual3d<false>, grid, RELAX_BX * RELAX_BY, 0, st, u, rhs, r, g, b, w.wx, w.wy, w.wz, w.wc, zc);
+  LAUNCHED();
+}
+
+void residual3d_batch(const ResidualBatch& bt, const Grid& g, const Weights& w, cudaStream_t st) {
+  const int npairs = (g.mcnt > 4) ? (((g.mcnt - 1) & ~1) - 2) / 2 : 0;
+  const int bx = cdiv(npairs, RELAX_BX) + 1, by = cdiv(g.ny, RELAX_BY);
+  const int zc = pick_zchunk(g.nzl * bt.n, bx * by * 2);
+  const int nz2 = cdiv(g.nzl, zc) * 2;
+  dim3 grid(bx, by, nz2 * bt.n);
+  if (bt.rhs[0]) launch_k(k_residual3d_batch<true>, grid, RELAX_BX * RELAX_BY, 0, st, bt, g, w.wx, w.wy, w.wz, w.wc, zc, nz2);
+  else launch_k(k_residual3d_batch<false>, grid, RELAX_BX * RELAX_BY, 0, st, bt, g, w.wx, w.wy, w.wz, w.wc, zc, nz2);
   LAUNCHED();
 }
 
@@ -1009,6 +1094,26 @@ __global__ void k_publish(const double* __restrict__ pairs, const int npairs, co
 }
 void publish_results(const double* pairs, int npairs, const int* info, double* host_mapped, cudaStream_t st) {
   launch_k(k_publish, 1, 64, 0, st, pairs, npairs, info, host_mapped);
+  LAUNCHED();
+}
+// the same for a batch of solves: npairs pairs, then two ints per member
+__global__ void k_publish_batch(const double* __restrict__ pairs, const int npairs, const int* __restrict__ i0,
+                                const int* __restrict__ i1, const int* __restrict__ i2, const int ninfo,
+                                double* __restrict__ host) {
+  pdl_enter();
+  const int t = threadIdx.x;
+  if (t < 2 * npairs) host[t] = pairs[t];
+  if (t < 2 * ninfo) {
+    const int* src = (t < 2) ? i0 : (t < 4 ? i1 : i2);
+    reinterpret_cast<int*>(host + 2 * npairs)[t] = src[t & 1];
+  }
+}
+void publish_results_batch(const double* pairs, int npairs, const int* const* info, int ninfo, double* host_mapped,
+                           cudaStream_t st) {
+  const int* i0 = info[0];
+  const int* i1 = ninfo > 1 ? info[1] : info[0];
+  const int* i2 = ninfo > 2 ? info[2] : info[0];
+  launch_k(k_publish_batch, 1, 128, 0, st, pairs, npairs, i0, i1, i2, ninfo, host_mapped);
   LAUNCHED();
 }
 
@@ -1459,12 +1564,16 @@ k_restrict_sep(const double* __restrict__ rf, const Grid gf, double* __restrict_
 #define RD_BY 8
 template <int MINB>
 __global__ void __launch_bounds__(RD_BX * RD_BY, MINB)
-k_restrict_direct(const double* __restrict__ rf, const Grid gf, double* __restrict__ rc, const Grid gc,
-                  const RestrictTab tx, const RestrictTab ty, const RestrictTab tz, const int kchunk) {
+k_restrict_direct(const TransferBatch bt, const Grid gf, const Grid gc, const RestrictTab tx, const RestrictTab ty,
+                  const RestrictTab tz, const int kchunk, const int nch) {
   pdl_enter();
+  // blockIdx.z = member * nch + z-chunk (one member unless the components of a slab solve are batched)
+  const int bi = blockIdx.z / nch, zb = blockIdx.z - bi * nch;
+  const double* __restrict__ rf = (bi == 0) ? bt.src[0] : (bi == 1 ? bt.src[1] : bt.src[2]);  // no dynamic indexing
+  double* __restrict__ rc = (bi == 0) ? bt.dst[0] : (bi == 1 ? bt.dst[1] : bt.dst[2]);        // of the parameter
   const int ic = blockIdx.x * RD_BX + (threadIdx.x & (RD_BX - 1));
   const int jc = blockIdx.y * RD_BY + threadIdx.x / RD_BX;
-  const int kc_beg = gc.k0 + blockIdx.z * kchunk;
+  const int kc_beg = gc.k0 + zb * kchunk;
   const int kc_end = min(kc_beg + kchunk, gc.k0 + gc.nzl) - 1;
   if (ic >= gc.nx || jc >= gc.ny || kc_beg > kc_end) return;
   // 1-D weights of my coarse column: c2*w2 (ndsm_interp.f90:277-282)
@@ -1569,18 +1678,28 @@ bool restrict_direct_fits(const int* const first[3], const int* const count[3], 
   return true;
 }
 
-void restrict_direct(const double* rf, const Grid& gf, double* rhsc, const Grid& gc, const RestrictTab& tx,
-                     const RestrictTab& ty, const RestrictTab& tz, cudaStream_t st) {
+void restrict_direct_batch(const TransferBatch& bt, const Grid& gf, const Grid& gc, const RestrictTab& tx,
+                           const RestrictTab& ty, const RestrictTab& tz, cudaStream_t st) {
   const int bx = cdiv(gc.nx, RD_BX), by = cdiv(gc.ny, RD_BY);
   int kchunk = 32;
-  while (kchunk > 2 && (i64)bx * by * cdiv(gc.nzl, kchunk) < 148 * 6) kchunk >>= 1;
-  dim3 grid(bx, by, cdiv(gc.nzl, kchunk));
+  while (kchunk > 2 && (i64)bx * by * cdiv(gc.nzl, kchunk) * bt.n < 148 * 6) kchunk >>= 1;
+  const int nch = cdiv(gc.nzl, kchunk);
+  dim3 grid(bx, by, nch * bt.n);
   const char* mb = getenv("NDSM_B200_RD_MINB");  // tuning: resident blocks per SM the register allocation aims at
   const int minb = mb ? atoi(mb) : 2;
-  if (minb == 4) launch_k(k_restrict_direct<4>, grid, RD_BX * RD_BY, 0, st, rf, gf, rhsc, gc, tx, ty, tz, kchunk);
-  else if (minb == 3) launch_k(k_restrict_direct<3>, grid, RD_BX * RD_BY, 0, st, rf, gf, rhsc, gc, tx, ty, tz, kchunk);
-  else launch_k(k_restrict_direct<2>, grid, RD_BX * RD_BY, 0, st, rf, gf, rhsc, gc, tx, ty, tz, kchunk);
+  if (minb == 4) launch_k(k_restrict_direct<4>, grid, RD_BX * RD_BY, 0, st, bt, gf, gc, tx, ty, tz, kchunk, nch);
+  else if (minb == 3) launch_k(k_restrict_direct<3>, grid, RD_BX * RD_BY, 0, st, bt, gf, gc, tx, ty, tz, kchunk, nch);
+  else launch_k(k_restrict_direct<2>, grid, RD_BX * RD_BY, 0, st, bt, gf, gc, tx, ty, tz, kchunk, nch);
   LAUNCHED();
+}
+void restrict_direct(const double* rf, const Grid& gf, double* rhsc, const Grid& gc, const RestrictTab& tx,
+                     const RestrictTab& ty, const RestrictTab& tz, cudaStream_t st) {
+  TransferBatch bt;
+  bt.n = 1;
+  bt.src[0] = rf;
+  bt.dst[0] = rhsc;
+  for (int q = 1; q < NDSM_BATCH_MAX; ++q) { bt.src[q] = nullptr; bt.dst[q] = nullptr; }
+  restrict_direct_batch(bt, gf, gc, tx, ty, tz, st);
 }
 
 // ---------------------------------------------------------------------------------------
@@ -1969,16 +2088,20 @@ k_interp_add_tiled(const double* __restrict__ uc, const Grid gc, double* __restr
 #define IZ_ZMAX 32  // longest z-chunk (planes) a block marches: its z table lives in shared memory
 template <int IZ_NP, int MINB>
 __global__ void __launch_bounds__(IZ_BX * IZ_BY, MINB)
-k_interp_add_zt(const double* __restrict__ uc, const Grid gc, double* __restrict__ uf, const Grid gf,
-                const InterpTab tx, const InterpTab ty, const InterpTab tz, const int zchunk) {
+k_interp_add_zt(const TransferBatch bt, const Grid gc, const Grid gf, const InterpTab tx, const InterpTab ty,
+                const InterpTab tz, const int zchunk, const int nch) {
   pdl_enter();
+  // blockIdx.z = member * nch + z-chunk (one member unless the components of a slab solve are batched)
+  const int bi = blockIdx.z / nch, zblk = blockIdx.z - bi * nch;
+  const double* __restrict__ uc = (bi == 0) ? bt.src[0] : (bi == 1 ? bt.src[1] : bt.src[2]);  // no dynamic indexing
+  double* __restrict__ uf = (bi == 0) ? bt.dst[0] : (bi == 1 ? bt.dst[1] : bt.dst[2]);        // of the parameter
   __shared__ double zt[2][IZ_NP][IZ_CYW * IZ_CXW];  // [buffer][plane of the step][coarse tile]
   __shared__ double s_wh[IZ_ZMAX], s_wl[IZ_ZMAX];
   __shared__ int s_lo[IZ_ZMAX];
   const int e = threadIdx.x;
   const int txi = e & (IZ_BX - 1), tyi = e / IZ_BX;
   const int ib = blockIdx.x * IZ_FX, j0 = blockIdx.y * IZ_BY;
-  const int kbeg = gf.k0 + blockIdx.z * zchunk;
+  const int kbeg = gf.k0 + zblk * zchunk;
   const int kend = min(kbeg + zchunk, gf.k0 + gf.nzl) - 1;
   if (kbeg > kend) return;
   const int n = kend - kbeg + 1;
@@ -2073,18 +2196,28 @@ bool interp_zt_fits(const int* lo_x, int nfx, int ncx, const int* lo_y, int nfy,
   return true;
 }
 
-void interp_add_zt(const double* uc, const Grid& gc, double* uf, const Grid& gf, const InterpTab& tx,
-                   const InterpTab& ty, const InterpTab& tz, cudaStream_t st) {
+void interp_add_zt_batch(const TransferBatch& bt, const Grid& gc, const Grid& gf, const InterpTab& tx,
+                         const InterpTab& ty, const InterpTab& tz, cudaStream_t st) {
   const int bx = cdiv(gf.nx, IZ_FX), by = cdiv(gf.ny, IZ_BY);
-  const int zc = pick_zchunk(gf.nzl, bx * by, IZ_ZMAX);
-  dim3 grid(bx, by, cdiv(gf.nzl, zc));
+  const int zc = pick_zchunk(gf.nzl * bt.n, bx * by, IZ_ZMAX);
+  const int nch = cdiv(gf.nzl, zc);
+  dim3 grid(bx, by, nch * bt.n);
   const char* npv = getenv("NDSM_B200_IZ_NP");  // tuning: fine planes per barrier / resident blocks
   const int npi = npv ? atoi(npv) : 4;
-  if (npi == 8) launch_k(k_interp_add_zt<8, 3>, grid, IZ_BX * IZ_BY, 0, st, uc, gc, uf, gf, tx, ty, tz, zc);
-  else if (npi == 6) launch_k(k_interp_add_zt<6, 4>, grid, IZ_BX * IZ_BY, 0, st, uc, gc, uf, gf, tx, ty, tz, zc);
-  else if (npi == 2) launch_k(k_interp_add_zt<2, 4>, grid, IZ_BX * IZ_BY, 0, st, uc, gc, uf, gf, tx, ty, tz, zc);
-  else launch_k(k_interp_add_zt<4, 4>, grid, IZ_BX * IZ_BY, 0, st, uc, gc, uf, gf, tx, ty, tz, zc);
+  if (npi == 8) launch_k(k_interp_add_zt<8, 3>, grid, IZ_BX * IZ_BY, 0, st, bt, gc, gf, tx, ty, tz, zc, nch);
+  else if (npi == 6) launch_k(k_interp_add_zt<6, 4>, grid, IZ_BX * IZ_BY, 0, st, bt, gc, gf, tx, ty, tz, zc, nch);
+  else if (npi == 2) launch_k(k_interp_add_zt<2, 4>, grid, IZ_BX * IZ_BY, 0, st, bt, gc, gf, tx, ty, tz, zc, nch);
+  else launch_k(k_interp_add_zt<4, 4>, grid, IZ_BX * IZ_BY, 0, st, bt, gc, gf, tx, ty, tz, zc, nch);
   LAUNCHED();
+}
+void interp_add_zt(const double* uc, const Grid& gc, double* uf, const Grid& gf, const InterpTab& tx,
+                   const InterpTab& ty, const InterpTab& tz, cudaStream_t st) {
+  TransferBatch bt;
+  bt.n = 1;
+  bt.src[0] = uc;
+  bt.dst[0] = uf;
+  for (int q = 1; q < NDSM_BATCH_MAX; ++q) { bt.src[q] = nullptr; bt.dst[q] = nullptr; }
+  interp_add_zt_batch(bt, gc, gf, tx, ty, tz, st);
 }
 
 // host check: every fine tile's coarse footprint fits the fixed shared-memory window
@@ -2468,10 +2601,8 @@ __device__ void sm_interp_add(const double* __restrict__ ucv, const SmallLevel& 
 }
 
 template <int NDIM>
-__global__ void __launch_bounds__(1024)
-k_vcycle_small(const double* __restrict__ rhs_in, double* __restrict__ u_out, const Grid g0, const SmallArgs a,
-               int* __restrict__ info) {
-  pdl_enter();
+__device__ __forceinline__ void vcycle_small_body(const double* __restrict__ rhs_in, double* __restrict__ u_out,
+                                                  const Grid& g0, const SmallArgs& a, int* __restrict__ info) {
   extern __shared__ double sm[];
   __shared__ double red[40];
   const int nl = a.nlev;
@@ -2586,11 +2717,41 @@ k_vcycle_small(const double* __restrict__ rhs_in, double* __restrict__ u_out, co
   }
 }
 
+template <int NDIM>
+__global__ void __launch_bounds__(1024)
+k_vcycle_small(const double* __restrict__ rhs_in, double* __restrict__ u_out, const Grid g0, const SmallArgs a,
+               int* __restrict__ info) {
+  pdl_enter();
+  vcycle_small_body<NDIM>(rhs_in, u_out, g0, a, info);
+}
+
+// One block per member of a batch of independent solves on the same grids (the three components of A): the
+// members' argument blocks differ (boundary types, first colour) and sit in device memory.
+__global__ void __launch_bounds__(1024)
+k_vcycle_small_batch(const SmallBatch bt, const Grid g0, const SmallArgs* __restrict__ args) {
+  pdl_enter();
+  const int m = blockIdx.x;
+  const double* rhs_in = (m == 0) ? bt.rhs_in[0] : (m == 1 ? bt.rhs_in[1] : bt.rhs_in[2]);
+  double* u_out = (m == 0) ? bt.u_out[0] : (m == 1 ? bt.u_out[1] : bt.u_out[2]);
+  int* info = (m == 0) ? bt.info[0] : (m == 1 ? bt.info[1] : bt.info[2]);
+  const int slot = (m == 0) ? bt.slot[0] : (m == 1 ? bt.slot[1] : bt.slot[2]);
+  __shared__ SmallArgs sa;  // the member's argument block, staged once
+  {
+    static_assert(sizeof(SmallArgs) % sizeof(int) == 0, "SmallArgs is copied as ints");
+    const int* src = reinterpret_cast<const int*>(args + slot);
+    int* dst = reinterpret_cast<int*>(&sa);
+    for (int i = threadIdx.x; i < (int)(sizeof(SmallArgs) / sizeof(int)); i += blockDim.x) dst[i] = src[i];
+    __syncthreads();
+  }
+  vcycle_small_body<3>(rhs_in, u_out, g0, sa, info);
+}
+
 void vcycle_small_prepare() {
   static bool done = false;
   if (done) return;
   cudaFuncSetAttribute(k_vcycle_small<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
   cudaFuncSetAttribute(k_vcycle_small<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  cudaFuncSetAttribute(k_vcycle_small_batch, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
   done = true;
 }
 
@@ -2602,6 +2763,16 @@ void vcycle_small(int ndim, const double* rhs_in, double* u_out, const Grid& g0,
   const int threads = std::min(1024, std::max(32, ((q0 + 31) / 32) * 32));
   if (ndim == 3) launch_k(k_vcycle_small<3>, 1, threads, bytes, st, rhs_in, u_out, g0, a, info);
   else launch_k(k_vcycle_small<2>, 1, threads, bytes, st, rhs_in, u_out, g0, a, info);
+  LAUNCHED();
+}
+
+void vcycle_small_batch(const SmallBatch& bt, const Grid& g0, const SmallArgs& a0, const SmallArgs* args_dev,
+                        cudaStream_t st) {
+  vcycle_small_prepare();
+  const size_t bytes = (size_t)a0.smem_doubles * sizeof(double);
+  const int q0 = ((a0.lv[0].nx + 1) / 2) * a0.lv[0].ny * a0.lv[0].nz;
+  const int threads = std::min(1024, std::max(32, ((q0 + 31) / 32) * 32));
+  launch_k(k_vcycle_small_batch, bt.n, threads, bytes, st, bt, g0, args_dev);
   LAUNCHED();
 }
 

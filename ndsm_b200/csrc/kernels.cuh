@@ -44,6 +44,36 @@ void relax3d_half(double* u, const double* rhs, const Grid& g, const Bounds& b, 
                   int ext, cudaStream_t st, const double* uread = nullptr);
 // dst := src on the points no colour pass updates (Dirichlet faces incl. edges), both colours
 void copy_fixed_points(const double* src, double* dst, const Grid& g, const Bounds& b, cudaStream_t st);
+// Batched variants: up to three independent problems on the same grid in ONE launch (the components Ax, Ay, Az on a
+// multi-GPU slab).  Every member brings its own arrays, Dirichlet pattern and pass colour; rhs is either given for
+// all members or for none.
+#define NDSM_BATCH_MAX 3
+struct RelaxBatch {
+  int n;
+  double* u[NDSM_BATCH_MAX];
+  const double* rhs[NDSM_BATCH_MAX];
+  Bounds b[NDSM_BATCH_MAX];
+  int colour[NDSM_BATCH_MAX];
+  int klo[NDSM_BATCH_MAX], khi[NDSM_BATCH_MAX];  // filled by the wrapper
+};
+void relax3d_half_batch(const RelaxBatch& bt, const Grid& g, const Weights& w, int ext, cudaStream_t st);
+struct ResidualBatch {
+  int n;
+  const double* u[NDSM_BATCH_MAX];
+  const double* rhs[NDSM_BATCH_MAX];
+  double* r[NDSM_BATCH_MAX];
+  Bounds b[NDSM_BATCH_MAX];
+};
+void residual3d_batch(const ResidualBatch& bt, const Grid& g, const Weights& w, cudaStream_t st);
+struct TransferBatch {  // restriction: src = r (fine), dst = rhs (coarse); prolongation: src = u (coarse), dst = u (fine)
+  int n;
+  const double* src[NDSM_BATCH_MAX];
+  double* dst[NDSM_BATCH_MAX];
+};
+void restrict_direct_batch(const TransferBatch& bt, const Grid& gf, const Grid& gc, const RestrictTab& tx,
+                           const RestrictTab& ty, const RestrictTab& tz, cudaStream_t st);
+void interp_add_zt_batch(const TransferBatch& bt, const Grid& gc, const Grid& gf, const InterpTab& tx,
+                         const InterpTab& ty, const InterpTab& tz, cudaStream_t st);
 // K2: residual r = rhs - L u on non-Dirichlet points, 0 elsewhere (ndsm_optimized.f90:346-447).
 void residual3d(const double* u, const double* rhs, double* r, const Grid& g, const Bounds& b, const Weights& w,
                 cudaStream_t st);
@@ -121,6 +151,16 @@ struct SmallArgs {
   int off_r, off_sav, smem_doubles;
 };
 void vcycle_small_prepare();
+// a batch of independent solves on the same grids: member m uses args_dev[slot[m]] (device memory)
+struct SmallBatch {
+  int n;
+  const double* rhs_in[NDSM_BATCH_MAX];
+  double* u_out[NDSM_BATCH_MAX];
+  int* info[NDSM_BATCH_MAX];
+  int slot[NDSM_BATCH_MAX];
+};
+void vcycle_small_batch(const SmallBatch& bt, const Grid& g0, const SmallArgs& a0, const SmallArgs* args_dev,
+                        cudaStream_t st);
 void vcycle_small(int ndim, const double* rhs_in, double* u_out, const Grid& g0, const SmallArgs& a, int* info,
                   cudaStream_t st);
 // K6: out[0] = max|a-b|, out[1] = sum|a-b| over owned planes; then a := b  (update_u: a=caller's u, b=V-cycled u;
@@ -128,6 +168,9 @@ void vcycle_small(int ndim, const double* rhs_in, double* u_out, const Grid& g0,
 void diff_reduce(double* a, const double* b, const Grid& g, bool copy, double* scratch, double* out, cudaStream_t st);
 // npairs (max,sum) pairs and info[2] -> mapped pinned host memory (device-accessible pointer), npairs <= 24
 void publish_results(const double* pairs, int npairs, const int* info, double* host_mapped, cudaStream_t st);
+// batch of ninfo <= 3 solves: npairs pairs (<= 60), then info[m][0..1] for every member
+void publish_results_batch(const double* pairs, int npairs, const int* const* info, int ninfo, double* host_mapped,
+                           cudaStream_t st);
 // nsweeps pure-Neumann 2D sweeps with the per-sweep mean subtraction folded into the passes (opt-in path of the
 // chi solves, see kernels.cu); scratch: relax2d_fused_mean_scratch(g) doubles, zero-initialised once
 size_t relax2d_fused_mean_scratch(const Grid& g);

@@ -238,8 +238,8 @@ struct VirtualComm : Comm {
       if (!found) throw NdsmError(6);
     }
   }
-  void gather2(int my_rank, const double* send2, double* recv_all, cudaStream_t st) override {
-    CUDA_CHECK(cudaMemcpyAsync(recv_all + 2 * my_rank, send2, 2 * sizeof(double), cudaMemcpyDeviceToDevice, st));
+  void gathern(int my_rank, const double* send, int n, double* recv_all, cudaStream_t st) override {
+    CUDA_CHECK(cudaMemcpyAsync(recv_all + (size_t)n * my_rank, send, n * sizeof(double), cudaMemcpyDeviceToDevice, st));
   }
   void bcast(int, double*, size_t, cudaStream_t) override {}
   std::unique_ptr<Comm> clone(cudaStream_t) override { return std::unique_ptr<Comm>(new VirtualComm(w)); }

@@ -9,6 +9,7 @@
 // slabs (virtual mode: every rank on one device, used to test the slab logic on a single GPU).
 #pragma once
 #include <array>
+#include <map>
 #include <memory>
 #include <vector>
 #include "kernels.cuh"
@@ -60,8 +61,9 @@ struct Comm {
   virtual void send(int my_rank, int to_rank, const double* src, size_t n, cudaStream_t st) = 0;
   virtual void recv(int my_rank, int from_rank, double* dst, size_t n, cudaStream_t st) = 0;
   virtual void end(cudaStream_t st) = 0;
-  // every rank contributes 2 doubles; result [2*world] on every process, ordered by rank
-  virtual void gather2(int my_rank, const double* send2, double* recv_all, cudaStream_t st) = 0;
+  // every rank contributes n doubles; result [n*world] on every process, ordered by rank
+  virtual void gathern(int my_rank, const double* send, int n, double* recv_all, cudaStream_t st) = 0;
+  void gather2(int my_rank, const double* send2, double* recv_all, cudaStream_t st) { gathern(my_rank, send2, 2, recv_all, st); }
   // in-place broadcast of buf[0..n) from root_rank into every rank's own copy of the same array; when all
   // local ranks share one copy (virtual mode) this is a no-op
   virtual void bcast(int root_rank, double* buf, size_t n, cudaStream_t st) = 0;
@@ -137,7 +139,10 @@ struct Slab {
   double* d_out = nullptr;  // [2] local max / sum of |du|
 };
 
+class MGBatch;
+
 class MG {
+  friend class MGBatch;
  public:
   // shape: (nx,ny,nz) with nz == 1 for ndim == 2.  ngrids < 0 => reference rule from min(shape).
   // comm == nullptr: one slab covering the whole grid.
@@ -266,6 +271,60 @@ class MG {
   void drop_graphs();
   double* u0_home_ = nullptr;       // the hierarchy's own level-0 array (single slab), where even cycles work
   const double* pp_read_ = nullptr;  // ping-pong: array the first colour pass of the cycle reads (previous iterate)
+};
+
+// Several independent solves on the same grids (the components Ax, Ay, Az) as ONE launch sequence: mg_batch.cu.
+// members[0] is the leader: its stream and communicator carry everything; every member keeps its own hierarchy.
+class MGBatch {
+ public:
+  explicit MGBatch(const std::vector<MG*>& members);
+  ~MGBatch();
+  MGBatch(const MGBatch&) = delete;
+  MGBatch& operator=(const MGBatch&) = delete;
+  // same grids / plan / options (after set_options), 3D, not pure Neumann, small-level kernel in use
+  static bool compatible(const std::vector<MG*>& members);
+  const std::vector<MG*>& members() const { return m_; }
+  // u[i][s]: member i's iterate on slab s (level-0 layout, local plane 0), in/out; rhs == 0 for every member.
+  // tr, du_last, ierr: per member (may be nullptr).
+  void solve(const std::vector<std::vector<double*>>& u, double vc_tol, int nmax, SolveTrace* const* tr,
+             double* du_last, int* ierr);
+  // np halo planes of every member's level-0 array in one exchange
+  void exchange_level0(const std::vector<std::vector<double*>>& u, int np);
+  void drop_graphs();
+
+ private:
+  struct Item {
+    MG* m;
+    int mask;                         // colours
+    const std::vector<double*>* arr;  // per slab, nullptr: the level's u (which == 0) or r scratch (which == 2)
+  };
+  struct Slot {
+    cudaGraphExec_t exec = nullptr;
+    std::vector<unsigned long long> key;
+    unsigned long long launches = 0;
+  };
+  std::vector<MG*> m_;
+  std::vector<char> on_;  // members still iterating
+  MG* lead_ = nullptr;
+  cudaStream_t st_ = nullptr;
+  Comm* comm_ = nullptr;
+  double* d_all_ = nullptr;      // gathered [rank][active member][max,sum]
+  SmallArgs* d_small_ = nullptr;  // the members' small-level argument blocks
+  double* h_out_ = nullptr;
+  double* h_out_dev_ = nullptr;
+  std::map<unsigned, Slot> graphs_;  // by mask of active members
+  std::vector<MG*> active() const;
+  unsigned mask() const;
+  std::vector<unsigned long long> graph_key() const;
+  void capture();
+  void exchange(int g, int which, const std::vector<Item>& items, int np);
+  void need_halo(int g, int depth);
+  void relax(int g);
+  void residual(int g);
+  void restrict_to(int g);
+  void interp_add_from(int c);
+  void v_cycle();
+  void enqueue_cycle();
 };
 
 }  // namespace ndsm

@@ -100,8 +100,8 @@ struct NcclComm : Comm {
     NCCL_CHECK(g_nccl.Recv(dst, n, ncclDouble, from_rank, comm, st));
   }
   void end(cudaStream_t) override { NCCL_CHECK(g_nccl.GroupEnd()); }
-  void gather2(int, const double* send2, double* recv_all, cudaStream_t st) override {
-    NCCL_CHECK(g_nccl.AllGather(send2, recv_all, 2, ncclDouble, comm, st));
+  void gathern(int, const double* send, int n, double* recv_all, cudaStream_t st) override {
+    NCCL_CHECK(g_nccl.AllGather(send, recv_all, (size_t)n, ncclDouble, comm, st));
   }
   void bcast(int root_rank, double* buf, size_t n, cudaStream_t st) override {
     NCCL_CHECK(g_nccl.Broadcast(buf, buf, n, ncclDouble, root_rank, comm, st));

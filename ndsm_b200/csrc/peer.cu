@@ -36,7 +36,7 @@ namespace {
 typedef unsigned long long u64;
 constexpr int MAX_WORLD = 16;
 constexpr int MAX_CH = 8;    // communicators alive at the same time (one per concurrent solve)
-constexpr int MAX_SEG = 32;  // copy segments per launch
+constexpr int MAX_SEG = 64;  // copy segments per launch (three batched components: 3 x 2 colours x 7 peers = 42)
 constexpr size_t SEG_MIN = (size_t)256 << 20;
 
 // ---------------------------------------------------------------------------------------------
@@ -492,20 +492,20 @@ struct PeerComm : Comm {
     sends.clear(); recvs.clear(); bcs.clear();
   }
 
-  void gather2(int, const double* send2, double* recv_all, cudaStream_t st) override {
+  void gathern(int, const double* send, int n, double* recv_all, cudaStream_t st) override {
     const int me = g_fab.rank, W = g_fab.world;
     std::vector<CopySeg> out, none;
     PeerSet pall;
     for (int r = 0; r < W; ++r) {
       CopySeg g;
-      g.src = send2;
-      g.n = 2;
+      g.src = send;
+      g.n = (u64)n;
       g.parity_stride = 0;
       if (r == me) {
-        g.dst = recv_all + 2 * me;
+        g.dst = recv_all + (size_t)n * me;
         g.peer = -1;
       } else {
-        g.dst = g_fab.peer(recv_all, r) + 2 * me;
+        g.dst = g_fab.peer(recv_all, r) + (size_t)n * me;
         g.peer = pall.add(r);
       }
       out.push_back(g);

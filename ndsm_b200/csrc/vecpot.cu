@@ -115,6 +115,8 @@ struct SolverSlot {
 // heap-allocated and never destroyed: at process exit the pool, the CUDA context and the communicators may already be
 // gone when static destructors run (the cache is emptied explicitly by solver_cache_clear())
 SolverSlot* const g_slots = new SolverSlot[9];
+// the batched driver over slots 6-8 (multi-GPU default): dropped before any of those hierarchies is
+std::unique_ptr<MGBatch>* const g_batch = new std::unique_ptr<MGBatch>();
 
 // hierarchy of slot `id` for this problem: the cached one when everything matches, a fresh one otherwise.
 // given_st == nullptr: the slot owns its stream.  clone: the slot works on its own clone of base_comm.
@@ -130,6 +132,7 @@ SolverSlot& acquire_slot(int id, int ndim, const int* shape3, const double* cons
   for (int d = 0; d < ndim && same; ++d)
     same = (S.mesh[d].size() == (size_t)shape3[d]) && !memcmp(S.mesh[d].data(), mesh[d], sizeof(double) * shape3[d]);
   if (!same) {
+    if (id >= 6) g_batch->reset();
     S.clear();
     S.ndim = ndim;
     S.device = dev;
@@ -165,6 +168,7 @@ bool cache_enabled(Comm* comm) {
 }  // namespace
 
 void solver_cache_clear() {
+  g_batch->reset();
   for (int i = 8; i >= 0; --i) g_slots[i].clear();
 }
 
@@ -368,21 +372,29 @@ int vector_solve_core(const int* nshape, const long long* iopt, const double* ro
   const bool conc_default = comm && comm->world() > 1 && comm->nlocal() == 1 && comm->one_sided();
   const bool conc_want = conc_env ? atoi(conc_env) != 0 : conc_default;
   const bool concurrent = conc_want && !prof_enabled() && !g_debug && (!comm || comm->nlocal() == 1);
+  // ... or, better on thin slabs, as ONE launch sequence (mg_batch.cu): a third of the launches and hand-shakes,
+  // three times the work per launch.  Default on the peer-memory transport; NDSM_BATCH_COMPONENTS=0/1 overrides
+  // (1 also batches virtual slabs and a single GPU, for tests).
+  const char* batch_env = getenv("NDSM_BATCH_COMPONENTS");
+  const bool batch_default = false;
+  const bool batch_want = (batch_env ? atoi(batch_env) != 0 : (batch_default && conc_default)) && !prof_enabled() &&
+                          !g_debug && (int)iopt[IOPT_MS] == 5 && (int)iopt[IOPT_NCYCLES] > 1;
   struct Ctx {
     MG* mg = nullptr;  // owned by the solver cache (slots 6-8)
     cudaStream_t st = nullptr;
   } ctx[3];
-  const int nctx = concurrent ? 3 : 1;
+  const int nctx = (concurrent || batch_want) ? 3 : 1;
   for (int q = 0; q < nctx; ++q) {
     // component 0 (and the sequential solves) work on the call's stream and communicator; concurrent
-    // components 1 and 2 get a stream and a channel of their own
-    SolverSlot& slot = acquire_slot(6 + q, 3, sh3, mesh, comm, q > 0 && comm != nullptr, q == 0 ? st : nullptr, nullptr);
+    // components 1 and 2 get a stream and a channel of their own, batched ones share the call's
+    SolverSlot& slot = batch_want ? acquire_slot(6 + q, 3, sh3, mesh, comm, false, st, nullptr)
+                                  : acquire_slot(6 + q, 3, sh3, mesh, comm, q > 0 && comm != nullptr, q == 0 ? st : nullptr, nullptr);
     ctx[q].mg = slot.mg.get();
     ctx[q].st = slot.st;
   }
   trace.mark("3D hierarchy construction");
   MG* mg3 = ctx[0].mg;
-  auto mgc = [&](int c) { return ctx[concurrent ? c : 0].mg; };
+  auto mgc = [&](int c) { return ctx[nctx == 3 ? c : 0].mg; };
   const int ns = mg3->nslabs();
   std::vector<SlabOut> outs = outs_in;
   if (ns == 1 && outs.size() > 1) {  // every virtual rank shares one undivided solve: one contiguous output
@@ -428,17 +440,34 @@ int vector_solve_core(const int* nshape, const long long* iopt, const double* ro
   // single slab writing the whole array in the default (flux first) order: a component of A is final as soon
   // as its solve has converged, so it is converted and handed out early
   const bool flux_first = (iopt[IOPT_FLXCRL] != 1);  // :453-477
-  const bool early_out = !concurrent && ns == 1 && flux_first && outs[0].k0 == 0 && outs[0].k1 == nz &&
+  const bool early_out = nctx == 1 && ns == 1 && flux_first && outs[0].k0 == 0 && outs[0].k1 == nz &&
                          mg3->plan().ndist == 0;
   // ... and a component of B = curl A as soon as the two components of A it depends on are (Bz after Ay)
   const bool early_b = early_out && hooks && hooks->b_ready;
-  if (!concurrent) {
+  bool batched = false;
+  if (batch_want) {
+    for (int c = 0; c < 3; ++c) set_opts(c);
+    const std::vector<MG*> mem{mgc(0), mgc(1), mgc(2)};
+    batched = MGBatch::compatible(mem);
+    if (batched) {
+      if (!*g_batch || (*g_batch)->members() != mem) g_batch->reset(new MGBatch(mem));
+      for (int c = 0; c < 3; ++c) prepare(c, st);
+      SolveTrace* trs[3] = {&rep.solves[6], &rep.solves[7], &rep.solves[8]};
+      const std::vector<std::vector<double*>> us{Ap[0], Ap[1], Ap[2]};
+      (*g_batch)->solve(us, ropt[ROPT_VTOL], (int)iopt[IOPT_NCYCLES], trs, nullptr, nullptr);
+      (*g_batch)->exchange_level0(us, 1);  // halo planes of the converged components (curl needs k-1, k+1)
+      CUDA_CHECK(cudaStreamSynchronize(st));
+    }
+  }
+  rep.components_mode = batched ? 2 : ((concurrent && !batch_want) ? 1 : 0);
+  if (batched) {
+  } else if (!concurrent || batch_want) {  // (batch_want: the three hierarchies share one stream and one channel)
     for (int c = 0; c < 3; ++c) {
       set_opts(c);
       prepare(c, st);
       double du_last;
-      mg3->solve(Ap[c], norhs, ropt[ROPT_VTOL], (int)iopt[IOPT_NCYCLES], &du_last, &rep.solves[6 + c]);
-      mg3->exchange(0, 0, 3, 1, &Ap[c]);  // halo planes of the converged component (curl needs k-1, k+1)
+      mgc(c)->solve(Ap[c], norhs, ropt[ROPT_VTOL], (int)iopt[IOPT_NCYCLES], &du_last, &rep.solves[6 + c]);
+      mgc(c)->exchange(0, 0, 3, 1, &Ap[c]);  // halo planes of the converged component (curl needs k-1, k+1)
       if (early_out) {
         unsplit_A(Ap[c][0], mg3->level(0, 0).g, c, dx_, dy_, dz_, phi, Lq, true, 0, nz, outs[0].A + c * outs[0].cstride, st);
         if (hooks && hooks->component_ready) hooks->component_ready(c);

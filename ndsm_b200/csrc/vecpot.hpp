@@ -19,6 +19,7 @@ struct Report {
   double ms_total = 0, ms_in = 0, ms_bc = 0, ms_solve3d = 0, ms_post = 0, ms_out = 0, ms_device = 0;
   unsigned long long launches = 0;
   int ndist = 0;  // number of z-partitioned multigrid levels in the 3D solves
+  int components_mode = 0;  // 0: one after the other, 1: three concurrent streams, 2: one batched launch sequence
   unsigned long long slab_points = 0;  // finest-level points this process smooths per component solve
 };
 extern Report g_report;

@@ -34,6 +34,7 @@ def _declare(lib):
     lib.ndsm_b200_poisson_solve_rank.argtypes = [vp, c.c_char_p, c.c_int, c.c_int, c.c_int, c.c_int, c.c_double,
                                                  c.c_double, vp, vp, vp, vp, vp, vp, vp]
     lib.ndsm_b200_last_partitioned_levels.restype = c.c_int
+    lib.ndsm_b200_last_components_mode.restype = c.c_int
     lib.ndsm_b200_new_mg_handle.argtypes = [c.c_int, vp, c.c_int, vp, vp, vp, c.c_int, c.c_int]
     lib.ndsm_b200_new_mg_handle.restype = vp
     lib.ndsm_b200_delete_mg_handle.argtypes = [vp]

@@ -179,3 +179,42 @@ def test_poisson_pure_neumann_3d_on_partitioned_levels(gpu_lib, slab_env, oracle
     assert rel_err(got[1], ora[1]) <= 1e-10
     assert abs(got[1].mean()) <= 1e-12 * np.abs(got[1]).max() + 1e-15          # the gauge: zero mean
     assert np.abs(got[1] - uex).max() < 5e-2                                    # O(h^2)
+
+
+@pytest.fixture
+def batch_env():
+    saved = os.environ.get("NDSM_BATCH_COMPONENTS")
+    yield
+    if saved is None:
+        os.environ.pop("NDSM_BATCH_COMPONENTS", None)
+    else:
+        os.environ["NDSM_BATCH_COMPONENTS"] = saved
+
+
+@pytest.mark.parametrize("shape,world,min_planes,kw", [
+    ((44, 44, 44), 1, 16, {}),                 # one slab, no communicator
+    ((40, 33, 52), 3, 4, {}),                  # ragged slabs, two partitioned levels
+    ((65, 65, 65), 4, 4, {}),
+    ((48, 40, 80), 2, 8, {"mean": True}),      # mean metric: the members' sums are gathered in one message
+    ((129, 129, 129), 2, 16, {}),              # the z-lerped prolongation and the direct restriction, batched
+])
+def test_batched_components_reproduce_member_by_member(gpu_lib, slab_env, batch_env, shape, world, min_planes, kw):
+    """Ax, Ay, Az as ONE launch sequence (mg_batch.cu, the multi-GPU default) against one solve after the other: the
+    same arithmetic per member, so du histories, V-cycle counts, A and B are bit-identical."""
+    os.environ["NDSM_BATCH_COMPONENTS"] = "0"
+    ref = solve(shape, world, min_planes, **kw)
+    assert gpu_lib.ndsm_b200_last_components_mode() == 0
+    os.environ["NDSM_BATCH_COMPONENTS"] = "1"
+    got = solve(shape, world, min_planes, **kw)
+    assert gpu_lib.ndsm_b200_last_components_mode() == 2
+    again = solve(shape, world, min_planes, **kw)   # cached hierarchies, replayed graphs
+    assert gpu_lib.ndsm_b200_last_components_mode() == 2
+    for out in (got, again):
+        assert out[0] == ref[0] == 0
+        for name in ("Ax", "Ay", "Az"):
+            assert out[3][name]["du"] == ref[3][name]["du"], name
+            assert out[3][name]["nexact"] == ref[3][name]["nexact"], name
+        assert np.array_equal(out[1], ref[1])
+        assert np.array_equal(out[2], ref[2])
+    # the members stop at their own V-cycle counts
+    assert len({len(ref[3][n]["du"]) for n in ("Ax", "Ay", "Az")}) >= 1
