@@ -1081,6 +1081,22 @@ void copy_fixed_points(const double* src, double* dst, const Grid& g, const Boun
   LAUNCHED();
 }
 
+// Holds a stream for `ns` nanoseconds (one thread): staggers concurrent solves so that their latency-bound phases
+// (coarse levels, halo hand-shakes) do not coincide -- see vecpot.cu, NDSM_STAGGER_US.
+__global__ void k_delay(const unsigned long long ns) {
+  pdl_enter();
+  unsigned long long t0, t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+  do {
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  } while (t - t0 < ns);
+}
+void stream_delay(double microseconds, cudaStream_t st) {
+  if (microseconds <= 0) return;
+  launch_k(k_delay, 1, 1, 0, st, (unsigned long long)(microseconds * 1e3));
+  LAUNCHED();
+}
+
 // Hands the results of one V-cycle to the host through MAPPED pinned memory: npairs (max,sum) pairs and the two
 // ints of the coarsest solve.  A copy node would queue behind bulk device-to-host transfers on the copy engine
 // (the host entry ships finished components of A and B while the next solve runs: measured +10 ms of solve time

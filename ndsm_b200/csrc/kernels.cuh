@@ -42,6 +42,8 @@ struct RestrictTab {  // restriction table of one dimension (ndsm_interp.f90:218
 // uread (optional): array whose OTHER colour is read instead of u's (first pass of a ping-pong V-cycle).
 void relax3d_half(double* u, const double* rhs, const Grid& g, const Bounds& b, int colour, const Weights& w,
                   int ext, cudaStream_t st, const double* uread = nullptr);
+// keeps the stream busy for that long (one thread spinning on %globaltimer)
+void stream_delay(double microseconds, cudaStream_t st);
 // dst := src on the points no colour pass updates (Dirichlet faces incl. edges), both colours
 void copy_fixed_points(const double* src, double* dst, const Grid& g, const Bounds& b, cudaStream_t st);
 // Batched variants: up to three independent problems on the same grid in ONE launch (the components Ax, Ay, Az on a

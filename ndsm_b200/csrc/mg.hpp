@@ -288,6 +288,13 @@ class MGBatch {
   // tr, du_last, ierr: per member (may be nullptr).
   void solve(const std::vector<std::vector<double*>>& u, double vc_tol, int nmax, SolveTrace* const* tr,
              double* du_last, int* ierr);
+  // the same as a state machine (cf. MG::solve_begin ...): several groups interleaved by one host thread
+  void solve_begin(const std::vector<std::vector<double*>>& u, double vc_tol, int nmax, SolveTrace* const* tr);
+  void solve_enqueue();
+  bool solve_poll();
+  bool solve_done() const { return mask() == 0; }
+  void solve_end(double* du_last, int* ierr);
+  cudaStream_t stream() const { return st_; }
   // np halo planes of every member's level-0 array in one exchange
   void exchange_level0(const std::vector<std::vector<double*>>& u, int np);
   void drop_graphs();
@@ -305,6 +312,14 @@ class MGBatch {
   };
   std::vector<MG*> m_;
   std::vector<char> on_;  // members still iterating
+  std::vector<double> du_;
+  std::vector<int> its_;
+  std::vector<char> conv_;
+  std::vector<SolveTrace*> tr_;
+  std::vector<SmallArgs> small_host_;  // what d_small_ holds
+  double vc_tol_ = 0;
+  int nmax_ = 0;
+  bool use_graph_ = false;
   MG* lead_ = nullptr;
   cudaStream_t st_ = nullptr;
   Comm* comm_ = nullptr;

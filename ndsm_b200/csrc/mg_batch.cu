@@ -24,7 +24,7 @@ namespace ndsm {
 extern unsigned long long g_launches;
 
 bool MGBatch::compatible(const std::vector<MG*>& m) {
-  if (m.size() < 2 || m.size() > NDSM_BATCH_MAX) return false;
+  if (m.empty() || m.size() > NDSM_BATCH_MAX) return false;
   const MG* a = m[0];
   if (a->ndim_ != 3 || a->ngrids() < 2 || a->ms_ < 1) return false;
   for (const MG* b : m) {
@@ -421,20 +421,24 @@ void MGBatch::capture() {
   gs.key = graph_key();
 }
 
-// The members' solve_poisson_bvp loops (ndsm_poisson.f90:63-155) in lock-step.  u[i]: member i's iterate per slab
-// (level-0 layout, local plane 0), in/out; rhs == 0 for every member.
-void MGBatch::solve(const std::vector<std::vector<double*>>& u, double vc_tol, int nmax, SolveTrace* const* tr,
-                    double* du_last, int* ierr) {
+// The members' solve_poisson_bvp loops (ndsm_poisson.f90:63-155) in lock-step, as a state machine like MG's (begin /
+// enqueue / poll / end) so that several groups can be interleaved by one host thread.  u[i]: member i's iterate per
+// slab (level-0 layout, local plane 0), in/out; rhs == 0 for every member.
+void MGBatch::solve_begin(const std::vector<std::vector<double*>>& u, double vc_tol, int nmax, SolveTrace* const* tr) {
   const MG& L = *lead_;
   const size_t nm = m_.size();
   if (u.size() != nm) throw NdsmError(NDSM_ERR_INTERNAL);
   if (!compatible(m_)) throw NdsmError(NDSM_ERR_INTERNAL);  // options may have changed since construction
   on_.assign(nm, nmax > 0);
-  std::vector<double> du(nm, 1.7976931348623157e308);
-  std::vector<int> its(nm, 0);
-  std::vector<char> conv(nm, 0);
+  du_.assign(nm, 1.7976931348623157e308);
+  its_.assign(nm, 0);
+  conv_.assign(nm, 0);
+  tr_.assign(nm, nullptr);
+  vc_tol_ = vc_tol;
+  nmax_ = nmax;
   for (size_t i = 0; i < nm; ++i) {
     MG* m = m_[i];
+    if (tr) tr_[i] = tr[i];
     if (u[i].size() != m->slabs_.size()) throw NdsmError(NDSM_ERR_INTERNAL);
     m->ss_ = MG::SolveState();
     m->ss_.u = u[i];
@@ -449,72 +453,99 @@ void MGBatch::solve(const std::vector<std::vector<double*>>& u, double vc_tol, i
     }
     for (auto& v : m->valid_) v = {{0, 0}};
     for (auto& v : m->static_ok_) v = {{false, false}};
-    // the small-level argument block of this member (boundary pattern, first colour) for the batched kernel
-    CUDA_CHECK(cudaMemcpyAsync(d_small_ + i, &m->small_args_, sizeof(SmallArgs), cudaMemcpyHostToDevice, st_));
+    // the small-level argument block of this member (boundary pattern, first colour) for the batched kernel;
+    // uploaded only when it changed (the source is pageable memory: the copy is synchronous then)
+    if (small_host_.size() != nm) small_host_.resize(nm);
+    if (memcmp(&small_host_[i], &m->small_args_, sizeof(SmallArgs)) != 0) {
+      memcpy(&small_host_[i], &m->small_args_, sizeof(SmallArgs));
+      CUDA_CHECK(cudaMemcpyAsync(d_small_ + i, &small_host_[i], sizeof(SmallArgs), cudaMemcpyHostToDevice, st_));
+      CUDA_CHECK(cudaStreamSynchronize(st_));
+    }
   }
-  CUDA_CHECK(cudaStreamSynchronize(st_));  // small_args_ is pageable: the copies above have left the host structs
   if (comm_ && L.plan_.ndist > 0) comm_->barrier(st_);  // see MG::solve_begin
   static const bool graphs_on = !(getenv("NDSM_B200_GRAPH") && atoi(getenv("NDSM_B200_GRAPH")) == 0);
-  bool use_graph = graphs_on && !prof_enabled() && nmax > 1;
+  use_graph_ = graphs_on && !prof_enabled() && nmax > 1;
+}
+
+void MGBatch::solve_enqueue() {
+  if (mask() == 0) return;
+  if (use_graph_) {
+    {
+      Slot& gs = graphs_[mask()];
+      if (!gs.exec || gs.key != graph_key()) capture();
+    }
+    Slot& gs = graphs_[mask()];
+    if (gs.exec) {
+      CUDA_CHECK(cudaGraphLaunch(gs.exec, st_));
+      g_launches += gs.launches;
+      return;
+    }
+    use_graph_ = false;  // instantiation failed: launch directly from here on
+  }
+  enqueue_cycle();
+}
+
+bool MGBatch::solve_poll() {
+  if (mask() == 0) return true;
+  const MG& L = *lead_;
+  const size_t nm = m_.size();
   const Grid& g0 = L.slabs_[0].lv[0].g;
   const double N = (double)((i64)g0.nx * g0.ny * g0.nz);
   const bool dist = L.plan_.ndist > 0 && comm_;
   const int world = dist ? L.plan_.world : 1;
-  while (mask() != 0) {
-    if (use_graph) {
-      Slot& gs = graphs_[mask()];
-      if (!gs.exec || gs.key != graph_key()) capture();
-      Slot& g2 = graphs_[mask()];
-      if (g2.exec) {
-        CUDA_CHECK(cudaGraphLaunch(g2.exec, st_));
-        g_launches += g2.launches;
-      } else {
-        use_graph = false;
-        enqueue_cycle();
-      }
-    } else {
-      enqueue_cycle();
-    }
-    CUDA_CHECK(cudaStreamSynchronize(st_));
-    prof_collect();
-    if (comm_ && comm_->failed()) {
-      fprintf(stderr, "ERROR(solve_poisson_bvp):a peer did not answer within the time-out (NDSM_P2P_TIMEOUT_MS):NDSM_B200_ERR_INTERNAL\n");
-      throw NdsmError(NDSM_ERR_INTERNAL);
-    }
-    // gathered layout: [rank][active member][max, sum], then two ints per active member
-    std::vector<size_t> act;
-    for (size_t i = 0; i < nm; ++i)
-      if (on_[i]) act.push_back(i);
-    const int na = (int)act.size();
-    const int* info = reinterpret_cast<const int*>(h_out_ + 2 * na * world);
-    for (int q = 0; q < na; ++q) {
-      const size_t i = act[q];
-      double dmax = 0.0, dsum = 0.0;
-      for (int r = 0; r < world; ++r) {  // fixed rank order: every rank takes the same decision
-        const double* p = h_out_ + ((size_t)r * na + q) * 2;
-        dmax = p[0] > dmax ? p[0] : dmax;
-        dsum += p[1];
-      }
-      du[i] = L.du_max_ ? dmax : dsum / N;
-      if (tr && tr[i]) { tr[i]->du.push_back(du[i]); tr[i]->nexact.push_back(info[2 * q]); }
-      if (!info[2 * q + 1]) printf(" Warning: IOPT_NMAXEX exceeded. Coarse-mesh solution may not have converged\n");
-      ++its[i];
-      if (du[i] < vc_tol) { conv[i] = 1; on_[i] = false; }  // :136 strict <
-      else if (its[i] >= nmax) on_[i] = false;
-    }
+  CUDA_CHECK(cudaStreamSynchronize(st_));
+  prof_collect();
+  if (comm_ && comm_->failed()) {
+    fprintf(stderr, "ERROR(solve_poisson_bvp):a peer did not answer within the time-out (NDSM_P2P_TIMEOUT_MS):NDSM_B200_ERR_INTERNAL\n");
+    throw NdsmError(NDSM_ERR_INTERNAL);
   }
-  for (size_t i = 0; i < nm; ++i) {
+  // gathered layout: [rank][active member][max, sum], then two ints per active member
+  std::vector<size_t> act;
+  for (size_t i = 0; i < nm; ++i)
+    if (on_[i]) act.push_back(i);
+  const int na = (int)act.size();
+  const int* info = reinterpret_cast<const int*>(h_out_ + 2 * na * world);
+  for (int q = 0; q < na; ++q) {
+    const size_t i = act[q];
+    double dmax = 0.0, dsum = 0.0;
+    for (int r = 0; r < world; ++r) {  // fixed rank order: every rank takes the same decision
+      const double* p = h_out_ + ((size_t)r * na + q) * 2;
+      dmax = p[0] > dmax ? p[0] : dmax;
+      dsum += p[1];
+    }
+    du_[i] = L.du_max_ ? dmax : dsum / N;
+    if (tr_[i]) { tr_[i]->du.push_back(du_[i]); tr_[i]->nexact.push_back(info[2 * q]); }
+    if (!info[2 * q + 1]) printf(" Warning: IOPT_NMAXEX exceeded. Coarse-mesh solution may not have converged\n");
+    ++its_[i];
+    if (du_[i] < vc_tol_) { conv_[i] = 1; on_[i] = false; }  // :136 strict <
+    else if (its_[i] >= nmax_) on_[i] = false;
+  }
+  return mask() == 0;
+}
+
+void MGBatch::solve_end(double* du_last, int* ierr) {
+  for (size_t i = 0; i < m_.size(); ++i) {
     MG* m = m_[i];
-    m->ss_.it = its[i];
-    m->ss_.du = du[i];
-    m->ss_.converged = conv[i] != 0;
+    m->ss_.it = its_[i];
+    m->ss_.du = du_[i];
+    m->ss_.converged = conv_[i] != 0;
     m->ss_.done = true;
-    if (du_last) du_last[i] = du[i];
-    const int e = conv[i] ? 0 : 1;
+    if (du_last) du_last[i] = du_[i];
+    const int e = conv_[i] ? 0 : 1;
     if (e) printf(" Warning: IOPT_NCYCLES exceeded. V-cycle iteration may not have converged\n");
     if (ierr) ierr[i] = e;
-    if (tr && tr[i]) tr[i]->ierr = e;
+    if (tr_[i]) tr_[i]->ierr = e;
   }
+}
+
+void MGBatch::solve(const std::vector<std::vector<double*>>& u, double vc_tol, int nmax, SolveTrace* const* tr,
+                    double* du_last, int* ierr) {
+  solve_begin(u, vc_tol, nmax, tr);
+  while (!solve_done()) {
+    solve_enqueue();
+    solve_poll();
+  }
+  solve_end(du_last, ierr);
 }
 
 // halo planes of the converged components (the curl stencil reads k-1, k+1), one exchange for all of them

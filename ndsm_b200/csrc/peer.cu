@@ -266,6 +266,28 @@ __global__ void __launch_bounds__(256) k_push(const PushArgs a) {
   if (threadIdx.x == 0) *a.ticket = 0u;
 }
 
+// Only the wait of k_wait_unpack, one block: with NDSM_P2P_SPLIT_WAIT=1 it runs in front of k_wait_unpack, whose up
+// to 128 blocks then find the flags already set instead of sitting on SM slots that the other component streams'
+// kernels could use while the neighbour's message is still on its way.
+__global__ void __launch_bounds__(32) k_wait_only(const WaitArgs a) {
+  pdl_enter_no_trigger();
+  if (threadIdx.x < a.npeer) {
+    const int p = threadIdx.x;
+    const u64 want = *a.expect[p] + 1ull;
+    if (*a.d_err == 0) {
+      const u64 t0 = global_timer_ns();
+      unsigned spins = 0;
+      while (ld_acquire_sys(a.flag[p]) < want) {
+        if ((++spins & 255u) == 0 && global_timer_ns() - t0 > a.timeout_ns) {
+          *a.d_err = 1;
+          *a.h_err_map = 1;
+          break;
+        }
+      }
+    }
+  }
+}
+
 __global__ void __launch_bounds__(256) k_wait_unpack(const WaitArgs a) {
   pdl_enter_no_trigger();
   __shared__ u64 par[MAX_WORLD];
@@ -420,7 +442,13 @@ struct PeerComm : Comm {
     a.d_err = g_fab.d_err();
     a.h_err_map = g_fab.d_err_map;
     a.timeout_ns = g_fab.timeout_ns;
-    launch_k(k_wait_unpack, blocks_for(a.seg, a.nseg), 256, 0, st, a);
+    const int nb = blocks_for(a.seg, a.nseg);
+    const char* sw = getenv("NDSM_P2P_SPLIT_WAIT");
+    if (nb > 1 && sw && atoi(sw) != 0) {
+      launch_k(k_wait_only, 1, 32, 0, st, a);
+      ++g_launches;
+    }
+    launch_k(k_wait_unpack, nb, 256, 0, st, a);
     CUDA_CHECK(cudaGetLastError());
     ++g_launches;
   }

@@ -6,6 +6,7 @@
 #include "pool.hpp"
 
 #include <chrono>
+#include <unistd.h>
 #include <algorithm>
 #include <cstring>
 #include <string>
@@ -45,7 +46,7 @@ struct HostTrace {
   void mark(const char* what) {
     if (!on) return;
     const auto now = std::chrono::steady_clock::now();
-    fprintf(stderr, "TRACE %-28s +%8.3f ms  (total %8.3f ms)\n", what,
+    fprintf(stderr, "TRACE[%d] %-28s +%8.3f ms  (total %8.3f ms)\n", (int)getpid(), what,
             std::chrono::duration<double, std::milli>(now - last).count(),
             std::chrono::duration<double, std::milli>(now - t0).count());
     last = now;
@@ -115,8 +116,8 @@ struct SolverSlot {
 // heap-allocated and never destroyed: at process exit the pool, the CUDA context and the communicators may already be
 // gone when static destructors run (the cache is emptied explicitly by solver_cache_clear())
 SolverSlot* const g_slots = new SolverSlot[9];
-// the batched driver over slots 6-8 (multi-GPU default): dropped before any of those hierarchies is
-std::unique_ptr<MGBatch>* const g_batch = new std::unique_ptr<MGBatch>();
+// the batched drivers over slots 6-8 (one per group of components): dropped before any of those hierarchies is
+std::vector<std::unique_ptr<MGBatch>>* const g_batches = new std::vector<std::unique_ptr<MGBatch>>();
 
 // hierarchy of slot `id` for this problem: the cached one when everything matches, a fresh one otherwise.
 // given_st == nullptr: the slot owns its stream.  clone: the slot works on its own clone of base_comm.
@@ -132,7 +133,12 @@ SolverSlot& acquire_slot(int id, int ndim, const int* shape3, const double* cons
   for (int d = 0; d < ndim && same; ++d)
     same = (S.mesh[d].size() == (size_t)shape3[d]) && !memcmp(S.mesh[d].data(), mesh[d], sizeof(double) * shape3[d]);
   if (!same) {
-    if (id >= 6) g_batch->reset();
+    if (id >= 6) {
+      // component slots are acquired in ascending order and a later one may work on an earlier one's stream and
+      // channel (a batched group): whatever comes after a rebuilt slot is rebuilt too
+      g_batches->clear();
+      for (int i = 8; i > id; --i) g_slots[i].clear();
+    }
     S.clear();
     S.ndim = ndim;
     S.device = dev;
@@ -168,7 +174,7 @@ bool cache_enabled(Comm* comm) {
 }  // namespace
 
 void solver_cache_clear() {
-  g_batch->reset();
+  g_batches->clear();
   for (int i = 8; i >= 0; --i) g_slots[i].clear();
 }
 
@@ -372,13 +378,44 @@ int vector_solve_core(const int* nshape, const long long* iopt, const double* ro
   const bool conc_default = comm && comm->world() > 1 && comm->nlocal() == 1 && comm->one_sided();
   const bool conc_want = conc_env ? atoi(conc_env) != 0 : conc_default;
   const bool concurrent = conc_want && !prof_enabled() && !g_debug && (!comm || comm->nlocal() == 1);
-  // ... or, better on thin slabs, as ONE launch sequence (mg_batch.cu): a third of the launches and hand-shakes,
-  // three times the work per launch.  Default on the peer-memory transport; NDSM_BATCH_COMPONENTS=0/1 overrides
-  // (1 also batches virtual slabs and a single GPU, for tests).
-  const char* batch_env = getenv("NDSM_BATCH_COMPONENTS");
-  const bool batch_default = false;
-  const bool batch_want = (batch_env ? atoi(batch_env) != 0 : (batch_default && conc_default)) && !prof_enabled() &&
-                          !g_debug && (int)iopt[IOPT_MS] == 5 && (int)iopt[IOPT_NCYCLES] > 1;
+  // ... or batched (mg_batch.cu): the components of a GROUP advance as one launch sequence -- a third of the launches
+  // and hand-shakes, three times the work per launch, but nothing to overlap the latency-bound parts with; groups
+  // run concurrently.  NDSM_COMPONENT_GROUPS names the groups ("012": one batch, "01,2": Ax+Ay batched next to
+  // Az, "0,1,2" = three batches of one); NDSM_BATCH_COMPONENTS=1 is short for "012".  Also usable with virtual
+  // slabs and on a single GPU (tests).
+  std::vector<std::vector<int>> groups;
+  {
+    const char* ge = getenv("NDSM_COMPONENT_GROUPS");
+    const char* be = getenv("NDSM_BATCH_COMPONENTS");
+    std::string spec = ge ? ge : ((be && atoi(be) != 0) ? "012" : "");
+    int seen[3] = {0, 0, 0};
+    bool ok = !spec.empty();
+    std::vector<int> cur;
+    for (size_t i = 0; ok && i <= spec.size(); ++i) {
+      const char ch = i < spec.size() ? spec[i] : ',';
+      if (ch == ',') {
+        if (cur.empty()) { ok = false; break; }
+        std::sort(cur.begin(), cur.end());
+        groups.push_back(cur);
+        cur.clear();
+      } else if (ch >= '0' && ch <= '2' && !seen[ch - '0']) {
+        seen[ch - '0'] = 1;
+        cur.push_back(ch - '0');
+      } else {
+        ok = false;
+      }
+    }
+    if (!ok || !(seen[0] && seen[1] && seen[2])) groups.clear();
+    // a group's first member (lowest component) owns the group's stream and channel: order the groups by it
+    std::sort(groups.begin(), groups.end(), [](const std::vector<int>& x, const std::vector<int>& y) { return x[0] < y[0]; });
+    if (prof_enabled() || g_debug || (int)iopt[IOPT_NCYCLES] <= 1) groups.clear();
+    if (groups.size() > 1 && comm && comm->nlocal() != 1) groups.clear();   // several channels: one rank per process
+    if (groups.size() > 1 && comm && !comm->one_sided()) groups.clear();
+  }
+  const bool batch_want = !groups.empty();
+  int group_of[3] = {0, 0, 0};
+  for (size_t gi = 0; gi < groups.size(); ++gi)
+    for (int c : groups[gi]) group_of[c] = (int)gi;
   struct Ctx {
     MG* mg = nullptr;  // owned by the solver cache (slots 6-8)
     cudaStream_t st = nullptr;
@@ -386,11 +423,23 @@ int vector_solve_core(const int* nshape, const long long* iopt, const double* ro
   const int nctx = (concurrent || batch_want) ? 3 : 1;
   for (int q = 0; q < nctx; ++q) {
     // component 0 (and the sequential solves) work on the call's stream and communicator; concurrent
-    // components 1 and 2 get a stream and a channel of their own, batched ones share the call's
-    SolverSlot& slot = batch_want ? acquire_slot(6 + q, 3, sh3, mesh, comm, false, st, nullptr)
-                                  : acquire_slot(6 + q, 3, sh3, mesh, comm, q > 0 && comm != nullptr, q == 0 ? st : nullptr, nullptr);
-    ctx[q].mg = slot.mg.get();
-    ctx[q].st = slot.st;
+    // components 1 and 2 get a stream and a channel of their own; a batched group shares its first member's
+    SolverSlot* slot;
+    if (batch_want) {
+      const std::vector<int>& G = groups[group_of[q]];
+      if (G[0] == 0) {
+        slot = &acquire_slot(6 + q, 3, sh3, mesh, comm, false, st, nullptr);
+      } else if (G[0] == q) {
+        slot = &acquire_slot(6 + q, 3, sh3, mesh, comm, comm != nullptr, nullptr, nullptr);
+      } else {
+        SolverSlot& first = g_slots[6 + G[0]];
+        slot = &acquire_slot(6 + q, 3, sh3, mesh, first.own_comm ? first.own_comm.get() : comm, false, first.st, nullptr);
+      }
+    } else {
+      slot = &acquire_slot(6 + q, 3, sh3, mesh, comm, q > 0 && comm != nullptr, q == 0 ? st : nullptr, nullptr);
+    }
+    ctx[q].mg = slot->mg.get();
+    ctx[q].st = slot->st;
   }
   trace.mark("3D hierarchy construction");
   MG* mg3 = ctx[0].mg;
@@ -447,16 +496,48 @@ int vector_solve_core(const int* nshape, const long long* iopt, const double* ro
   bool batched = false;
   if (batch_want) {
     for (int c = 0; c < 3; ++c) set_opts(c);
-    const std::vector<MG*> mem{mgc(0), mgc(1), mgc(2)};
-    batched = MGBatch::compatible(mem);
+    std::vector<std::vector<MG*>> mem(groups.size());
+    batched = true;
+    for (size_t gi = 0; gi < groups.size(); ++gi) {
+      for (int c : groups[gi]) mem[gi].push_back(mgc(c));
+      batched = batched && MGBatch::compatible(mem[gi]);
+    }
     if (batched) {
-      if (!*g_batch || (*g_batch)->members() != mem) g_batch->reset(new MGBatch(mem));
-      for (int c = 0; c < 3; ++c) prepare(c, st);
-      SolveTrace* trs[3] = {&rep.solves[6], &rep.solves[7], &rep.solves[8]};
-      const std::vector<std::vector<double*>> us{Ap[0], Ap[1], Ap[2]};
-      (*g_batch)->solve(us, ropt[ROPT_VTOL], (int)iopt[IOPT_NCYCLES], trs, nullptr, nullptr);
-      (*g_batch)->exchange_level0(us, 1);  // halo planes of the converged components (curl needs k-1, k+1)
-      CUDA_CHECK(cudaStreamSynchronize(st));
+      bool same = g_batches->size() == groups.size();
+      for (size_t gi = 0; same && gi < groups.size(); ++gi) same = (*g_batches)[gi]->members() == mem[gi];
+      if (!same) {
+        g_batches->clear();
+        for (size_t gi = 0; gi < groups.size(); ++gi) g_batches->emplace_back(new MGBatch(mem[gi]));
+      }
+      std::vector<std::vector<std::vector<double*>>> us(groups.size());
+      for (size_t gi = 0; gi < groups.size(); ++gi) {
+        MGBatch& B = *(*g_batches)[gi];
+        SolveTrace* trs[3] = {nullptr, nullptr, nullptr};
+        for (size_t q = 0; q < groups[gi].size(); ++q) {
+          const int c = groups[gi][q];
+          prepare(c, B.stream());
+          trs[q] = &rep.solves[6 + c];
+          us[gi].push_back(Ap[c]);
+        }
+        B.solve_begin(us[gi], ropt[ROPT_VTOL], (int)iopt[IOPT_NCYCLES], trs);
+      }
+      // every group always has its next V-cycle queued (cf. the concurrent loop below)
+      for (auto& B : *g_batches) B->solve_enqueue();
+      bool any = true;
+      while (any) {
+        any = false;
+        for (auto& B : *g_batches) {
+          if (B->solve_done()) continue;
+          if (!B->solve_poll()) B->solve_enqueue();
+          any = true;
+        }
+      }
+      for (size_t gi = 0; gi < groups.size(); ++gi) {
+        MGBatch& B = *(*g_batches)[gi];
+        B.solve_end(nullptr, nullptr);
+        B.exchange_level0(us[gi], 1);  // halo planes of the converged components (curl needs k-1, k+1)
+        CUDA_CHECK(cudaStreamSynchronize(B.stream()));
+      }
     }
   }
   rep.components_mode = batched ? 2 : ((concurrent && !batch_want) ? 1 : 0);
@@ -464,10 +545,11 @@ int vector_solve_core(const int* nshape, const long long* iopt, const double* ro
   } else if (!concurrent || batch_want) {  // (batch_want: the three hierarchies share one stream and one channel)
     for (int c = 0; c < 3; ++c) {
       set_opts(c);
-      prepare(c, st);
+      prepare(c, mgc(c)->stream());
       double du_last;
       mgc(c)->solve(Ap[c], norhs, ropt[ROPT_VTOL], (int)iopt[IOPT_NCYCLES], &du_last, &rep.solves[6 + c]);
       mgc(c)->exchange(0, 0, 3, 1, &Ap[c]);  // halo planes of the converged component (curl needs k-1, k+1)
+      if (mgc(c)->stream() != st) CUDA_CHECK(cudaStreamSynchronize(mgc(c)->stream()));
       if (early_out) {
         unsplit_A(Ap[c][0], mg3->level(0, 0).g, c, dx_, dy_, dz_, phi, Lq, true, 0, nz, outs[0].A + c * outs[0].cstride, st);
         if (hooks && hooks->component_ready) hooks->component_ready(c);
@@ -483,6 +565,12 @@ int vector_solve_core(const int* nshape, const long long* iopt, const double* ro
       prepare(c, ctx[c].st);
       mgc(c)->solve_begin(Ap[c], norhs, ropt[ROPT_VTOL], (int)iopt[IOPT_NCYCLES], &rep.solves[6 + c]);
     }
+    // The three streams run the same program: started together they would sit in their latency-bound phases
+    // (coarse levels, hand-shakes) at the same time and fight for HBM at the same time.  Component c starts
+    // c * NDSM_STAGGER_US later, so that one stream's tail overlaps the others' smoothing.
+    const double stagger_us = getenv("NDSM_STAGGER_US") ? atof(getenv("NDSM_STAGGER_US")) : 0.0;
+    if (stagger_us > 0)
+      for (int c = 1; c < 3; ++c) stream_delay(c * stagger_us, ctx[c].st);
     // every stream always has its next V-cycle queued: a component is re-enqueued right after its own poll
     for (int c = 0; c < 3; ++c) mgc(c)->solve_enqueue();
     bool any = true;

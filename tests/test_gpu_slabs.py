@@ -183,28 +183,36 @@ def test_poisson_pure_neumann_3d_on_partitioned_levels(gpu_lib, slab_env, oracle
 
 @pytest.fixture
 def batch_env():
-    saved = os.environ.get("NDSM_BATCH_COMPONENTS")
+    keys = ("NDSM_BATCH_COMPONENTS", "NDSM_COMPONENT_GROUPS")
+    saved = {k: os.environ.get(k) for k in keys}
     yield
-    if saved is None:
-        os.environ.pop("NDSM_BATCH_COMPONENTS", None)
-    else:
-        os.environ["NDSM_BATCH_COMPONENTS"] = saved
+    for k, v in saved.items():
+        if v is None:
+            os.environ.pop(k, None)
+        else:
+            os.environ[k] = v
 
 
-@pytest.mark.parametrize("shape,world,min_planes,kw", [
-    ((44, 44, 44), 1, 16, {}),                 # one slab, no communicator
-    ((40, 33, 52), 3, 4, {}),                  # ragged slabs, two partitioned levels
-    ((65, 65, 65), 4, 4, {}),
-    ((48, 40, 80), 2, 8, {"mean": True}),      # mean metric: the members' sums are gathered in one message
-    ((129, 129, 129), 2, 16, {}),              # the z-lerped prolongation and the direct restriction, batched
+@pytest.mark.parametrize("shape,world,min_planes,groups,kw", [
+    ((44, 44, 44), 1, 16, "012", {}),                 # one slab, no communicator
+    ((44, 40, 48), 1, 16, "01,2", {}),                # Ax+Ay batched next to Az on a second stream
+    ((40, 36, 44), 1, 16, "0,12", {"mean": True}),
+    ((40, 33, 52), 3, 4, "012", {}),                  # ragged slabs, two partitioned levels
+    ((65, 65, 65), 4, 4, "012", {}),
+    ((48, 40, 80), 2, 8, "012", {"mean": True}),      # mean metric: the members' sums are gathered in one message
+    ((129, 129, 129), 2, 16, "012", {}),              # the z-lerped prolongation and the direct restriction, batched
 ])
-def test_batched_components_reproduce_member_by_member(gpu_lib, slab_env, batch_env, shape, world, min_planes, kw):
-    """Ax, Ay, Az as ONE launch sequence (mg_batch.cu, the multi-GPU default) against one solve after the other: the
-    same arithmetic per member, so du histories, V-cycle counts, A and B are bit-identical."""
-    os.environ["NDSM_BATCH_COMPONENTS"] = "0"
+def test_batched_components_reproduce_member_by_member(gpu_lib, slab_env, batch_env, shape, world, min_planes, groups, kw):
+    """Groups of components as ONE launch sequence each (mg_batch.cu) against one solve after the other: the same
+    arithmetic per member, so du histories, V-cycle counts, A and B are bit-identical."""
+    os.environ.pop("NDSM_BATCH_COMPONENTS", None)
+    os.environ.pop("NDSM_COMPONENT_GROUPS", None)
     ref = solve(shape, world, min_planes, **kw)
     assert gpu_lib.ndsm_b200_last_components_mode() == 0
-    os.environ["NDSM_BATCH_COMPONENTS"] = "1"
+    if groups == "012" and world > 1:
+        os.environ["NDSM_BATCH_COMPONENTS"] = "1"     # the short form
+    else:
+        os.environ["NDSM_COMPONENT_GROUPS"] = groups
     got = solve(shape, world, min_planes, **kw)
     assert gpu_lib.ndsm_b200_last_components_mode() == 2
     again = solve(shape, world, min_planes, **kw)   # cached hierarchies, replayed graphs
@@ -216,5 +224,3 @@ def test_batched_components_reproduce_member_by_member(gpu_lib, slab_env, batch_
             assert out[3][name]["nexact"] == ref[3][name]["nexact"], name
         assert np.array_equal(out[1], ref[1])
         assert np.array_equal(out[2], ref[2])
-    # the members stop at their own V-cycle counts
-    assert len({len(ref[3][n]["du"]) for n in ("Ax", "Ay", "Az")}) >= 1
