@@ -38,9 +38,10 @@ struct DevBuf {  // RAII device allocation
 // NDSM_B200_TRACE=1: wall-clock checkpoints of the host orchestration on stderr (where does a stage's time go:
 // hierarchy construction, graph capture/instantiation, the V-cycle loop)
 struct HostTrace {
-  bool on;
+  bool on, verbose = false;  // NDSM_B200_TRACE=1: stages, =2: every chi V-cycle as well
   std::chrono::steady_clock::time_point t0, last;
   HostTrace() : on(getenv("NDSM_B200_TRACE") && atoi(getenv("NDSM_B200_TRACE")) != 0) {
+    verbose = on && atoi(getenv("NDSM_B200_TRACE")) >= 2;
     t0 = last = std::chrono::steady_clock::now();
   }
   void mark(const char* what) {
@@ -303,7 +304,13 @@ int vector_solve_core(const int* nshape, const long long* iopt, const double* ro
         any = false;
         for (int f = 0; f < 6; ++f) {
           if (!mine(f) || fs[f].mg->solve_done()) continue;
-          if (!fs[f].mg->solve_poll()) fs[f].mg->solve_enqueue();
+          const bool done = fs[f].mg->solve_poll();
+          if (trace.on && trace.verbose) {
+            char what[48];
+            snprintf(what, sizeof what, "  chi face %d cycle polled", f);
+            trace.mark(what);
+          }
+          if (!done) fs[f].mg->solve_enqueue();
           any = true;
         }
       }
