@@ -5,6 +5,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 
@@ -1003,7 +1004,18 @@ void MG::solve_enqueue() {
     const int parity = ss_.pingpong ? (ss_.it & 1) : 0;
     GraphSlot& gs = gslot_[parity];
     if (ss_.pingpong) slabs_[0].lv[0].u = (ss_.it & 1) ? ss_.u[0] : u0_home_;  // the array this cycle works in (part of the key)
-    if (!gs.exec || gs.key != graph_key(parity)) capture_cycle(parity);
+    if (!gs.exec || gs.key != graph_key(parity)) {
+      static const bool say = getenv("NDSM_B200_TRACE") && atoi(getenv("NDSM_B200_TRACE")) >= 2;
+      if (say) {
+        const std::vector<unsigned long long> k = graph_key(parity);
+        int diff = -1;
+        for (size_t i = 0; i < k.size() && i < gs.key.size(); ++i)
+          if (k[i] != gs.key[i]) { diff = (int)i; break; }
+        fprintf(stderr, "TRACE graph capture: ndim %d parity %d had_exec %d first differing key word %d of %zu\n", ndim_, parity,
+                gs.exec != nullptr, diff, k.size());
+      }
+      capture_cycle(parity);
+    }
     if (gs.exec) {
       CUDA_CHECK(cudaGraphLaunch(gs.exec, st_));
       g_launches += gs.launches;

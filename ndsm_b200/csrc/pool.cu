@@ -2,6 +2,7 @@
 #include "pool.hpp"
 
 #include <cstdlib>
+#include <iterator>
 #include <map>
 #include <mutex>
 #include <unordered_map>
@@ -43,7 +44,11 @@ struct Pool {
   void* alloc(size_t bytes) {
     const size_t b = round(bytes ? bytes : 1);
     const Key key(device_key(), b);
-    auto it = free_blocks.find(key);
+    // among cached blocks of this size take the one freed LAST: scoped buffers are released in reverse order of
+    // their allocation, so a call sequence that repeats gets the same block for the same buffer every time
+    // (addresses are baked into captured graphs; first-in-first-out permuted them from call to call)
+    auto range = free_blocks.equal_range(key);
+    auto it = (range.first == range.second) ? free_blocks.end() : std::prev(range.second);
     void* p = nullptr;
     if (it != free_blocks.end()) {
       p = it->second;

@@ -103,7 +103,26 @@ struct SolverSlot {
   std::unique_ptr<Comm> own_comm;
   std::unique_ptr<MG> mg;
   bool used = false;
+  // Work arrays that live as long as the hierarchy (the chi faces' iterate and right-hand side): their addresses
+  // are baked into the captured V-cycle graph, so they must not change from call to call -- blocks taken from the
+  // pool per call came back permuted every call and every chi graph was re-captured every call (0.6 ms each, and
+  // every ~30 instantiations the driver took 25 ms for one).
+  double* buf[2] = {nullptr, nullptr};
+  size_t buf_n[2] = {0, 0};
+  double* buffer(int i, size_t n) {
+    if (buf_n[i] < n) {
+      if (buf[i]) pool_free(buf[i]);
+      buf[i] = static_cast<double*>(pool_alloc(n * sizeof(double)));
+      buf_n[i] = n;
+    }
+    return buf[i];
+  }
   void clear() {
+    for (int i = 0; i < 2; ++i) {
+      if (buf[i]) pool_free(buf[i]);
+      buf[i] = nullptr;
+      buf_n[i] = 0;
+    }
     mg.reset();
     own_comm.reset();
     if (own_stream && st) cudaStreamDestroy(st);
@@ -264,7 +283,7 @@ int vector_solve_core(const int* nshape, const long long* iopt, const double* ro
     // run one after the other so that the reference's message order is kept.)
     struct FaceSolve {
       MG* mg = nullptr;  // owned by the solver cache (slot f)
-      DevBuf chi, rhs;
+      struct { double* p = nullptr; } chi, rhs;  // owned by the solver slot
       cudaStream_t st = nullptr;
       int ierr = 0;
     } fs[6];
@@ -278,8 +297,8 @@ int vector_solve_core(const int* nshape, const long long* iopt, const double* ro
       fs[f].st = slot.st;
       fs[f].mg->set_options((int)iopt[IOPT_MS], ropt[ROPT_CTOL], "NNNN", use_du_max, (int)iopt[IOPT_NMAXEX]);  // :355-357
       const Grid g2 = fs[f].mg->level(0).g;
-      fs[f].chi.alloc(2 * (size_t)g2.cs);
-      fs[f].rhs.alloc(2 * (size_t)g2.cs);
+      fs[f].chi.p = slot.buffer(0, 2 * (size_t)g2.cs);
+      fs[f].rhs.p = slot.buffer(1, 2 * (size_t)g2.cs);
       CUDA_CHECK(cudaMemsetAsync(fs[f].rhs.p, 0, 2 * (size_t)g2.cs * sizeof(double), fs[f].st));
       CUDA_CHECK(cudaMemsetAsync(fs[f].chi.p, 0, 2 * (size_t)g2.cs * sizeof(double), fs[f].st));  // :345
       split_from_dense(bn[f], fs[f].rhs.p, g2, phi[f] / Aq[f], fs[f].st);                         // :348
@@ -298,7 +317,10 @@ int vector_solve_core(const int* nshape, const long long* iopt, const double* ro
           fs[f].mg->solve_begin(fs[f].chi.p, fs[f].rhs.p, ropt[ROPT_VTOL], (int)iopt[IOPT_NCYCLES], &rep.solves[f]);
       trace.mark("chi solve_begin (graph capture)");
       for (int f = 0; f < 6; ++f)
-        if (mine(f)) fs[f].mg->solve_enqueue();
+        if (mine(f)) {
+          fs[f].mg->solve_enqueue();
+          if (trace.on && trace.verbose) trace.mark("  chi face first enqueue");
+        }
       bool any = true;
       while (any) {  // a face is re-enqueued right after its own poll, so its stream never waits for the others
         any = false;
