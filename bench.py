@@ -456,6 +456,7 @@ def run_ours(args, rank, world):
     torch.cuda.synchronize(); barrier()
     clocks.mark_begin()
     l0 = lib.ndsm_b200_launch_count()
+    pb0, pm0 = lib.ndsm_b200_peer_bytes_sent(), lib.ndsm_b200_peer_messages_sent()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t0 = time.perf_counter()
     ev0.record()
@@ -476,6 +477,20 @@ def run_ours(args, rank, world):
     wall = maxr(time.perf_counter() - t0)
     clocks.mark_end()
     launches = lib.ndsm_b200_launch_count() - l0
+    # NVLink traffic of the timed region: bytes / messages this rank stored into other GPUs' memory (peer transport)
+    nvlink = None
+    if world > 1:
+        t = torch.tensor([lib.ndsm_b200_peer_bytes_sent() - pb0, lib.ndsm_b200_peer_messages_sent() - pm0],
+                         dtype=torch.float64, device="cuda")
+        tmax = t.clone()
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        nvlink = {"bytes_per_step_all_ranks": float(t[0].item()) / args.steps,
+                  "messages_per_step_all_ranks": float(t[1].item()) / args.steps,
+                  "bytes_per_step_busiest_rank": float(tmax[0].item()) / args.steps,
+                  "messages_per_step_busiest_rank": float(tmax[1].item()) / args.steps,
+                  "counted": "remote stores of k_push (halo planes, replicated coarse levels, At faces, result pairs; "
+                             "flag words excluded), counted on the host per launch / per graph replay"}
     clk = clocks.stop()
     value = upd_total / wall / 1e9
     nexact = [max([lib.ndsm_b200_trace_nexact(s, c) for c in range(lib.ndsm_b200_trace_ncycles(s))] or [0])
@@ -585,7 +600,7 @@ def run_ours(args, rank, world):
                         "decomposition": ("single GPU" if world == 1 else
                                           "%d ranks: every rank holds a z-slab of all three components (solved concurrently "
                                           "on three streams), chi faces distributed, transport: %s" % (world, transport)),
-                        "steps_ms": step_ms, "timed_region": timed},
+                        "steps_ms": step_ms, "timed_region": timed, "nvlink": nvlink},
             "time_to_vc_tol_ms": {"device_events": dev_ms / args.steps, "wall": wall / args.steps * 1e3, **stage,
                                   "torch_events_rank0": ev0.elapsed_time(ev1) / args.steps},
             "clocks": clk, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,

@@ -180,6 +180,10 @@ int ndsm_b200_flux_curl(const int* nshape4, int flxcrl, const double* x, const d
  * ------------------------------------------------------------------------------------------ */
 int ndsm_b200_device_count(void);               /* 0 when no usable CUDA device */
 unsigned long long ndsm_b200_launch_count(void); /* kernels launched by this library so far */
+/* peer-memory transport: bytes this process has stored into other GPUs' memory over NVLink so far, and the number of
+ * messages (one k_push launch with remote segments each); 0 on the NCCL data path */
+unsigned long long ndsm_b200_peer_bytes_sent(void);
+unsigned long long ndsm_b200_peer_messages_sent(void);
 /* trace of the last ndsm_vector_solve / _device / poisson_solve / mg_solve call:
  * solves 0..5 = chi faces 1..6, 6..8 = Ax, Ay, Az (poisson/mg_solve: solve 0) */
 int ndsm_b200_trace_nsolves(void);

@@ -1061,6 +1061,8 @@ int ndsm_b200_device_count(void) {
   return n;
 }
 unsigned long long ndsm_b200_launch_count(void) { return g_launches; }
+unsigned long long ndsm_b200_peer_bytes_sent(void) { return g_peer_bytes; }
+unsigned long long ndsm_b200_peer_messages_sent(void) { return g_peer_msgs; }
 int ndsm_b200_trace_nsolves(void) { return 9; }
 int ndsm_b200_trace_ncycles(int s) { return (s >= 0 && s < 9) ? (int)g_report.solves[s].du.size() : -1; }
 double ndsm_b200_trace_du(int s, int c) {

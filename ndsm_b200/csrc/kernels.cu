@@ -19,6 +19,10 @@ bool pdl_enabled() {  // declared in common.cuh; read per launch: tests and benc
 namespace ndsm {
 
 unsigned long long g_launches = 0;
+// peer-memory transport (peer.cu): bytes this process has stored into other GPUs' memory over NVLink, and the
+// number of messages (push launches with at least one remote segment); counted when a launch is enqueued, and per
+// replay for launches captured in a graph (like g_launches)
+unsigned long long g_peer_bytes = 0, g_peer_msgs = 0;
 #define LAUNCHED() (++g_launches)
 
 

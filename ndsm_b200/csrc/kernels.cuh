@@ -7,6 +7,7 @@
 namespace ndsm {
 
 extern unsigned long long g_launches;  // number of kernels this library has launched
+extern unsigned long long g_peer_bytes, g_peer_msgs;  // peer-memory transport: bytes / messages stored into other GPUs
 
 // Optional per-kernel-class timing with CUDA events on the launching stream (bench.py roofline numbers).
 // Classes are recorded only for level-0 launches (tagged by the MG driver through prof_scope()).

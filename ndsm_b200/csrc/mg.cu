@@ -979,7 +979,7 @@ void MG::capture_cycle(int parity) {
   // the halo state is whatever the previous cycle left when the graph is replayed; capture the pessimistic pattern
   for (auto& v : valid_) v = {{0, 0}};
   for (auto& v : static_ok_) v = {{false, false}};
-  const unsigned long long l0 = g_launches;
+  const unsigned long long l0 = g_launches, b0 = g_peer_bytes, m0 = g_peer_msgs;
   cudaGraph_t graph = nullptr;
   CUDA_CHECK(cudaStreamBeginCapture(st_, cudaStreamCaptureModeThreadLocal));
   try {
@@ -991,7 +991,11 @@ void MG::capture_cycle(int parity) {
   }
   CUDA_CHECK(cudaStreamEndCapture(st_, &graph));
   gs.launches = g_launches - l0;
+  gs.peer_bytes = g_peer_bytes - b0;
+  gs.peer_msgs = g_peer_msgs - m0;
   g_launches = l0;  // nothing ran during capture
+  g_peer_bytes = b0;
+  g_peer_msgs = m0;
   cudaError_t e = cudaGraphInstantiate(&gs.exec, graph, 0);
   cudaGraphDestroy(graph);
   if (e != cudaSuccess) { gs.exec = nullptr; cudaGetLastError(); }
@@ -1019,6 +1023,8 @@ void MG::solve_enqueue() {
     if (gs.exec) {
       CUDA_CHECK(cudaGraphLaunch(gs.exec, st_));
       g_launches += gs.launches;
+      g_peer_bytes += gs.peer_bytes;
+      g_peer_msgs += gs.peer_msgs;
       return;
     }
     ss_.use_graph = false;  // instantiation failed: launch directly from here on

@@ -264,7 +264,7 @@ class MG {
   struct GraphSlot {
     cudaGraphExec_t exec = nullptr;
     std::vector<unsigned long long> key;
-    unsigned long long launches = 0;
+    unsigned long long launches = 0, peer_bytes = 0, peer_msgs = 0;
   } gslot_[2];
   std::vector<unsigned long long> graph_key(int parity) const;
   void capture_cycle(int parity);
@@ -308,7 +308,7 @@ class MGBatch {
   struct Slot {
     cudaGraphExec_t exec = nullptr;
     std::vector<unsigned long long> key;
-    unsigned long long launches = 0;
+    unsigned long long launches = 0, peer_bytes = 0, peer_msgs = 0;
   };
   std::vector<MG*> m_;
   std::vector<char> on_;  // members still iterating

@@ -402,7 +402,7 @@ void MGBatch::capture() {
     for (auto& v : m->valid_) v = {{0, 0}};
     for (auto& v : m->static_ok_) v = {{false, false}};
   }
-  const unsigned long long l0 = g_launches;
+  const unsigned long long l0 = g_launches, b0 = g_peer_bytes, m0 = g_peer_msgs;
   cudaGraph_t graph = nullptr;
   CUDA_CHECK(cudaStreamBeginCapture(st_, cudaStreamCaptureModeThreadLocal));
   try {
@@ -414,7 +414,11 @@ void MGBatch::capture() {
   }
   CUDA_CHECK(cudaStreamEndCapture(st_, &graph));
   gs.launches = g_launches - l0;
+  gs.peer_bytes = g_peer_bytes - b0;
+  gs.peer_msgs = g_peer_msgs - m0;
   g_launches = l0;
+  g_peer_bytes = b0;
+  g_peer_msgs = m0;
   cudaError_t e = cudaGraphInstantiate(&gs.exec, graph, 0);
   cudaGraphDestroy(graph);
   if (e != cudaSuccess) { gs.exec = nullptr; cudaGetLastError(); }
@@ -478,6 +482,8 @@ void MGBatch::solve_enqueue() {
     if (gs.exec) {
       CUDA_CHECK(cudaGraphLaunch(gs.exec, st_));
       g_launches += gs.launches;
+      g_peer_bytes += gs.peer_bytes;
+      g_peer_msgs += gs.peer_msgs;
       return;
     }
     use_graph_ = false;  // instantiation failed: launch directly from here on

@@ -416,6 +416,9 @@ struct PeerComm : Comm {
       a.sent_st[p] = g_fab.word(CW_SENT_ST, ch, r);
     }
     a.ticket = g_fab.ticket(ch, 0);
+    for (const CopySeg& g : segs)
+      if (g.peer >= 0) g_peer_bytes += g.n * sizeof(double);
+    if (ps.n > 0) ++g_peer_msgs;
     launch_k(k_push, blocks_for(a.seg, a.nseg), 256, 0, st, a);
     CUDA_CHECK(cudaGetLastError());
     ++g_launches;

@@ -69,6 +69,8 @@ def _declare(lib):
     lib.ndsm_b200_bc_setup.argtypes = [vp] * 11
     lib.ndsm_b200_flux_curl.argtypes = [vp, c.c_int, vp, vp, vp, vp, vp, vp]
     lib.ndsm_b200_launch_count.restype = c.c_ulonglong
+    lib.ndsm_b200_peer_bytes_sent.restype = c.c_ulonglong
+    lib.ndsm_b200_peer_messages_sent.restype = c.c_ulonglong
     lib.ndsm_b200_trace_ncycles.argtypes = [c.c_int]
     lib.ndsm_b200_trace_du.argtypes = [c.c_int, c.c_int]
     lib.ndsm_b200_trace_du.restype = c.c_double
