@@ -200,6 +200,9 @@ int ndsm_b200_last_partitioned_levels(void);
 /* how the three component solves of the last call were scheduled: 0 = one after the other (one GPU), 1 = three
  * concurrent streams, 2 = one batched launch sequence (NDSM_BATCH_COMPONENTS) */
 int ndsm_b200_last_components_mode(void);
+/* how a NDSM_COMPONENT_GROUPS value is read (host only, no GPU needed): returns the number of groups (0: the value is
+ * not a partition of {0,1,2} and is ignored) and, per component, the index of its group */
+int ndsm_b200_parse_component_groups(const char* spec, int* group_of3);
 /* CUDA-event timing of the finest-level 3D kernels (off by default).  cls: 0 = k_relax3d colour pass,
  * 1 = k_residual3d, 2 = restriction, 3 = prolongation, 4 = update_u reduction (2 launches), 5 = one halo exchange,
  * 6 = all work on levels >= 2 of one V-cycle, 7 = all work on level 1 of one V-cycle (two brackets per cycle). */

@@ -1095,6 +1095,15 @@ unsigned long long ndsm_b200_workspace_bytes(void) { return (unsigned long long)
 unsigned long long ndsm_b200_last_slab_points(void) { return g_report.slab_points; }
 int ndsm_b200_last_partitioned_levels(void) { return g_report.ndist; }
 int ndsm_b200_last_components_mode(void) { return g_report.components_mode; }
+int ndsm_b200_parse_component_groups(const char* spec, int* group_of3) {  // host only
+  const std::vector<std::vector<int>> g = parse_component_groups(spec);
+  if (group_of3)
+    for (int c = 0; c < 3; ++c) group_of3[c] = -1;
+  for (size_t gi = 0; gi < g.size(); ++gi)
+    for (int c : g[gi])
+      if (group_of3) group_of3[c] = (int)gi;
+  return (int)g.size();
+}
 const char* ndsm_b200_version(void) { return "ndsm-b200 0.1 (sm_100a, fp64, -fmad=false)"; }
 
 }  // extern "C"

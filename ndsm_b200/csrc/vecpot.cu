@@ -193,6 +193,33 @@ bool cache_enabled(Comm* comm) {
 }
 }  // namespace
 
+// "012" | "01,2" | "0,12" | "02,1" | "0,1,2": every component exactly once; anything else gives no groups.  A group's
+// first member (lowest component) owns the group's stream and channel: members and groups come back sorted.
+std::vector<std::vector<int>> parse_component_groups(const char* spec_in) {
+  std::vector<std::vector<int>> groups;
+  const std::string spec = spec_in ? spec_in : "";
+  int seen[3] = {0, 0, 0};
+  bool ok = !spec.empty();
+  std::vector<int> cur;
+  for (size_t i = 0; ok && i <= spec.size(); ++i) {
+    const char ch = i < spec.size() ? spec[i] : ',';
+    if (ch == ',') {
+      if (cur.empty()) { ok = false; break; }
+      std::sort(cur.begin(), cur.end());
+      groups.push_back(cur);
+      cur.clear();
+    } else if (ch >= '0' && ch <= '2' && !seen[ch - '0']) {
+      seen[ch - '0'] = 1;
+      cur.push_back(ch - '0');
+    } else {
+      ok = false;
+    }
+  }
+  if (!ok || !(seen[0] && seen[1] && seen[2])) groups.clear();
+  std::sort(groups.begin(), groups.end(), [](const std::vector<int>& x, const std::vector<int>& y) { return x[0] < y[0]; });
+  return groups;
+}
+
 void solver_cache_clear() {
   g_batches->clear();
   for (int i = 8; i >= 0; --i) g_slots[i].clear();
@@ -416,27 +443,7 @@ int vector_solve_core(const int* nshape, const long long* iopt, const double* ro
   {
     const char* ge = getenv("NDSM_COMPONENT_GROUPS");
     const char* be = getenv("NDSM_BATCH_COMPONENTS");
-    std::string spec = ge ? ge : ((be && atoi(be) != 0) ? "012" : "");
-    int seen[3] = {0, 0, 0};
-    bool ok = !spec.empty();
-    std::vector<int> cur;
-    for (size_t i = 0; ok && i <= spec.size(); ++i) {
-      const char ch = i < spec.size() ? spec[i] : ',';
-      if (ch == ',') {
-        if (cur.empty()) { ok = false; break; }
-        std::sort(cur.begin(), cur.end());
-        groups.push_back(cur);
-        cur.clear();
-      } else if (ch >= '0' && ch <= '2' && !seen[ch - '0']) {
-        seen[ch - '0'] = 1;
-        cur.push_back(ch - '0');
-      } else {
-        ok = false;
-      }
-    }
-    if (!ok || !(seen[0] && seen[1] && seen[2])) groups.clear();
-    // a group's first member (lowest component) owns the group's stream and channel: order the groups by it
-    std::sort(groups.begin(), groups.end(), [](const std::vector<int>& x, const std::vector<int>& y) { return x[0] < y[0]; });
+    groups = parse_component_groups(ge ? ge : ((be && atoi(be) != 0) ? "012" : ""));
     if (prof_enabled() || g_debug || (int)iopt[IOPT_NCYCLES] <= 1) groups.clear();
     if (groups.size() > 1 && comm && comm->nlocal() != 1) groups.clear();   // several channels: one rank per process
     if (groups.size() > 1 && comm && !comm->one_sided()) groups.clear();

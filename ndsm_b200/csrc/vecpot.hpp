@@ -24,6 +24,10 @@ struct Report {
 };
 extern Report g_report;
 
+// NDSM_COMPONENT_GROUPS: "012" | "01,2" | "0,12" | "02,1" | "0,1,2" (every component once) -> sorted groups; anything
+// else -> none.  Host only.
+std::vector<std::vector<int>> parse_component_groups(const char* spec);
+
 // Optional capture of BC-setup intermediates for parity tests (device -> host copies, dense faces)
 struct BcCapture {
   double* chi[6] = {nullptr};

@@ -35,6 +35,8 @@ def _declare(lib):
                                                  c.c_double, vp, vp, vp, vp, vp, vp, vp]
     lib.ndsm_b200_last_partitioned_levels.restype = c.c_int
     lib.ndsm_b200_last_components_mode.restype = c.c_int
+    lib.ndsm_b200_parse_component_groups.argtypes = [c.c_char_p, vp]
+    lib.ndsm_b200_parse_component_groups.restype = c.c_int
     lib.ndsm_b200_new_mg_handle.argtypes = [c.c_int, vp, c.c_int, vp, vp, vp, c.c_int, c.c_int]
     lib.ndsm_b200_new_mg_handle.restype = vp
     lib.ndsm_b200_delete_mg_handle.argtypes = [vp]

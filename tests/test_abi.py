@@ -144,3 +144,27 @@ def test_plan_rejects_shapes_without_a_hierarchy(lib):
     from ndsm_b200.mg import Plan
     with pytest.raises(ValueError):
         Plan(aniso_mesh((3, 9, 9)))
+
+
+@pytest.mark.parametrize("spec,ngroups,group_of", [
+    ("012", 1, [0, 0, 0]),
+    ("210", 1, [0, 0, 0]),
+    ("01,2", 2, [0, 0, 1]),
+    ("2,01", 2, [0, 0, 1]),          # groups are ordered by their lowest component
+    ("02,1", 2, [0, 1, 0]),
+    ("0,12", 2, [0, 1, 1]),
+    ("0,1,2", 3, [0, 1, 2]),
+    ("", 0, [-1, -1, -1]),           # not a partition of {0,1,2}: ignored
+    ("01", 0, [-1, -1, -1]),
+    ("011,2", 0, [-1, -1, -1]),
+    ("0,,12", 0, [-1, -1, -1]),
+    ("013", 0, [-1, -1, -1]),
+    ("01,2,", 0, [-1, -1, -1]),
+    ("0 1 2", 0, [-1, -1, -1]),
+])
+def test_component_group_specs(lib, spec, ngroups, group_of):
+    """NDSM_COMPONENT_GROUPS (which component solves are batched into one launch sequence, mg_batch.cu): only a
+    partition of the three components is accepted, anything else leaves the default scheduling in place."""
+    out = (ctypes.c_int * 3)(7, 7, 7)
+    assert lib.ndsm_b200_parse_component_groups(spec.encode(), out) == ngroups
+    assert list(out) == group_of
