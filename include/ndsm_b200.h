@@ -161,7 +161,9 @@ int ndsm_b200_plan_restrict(const ndsm_b200_plan* p, int level, int dim, int* fi
 int ndsm_b200_ngrids_for(int nmin); /* FLOOR(LOG(nmin/2.0)/LOG(2.0)), ndsm_vector_potential.f90:341-342 */
 /* z-slab partition of the hierarchy over `world` ranks: *ndist = number of partitioned levels; zs holds
  * (ndist+1) rows of world+1 plane boundaries (row ndist = producers of the first replicated level).
- * zs must have room for ngrids*(world+1) ints. */
+ * zs must have room for ngrids*(world+1) ints.  min_planes >= 0: every level whose slabs keep that many planes is
+ * partitioned; min_planes < 0: the thresholds a solve on `world` ranks uses (16 planes per rank; 8e6 points per level,
+ * 1e6 from 8 ranks on; NDSM_SLAB_MIN_PLANES / NDSM_SLAB_MIN_POINTS override). */
 int ndsm_b200_plan_slab_partition(const ndsm_b200_plan* p, int world, int min_planes, int* ndist, int* zs);
 /* Host-only replay of the offset allocator of the multi-GPU symmetric heap (csrc/sym_alloc.hpp): ops[i] > 0 allocates
  * that many bytes and stores the offset in out[i] (-1: no room); ops[i] < 0 frees the block of operation -ops[i]-1.

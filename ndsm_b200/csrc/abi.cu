@@ -484,7 +484,10 @@ int ndsm_b200_plan_sym_heap(long long segment_bytes, const long long* ops, int n
 int ndsm_b200_plan_slab_partition(const ndsm_b200_plan* p, int world, int min_planes, int* ndist, int* zs) {
   if (!p || !ndist || !zs || world < 1) return NDSM_B200_ERR_ARG;
   try {
-    SlabPlan sp = plan_slabs(p->lv, p->ndim, world, min_planes);
+    // min_planes < 0: the thresholds a solve on `world` ranks uses (planes per rank and points per level)
+    long long min_points = 0;
+    if (min_planes < 0) slab_policy(world, &min_planes, &min_points);
+    SlabPlan sp = plan_slabs(p->lv, p->ndim, world, min_planes, min_points);
     *ndist = sp.ndist;
     for (size_t l = 0; l < sp.zs.size(); ++l)
       for (int r = 0; r <= world; ++r) zs[l * (world + 1) + r] = sp.zs[l][r];

@@ -250,6 +250,19 @@ struct VirtualComm : Comm {
 }  // namespace
 std::unique_ptr<Comm> make_virtual_comm(int world) { return std::unique_ptr<Comm>(new VirtualComm(world)); }
 
+// which levels are worth partitioning (the defaults and their environment overrides)
+void slab_policy(int world, int* min_planes, long long* min_points) {
+  *min_planes = 16;
+  // measured at 513^3: level 1 (256^3) costs 1.66 ms per V-cycle replicated and 1.52 ms partitioned over two
+  // ranks (8 halo exchanges included); 128^3 and below are cheaper replicated than exchanged
+  *min_points = 8000000;
+  // ... for up to four ranks.  From eight ranks on a replicated 129^3 level is seven eighths redundant work: measured
+  // at 513^3 on 8 GPUs, partitioning it as well takes the three solves from 64.6 to 62.7 ms (same results, bit for bit)
+  if (world >= 8) *min_points = 1000000;
+  if (const char* e = getenv("NDSM_SLAB_MIN_PLANES")) *min_planes = atoi(e);
+  if (const char* e = getenv("NDSM_SLAB_MIN_POINTS")) *min_points = atoll(e);
+}
+
 // ---------------------------------------------------------------------------------------------
 // MG
 // ---------------------------------------------------------------------------------------------
@@ -272,15 +285,9 @@ MG::MG(int ndim, const int* shape, int ngrids, const double* const* mesh, cudaSt
     for (int d = 0; d < 3; ++d) mesh_[g][d] = hl[g].mesh[d];
   }
   const int world = comm_ ? comm_->world() : 1;
-  int min_planes = 16;
-  // measured at 513^3: level 1 (256^3) costs 1.66 ms per V-cycle replicated and 1.52 ms partitioned over two
-  // ranks (8 halo exchanges included); 128^3 and below are cheaper replicated than exchanged
-  long long min_points = 8000000;
-  // ... for up to four ranks.  From eight ranks on a replicated 129^3 level is seven eighths redundant work: measured
-  // at 513^3 on 8 GPUs, partitioning it as well takes the three solves from 64.6 to 62.7 ms (same results, bit for bit)
-  if (world >= 8) min_points = 1000000;
-  if (const char* e = getenv("NDSM_SLAB_MIN_PLANES")) min_planes = atoi(e);
-  if (const char* e = getenv("NDSM_SLAB_MIN_POINTS")) min_points = atoll(e);
+  int min_planes;
+  long long min_points;
+  slab_policy(world, &min_planes, &min_points);
   plan_ = plan_slabs(hl, ndim, world, min_planes, min_points);
   valid_.assign(ngrids, std::array<int, 2>{{0, 0}});
   static_ok_.assign(ngrids, std::array<bool, 2>{{false, false}});

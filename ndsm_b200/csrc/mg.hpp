@@ -49,6 +49,9 @@ struct SlabPlan {
 // a level is partitioned only while every rank keeps at least min_planes planes and the level has at least
 // min_points points (smaller levels are replicated)
 SlabPlan plan_slabs(const std::vector<HostLevel>& hl, int ndim, int world, int min_planes, long long min_points = 0);
+// the thresholds MG uses for `world` ranks: 16 planes per rank; 8e6 points per level, 1e6 from 8 ranks on;
+// NDSM_SLAB_MIN_PLANES / NDSM_SLAB_MIN_POINTS override
+void slab_policy(int world, int* min_planes, long long* min_points);
 
 // Communication between slabs.  Two-sided, matched in call order per (from,to) pair; all calls are
 // enqueued on the stream and may be captured into a CUDA graph.

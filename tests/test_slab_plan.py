@@ -71,3 +71,31 @@ def test_expected_depth_for_headline_config():
     ndist1, zs1 = p.slab_partition(1, 16)
     assert ndist1 == 0 and len(zs1) == 0
     p.close()
+
+
+@pytest.mark.parametrize("shape,world,ndist_expected", [
+    ((513, 513, 513), 2, 2),      # 513^3 and 257^3 partitioned, 129^3 (2.1e6 points < 8e6) replicated
+    ((513, 513, 513), 4, 2),
+    ((513, 513, 513), 8, 3),      # from 8 ranks on the 129^3 level is partitioned too (16 planes per rank)
+    ((513, 513, 513), 16, 2),     # 129 / 16 = 8 planes per rank: below the 16-plane minimum
+    ((1025, 1025, 257), 8, 2),    # config 4: 257 and 129 planes; 65 / 8 = 8 planes: replicated
+    ((129, 129, 129), 8, 1),
+    ((129, 129, 129), 4, 0),      # 2.1e6 points: not worth exchanging on four ranks
+])
+def test_default_partition_depth(shape, world, ndist_expected):
+    """The thresholds a solve uses (min_planes < 0 in ndsm_b200_plan_slab_partition): measured choices, DESIGN.md 5."""
+    from ndsm_b200.mg import Plan
+    saved = {k: os.environ.pop(k, None) for k in ("NDSM_SLAB_MIN_PLANES", "NDSM_SLAB_MIN_POINTS", "NDSM_HALO_PLANES")}
+    try:
+        p = Plan(aniso_mesh(shape))
+        ndist, zs = p.slab_partition(world, -1)
+        assert ndist == ndist_expected
+        os.environ["NDSM_SLAB_MIN_POINTS"] = "0"       # the override is honoured
+        nd0, _ = p.slab_partition(world, -1)
+        assert nd0 >= ndist
+        p.close()
+    finally:
+        os.environ.pop("NDSM_SLAB_MIN_POINTS", None)
+        for k, v in saved.items():
+            if v is not None:
+                os.environ[k] = v
